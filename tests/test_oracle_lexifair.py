@@ -1,0 +1,62 @@
+"""Known-answer and cross-checks for the lexifair (lexicographic bottleneck) oracles."""
+import numpy as np
+import pytest
+
+from oracle import lexifair as lf
+
+
+def test_reference_fixed_instance():
+    # marl_fair_assign.py:63-64: the one instance the reference carries
+    goals = np.array([[0., -0.5], [0.45, -0.5], [0.9, -0.5]])
+    agents = np.array([[-0.9, -0.9], [-0.9, 0.], [-0.9, 0.9]])
+    d = agents[:, None, :] - goals[None, :, :]
+    costs = np.sqrt((d ** 2).sum(-1))
+    x, objs = lf.solve_fair_assignment(costs)
+    assert (np.where(x == 1)[1] == [2, 1, 0]).all()
+    np.testing.assert_allclose(objs, [1.843909, 1.664332, 1.439618], atol=1e-6)
+    assert (lf.lexifair_descent(costs) == [2, 1, 0]).all()
+    assert (np.argmax(lf.lexifair_milp(costs)[0], axis=1) == [2, 1, 0]).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7])
+def test_descent_equals_bruteforce(n):
+    rng = np.random.default_rng(n)
+    c = rng.random((120, n, n))
+    bf = lf.lexifair_bruteforce_batched(c)
+    for k in range(c.shape[0]):
+        assert (lf.lexifair_descent(c[k]) == bf[k]).all()
+        assert sorted(bf[k]) == list(range(n))
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_ties_follow_cost_i_j_order(n):
+    rng = np.random.default_rng(100 + n)
+    c = rng.integers(0, 3, (150, n, n)).astype(np.float64)
+    bf = lf.lexifair_bruteforce_batched(c)
+    for k in range(c.shape[0]):
+        assert (lf.lexifair_descent(c[k]) == bf[k]).all()
+
+
+@pytest.mark.parametrize("n", [3, 5])
+def test_milp_restatement_equals_bruteforce(n):
+    rng = np.random.default_rng(7 + n)
+    for _ in range(6):
+        c = rng.random((n, n)) * 2.0
+        x, _ = lf.lexifair_milp(c)
+        assert (np.argmax(x, axis=1) == lf.lexifair_bruteforce(c)).all()
+
+
+def test_descent_n16_is_lexicographically_minimal_against_random_swaps():
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        c = rng.random((16, 16))
+        m = lf.lexifair_descent(c)
+        assert sorted(m) == list(range(16))
+        best = np.sort(c[np.arange(16), m])[::-1]
+        for _ in range(300):                          # any 2- or 3-cycle change must not improve
+            p = m.copy()
+            idx = rng.choice(16, size=rng.integers(2, 4), replace=False)
+            p[idx] = p[np.roll(idx, 1)]
+            alt = np.sort(c[np.arange(16), p])[::-1]
+            k = np.nonzero(alt != best)[0]
+            assert k.size == 0 or alt[k[0]] > best[k[0]]
