@@ -1,0 +1,112 @@
+"""ctypes binding of ``libfairmarl.so`` (include/fairmarl.h).  Loading fails loudly: there is no
+fallback implementation."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from fair_marl_b200.build import library_path
+
+OBS_DIM, NODE_FEAT_DIM, INFO_DIM = 7, 11, 14
+INFO_KEYS = (
+    "individual_reward", "Dist_to_goal", "Time_req_to_goal", "Num_agent_collisions",
+    "Num_obst_collisions", "Distance_mean", "Distance_variance", "Mean_by_variance",
+    "Dists_traveled", "Time_taken", "Time_mean", "Time_stddev", "Time_mean_by_stddev",
+    "Min_time_to_goal",
+)
+
+
+class FmConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_agents", C.c_int32), ("num_obstacles", C.c_int32),
+        ("episode_length", C.c_int32), ("env_offset", C.c_int64), ("seed", C.c_uint64),
+        ("world_size", C.c_double), ("max_speed", C.c_double), ("collision_rew", C.c_double),
+        ("goal_rew", C.c_double), ("min_dist_thresh", C.c_double), ("fair_rew", C.c_double),
+        ("zeroshift", C.c_double), ("max_edge_dist", C.c_double),
+        ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32),
+        ("info_every_step", C.c_int32),
+    ]
+
+
+class FmOutputs(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("node_obs", C.c_void_p), ("adj", C.c_void_p),
+                ("reward", C.c_void_p), ("done", C.c_void_p), ("info", C.c_void_p)]
+
+
+STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_match", "dists_to_goal",
+                "times_required", "dist_left_to_goal", "num_agent_collisions", "num_obstacle_collisions",
+                "dist_traveled_mean", "dist_traveled_stddev", "step", "min_time", "episode")
+STATE_INT_FIELDS = ("goal_match", "num_agent_collisions", "num_obstacle_collisions", "step", "episode")
+
+
+class FmState(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in STATE_FIELDS]
+
+
+class FairMarlError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.isfile(path):
+        raise FairMarlError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  fair_marl_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    sig = {
+        "fm_abi_version": ([], C.c_int),
+        "fm_last_error": ([], C.c_char_p),
+        "fm_stats_len": ([i32], C.c_int),
+        "fm_create": ([C.POINTER(FmConfig), C.c_int, C.POINTER(vp)], C.c_int),
+        "fm_destroy": ([vp], C.c_int),
+        "fm_reset": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_step": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_step_onehot": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_step_host": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_reset_host": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_read_info_host": ([vp, vp, vp], C.c_int),
+        "fm_set_state": ([vp, C.POINTER(FmState), vp], C.c_int),
+        "fm_get_state": ([vp, C.POINTER(FmState), vp], C.c_int),
+        "fm_assign_costs": ([C.c_int, vp, i32, i32, vp, vp], C.c_int),
+        "fm_assign_positions": ([C.c_int, vp, vp, i32, i32, vp, vp], C.c_int),
+        "fm_edge_list": ([C.c_int, vp, i32, i32, C.c_double, i32, i32, i64, vp, vp, vp, vp, vp], C.c_int),
+        "fm_stats_read": ([vp, vp, i32, vp], C.c_int),
+        "fm_num_entities": ([vp], C.c_int),
+        "fm_algorithmic_bytes_per_step": ([vp], i64),
+        "fm_kernel_launches": ([vp, C.POINTER(i64)], C.c_int),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export the ABI
+        fn.argtypes, fn.restype = argtypes, restype
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "fm_abi_version", "fm_last_error", "fm_stats_len", "fm_create", "fm_destroy", "fm_reset", "fm_step",
+    "fm_step_onehot", "fm_step_host", "fm_reset_host", "fm_read_info_host", "fm_set_state", "fm_get_state",
+    "fm_assign_costs", "fm_assign_positions", "fm_edge_list", "fm_stats_read", "fm_num_entities",
+    "fm_algorithmic_bytes_per_step", "fm_kernel_launches",
+)
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().fm_last_error().decode(errors="replace")
+        raise FairMarlError(f"{what or 'libfairmarl'} failed ({rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise FairMarlError("no CUDA device visible: fair_marl_b200 has no CPU path")
+    return torch

@@ -1,0 +1,54 @@
+"""Simulator configuration: the argparse fields ``Scenario.make_world`` reads
+(navigation_graph.py:94-129, :144, :188, :208; defaults config.py:176-253, train_mpe.py:72-101)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, fields
+from typing import Any, Optional
+
+
+@dataclass
+class SimConfig:
+    num_agents: int = 3
+    num_obstacles: int = 3
+    world_size: float = 2.0
+    max_speed: Optional[float] = 2.0
+    collision_rew: float = 5.0
+    goal_rew: float = 5.0
+    min_dist_thresh: float = 0.05
+    episode_length: int = 25
+    fair_rew: float = 1.0
+    zeroshift: float = 5.0
+    max_edge_dist: float = 1.0
+    collaborative: bool = False
+    # navigation_graph.py (FA+FR) vs nav_graph_goalassign_noFair.py (FA)
+    fairness_reward: bool = True
+    auto_reset: bool = True
+    info_every_step: bool = False
+
+    @property
+    def num_entities(self) -> int:
+        return 2 * self.num_agents + self.num_obstacles
+
+    @classmethod
+    def from_args(cls, args: Any, **overrides) -> "SimConfig":
+        """Build from the reference's flat ``all_args`` Namespace (or any object with those fields)."""
+        kw = {}
+        for f in fields(cls):
+            if hasattr(args, f.name):
+                kw[f.name] = getattr(args, f.name)
+        if hasattr(args, "num_landmarks") and args.num_landmarks != kw.get("num_agents", 3):
+            raise ValueError("navigation_graph needs num_landmarks == num_agents "
+                             f"(got {args.num_landmarks} vs {kw.get('num_agents')})")
+        if getattr(args, "num_walls", 0):
+            raise NotImplementedError("num_walls > 0 is not supported (SURVEY.md row N4)")
+        if getattr(args, "graph_feat_type", "relative") != "relative":
+            raise NotImplementedError("graph_feat_type='global' is not supported (SURVEY.md row N4)")
+        if getattr(args, "num_scripted_agents", 0):
+            raise NotImplementedError("scripted agents are not supported")
+        scen = getattr(args, "scenario_name", "navigation_graph")
+        if scen == "nav_graph_goalassign_noFair":
+            kw["fairness_reward"] = False
+        elif scen != "navigation_graph":
+            raise NotImplementedError(f"scenario {scen!r} is not supported (navigation_graph family only)")
+        kw.update(overrides)
+        return cls(**kw)

@@ -1,0 +1,380 @@
+// C ABI of libfairmarl.so (include/fairmarl.h): handle management, argument checking, launches.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "fm_device.cuh"
+#include "fm_launch.h"
+
+using fm::DevParams;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define FM_CUDA(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(FM_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct FmHandle {
+  FmConfig cfg;
+  int device;
+  DevParams p;
+  void* state_block;
+  double* stats;
+  int stats_rows, K;
+  long long launches;
+  // device staging for the *_host entry points (allocated on first use)
+  float* st_onehot;
+  uint8_t* st_mask;
+  FmOutputs st_out;
+  bool staging;
+};
+
+static inline int round4(long long x) { return (int)((x + 3) & ~3LL); }
+
+static int use_device(int device) {
+  int cur = -1;
+  FM_CUDA(cudaGetDevice(&cur));
+  if (cur != device) FM_CUDA(cudaSetDevice(device));
+  return FM_OK;
+}
+
+extern "C" {
+
+int fm_abi_version(void) { return FM_ABI_VERSION; }
+const char* fm_last_error(void) { return g_err; }
+int fm_stats_len(int32_t n) { return 15 * n + 2; }
+
+int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
+  if (!cfg || !out) return fail(FM_ERR_INVALID_ARG, "fm_create: null argument");
+  *out = nullptr;
+  if (cfg->num_envs <= 0) return fail(FM_ERR_INVALID_ARG, "fm_create: num_envs must be > 0 (got %d)", cfg->num_envs);
+  if (cfg->num_agents < 1 || cfg->num_agents > FM_MAX_AGENTS)
+    return fail(FM_ERR_INVALID_ARG, "fm_create: num_agents must be in 1..%d (got %d)", FM_MAX_AGENTS, cfg->num_agents);
+  if (cfg->num_obstacles < 0 || cfg->num_obstacles > 64)
+    return fail(FM_ERR_INVALID_ARG, "fm_create: num_obstacles must be in 0..64 (got %d)", cfg->num_obstacles);
+  if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_create: episode_length must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(FM_ERR_NO_DEVICE, "fm_create: no CUDA device (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(FM_ERR_INVALID_ARG, "fm_create: device %d out of range (%d devices)", device, ndev);
+  int rc = use_device(device);
+  if (rc) return rc;
+
+  FmHandle* h = new (std::nothrow) FmHandle();
+  if (!h) return fail(FM_ERR_CUDA, "fm_create: out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  DevParams& p = h->p;
+  const int B = cfg->num_envs, N = cfg->num_agents, O = cfg->num_obstacles, E = 2 * N + O;
+  p.B = B; p.N = N; p.O = O; p.E = E;
+  p.Bp = (B + 31) & ~31;
+  const size_t Bp = (size_t)p.Bp;
+  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4);
+  cudaError_t e = cudaMalloc(&h->state_block, words * 4);
+  if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc(%zu B): %s", words * 4, cudaGetErrorString(e)); }
+  cudaMemset(h->state_block, 0, words * 4);
+  float* f = (float*)h->state_block;
+  auto take = [&](size_t n) { float* r = f; f += n; return r; };
+  p.px = take(Bp * N); p.py = take(Bp * N); p.vx = take(Bp * N); p.vy = take(Bp * N); p.pdist = take(Bp * N);
+  p.dtg = take(Bp * N); p.treq = take(Bp * N); p.dleft = take(Bp * N); p.mintime = take(Bp * N);
+  p.gm = (int*)take(Bp * N); p.nac = (int*)take(Bp * N); p.noc = (int*)take(Bp * N);
+  p.lx = take(Bp * N); p.ly = take(Bp * N);
+  p.ox = take(Bp * O); p.oy = take(Bp * O);
+  p.dmean = take(Bp); p.dstd = take(Bp); p.step = (int*)take(Bp); p.episode = (int*)take(Bp);
+
+  // config -> device constants.  Collision threshold exactly as the reference spells it:
+  // 1.05*(size + size) (navigation_graph.py:655, :704); cached min_dist = size + size (core.py:215).
+  const double size = 0.05;
+  p.min_dist_thresh = cfg->min_dist_thresh;
+  p.dcoll = 1.05 * (size + size);
+  p.max_speed = cfg->max_speed;
+  p.has_max_speed = cfg->max_speed > 0.0;
+  p.dt = 0.1;
+  p.damping_keep = 1 - 0.25;
+  p.zeroshift = cfg->zeroshift;
+  p.fair_rew_d = cfg->fair_rew;
+  p.goal_rew = (float)cfg->goal_rew;
+  p.coll_rew = (float)cfg->collision_rew;
+  p.fair_rew = (float)cfg->fair_rew;
+  p.world_size = (float)cfg->world_size;
+  p.half_world = (float)(cfg->world_size / 2);
+  p.clip_lo = (float)(-2 * cfg->collision_rew);             // navigation_graph.py:824
+  p.clip_hi = (float)(cfg->goal_rew + cfg->fair_rew);
+  p.contact_force = 3e2f;                                    // core.py:153-160
+  p.contact_margin = 2e-2f;
+  p.dist_min = (float)(size + size);
+  p.episode_length = cfg->episode_length;
+  p.fairness_reward = cfg->fairness_reward;
+  p.collaborative = cfg->collaborative;
+  p.auto_reset = cfg->auto_reset;
+  p.info_every_step = cfg->info_every_step;
+  p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull);
+  p.seed_hi = (uint32_t)(cfg->seed >> 32);
+  p.env_offset = cfg->env_offset;
+
+  const int G = fm::group_size(N), EPW = 32 / G;
+  p.sm_cost = round4(2LL * EPW * N * N);
+  p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
+  p.sm_adj = round4((long long)EPW * E * E);
+  p.sm_stage = 32 * fm::NODE_F;
+  p.sm_obs = round4((long long)EPW * N * fm::OBS_F);
+  p.sm_asg = round4((long long)EPW * (5 * N + 1));
+  p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_stage + p.sm_obs + p.sm_asg;
+  if ((size_t)p.sm_per_warp * 4 * 4 > 227 * 1024) {
+    cudaFree(h->state_block); delete h;
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: N=%d O=%d needs %d B of shared memory per CTA", N, O, p.sm_per_warp * 16);
+  }
+  h->K = fm_stats_len(N);
+  h->stats_rows = fm::num_warps(B, N);
+  e = cudaMalloc(&h->stats, (size_t)h->stats_rows * h->K * sizeof(double));
+  if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc stats: %s", cudaGetErrorString(e)); }
+  cudaMemset(h->stats, 0, (size_t)h->stats_rows * h->K * sizeof(double));
+  p.stats = h->stats;
+  e = fm::prepare_kernels(p);
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
+  e = fm::launch_state_init(p, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
+  h->launches = 1;
+  *out = h;
+  return FM_OK;
+}
+
+static void free_staging(FmHandle* h) {
+  if (!h->staging) return;
+  cudaFree(h->st_onehot); cudaFree(h->st_mask);
+  cudaFree(h->st_out.obs); cudaFree(h->st_out.node_obs); cudaFree(h->st_out.adj);
+  cudaFree(h->st_out.reward); cudaFree(h->st_out.done); cudaFree(h->st_out.info);
+  h->staging = false;
+}
+
+int fm_destroy(FmHandle* h) {
+  if (!h) return FM_OK;
+  use_device(h->device);
+  free_staging(h);
+  cudaFree(h->stats);
+  cudaFree(h->state_block);
+  delete h;
+  return FM_OK;
+}
+
+static void set_outputs(DevParams& p, const FmOutputs* out) {
+  p.o_obs = out ? out->obs : nullptr;
+  p.o_node = out ? out->node_obs : nullptr;
+  p.o_adj = out ? out->adj : nullptr;
+  p.o_rew = out ? out->reward : nullptr;
+  p.o_done = out ? out->done : nullptr;
+  p.o_info = out ? out->info : nullptr;
+}
+
+int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* stream) {
+  if (!h) return fail(FM_ERR_INVALID_ARG, "fm_reset: null handle");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  DevParams p = h->p;
+  set_outputs(p, out);
+  p.reset_mask = mask;
+  p.act_idx = nullptr; p.act_onehot = nullptr;
+  FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, true));
+  h->launches += 1;
+  return FM_OK;
+}
+
+static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, const FmOutputs* out, void* stream) {
+  if (!h) return fail(FM_ERR_INVALID_ARG, "fm_step: null handle");
+  if (!idx && !onehot) return fail(FM_ERR_INVALID_ARG, "fm_step: null actions");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  DevParams p = h->p;
+  set_outputs(p, out);
+  p.act_idx = idx; p.act_onehot = onehot; p.reset_mask = nullptr;
+  FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, false));
+  h->launches += 1;
+  return FM_OK;
+}
+
+int fm_step(FmHandle* h, const int32_t* actions, const FmOutputs* out, void* stream) {
+  return step_common(h, actions, nullptr, out, stream);
+}
+
+int fm_step_onehot(FmHandle* h, const float* onehot, const FmOutputs* out, void* stream) {
+  return step_common(h, nullptr, onehot, out, stream);
+}
+
+static int ensure_staging(FmHandle* h) {
+  if (h->staging) return FM_OK;
+  const size_t B = h->p.B, N = h->p.N, E = h->p.E;
+  FM_CUDA(cudaMalloc(&h->st_onehot, B * N * 5 * sizeof(float)));
+  FM_CUDA(cudaMalloc(&h->st_mask, B));
+  FM_CUDA(cudaMalloc(&h->st_out.obs, B * N * fm::OBS_F * sizeof(float)));
+  FM_CUDA(cudaMalloc(&h->st_out.node_obs, B * N * E * fm::NODE_F * sizeof(float)));
+  FM_CUDA(cudaMalloc(&h->st_out.adj, B * E * E * sizeof(float)));
+  FM_CUDA(cudaMalloc(&h->st_out.reward, B * N * sizeof(float)));
+  FM_CUDA(cudaMalloc(&h->st_out.done, B * N));
+  FM_CUDA(cudaMalloc(&h->st_out.info, B * N * fm::INFO_F * sizeof(float)));
+  FM_CUDA(cudaMemset(h->st_out.info, 0, B * N * fm::INFO_F * sizeof(float)));
+  h->staging = true;
+  return FM_OK;
+}
+
+static int copy_outputs_to_host(FmHandle* h, const FmOutputs* out_host, bool with_step_outputs, cudaStream_t st) {
+  const size_t B = h->p.B, N = h->p.N, E = h->p.E;
+  if (!out_host) return FM_OK;
+  if (out_host->obs) FM_CUDA(cudaMemcpyAsync(out_host->obs, h->st_out.obs, B * N * fm::OBS_F * 4, cudaMemcpyDeviceToHost, st));
+  if (out_host->node_obs) FM_CUDA(cudaMemcpyAsync(out_host->node_obs, h->st_out.node_obs, B * N * E * fm::NODE_F * 4, cudaMemcpyDeviceToHost, st));
+  if (out_host->adj) FM_CUDA(cudaMemcpyAsync(out_host->adj, h->st_out.adj, B * E * E * 4, cudaMemcpyDeviceToHost, st));
+  if (with_step_outputs) {
+    if (out_host->reward) FM_CUDA(cudaMemcpyAsync(out_host->reward, h->st_out.reward, B * N * 4, cudaMemcpyDeviceToHost, st));
+    if (out_host->done) FM_CUDA(cudaMemcpyAsync(out_host->done, h->st_out.done, B * N, cudaMemcpyDeviceToHost, st));
+    if (out_host->info) FM_CUDA(cudaMemcpyAsync(out_host->info, h->st_out.info, B * N * fm::INFO_F * 4, cudaMemcpyDeviceToHost, st));
+  }
+  return FM_OK;
+}
+
+int fm_step_host(FmHandle* h, const float* onehot_host, const FmOutputs* out_host, void* stream) {
+  if (!h || !onehot_host) return fail(FM_ERR_INVALID_ARG, "fm_step_host: null argument");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = h->p.B, N = h->p.N;
+  FM_CUDA(cudaMemcpyAsync(h->st_onehot, onehot_host, B * N * 5 * sizeof(float), cudaMemcpyHostToDevice, st));
+  FmOutputs dev = h->st_out;
+  rc = step_common(h, nullptr, h->st_onehot, &dev, stream);
+  if (rc) return rc;
+  rc = copy_outputs_to_host(h, out_host, true, st);
+  if (rc) return rc;
+  FM_CUDA(cudaStreamSynchronize(st));
+  return FM_OK;
+}
+
+int fm_read_info_host(FmHandle* h, float* info_host, void* stream) {
+  if (!h || !info_host) return fail(FM_ERR_INVALID_ARG, "fm_read_info_host: null argument");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  FM_CUDA(cudaMemcpyAsync(info_host, h->st_out.info, (size_t)h->p.B * h->p.N * fm::INFO_F * 4, cudaMemcpyDeviceToHost, st));
+  FM_CUDA(cudaStreamSynchronize(st));
+  return FM_OK;
+}
+
+int fm_reset_host(FmHandle* h, const uint8_t* mask_host, const FmOutputs* out_host, void* stream) {
+  if (!h) return fail(FM_ERR_INVALID_ARG, "fm_reset_host: null handle");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mask_host) FM_CUDA(cudaMemcpyAsync(h->st_mask, mask_host, (size_t)h->p.B, cudaMemcpyHostToDevice, st));
+  FmOutputs dev = h->st_out;
+  dev.reward = nullptr; dev.done = nullptr; dev.info = nullptr;
+  rc = fm_reset(h, mask_host ? h->st_mask : nullptr, &dev, stream);
+  if (rc) return rc;
+  rc = copy_outputs_to_host(h, out_host, false, st);
+  if (rc) return rc;
+  FM_CUDA(cudaStreamSynchronize(st));
+  return FM_OK;
+}
+
+int fm_set_state(FmHandle* h, const FmState* st, void* stream) {
+  if (!h || !st) return fail(FM_ERR_INVALID_ARG, "fm_set_state: null argument");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_state_io(h->p, *st, 1, (cudaStream_t)stream));
+  h->launches += 1;
+  return FM_OK;
+}
+
+int fm_get_state(FmHandle* h, const FmState* st, void* stream) {
+  if (!h || !st) return fail(FM_ERR_INVALID_ARG, "fm_get_state: null argument");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_state_io(h->p, *st, 0, (cudaStream_t)stream));
+  h->launches += 1;
+  return FM_OK;
+}
+
+int fm_assign_costs(int device, const double* costs, int32_t num, int32_t n, int32_t* out, void* stream) {
+  if (!costs || !out) return fail(FM_ERR_INVALID_ARG, "fm_assign_costs: null argument");
+  if (n < 1 || n > FM_MAX_AGENTS) return fail(FM_ERR_INVALID_ARG, "fm_assign_costs: n must be in 1..%d (got %d)", FM_MAX_AGENTS, n);
+  if (num < 0) return fail(FM_ERR_INVALID_ARG, "fm_assign_costs: num < 0");
+  int rc = use_device(device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_assign(costs, nullptr, nullptr, num, n, out, (cudaStream_t)stream));
+  return FM_OK;
+}
+
+int fm_assign_positions(int device, const float* agent_pos, const float* goal_pos, int32_t num, int32_t n,
+                        int32_t* out, void* stream) {
+  if (!agent_pos || !goal_pos || !out) return fail(FM_ERR_INVALID_ARG, "fm_assign_positions: null argument");
+  if (n < 1 || n > FM_MAX_AGENTS) return fail(FM_ERR_INVALID_ARG, "fm_assign_positions: n must be in 1..%d (got %d)", FM_MAX_AGENTS, n);
+  if (num < 0) return fail(FM_ERR_INVALID_ARG, "fm_assign_positions: num < 0");
+  int rc = use_device(device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_assign(nullptr, agent_pos, goal_pos, num, n, out, (cudaStream_t)stream));
+  return FM_OK;
+}
+
+int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, double max_edge_dist, int32_t inclusive,
+                 int32_t repeat, int64_t capacity, int64_t* graph_offsets, int64_t* edge_index, float* edge_attr,
+                 int64_t* nnz_out, void* stream) {
+  if (!graph_offsets || !edge_index || !edge_attr) return fail(FM_ERR_INVALID_ARG, "fm_edge_list: null output");
+  if (num_graphs < 0 || E < 1 || repeat < 1 || capacity < 0) return fail(FM_ERR_INVALID_ARG, "fm_edge_list: bad sizes");
+  if (num_graphs > 0 && !adj) return fail(FM_ERR_INVALID_ARG, "fm_edge_list: null adj");
+  int rc = use_device(device);
+  if (rc) return rc;
+  // counts scratch lives at the tail of graph_offsets' own storage? No: keep the ABI honest and
+  // allocate it stream-ordered.
+  int* counts = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  FM_CUDA(cudaMallocAsync((void**)&counts, sizeof(int) * (size_t)(num_graphs > 0 ? num_graphs : 1), st));
+  cudaError_t e = fm::launch_edge_list(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity,
+                                       counts, (long long*)graph_offsets, (long long*)edge_index, edge_attr,
+                                       (long long*)nnz_out, st);
+  cudaFreeAsync(counts, st);
+  if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_edge_list: %s", cudaGetErrorString(e));
+  return FM_OK;
+}
+
+int fm_stats_read(FmHandle* h, double* out_dev, int32_t clear, void* stream) {
+  if (!h || !out_dev) return fail(FM_ERR_INVALID_ARG, "fm_stats_read: null argument");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_stats_reduce(h->stats, h->stats_rows, h->K, out_dev, clear, (cudaStream_t)stream));
+  h->launches += 1;
+  return FM_OK;
+}
+
+int fm_num_entities(const FmHandle* h) { return h ? h->p.E : 0; }
+
+int64_t fm_algorithmic_bytes_per_step(const FmHandle* h) {
+  if (!h) return 0;
+  const int64_t N = h->p.N, O = h->p.O, E = h->p.E;
+  return (30 * N + 2 * O + 5 + 11 * N * E + E * E) * 4 * (int64_t)h->p.B;
+}
+
+int fm_kernel_launches(const FmHandle* h, int64_t* out) {
+  if (!h || !out) return fail(FM_ERR_INVALID_ARG, "fm_kernel_launches: null argument");
+  *out = h->launches;
+  return FM_OK;
+}
+
+}  // extern "C"

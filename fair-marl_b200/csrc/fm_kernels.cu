@@ -1,0 +1,626 @@
+// Kernels of the B200-native navigation_graph simulator (compiled for sm_100a only).
+//
+//   step_kernel<G>    fused env step: action decode -> forces -> integration -> E x E distances ->
+//                     per-agent observation / reward / info latches in the reference's sequential
+//                     order -> done -> auto-reset (randomised placement + lexifair assignment) ->
+//                     node features, adjacency, obs streamed out in API layout with 16-byte stores.
+//   reset_kernel<G>   masked reset + observation of the current state (reset() path).
+//   assign_kernel<G>  stand-alone batched lexifair assignment.
+//   pack/unpack       API-layout FmState <-> internal SoA state.
+//   edge_*            policy-side edge list (process_adj) by warp ballot + prefix compaction.
+//   stats_reduce      fixed-order reduction of the per-warp statistic partial sums.
+#include "fm_device.cuh"
+#include "fm_launch.h"
+
+namespace fm {
+
+constexpr int THREADS = 128;   // 4 warps per CTA; no block-level barrier is used
+
+// =============================================================================================
+// The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
+template <int G>
+__global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ DevParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int EPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (THREADS / 32) + wib;
+  const int env0 = gw * EPW;
+  if (env0 >= p.B) return;                       // warp-uniform
+  const int nenv = min(EPW, p.B - env0);
+  const int el = lane / G, i = lane % G;
+  const int env = env0 + el;
+  const int N = p.N, O = p.O, E = p.E;
+  const bool venv = el < nenv;
+  const bool act = venv && i < N;
+  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
+  const int gl = el * G;                         // first lane of my group
+  const WarpSmem s = carve(p, smem, wib);
+  float* ent = s.ent + (size_t)el * E * ENT_STRIDE;
+  float* adj = s.adj + (size_t)el * E * E;
+  float* obs = s.obs + (size_t)el * N * OBS_F;
+  const size_t idx = (size_t)i * p.Bp + env;
+
+  // ---- load state ---------------------------------------------------------------------------
+  float px = 0.f, py = 0.f, vx = 0.f, vy = 0.f, pd = 0.f, dtg = -1.f, treq = -1.f, dleft = -1.f, mint = 0.f;
+  int gm = 0, nac = 0, noc = 0;
+  float ux = 0.f, uy = 0.f;
+  if (act) {
+    px = p.px[idx]; py = p.py[idx]; vx = p.vx[idx]; vy = p.vy[idx]; pd = p.pdist[idx];
+    dtg = p.dtg[idx]; treq = p.treq[idx]; dleft = p.dleft[idx];
+    gm = p.gm[idx]; nac = p.nac[idx]; noc = p.noc[idx];
+    // action decode, environment.py:301-311: u = [a1 - a2, a3 - a4] * sensitivity (5.0)
+    if (p.act_idx) {
+      const int a = p.act_idx[(size_t)env * N + i];
+      ux = ((a == 1) ? 1.f : 0.f) - ((a == 2) ? 1.f : 0.f);
+      uy = ((a == 3) ? 1.f : 0.f) - ((a == 4) ? 1.f : 0.f);
+    } else {
+      const float* oh = p.act_onehot + ((size_t)env * N + i) * 5;
+      ux = oh[1] - oh[2];
+      uy = oh[3] - oh[4];
+    }
+    ux *= 5.0f; uy *= 5.0f;
+    const float lxx = p.lx[idx], lyy = p.ly[idx];
+    float* l = ent + (N + i) * ENT_STRIDE;
+    l[0] = lxx; l[1] = lyy; l[2] = 0.f; l[3] = 0.f; l[4] = lxx; l[5] = lyy;
+  }
+  int step = 0; uint32_t episode = 0; float dmean = 0.f, dstd = 0.f;
+  if (venv) {
+    step = p.step[env]; episode = (uint32_t)p.episode[env]; dmean = p.dmean[env]; dstd = p.dstd[env];
+    for (int k = i; k < O; k += G) {
+      const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
+      float* o = ent + (2 * N + k) * ENT_STRIDE;
+      o[0] = x; o[1] = y; o[2] = 0.f; o[3] = 0.f; o[4] = x; o[5] = y;
+    }
+  }
+  __syncwarp();
+
+  // ---- World.step: forces (core.py:277-316, :370-404) from the positions at step entry --------
+  // (== the reference's end-of-previous-step distance cache), partners in ascending entity index.
+  float Fx = ux, Fy = uy;                        // mass(1.0) * u + noise(0.0), core.py:291-293
+  for (int j = 0; j < N; ++j) {
+    const float qx = __shfl_sync(FULL, px, gl + j), qy = __shfl_sync(FULL, py, gl + j);
+    if (act && j != i) contact_force(p, px, py, qx, qy, Fx, Fy);
+  }
+  if (act) {
+    for (int k = 0; k < O; ++k) {
+      const float* o = ent + (2 * N + k) * ENT_STRIDE;
+      contact_force(p, px, py, o[0], o[1], Fx, Fy);
+    }
+  }
+  // ---- integrate_state (core.py:338-356), float64 so that p_dist keeps its low bits for the
+  // ill-conditioned mean/std fairness ratio; state is stored rounded to fp32.
+  double v64x = (double)vx * p.damping_keep + (double)Fx * p.dt;
+  double v64y = (double)vy * p.damping_keep + (double)Fy * p.dt;
+  if (p.has_max_speed) {
+    const double speed = sqrt(v64x * v64x + v64y * v64y);
+    if (speed > p.max_speed) { v64x = v64x / speed * p.max_speed; v64y = v64y / speed * p.max_speed; }
+  }
+  const double sx = v64x * p.dt, sy = v64y * p.dt;
+  const double pd64 = (double)pd + sqrt(sx * sx + sy * sy);
+  const float npx0 = (float)((double)px + sx), npy0 = (float)((double)py + sy);
+  float npx = npx0, npy = npy0;
+  float nvx = (float)v64x, nvy = (float)v64y;
+  float npd = (float)pd64;
+  const int nstep = step + 1;                    // environment.py:819, :823
+  if (act) {
+    float* a = ent + i * ENT_STRIDE;
+    const float* g = ent + (N + gm) * ENT_STRIDE;
+    a[0] = npx; a[1] = npy; a[2] = nvx; a[3] = nvy; a[4] = g[0]; a[5] = g[1];
+  }
+  __syncwarp();
+
+  // ---- calculate_distances (core.py:204-228) at the new positions -----------------------------
+  double dgoal; int ncoll; bool ocoll;
+  if (venv) distance_tile<G>(p, ent, adj, i, act, gm, dgoal, ncoll, ocoll);
+  else { dgoal = 0.0; ncoll = 0; ocoll = false; }
+
+  // ---- per-agent loop of MultiAgentGraphEnv.step (environment.py:832-864): agent i's observation
+  // and reward read world.dist_traveled_mean/stddev as left by agent i-1's info_callback
+  // (navigation_graph.py:617-618), agent 0 reads last step's values.  dists_to_goal after agent j's
+  // info_callback is p_dist_j unless it latched in an earlier step (:587-598).
+  const bool latched = treq != -1.0f;
+  const double dtg_prev = (double)dtg;
+  const double dtg_new = latched ? dtg_prev : pd64;
+  const bool reached = dgoal < p.min_dist_thresh;
+  const double treq_prev = (double)treq;
+  const double treq_new = (!latched && reached) ? (double)nstep * p.dt : treq_prev;   // :588
+  const float dleft_new = latched ? dleft : (float)dgoal;
+  double sum_p = 0.0, sum_v = 0.0, sum_a = 0.0;
+  for (int j = 0; j < N; ++j) {
+    const double pj = __shfl_sync(FULL, pd64, gl + j);
+    const double aj = __shfl_sync(FULL, dtg_new, gl + j);
+    const double bj = __shfl_sync(FULL, dtg_prev, gl + j);
+    sum_p += pj; sum_a += aj; sum_v += (j < i) ? aj : bj;
+  }
+  const double mean_p = sum_p / N, mean_v = sum_v / N, mean_a = sum_a / N;
+  double q_p = 0.0, q_v = 0.0, q_a = 0.0;
+  for (int j = 0; j < N; ++j) {
+    const double pj = __shfl_sync(FULL, pd64, gl + j);
+    const double aj = __shfl_sync(FULL, dtg_new, gl + j);
+    const double bj = __shfl_sync(FULL, dtg_prev, gl + j);
+    const double dp = pj - mean_p, da = aj - mean_a, dv = ((j < i) ? aj : bj) - mean_v;
+    q_p += dp * dp; q_a += da * da; q_v += dv * dv;
+  }
+  const double std_p = sqrt(q_p / N), std_v = sqrt(q_v / N), std_a = sqrt(q_a / N);
+  double fparam;                                 // navigation_graph.py:764-769 / :849-853
+  if (dtg == -1.0f) fparam = mean_p / (std_p + 0.0001);
+  else if (i == 0) fparam = (double)dmean / ((double)dstd + 0.0001);
+  else fparam = mean_v / (std_v + 0.0001);
+
+  // reward (navigation_graph.py:760-824)
+  float rew = reached ? p.goal_rew : -(float)dgoal;
+  rew -= p.coll_rew * (float)ncoll;
+  if (ocoll) rew -= p.coll_rew;
+  if (p.fairness_reward) {
+    float fair = p.fair_rew * tanhf((float)(fparam - p.zeroshift));
+    if (fair < -2.0f) fair = -2.0f;
+    rew += fair;
+  }
+  rew = fminf(fmaxf(rew, p.clip_lo), p.clip_hi);
+  const float own_rew = rew;
+  if (p.collaborative) {                         // environment.py:866-870
+    float tot = 0.f;
+    for (int j = 0; j < N; ++j) tot += __shfl_sync(FULL, own_rew, gl + j);
+    rew = tot;
+  }
+  nac += ncoll;                                  // :604-613
+  noc += ocoll ? 1 : 0;                          // :602-603
+  const bool done = nstep >= p.episode_length;   // environment.py:237-247 (agent.status is never set)
+  const bool do_reset = venv && done && (p.auto_reset != 0);
+
+  // ---- info rows (navigation_graph.py:625-647); world-level means as seen right after agent i's own
+  // info_callback, i.e. over [new_0..new_i, prev_i+1..prev_N-1].
+  const bool want_info = venv && (p.o_info != nullptr || p.stats != nullptr) && (done || p.info_every_step);
+  float info[INFO_F];
+  if (__any_sync(FULL, want_info)) {
+    double sd = 0.0, st = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double aj = __shfl_sync(FULL, dtg_new, gl + j), bj = __shfl_sync(FULL, dtg_prev, gl + j);
+      const double tj = __shfl_sync(FULL, treq_new, gl + j), uj = __shfl_sync(FULL, treq_prev, gl + j);
+      sd += (j <= i) ? aj : bj; st += (j <= i) ? tj : uj;
+    }
+    const double md = sd / N, mt = st / N;
+    double qd = 0.0, qt = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double aj = __shfl_sync(FULL, dtg_new, gl + j), bj = __shfl_sync(FULL, dtg_prev, gl + j);
+      const double tj = __shfl_sync(FULL, treq_new, gl + j), uj = __shfl_sync(FULL, treq_prev, gl + j);
+      const double dd = ((j <= i) ? aj : bj) - md, dtt = ((j <= i) ? tj : uj) - mt;
+      qd += dd * dd; qt += dtt * dtt;
+    }
+    const double sdv = sqrt(qd / N), stv = sqrt(qt / N);
+    double tacc = 0.0;                           // entity.state.time += dt per step (core.py:355)
+    for (int k = 0; k < nstep; ++k) tacc += p.dt;
+    info[0] = own_rew; info[1] = dleft_new; info[2] = (float)treq_new; info[3] = (float)nac; info[4] = (float)noc;
+    info[5] = (float)md; info[6] = (float)sdv; info[7] = (float)(md / (sdv + 0.0001)); info[8] = (float)dtg_new;
+    info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv; info[12] = (float)(mt / (stv + 0.0001));
+    info[13] = mint = act ? p.mintime[idx] : 0.f;
+    if (act && want_info && p.o_info) {
+      float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
+#pragma unroll
+      for (int k = 0; k < INFO_F; ++k) o[k] = info[k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < INFO_F; ++k) info[k] = 0.f;
+  }
+
+  // ---- episode statistics: per-warp partial sums, fixed order, no atomics ----------------------
+  if (p.stats) {
+    double* row = p.stats + (size_t)gw * (15 * N + 2);
+    double r = act ? (double)rew : 0.0;
+    for (int off = G; off < 32; off <<= 1) r += __shfl_xor_sync(FULL, r, off);
+    if (el == 0 && i < N) row[i] += r;
+    const bool term = venv && done;
+    if (__any_sync(FULL, term)) {
+#pragma unroll
+      for (int k = 0; k < INFO_F; ++k) {
+        double v = (act && done) ? (double)info[k] : 0.0;
+        for (int off = G; off < 32; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
+        if (el == 0 && i < N) row[N + i * INFO_F + k] += v;
+      }
+    }
+    const unsigned termb = __ballot_sync(FULL, term && i == 0);
+    if (lane == 0) { row[15 * N] += (double)__popc(termb); row[15 * N + 1] += (double)nenv; }
+  }
+
+  // ---- write back state; observation row --------------------------------------------------------
+  float fobs = (float)fparam;
+  float ndtg = (float)dtg_new, ntreq = (float)treq_new, ndleft = dleft_new;
+  float ndmean = (float)mean_a, ndstd = (float)std_a;     // after the last agent's info_callback
+  int nstep_store = nstep;
+  uint32_t nepisode = episode;
+  if (__any_sync(FULL, do_reset)) {
+    // graphworker auto-reset (env_wrappers.py:859-865): obs / node_obs / adj come from the new
+    // episode; reward / done / info stay terminal.
+    float rx = npx, ry = npy, rmint = act ? p.mintime[idx] : 0.f;
+    int rgm = gm;
+    reset_group<G>(p, s, el, i, env, do_reset, gmask, episode, rgm, rx, ry, rmint);
+    if (do_reset) {
+      gm = rgm; npx = rx; npy = ry; nvx = 0.f; nvy = 0.f; npd = 0.f;
+      ndtg = -1.f; ntreq = -1.f; ndleft = -1.f; nac = 0; noc = 0; nstep_store = 0; nepisode = episode + 1;
+      fobs = 0.f;                                // mean(p_dist = 0) / (std + 1e-4)
+      if (act) p.mintime[idx] = rmint;
+      double d2; int c2; bool o2;
+      distance_tile<G>(p, ent, adj, i, act, gm, d2, c2, o2);
+    }
+  }
+  if (act) {
+    p.px[idx] = npx; p.py[idx] = npy; p.vx[idx] = nvx; p.vy[idx] = nvy; p.pdist[idx] = npd;
+    p.dtg[idx] = ndtg; p.treq[idx] = ntreq; p.dleft[idx] = ndleft;
+    p.gm[idx] = gm; p.nac[idx] = nac; p.noc[idx] = noc;
+    const float gx = ent[i * ENT_STRIDE + 4], gy = ent[i * ENT_STRIDE + 5];
+    obs[i * OBS_F + 0] = nvx; obs[i * OBS_F + 1] = nvy; obs[i * OBS_F + 2] = npx; obs[i * OBS_F + 3] = npy;
+    obs[i * OBS_F + 4] = gx - npx; obs[i * OBS_F + 5] = gy - npy; obs[i * OBS_F + 6] = fobs;
+    if (p.o_rew) p.o_rew[(size_t)env * N + i] = rew;
+    if (p.o_done) p.o_done[(size_t)env * N + i] = done ? 1 : 0;
+  }
+  if (venv && i == 0) {
+    p.step[env] = nstep_store; p.episode[env] = (int)nepisode; p.dmean[env] = ndmean; p.dstd[env] = ndstd;
+  }
+  __syncwarp();
+  emit_tiles(p, s, env0, nenv, lane);
+}
+
+// =============================================================================================
+// reset() / observe: GraphSubprocVecEnv.reset -> MultiAgentGraphEnv.reset (environment.py:882-898).
+template <int G>
+__global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ DevParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int EPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (THREADS / 32) + wib;
+  const int env0 = gw * EPW;
+  if (env0 >= p.B) return;
+  const int nenv = min(EPW, p.B - env0);
+  const int el = lane / G, i = lane % G;
+  const int env = env0 + el;
+  const int N = p.N, O = p.O, E = p.E;
+  const bool venv = el < nenv;
+  const bool act = venv && i < N;
+  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
+  const int gl = el * G;
+  const WarpSmem s = carve(p, smem, wib);
+  float* ent = s.ent + (size_t)el * E * ENT_STRIDE;
+  float* adj = s.adj + (size_t)el * E * E;
+  float* obs = s.obs + (size_t)el * N * OBS_F;
+  const size_t idx = (size_t)i * p.Bp + env;
+
+  float px = 0.f, py = 0.f, vx = 0.f, vy = 0.f, pd = 0.f, dtg = -1.f, mint = 0.f;
+  int gm = 0;
+  if (act) {
+    px = p.px[idx]; py = p.py[idx]; vx = p.vx[idx]; vy = p.vy[idx]; pd = p.pdist[idx]; dtg = p.dtg[idx];
+    gm = p.gm[idx]; mint = p.mintime[idx];
+    const float lxx = p.lx[idx], lyy = p.ly[idx];
+    float* l = ent + (N + i) * ENT_STRIDE;
+    l[0] = lxx; l[1] = lyy; l[2] = 0.f; l[3] = 0.f; l[4] = lxx; l[5] = lyy;
+  }
+  uint32_t episode = 0; float dmean = 0.f, dstd = 0.f;
+  bool do_reset = false;
+  if (venv) {
+    episode = (uint32_t)p.episode[env]; dmean = p.dmean[env]; dstd = p.dstd[env];
+    do_reset = p.reset_mask ? (p.reset_mask[env] != 0) : true;
+    for (int k = i; k < O; k += G) {
+      const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
+      float* o = ent + (2 * N + k) * ENT_STRIDE;
+      o[0] = x; o[1] = y; o[2] = 0.f; o[3] = 0.f; o[4] = x; o[5] = y;
+    }
+  }
+  __syncwarp();
+  if (act) {
+    float* a = ent + i * ENT_STRIDE;
+    const float* g = ent + (N + gm) * ENT_STRIDE;
+    a[0] = px; a[1] = py; a[2] = vx; a[3] = vy; a[4] = g[0]; a[5] = g[1];
+  }
+  __syncwarp();
+  if (__any_sync(FULL, do_reset)) {
+    reset_group<G>(p, s, el, i, env, do_reset, gmask, episode, gm, px, py, mint);
+    if (do_reset && act) {
+      vx = 0.f; vy = 0.f; pd = 0.f; dtg = -1.f;
+      p.px[idx] = px; p.py[idx] = py; p.vx[idx] = 0.f; p.vy[idx] = 0.f; p.pdist[idx] = 0.f;
+      p.dtg[idx] = -1.f; p.treq[idx] = -1.f; p.dleft[idx] = -1.f;
+      p.gm[idx] = gm; p.nac[idx] = 0; p.noc[idx] = 0; p.mintime[idx] = mint;
+    }
+    if (do_reset && i == 0) { p.step[env] = 0; p.episode[env] = (int)(episode + 1); }
+  }
+  // observation() on the current state (navigation_graph.py:826-857)
+  double sum_p = 0.0;
+  const double pd64 = (double)pd;
+  for (int j = 0; j < N; ++j) sum_p += __shfl_sync(FULL, pd64, gl + j);
+  const double mean_p = sum_p / N;
+  double q_p = 0.0;
+  for (int j = 0; j < N; ++j) { const double d = __shfl_sync(FULL, pd64, gl + j) - mean_p; q_p += d * d; }
+  const double std_p = sqrt(q_p / N);
+  const double fparam = (dtg == -1.0f) ? mean_p / (std_p + 0.0001) : (double)dmean / ((double)dstd + 0.0001);
+  double dgoal; int ncoll; bool ocoll;
+  if (venv) distance_tile<G>(p, ent, adj, i, act, gm, dgoal, ncoll, ocoll);
+  if (act) {
+    const float gx = ent[i * ENT_STRIDE + 4], gy = ent[i * ENT_STRIDE + 5];
+    obs[i * OBS_F + 0] = vx; obs[i * OBS_F + 1] = vy; obs[i * OBS_F + 2] = px; obs[i * OBS_F + 3] = py;
+    obs[i * OBS_F + 4] = gx - px; obs[i * OBS_F + 5] = gy - py; obs[i * OBS_F + 6] = (float)fparam;
+  }
+  __syncwarp();
+  emit_tiles(p, s, env0, nenv, lane);
+}
+
+// =============================================================================================
+// Stand-alone batched lexifair (marl_fair_assign.py:16-55).
+template <int G>
+__global__ void __launch_bounds__(THREADS) assign_kernel(const double* __restrict__ costs, const float* __restrict__ apos,
+                                                         const float* __restrict__ gpos, int num, int n, int* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int EPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (THREADS / 32) + wib;
+  const int el = lane / G, i = lane % G;
+  const int prob = gw * EPW + el;
+  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
+  const int per_group = 2 * n * n + ((5 * n + 1 + 1) & ~1);      // floats: cost (doubles) + int scratch, even
+  float* base = smem + (size_t)(wib * EPW + el) * per_group;
+  double* cost = reinterpret_cast<double*>(base);
+  int* asg = reinterpret_cast<int*>(base + 2 * n * n);
+  if (prob >= num) return;                                        // group-uniform; only group syncs below
+  if (i < n) {
+    for (int j = 0; j < n; ++j) {
+      if (costs) cost[i * n + j] = costs[((size_t)prob * n + i) * n + j];
+      else {
+        const float* a = apos + ((size_t)prob * n + i) * 2;
+        const float* g = gpos + ((size_t)prob * n + j) * 2;
+        cost[i * n + j] = dist64(a[0], a[1], g[0], g[1]);
+      }
+    }
+  }
+  __syncwarp(gmask);
+  const int g = lexifair_group<G>(cost, asg, n, i, gmask, 0);
+  if (i < n) out[(size_t)prob * n + i] = g;
+}
+
+// =============================================================================================
+// FmState (API layout) <-> internal SoA.  One thread per (env, slot), slot < max(N, O).
+__global__ void state_io_kernel(const DevParams p, const HostState st, int to_internal) {
+  const int S = max(p.N, max(p.O, 1));
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)p.B * S) return;
+  const int env = (int)(t / S), k = (int)(t % S);
+  const int N = p.N, O = p.O;
+  const size_t si = (size_t)k * p.Bp + env;
+  if (k < N) {
+    const size_t ai = (size_t)env * N + k;
+#define FM_IO_F(ptr, arr, stride, comp) \
+  if (st.ptr) { if (to_internal) p.arr[si] = st.ptr[ai * stride + comp]; else st.ptr[ai * stride + comp] = p.arr[si]; }
+    FM_IO_F(pos, px, 2, 0) FM_IO_F(pos, py, 2, 1) FM_IO_F(vel, vx, 2, 0) FM_IO_F(vel, vy, 2, 1)
+    FM_IO_F(p_dist, pdist, 1, 0) FM_IO_F(landmark_pos, lx, 2, 0) FM_IO_F(landmark_pos, ly, 2, 1)
+    FM_IO_F(goal_match, gm, 1, 0) FM_IO_F(dists_to_goal, dtg, 1, 0) FM_IO_F(times_required, treq, 1, 0)
+    FM_IO_F(dist_left_to_goal, dleft, 1, 0) FM_IO_F(num_agent_collisions, nac, 1, 0)
+    FM_IO_F(num_obstacle_collisions, noc, 1, 0) FM_IO_F(min_time, mintime, 1, 0)
+#undef FM_IO_F
+  }
+  if (k < O && st.obstacle_pos) {
+    const size_t oi = ((size_t)env * O + k) * 2;
+    if (to_internal) { p.ox[si] = st.obstacle_pos[oi]; p.oy[si] = st.obstacle_pos[oi + 1]; }
+    else { st.obstacle_pos[oi] = p.ox[si]; st.obstacle_pos[oi + 1] = p.oy[si]; }
+  }
+  if (k == 0) {
+#define FM_IO_E(ptr, arr) \
+  if (st.ptr) { if (to_internal) p.arr[env] = st.ptr[env]; else st.ptr[env] = p.arr[env]; }
+    FM_IO_E(dist_traveled_mean, dmean) FM_IO_E(dist_traveled_stddev, dstd) FM_IO_E(step, step) FM_IO_E(episode, episode)
+#undef FM_IO_E
+  }
+}
+
+// make_world defaults (navigation_graph.py:93, :137-138): goal_match = arange(N), latches = -1.
+__global__ void state_init_kernel(const DevParams p) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)p.Bp * p.N) return;
+  const int k = (int)(t / p.Bp);
+  p.gm[t] = k; p.dtg[t] = -1.f; p.treq[t] = -1.f; p.dleft[t] = -1.f;
+  p.mintime[t] = __int_as_float(0x7f800000);   // agent.goal_min_time = np.inf (core.py:127)
+}
+
+// =============================================================================================
+// Edge list (gnn_new.py:381-413).  One warp per graph.
+__device__ __forceinline__ bool edge_pred(float d, float thr, int inclusive) {
+  return (inclusive ? (d <= thr) : (d < thr)) && (d > 0.0f);
+}
+
+__global__ void edge_count_kernel(const float* __restrict__ adj, int num_graphs, int EE, float thr, int inclusive,
+                                  int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (g >= num_graphs) return;
+  const float* a = adj + (size_t)g * EE;
+  int c = 0;
+  for (int q = lane; q < EE; q += 32) c += edge_pred(a[q], thr, inclusive) ? 1 : 0;
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(FULL, c, off);
+  if (lane == 0) counts[g] = c;
+}
+
+// Exclusive scan of counts (as int64, each graph counted `repeat` times) by ONE block, sequential
+// over tiles: num_graphs is at most a few hundred thousand, so this is a few microseconds.
+__global__ void edge_scan_kernel(const int* __restrict__ counts, int num_graphs, int repeat,
+                                 long long* __restrict__ graph_offsets, long long* __restrict__ nnz_out) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < num_graphs; base += blockDim.x) {
+    const int g = base + threadIdx.x;
+    const long long c = (g < num_graphs) ? (long long)counts[g] : 0;
+    long long v = c * repeat;
+    long long incl = v;
+    for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += o; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      long long x = (lane < nw) ? wsum[lane] : 0, xi = x;
+      for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(FULL, xi, off); if (lane >= off) xi += o; }
+      wsum[lane] = xi - x;
+    }
+    __syncthreads();
+    const long long excl = carry + wsum[w] + incl - v;
+    if (g < num_graphs)
+      for (int a = 0; a < repeat; ++a) graph_offsets[(size_t)g * repeat + a] = excl + (long long)a * c;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { graph_offsets[(size_t)num_graphs * repeat] = carry; if (nnz_out) *nnz_out = carry; }
+}
+
+__global__ void edge_emit_kernel(const float* __restrict__ adj, int num_graphs, int E, float thr, int inclusive, int repeat,
+                                 long long capacity, const long long* __restrict__ graph_offsets,
+                                 long long* __restrict__ edge_index, float* __restrict__ edge_attr) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (g >= num_graphs) return;
+  const int EE = E * E;
+  const float* a = adj + (size_t)g * EE;
+  const long long base0 = graph_offsets[(size_t)g * repeat];
+  const long long cnt = graph_offsets[(size_t)g * repeat + 1] - base0;   // per copy (offsets has +1 sentinel)
+  int run = 0;
+  for (int q0 = 0; q0 < EE; q0 += 32) {
+    const int q = q0 + lane;
+    const float d = (q < EE) ? a[q] : 0.0f;
+    const bool pr = (q < EE) && edge_pred(d, thr, inclusive);
+    const unsigned b = __ballot_sync(FULL, pr);
+    if (pr) {
+      const int k = run + __popc(b & ((1u << lane) - 1u));
+      const int r = q / E, c = q - r * E;
+      for (int cp = 0; cp < repeat; ++cp) {
+        const long long pos = base0 + (long long)cp * cnt + k;
+        if (pos < capacity) {
+          const long long node0 = ((long long)g * repeat + cp) * E;
+          edge_index[pos] = node0 + r;
+          edge_index[capacity + pos] = node0 + c;
+          edge_attr[pos] = d;
+        }
+      }
+    }
+    run += __popc(b);
+  }
+}
+
+// =============================================================================================
+// One block per statistic: fixed thread -> row mapping and a fixed-shape tree, so the result does
+// not depend on scheduling (deterministic for a given launch geometry).
+__global__ void stats_reduce_kernel(double* __restrict__ partial, int rows, int K, double* __restrict__ out, int clear) {
+  __shared__ double sh[256];
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    acc += partial[(size_t)r * K + k];
+    if (clear) partial[(size_t)r * K + k] = 0.0;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = sh[0];
+}
+
+// =============================================================================================
+// Launchers (host side of this translation unit).
+template <int G>
+static cudaError_t launch_step_g(const DevParams& p, cudaStream_t st, bool is_reset) {
+  constexpr int EPW = 32 / G;
+  const int warps = (p.B + EPW - 1) / EPW;
+  const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
+  const size_t smem = (size_t)p.sm_per_warp * (THREADS / 32) * sizeof(float);
+  if (is_reset) reset_kernel<G><<<blocks, THREADS, smem, st>>>(p);
+  else step_kernel<G><<<blocks, THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t prepare_g(const DevParams& p) {
+  const int smem = p.sm_per_warp * (THREADS / 32) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(reset_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); }
+
+int num_warps(int B, int N) { const int epw = 32 / group_size(N); return (B + epw - 1) / epw; }
+
+cudaError_t prepare_kernels(const DevParams& p) {
+  switch (group_size(p.N)) {
+    case 4: return prepare_g<4>(p);
+    case 8: return prepare_g<8>(p);
+    case 16: return prepare_g<16>(p);
+    default: return prepare_g<32>(p);
+  }
+}
+
+cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset) {
+  switch (group_size(p.N)) {
+    case 4: return launch_step_g<4>(p, st, is_reset);
+    case 8: return launch_step_g<8>(p, st, is_reset);
+    case 16: return launch_step_g<16>(p, st, is_reset);
+    default: return launch_step_g<32>(p, st, is_reset);
+  }
+}
+
+template <int G>
+static cudaError_t launch_assign_g(const double* costs, const float* apos, const float* gpos, int num, int n, int* out,
+                                   cudaStream_t st) {
+  constexpr int EPW = 32 / G;
+  const int warps = (num + EPW - 1) / EPW;
+  const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
+  const int per_group = 2 * n * n + ((5 * n + 1 + 1) & ~1);
+  const size_t smem = (size_t)per_group * EPW * (THREADS / 32) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(assign_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  assign_kernel<G><<<blocks, THREADS, smem, st>>>(costs, apos, gpos, num, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assign(const double* costs, const float* apos, const float* gpos, int num, int n, int* out,
+                          cudaStream_t st) {
+  if (num <= 0) return cudaSuccess;
+  switch (group_size(n)) {
+    case 4: return launch_assign_g<4>(costs, apos, gpos, num, n, out, st);
+    case 8: return launch_assign_g<8>(costs, apos, gpos, num, n, out, st);
+    case 16: return launch_assign_g<16>(costs, apos, gpos, num, n, out, st);
+    default: return launch_assign_g<32>(costs, apos, gpos, num, n, out, st);
+  }
+}
+
+cudaError_t launch_state_io(const DevParams& p, const HostState& hs, int to_internal, cudaStream_t st) {
+  const int S = p.N > p.O ? p.N : (p.O > 1 ? p.O : 1);
+  const long long total = (long long)p.B * S;
+  const int blocks = (int)((total + 255) / 256);
+  state_io_kernel<<<blocks, 256, 0, st>>>(p, hs, to_internal);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_state_init(const DevParams& p, cudaStream_t st) {
+  const long long total = (long long)p.Bp * p.N;
+  state_init_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
+                             long long capacity, int* counts, long long* graph_offsets, long long* edge_index,
+                             float* edge_attr, long long* nnz_out, cudaStream_t st) {
+  const int wpb = 8;
+  const int blocks = (num_graphs + wpb - 1) / wpb;
+  if (num_graphs > 0) edge_count_kernel<<<blocks, wpb * 32, 0, st>>>(adj, num_graphs, E * E, thr, inclusive, counts);
+  edge_scan_kernel<<<1, 1024, 0, st>>>(counts, num_graphs, repeat, graph_offsets, nnz_out);
+  if (num_graphs > 0)
+    edge_emit_kernel<<<blocks, wpb * 32, 0, st>>>(adj, num_graphs, E, thr, inclusive, repeat, capacity, graph_offsets,
+                                                  edge_index, edge_attr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st) {
+  stats_reduce_kernel<<<K, 256, 0, st>>>(partial, rows, K, out, clear);
+  return cudaGetLastError();
+}
+
+}  // namespace fm

@@ -1,0 +1,24 @@
+// Host-callable launchers implemented in fm_kernels.cu (internal to libfairmarl.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fairmarl.h"
+
+namespace fm {
+struct DevParams;
+typedef FmState HostState;   // API-layout device pointers
+
+int group_size(int n);
+int num_warps(int B, int N);
+cudaError_t prepare_kernels(const DevParams& p);   // opt in to > 48 KB dynamic shared memory, once per handle
+cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset);
+cudaError_t launch_assign(const double* costs, const float* apos, const float* gpos, int num, int n, int* out,
+                          cudaStream_t st);
+cudaError_t launch_state_io(const DevParams& p, const HostState& hs, int to_internal, cudaStream_t st);
+cudaError_t launch_state_init(const DevParams& p, cudaStream_t st);
+cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
+                             long long capacity, int* counts, long long* graph_offsets, long long* edge_index,
+                             float* edge_attr, long long* nnz_out, cudaStream_t st);
+cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st);
+}  // namespace fm

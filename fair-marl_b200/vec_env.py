@@ -1,0 +1,382 @@
+"""``B200GraphVecEnv``: device-resident, batched replacement of the reference's GraphMPE vector env.
+
+Replaces, behind the same interface, the stack
+``GraphSubprocVecEnv`` (onpolicy/envs/env_wrappers.py:951-1025) -> ``graphworker`` (:850-893) ->
+``GraphMPEEnv`` (multiagent/MPE_env.py:55-77) -> ``MultiAgentGraphEnv`` (multiagent/environment.py:719-908)
+-> ``World`` (multiagent/core.py:131-503) + ``navigation_graph.Scenario`` + ``marl_fair_assign``.
+
+Two call styles:
+
+* the reference API -- ``reset()`` / ``step(actions_env)`` with numpy in, numpy out (host buffers,
+  one ``fm_step_host`` C-ABI call per step, which moves actions H2D and results D2H);
+* the tensor fast path -- ``reset_tensor()`` / ``step_tensor(actions)`` with CUDA tensors in and
+  out, no host synchronisation, outputs written into a ring of rollout slabs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from fair_marl_b200 import _lib
+from fair_marl_b200.config import SimConfig
+from fair_marl_b200.spaces import Box, Discrete
+
+
+class LazyInfos(Sequence):
+    """``infos`` as the reference returns it -- a length-B sequence of length-N lists of dicts
+    (env_wrappers.py:988-996) -- materialised from the device info rows only when indexed
+    (the runner touches it at log time only, graph_mpe_runner.py:143-146)."""
+
+    def __init__(self, env: "B200GraphVecEnv", version: int):
+        self._env, self._version, self._rows = env, version, None
+
+    def _fetch(self) -> np.ndarray:
+        if self._rows is None:
+            if self._env._step_version != self._version:
+                raise RuntimeError("infos of an earlier step were not read before the next step()")
+            self._rows = self._env._read_info_rows()
+        return self._rows
+
+    def __len__(self) -> int:
+        return self._env.num_envs
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        rows = self._fetch()[b]
+        keys = _lib.INFO_KEYS if self._env.cfg.max_speed is not None else _lib.INFO_KEYS[:-1]
+        return [{k: float(rows[i, j]) for j, k in enumerate(keys)} for i in range(rows.shape[0])]
+
+    def as_array(self) -> np.ndarray:
+        """[B, N, 14] float32, columns in ``INFO_KEYS`` order."""
+        return self._fetch()
+
+
+class B200GraphVecEnv:
+    """ShareVecEnv-compatible batched ``navigation_graph`` simulator on one B200.
+
+    Parameters
+    ----------
+    args : the reference's ``all_args`` Namespace (fields listed in ``SimConfig``) or a ``SimConfig``.
+    num_envs : envs on THIS device (default ``args.n_rollout_threads``).
+    device : CUDA device index.
+    seed : base seed (default ``args.seed``); reset streams are keyed by (seed, global env index).
+    env_offset : global index of local env 0 when the batch is sharded over ranks.
+    num_slots : rollout slabs for the tensor path (``step_tensor`` writes slot (t+1) % num_slots).
+    """
+
+    closed = False
+
+    def __init__(self, args: Any = None, num_envs: Optional[int] = None, device: int = 0,
+                 seed: Optional[int] = None, env_offset: int = 0, num_slots: int = 2, **overrides):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.load()
+        self.cfg = args if isinstance(args, SimConfig) else SimConfig.from_args(args if args is not None else object(), **overrides)
+        if num_envs is None:
+            num_envs = getattr(args, "n_rollout_threads", None)
+        if not num_envs or num_envs <= 0:
+            raise ValueError("num_envs must be given (or args.n_rollout_threads)")
+        if seed is None:
+            seed = getattr(args, "seed", 1)
+        self.num_envs = int(num_envs)
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.seed = int(seed)
+        self.env_offset = int(env_offset)
+        cfg = self.cfg
+        N, E = cfg.num_agents, cfg.num_entities
+        self.num_agents, self.num_entities = N, E
+
+        c = _lib.FmConfig(
+            num_envs=self.num_envs, num_agents=N, num_obstacles=cfg.num_obstacles,
+            episode_length=cfg.episode_length, env_offset=self.env_offset, seed=self.seed & (2 ** 64 - 1),
+            world_size=cfg.world_size, max_speed=(cfg.max_speed if cfg.max_speed is not None else 0.0),
+            collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
+            fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
+            fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative),
+            auto_reset=int(cfg.auto_reset), info_every_step=int(cfg.info_every_step))
+        self._h = C.c_void_p()
+        _lib.check(self.lib.fm_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_create")
+
+        # spaces (environment.py:117-190, :781-813)
+        inf = float("inf")
+        self.observation_space = [Box(-inf, inf, (_lib.OBS_DIM,)) for _ in range(N)]
+        self.share_observation_space = [Box(-inf, inf, (_lib.OBS_DIM * N,)) for _ in range(N)]
+        self.action_space = [Discrete(5) for _ in range(N)]
+        self.node_observation_space = [Box(-inf, inf, (E, _lib.NODE_FEAT_DIM)) for _ in range(N)]
+        self.adj_observation_space = [Box(-inf, inf, (E, E)) for _ in range(N)]
+        self.edge_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
+        self.agent_id_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
+        self.share_agent_id_observation_space = [Box(-inf, inf, (N,)) for _ in range(N)]
+
+        # get_id (navigation_graph.py:875-876): global_id == agent index
+        self._agent_id_host = np.tile(np.arange(N, dtype=np.int64)[None, :, None], (self.num_envs, 1, 1))
+        self._agent_id_dev = None
+        self._host = None               # pinned host buffers for the numpy API
+        self._slabs = None              # device rollout slabs for the tensor API
+        self.num_slots = int(num_slots)
+        self._slot = 0
+        self._step_version = 0
+        self._pending_actions = None
+        self._last_step_api = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ensure_host(self):
+        if self._host is None:
+            t, B, N, E = self.torch, self.num_envs, self.num_agents, self.num_entities
+            pin = dict(pin_memory=True)
+            self._host = {
+                "onehot": t.empty((B, N, 5), dtype=t.float32, **pin),
+                "obs": [t.empty((B, N, _lib.OBS_DIM), dtype=t.float32, **pin) for _ in range(2)],
+                "node_obs": [t.empty((B, N, E, _lib.NODE_FEAT_DIM), dtype=t.float32, **pin) for _ in range(2)],
+                "adj": [t.empty((B, E, E), dtype=t.float32, **pin) for _ in range(2)],
+                "reward": [t.empty((B, N), dtype=t.float32, **pin) for _ in range(2)],
+                "done": [t.empty((B, N), dtype=t.uint8, **pin) for _ in range(2)],
+                "info": t.empty((B, N, _lib.INFO_DIM), dtype=t.float32, **pin),
+                "flip": 0,
+            }
+        return self._host
+
+    def _ensure_slabs(self):
+        if self._slabs is None:
+            t, B, N, E, S = self.torch, self.num_envs, self.num_agents, self.num_entities, self.num_slots
+            kw = dict(device=self.device)
+            self._slabs = {
+                "obs": t.empty((S, B, N, _lib.OBS_DIM), dtype=t.float32, **kw),
+                "node_obs": t.empty((S, B, N, E, _lib.NODE_FEAT_DIM), dtype=t.float32, **kw),
+                "adj": t.empty((S, B, E, E), dtype=t.float32, **kw),
+                "reward": t.empty((S, B, N), dtype=t.float32, **kw),
+                "done": t.empty((S, B, N), dtype=t.uint8, **kw),
+                "info": t.zeros((B, N, _lib.INFO_DIM), dtype=t.float32, **kw),
+            }
+            self._agent_id_dev = t.arange(N, dtype=t.int32, device=self.device)[None, :, None].expand(B, N, 1)
+        return self._slabs
+
+    def _outputs_struct(self, tensors: Dict[str, Any], with_step: bool) -> _lib.FmOutputs:
+        o = _lib.FmOutputs()
+        o.obs = tensors["obs"].data_ptr()
+        o.node_obs = tensors["node_obs"].data_ptr()
+        o.adj = tensors["adj"].data_ptr()
+        if with_step:
+            o.reward = tensors["reward"].data_ptr()
+            o.done = tensors["done"].data_ptr()
+            if tensors.get("info") is not None:
+                o.info = tensors["info"].data_ptr()
+        return o
+
+    def _package(self, slot: int, with_step: bool) -> Dict[str, Any]:
+        s, B, N, E = self._slabs, self.num_envs, self.num_agents, self.num_entities
+        out = {"obs": s["obs"][slot], "node_obs": s["node_obs"][slot],
+               "adj": s["adj"][slot][:, None].expand(B, N, E, E),      # written once per env
+               "adj_env": s["adj"][slot], "agent_id": self._agent_id_dev, "slot": slot}
+        if with_step:
+            out.update(reward=s["reward"][slot], done=s["done"][slot].bool(), info=s["info"])
+        return out
+
+    # ------------------------------------------------------------------ tensor fast path
+    def reset_tensor(self, mask=None) -> Dict[str, Any]:
+        """Reset envs (all, or those with ``mask`` != 0: uint8 CUDA tensor [B]); returns device tensors
+        ``obs [B,N,7]``, ``node_obs [B,N,E,11]``, ``adj [B,N,E,E]`` (stride-0 view), ``agent_id``."""
+        s = self._ensure_slabs()
+        slot = self._slot
+        views = {k: s[k][slot] for k in ("obs", "node_obs", "adj")}
+        o = self._outputs_struct(views, with_step=False)
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        _lib.check(self.lib.fm_reset(self._h, mptr, C.byref(o), self._stream()), "fm_reset")
+        return self._package(slot, with_step=False)
+
+    def observe_tensor(self) -> Dict[str, Any]:
+        """Observation of the current state without stepping or resetting."""
+        z = self.torch.zeros(self.num_envs, dtype=self.torch.uint8, device=self.device)
+        return self.reset_tensor(mask=z)
+
+    def step_tensor(self, actions) -> Dict[str, Any]:
+        """One env step.  ``actions``: int32 CUDA tensor [B, N] in {0..4}, or float32 [B, N, 5] one-hot.
+        Asynchronous on the current stream; the returned tensors are views of slab ``slot``."""
+        t = self.torch
+        s = self._ensure_slabs()
+        self._slot = slot = (self._slot + 1) % self.num_slots
+        views = {k: s[k][slot] for k in ("obs", "node_obs", "adj", "reward", "done")}
+        views["info"] = s["info"]
+        o = self._outputs_struct(views, with_step=True)
+        B, N = self.num_envs, self.num_agents
+        if actions.dim() == 2:
+            if actions.dtype != t.int32 or not actions.is_contiguous() or actions.shape != (B, N):
+                actions = actions.to(t.int32).contiguous().view(B, N)
+            rc = self.lib.fm_step(self._h, actions.data_ptr(), C.byref(o), self._stream())
+        else:
+            if actions.dtype != t.float32 or not actions.is_contiguous() or actions.shape != (B, N, 5):
+                actions = actions.to(t.float32).contiguous().view(B, N, 5)
+            rc = self.lib.fm_step_onehot(self._h, actions.data_ptr(), C.byref(o), self._stream())
+        _lib.check(rc, "fm_step")
+        self._step_version += 1
+        self._last_step_api = "tensor"
+        return self._package(slot, with_step=True)
+
+    # ------------------------------------------------------------------ reference (numpy) API
+    def _host_outputs(self, with_step: bool):
+        h = self._ensure_host()
+        h["flip"] ^= 1
+        f = h["flip"]
+        cur = {k: h[k][f] for k in ("obs", "node_obs", "adj", "reward", "done")}
+        o = _lib.FmOutputs()
+        o.obs, o.node_obs, o.adj = cur["obs"].data_ptr(), cur["node_obs"].data_ptr(), cur["adj"].data_ptr()
+        if with_step:
+            o.reward, o.done = cur["reward"].data_ptr(), cur["done"].data_ptr()
+        return cur, o
+
+    def _numpy_obs(self, cur, copy: bool):
+        B, N, E = self.num_envs, self.num_agents, self.num_entities
+        obs, node, adj = cur["obs"].numpy(), cur["node_obs"].numpy(), cur["adj"].numpy()
+        if copy:
+            obs, node, adj = obs.copy(), node.copy(), adj.copy()
+        adj_n = np.broadcast_to(adj[:, None], (B, N, E, E))     # same matrix for the N agents of an env
+        return obs, self._agent_id_host, node, adj_n
+
+    def reset(self, copy: bool = False):
+        """``(obs [B,N,7], agent_id [B,N,1], node_obs [B,N,E,11], adj [B,N,E,E])`` as numpy
+        (env_wrappers.py:997-1002).  Arrays are views of pinned double buffers (valid until the call
+        after next) unless ``copy=True``."""
+        cur, o = self._host_outputs(with_step=False)
+        _lib.check(self.lib.fm_reset_host(self._h, None, C.byref(o), self._stream()), "fm_reset_host")
+        return self._numpy_obs(cur, copy)
+
+    def step_async(self, actions) -> None:
+        self._pending_actions = actions
+
+    def step_wait(self, copy: bool = False):
+        actions = self._pending_actions
+        self._pending_actions = None
+        if actions is None:
+            raise RuntimeError("step_wait() without step_async()")
+        h = self._ensure_host()
+        B, N = self.num_envs, self.num_agents
+        a = np.asarray(actions)
+        if a.shape == (B, N, 5):
+            h["onehot"].numpy()[...] = a                              # cast to float32 into pinned memory
+        elif a.shape in ((B, N), (B, N, 1)):                          # convenience: action indices
+            oh = h["onehot"].numpy()
+            oh[...] = 0.0
+            np.put_along_axis(oh, a.reshape(B, N, 1).astype(np.int64), 1.0, axis=2)
+        else:
+            raise ValueError(f"actions must be [B,N,5] one-hot (or [B,N] indices), got {a.shape}")
+        cur, o = self._host_outputs(with_step=True)
+        _lib.check(self.lib.fm_step_host(self._h, h["onehot"].data_ptr(), C.byref(o), self._stream()), "fm_step_host")
+        self._step_version += 1
+        self._last_step_api = "host"
+        obs, ag_id, node, adj_n = self._numpy_obs(cur, copy)
+        rew = cur["reward"].numpy()
+        done = cur["done"].numpy().astype(bool)
+        if copy:
+            rew = rew.copy()
+        return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version)
+
+    def step(self, actions, copy: bool = False):
+        """``(obs, agent_id, node_obs, adj, rewards [B,N], dones [B,N] bool, infos)`` -- the 7-tuple of
+        GraphSubprocVecEnv.step_wait (env_wrappers.py:988-996), auto-reset included (:859-865)."""
+        self.step_async(actions)
+        return self.step_wait(copy=copy)
+
+    def _read_info_rows(self) -> np.ndarray:
+        if self._last_step_api == "host":
+            h = self._host
+            _lib.check(self.lib.fm_read_info_host(self._h, h["info"].data_ptr(), self._stream()), "fm_read_info_host")
+            return h["info"].numpy().copy()
+        return self._slabs["info"].cpu().numpy()
+
+    # ------------------------------------------------------------------ state, stats, misc
+    def _state_struct(self, tensors: Dict[str, Any]) -> _lib.FmState:
+        st = _lib.FmState()
+        for name in _lib.STATE_FIELDS:
+            v = tensors.get(name)
+            setattr(st, name, v.data_ptr() if v is not None else None)
+        return st
+
+    def _state_shapes(self):
+        B, N, O = self.num_envs, self.num_agents, self.cfg.num_obstacles
+        return {"pos": (B, N, 2), "vel": (B, N, 2), "p_dist": (B, N), "landmark_pos": (B, N, 2),
+                "obstacle_pos": (B, O, 2), "goal_match": (B, N), "dists_to_goal": (B, N),
+                "times_required": (B, N), "dist_left_to_goal": (B, N), "num_agent_collisions": (B, N),
+                "num_obstacle_collisions": (B, N), "dist_traveled_mean": (B,), "dist_traveled_stddev": (B,),
+                "step": (B,), "min_time": (B, N), "episode": (B,)}
+
+    def get_state(self) -> Dict[str, Any]:
+        """Full simulator state as CUDA tensors in API layout (float32 / int32)."""
+        t = self.torch
+        tensors = {}
+        for name, shape in self._state_shapes().items():
+            dt = t.int32 if name in _lib.STATE_INT_FIELDS else t.float32
+            tensors[name] = t.empty(shape, dtype=dt, device=self.device)
+        st = self._state_struct(tensors)
+        _lib.check(self.lib.fm_get_state(self._h, C.byref(st), self._stream()), "fm_get_state")
+        return tensors
+
+    def set_state(self, state: Dict[str, Any]) -> None:
+        """Inject (a subset of) the state; values may be numpy or tensors, cast to float32 / int32."""
+        t = self.torch
+        shapes = self._state_shapes()
+        tensors = {}
+        for name, v in state.items():
+            if name not in shapes:
+                raise KeyError(name)
+            dt = t.int32 if name in _lib.STATE_INT_FIELDS else t.float32
+            x = t.as_tensor(np.asarray(v) if not t.is_tensor(v) else v).to(device=self.device, dtype=dt).contiguous()
+            if tuple(x.shape) != shapes[name]:
+                raise ValueError(f"state[{name!r}] must have shape {shapes[name]}, got {tuple(x.shape)}")
+            tensors[name] = x
+        st = self._state_struct(tensors)
+        _lib.check(self.lib.fm_set_state(self._h, C.byref(st), self._stream()), "fm_set_state")
+        self.torch.cuda.current_stream(self.device).synchronize()      # keep `tensors` alive until consumed
+
+    def read_stats(self, clear: bool = False):
+        """Local episode-statistics vector (float64 CUDA tensor [15N+2]); see fm_stats_read."""
+        t = self.torch
+        out = t.empty(self.lib.fm_stats_len(self.num_agents), dtype=t.float64, device=self.device)
+        _lib.check(self.lib.fm_stats_read(self._h, out.data_ptr(), int(clear), self._stream()), "fm_stats_read")
+        return out
+
+    @property
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        _lib.check(self.lib.fm_kernel_launches(self._h, C.byref(n)))
+        return int(n.value)
+
+    @property
+    def algorithmic_bytes_per_step(self) -> int:
+        return int(self.lib.fm_algorithmic_bytes_per_step(self._h))
+
+    def render(self, mode: str = "human"):
+        raise NotImplementedError("rendering is out of scope (SURVEY.md section 2, row 15)")
+
+    def close(self) -> None:
+        if self.closed:
+            return
+        self.torch.cuda.synchronize(self.device)
+        self.lib.fm_destroy(self._h)
+        self._h = None
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_train_env(all_args, device: int = 0, rank: int = 0, world_size: int = 1) -> B200GraphVecEnv:
+    """Drop-in for ``make_train_env`` in onpolicy/scripts/train_mpe.py:21-43 when
+    ``env_name == 'GraphMPE'``: ``n_rollout_threads`` envs, sharded over ranks if world_size > 1."""
+    from fair_marl_b200.sharding import shard_range
+    if getattr(all_args, "env_name", "GraphMPE") != "GraphMPE":
+        raise NotImplementedError(f"Can not support the {all_args.env_name} environment")
+    off, cnt = shard_range(all_args.n_rollout_threads, world_size, rank)
+    return B200GraphVecEnv(all_args, num_envs=cnt, device=device, seed=all_args.seed, env_offset=off)

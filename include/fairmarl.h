@@ -1,0 +1,186 @@
+/*
+ * fairmarl.h -- C ABI of the B200-native batched GraphMPE `navigation_graph` simulator.
+ *
+ * One shared library (libfairmarl.so), plain pointers and sizes, no torch / C++ types.
+ * Every entry point states the reference interface it replaces (paths relative to the
+ * Jaroan/Fair-MARL checkout).  The reference is pure Python: there is no existing FFI, so the
+ * "binding a maintainer would add" is a ctypes stub selected in
+ * onpolicy/scripts/train_mpe.py:21-43 (make_train_env) instead of GraphSubprocVecEnv.
+ *
+ * Conventions
+ *   - All pointers in FmState / FmOutputs / actions are DEVICE pointers unless the function name
+ *     ends in _host.  Any output pointer may be NULL (= not wanted).
+ *   - All calls are asynchronous on the caller-supplied stream (a cudaStream_t passed as void*),
+ *     except the *_host calls, which synchronise that stream before returning.
+ *   - The handle owns the internal SoA state, RNG counters and statistic accumulators; the caller
+ *     owns every buffer it passes in.  A handle is bound to one device and is not thread-safe.
+ *   - Return value: 0 on success, a negative FmStatus otherwise; fm_last_error() gives the text.
+ *     Nothing here throws, aborts or falls back to a CPU path.
+ *   - Entity order (reference World.entities, multiagent/core.py:186):
+ *     agents 0..N-1, landmarks N..2N-1, obstacles 2N..2N+O-1;  E = 2N + O.
+ */
+#ifndef FAIRMARL_H_
+#define FAIRMARL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_ABI_VERSION 1
+#define FM_OBS_DIM 7         /* navigation_graph.py:826-857 */
+#define FM_NODE_FEAT_DIM 11  /* navigation_graph.py:1079-1124 (relative features) */
+#define FM_INFO_DIM 14       /* navigation_graph.py:625-647 + environment.py:857 */
+#define FM_MAX_AGENTS 32
+
+typedef enum FmStatus {
+  FM_OK = 0,
+  FM_ERR_INVALID_ARG = -1,
+  FM_ERR_CUDA = -2,
+  FM_ERR_UNSUPPORTED = -3,
+  FM_ERR_NO_DEVICE = -4
+} FmStatus;
+
+/* The argparse fields Scenario.make_world reads (navigation_graph.py:94-129, :144, :188, :208).
+ * Reals are double because the reference holds them as Python floats and compares float64
+ * distances against them (thresholds must be the same IEEE doubles). */
+typedef struct FmConfig {
+  int32_t num_envs;        /* B on THIS device */
+  int32_t num_agents;      /* N = num_landmarks, 1..32 */
+  int32_t num_obstacles;   /* O >= 0 */
+  int32_t episode_length;  /* world_length, environment.py:237-247 */
+  int64_t env_offset;      /* global index of local env 0: RNG streams are keyed by global index */
+  uint64_t seed;
+  double world_size;       /* 2 */
+  double max_speed;        /* 2; <= 0 means None (no clamp, no Min_time_to_goal) */
+  double collision_rew;
+  double goal_rew;
+  double min_dist_thresh;
+  double fair_rew;
+  double zeroshift;
+  double max_edge_dist;
+  int32_t fairness_reward; /* 1: navigation_graph.py (FA+FR); 0: nav_graph_goalassign_noFair.py (FA) */
+  int32_t collaborative;   /* environment.py:867-870 */
+  int32_t auto_reset;      /* env_wrappers.py:859-865 (graphworker) */
+  int32_t info_every_step; /* 0: info rows are written on terminal steps only */
+} FmConfig;
+
+/* Per-step outputs, API layout (what GraphSubprocVecEnv.step_wait stacks, env_wrappers.py:988-996). */
+typedef struct FmOutputs {
+  float* obs;        /* [B, N, 7] */
+  float* node_obs;   /* [B, N, E, 11] */
+  float* adj;        /* [B, E, E]   (identical for the N agents of an env: written once) */
+  float* reward;     /* [B, N] */
+  uint8_t* done;     /* [B, N] */
+  float* info;       /* [B, N, 14] in FM_INFO_* order; terminal-step values survive auto-reset */
+} FmOutputs;
+
+enum {
+  FM_INFO_INDIVIDUAL_REWARD = 0, FM_INFO_DIST_TO_GOAL, FM_INFO_TIME_REQ_TO_GOAL,
+  FM_INFO_NUM_AGENT_COLLISIONS, FM_INFO_NUM_OBST_COLLISIONS, FM_INFO_DISTANCE_MEAN,
+  FM_INFO_DISTANCE_VARIANCE, FM_INFO_MEAN_BY_VARIANCE, FM_INFO_DISTS_TRAVELED, FM_INFO_TIME_TAKEN,
+  FM_INFO_TIME_MEAN, FM_INFO_TIME_STDDEV, FM_INFO_TIME_MEAN_BY_STDDEV, FM_INFO_MIN_TIME_TO_GOAL
+};
+
+/* Complete simulator state in API layout (what World + Scenario carry between steps:
+ * core.py:11-20, navigation_graph.py:93, :214-225, :617-618).  NULL members are skipped. */
+typedef struct FmState {
+  float* pos;                      /* [B, N, 2] */
+  float* vel;                      /* [B, N, 2] */
+  float* p_dist;                   /* [B, N] */
+  float* landmark_pos;             /* [B, N, 2] */
+  float* obstacle_pos;             /* [B, O, 2] */
+  int32_t* goal_match;             /* [B, N] */
+  float* dists_to_goal;            /* [B, N]  (-1: not yet visited this episode) */
+  float* times_required;           /* [B, N]  (-1: goal not reached) */
+  float* dist_left_to_goal;        /* [B, N] */
+  int32_t* num_agent_collisions;   /* [B, N] */
+  int32_t* num_obstacle_collisions;/* [B, N] */
+  float* dist_traveled_mean;       /* [B] */
+  float* dist_traveled_stddev;     /* [B] */
+  int32_t* step;                   /* [B] */
+  float* min_time;                 /* [B, N] */
+  int32_t* episode;                /* [B]  resets so far (RNG counter) */
+} FmState;
+
+typedef struct FmHandle FmHandle;
+
+/* GraphSubprocVecEnv.__init__ + GraphMPEEnv + Scenario.make_world
+ * (env_wrappers.py:951-981, MPE_env.py:55-77, navigation_graph.py:48-210). */
+int fm_create(const FmConfig* cfg, int device, FmHandle** out);
+/* GraphSubprocVecEnv.close (env_wrappers.py:1010-1021). */
+int fm_destroy(FmHandle* h);
+
+/* GraphSubprocVecEnv.reset -> MultiAgentGraphEnv.reset -> Scenario.reset_world/random_scenario
+ * (env_wrappers.py:997-1002, environment.py:882-898, navigation_graph.py:212-570), incl. the
+ * lexifair goal assignment (navigation_graph.py:555-561).  mask: uint8 [B] or NULL (= all envs).
+ * Envs with mask 0 keep their state; obs / node_obs / adj of ALL envs are written to `out`. */
+int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* stream);
+
+/* GraphSubprocVecEnv.step -> graphworker -> MultiAgentGraphEnv.step (env_wrappers.py:983-996,
+ * :856-865, environment.py:816-877): action decode, World.step (core.py:250-274), observation /
+ * reward / graph_observation / done / info_callback per agent in the reference's order, and the
+ * worker's auto-reset.  actions: int32 [B, N] in {0..4} (0 no-op, 1 +x, 2 -x, 3 +y, 4 -y). */
+int fm_step(FmHandle* h, const int32_t* actions, const FmOutputs* out, void* stream);
+/* Same, with the [B, N, 5] float one-hot (or any float 5-vector) the runner sends
+ * (graph_mpe_runner.py:429-431; decode environment.py:301-311). */
+int fm_step_onehot(FmHandle* h, const float* onehot, const FmOutputs* out, void* stream);
+
+/* Host-buffer form of fm_step_onehot: `onehot` and every member of `out` are HOST pointers
+ * (pinned for full speed).  Copies actions in, steps, copies the requested outputs back and
+ * synchronises `stream`.  This is the call a ShareVecEnv.step() drop-in makes. */
+int fm_step_host(FmHandle* h, const float* onehot_host, const FmOutputs* out_host, void* stream);
+int fm_reset_host(FmHandle* h, const uint8_t* mask_host, const FmOutputs* out_host, void* stream);
+/* Info rows of the most recent fm_step_host call, copied to host on demand ([B, N, 14] floats).
+ * The runner reads infos only at log time (graph_mpe_runner.py:143-146), so fm_step_host does not
+ * copy them unless out_host->info is set. */
+int fm_read_info_host(FmHandle* h, float* info_host, void* stream);
+
+/* State injection / extraction (the reference has no API for this; tests assign
+ * entity.state.* and world.* directly -- SURVEY.md section 8c). */
+int fm_set_state(FmHandle* h, const FmState* st, void* stream);
+int fm_get_state(FmHandle* h, const FmState* st, void* stream);
+
+/* marl_fair_assign.solve_fair_assignment (marl_fair_assign.py:16-55), batched: one problem per
+ * lane group.  costs: double [num, n, n] (cost[i][j] = agent i -> goal j); out: int32 [num, n]
+ * goal index per agent (np.where(x == 1)[1], navigation_graph.py:558).  n <= 32. */
+int fm_assign_costs(int device, const double* costs, int32_t num, int32_t n, int32_t* out, void* stream);
+/* Same from positions: cdist(agent_pos, goal_pos) (navigation_graph.py:555) in float64 from
+ * float [num, n, 2] inputs. */
+int fm_assign_positions(int device, const float* agent_pos, const float* goal_pos, int32_t num,
+                        int32_t n, int32_t* out, void* stream);
+
+/* Policy-side edge list, TransformerConvNet.process_adj (onpolicy/algorithms/utils/gnn_new.py:381-413)
+ * on adj float [num_graphs, E, E]: mask (adj < max_edge_dist) & (adj > 0) (inclusive != 0: <=, the
+ * env-side Scenario.update_graph rule, navigation_graph.py:1037-1056), edges in (b, i, j) order.
+ * repeat >= 1 emits every graph `repeat` times consecutively (graph b*repeat + a, node offset
+ * (b*repeat + a)*E): the [B*N, E, E] batch the policy sees repeats each env's adj N times.
+ * graph_offsets: int64 [num_graphs*repeat + 1] exclusive prefix of edge counts (out);
+ * edge_index: int64 [2, capacity]; edge_attr: float [capacity]; nnz_out: int64 [1] (device, may be NULL).
+ * Edges beyond `capacity` are not written (capacity num_graphs*repeat*E*(E-1) always suffices). */
+int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, double max_edge_dist,
+                 int32_t inclusive, int32_t repeat, int64_t capacity, int64_t* graph_offsets,
+                 int64_t* edge_index, float* edge_attr, int64_t* nnz_out, void* stream);
+
+/* Episode statistics (what base_runner.process_infos aggregates, base_runner.py:197-276).
+ * Layout of the vector, K = fm_stats_len(N) doubles:
+ *   [0 .. N)            sum of rewards per agent over all env-steps since the last clear
+ *   [N .. N + 14 N)     per agent, the 14 info values summed over envs at their terminal step
+ *   [15 N]              finished episodes,   [15 N + 1]  env-steps
+ * fm_stats_read reduces the per-warp partial sums in a fixed order (deterministic) into
+ * out_dev (device, K doubles); the caller all-reduces it across ranks (NCCL sum). */
+int fm_stats_len(int32_t num_agents);
+int fm_stats_read(FmHandle* h, double* out_dev, int32_t clear, void* stream);
+
+/* Introspection. */
+int fm_num_entities(const FmHandle* h);
+int64_t fm_algorithmic_bytes_per_step(const FmHandle* h); /* W * 4 * B */
+int fm_kernel_launches(const FmHandle* h, int64_t* out);   /* kernels launched by this handle so far */
+int fm_abi_version(void);
+const char* fm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAIRMARL_H_ */

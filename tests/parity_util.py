@@ -1,0 +1,79 @@
+"""Shared helpers for the parity tests (device vs oracle)."""
+from dataclasses import fields
+
+import numpy as np
+
+from oracle.navgraph import NavConfig, NavGraphOracle, NavState
+
+RTOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative in fp32"
+
+
+def assert_close(dev, ref, name="", rtol=RTOL):
+    """|dev - ref| <= rtol * max(|ref|, 1)  (== allclose(rtol, atol=rtol)); a pure per-component
+    relative metric is not satisfiable at zero crossings."""
+    dev = np.asarray(dev, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert dev.shape == ref.shape, (name, dev.shape, ref.shape)
+    fin = np.isfinite(ref)
+    assert (np.isfinite(dev) == fin).all(), name
+    err = np.abs(dev[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    worst = err.max() if err.size else 0.0
+    assert worst <= rtol, f"{name}: max err {worst:.3e} > {rtol:.1e}"
+    return worst
+
+
+def assert_fairness_close(dev, ref, name="fairness_param"):
+    """obs channel 6 = mean/(std + 1e-4) of travelled distances is ill-conditioned when all agents
+    travelled almost the same distance: 1e-5 while |ref| <= 1e3, 1e-3 beyond,
+    where tanh(fairness - 5) is saturated and the reward does not see the difference."""
+    dev = np.asarray(dev, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.abs(dev - ref) / np.maximum(np.abs(ref), 1.0)
+    tol = np.where(np.abs(ref) <= 1e3, RTOL, 1e-3)
+    assert (err <= tol).all(), f"{name}: max err {err.max():.3e}"
+
+
+def sim_config_from(cfg: NavConfig, **kw):
+    from fair_marl_b200 import SimConfig
+    return SimConfig(num_agents=cfg.num_agents, num_obstacles=cfg.num_obstacles, world_size=cfg.world_size,
+                     max_speed=cfg.max_speed, collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew,
+                     min_dist_thresh=cfg.min_dist_thresh, episode_length=cfg.episode_length,
+                     fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
+                     collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, **kw)
+
+
+def state_to_fp32(st: NavState) -> NavState:
+    """Round a float64 state to the device dtype (and back to float64 for the oracle)."""
+    d = {}
+    for f in fields(NavState):
+        a = np.asarray(getattr(st, f.name))
+        if f.name in ("goal_match", "step", "episode"):
+            d[f.name] = a.astype(np.int64)
+        else:
+            with np.errstate(over="ignore"):
+                d[f.name] = a.astype(np.float32).astype(np.float64)
+    return NavState(**d)
+
+
+def state_to_device_dict(st: NavState):
+    return {f.name: np.asarray(getattr(st, f.name)) for f in fields(NavState)}
+
+
+def device_state_to_nav(dev_state) -> NavState:
+    d = {}
+    for f in fields(NavState):
+        a = dev_state[f.name].cpu().numpy()
+        d[f.name] = a.astype(np.int64) if f.name in ("goal_match", "step", "episode") else a.astype(np.float64)
+    return NavState(**d)
+
+
+def compare_step_outputs(out_dev, out_ref, cfg: NavConfig, check_info=True):
+    """out_dev: dict of numpy arrays from the device; out_ref: oracle step() dict."""
+    worst = {}
+    worst["obs"] = assert_close(out_dev["obs"][..., :6], out_ref["obs"][..., :6], "obs[0:6]")
+    assert_fairness_close(out_dev["obs"][..., 6], out_ref["obs"][..., 6])
+    worst["node_obs"] = assert_close(out_dev["node_obs"], out_ref["node_obs"], "node_obs")
+    worst["adj"] = assert_close(out_dev["adj"], out_ref["adj"], "adj")
+    worst["reward"] = assert_close(out_dev["reward"], out_ref["reward"], "reward")
+    assert (out_dev["done"].astype(bool) == out_ref["done"]).all(), "done"
+    return worst

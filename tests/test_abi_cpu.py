@@ -1,0 +1,103 @@
+"""CPU-side checks of the C ABI: the library builds for sm_100a, loads, exports every symbol
+include/fairmarl.h declares, and refuses to work without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    import fair_marl_b200
+    return fair_marl_b200.build_library()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fairmarl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fairmarl.h but not exported"
+
+
+def test_binding_covers_header(lib_path):
+    from fair_marl_b200 import _lib
+    assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
+    lib = _lib.load()
+    assert lib.fm_abi_version() == 1
+    assert lib.fm_stats_len(3) == 47
+
+
+def test_struct_layouts_match_header():
+    from fair_marl_b200 import _lib
+    assert ctypes.sizeof(_lib.FmConfig) == 4 * 4 + 8 + 8 + 8 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8
+    assert ctypes.sizeof(_lib.FmState) == 16 * 8
+
+
+def test_library_is_sm100a_only(lib_path):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback(lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import fair_marl_b200
+    from fair_marl_b200._lib import FairMarlError
+    with pytest.raises(FairMarlError):
+        fair_marl_b200.B200GraphVecEnv(fair_marl_b200.SimConfig(), num_envs=4)
+    # the C entry point itself reports "no device" instead of computing anything
+    from fair_marl_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.FmConfig(num_envs=4, num_agents=3, num_obstacles=3, episode_length=25)
+    h = ctypes.c_void_p()
+    rc = lib.fm_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc == -4 and b"no CUDA device" in lib.fm_last_error()
+
+
+def test_invalid_config_is_rejected(lib_path):
+    from fair_marl_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _lib.FmConfig(num_envs=0, num_agents=3, num_obstacles=3, episode_length=25)
+    assert lib.fm_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+    cfg = _lib.FmConfig(num_envs=4, num_agents=33, num_obstacles=3, episode_length=25)
+    assert lib.fm_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+    assert b"num_agents" in lib.fm_last_error()
+
+
+def test_config_from_reference_namespace():
+    from argparse import Namespace
+    from fair_marl_b200 import SimConfig
+    a = Namespace(num_agents=3, num_landmarks=3, num_obstacles=3, world_size=2, max_speed=2, collision_rew=30,
+                  goal_rew=30, min_dist_thresh=0.05, episode_length=25, fair_rew=1, zeroshift=5, max_edge_dist=1,
+                  collaborative=False, num_walls=0, graph_feat_type="relative", num_scripted_agents=0,
+                  scenario_name="navigation_graph", use_dones=False, fair_wt=1)
+    c = SimConfig.from_args(a)
+    assert c.num_entities == 9 and c.goal_rew == 30 and c.fairness_reward
+    a.scenario_name = "nav_graph_goalassign_noFair"
+    assert not SimConfig.from_args(a).fairness_reward
+    a.num_walls = 1
+    with pytest.raises(NotImplementedError):
+        SimConfig.from_args(a)
+
+
+def test_shard_range_partitions():
+    from fair_marl_b200 import shard_range
+    for total, world in [(65536, 8), (10, 3), (1, 1), (7, 8)]:
+        spans = [shard_range(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (o1, c1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 + c1 == o2

@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors the
+UNMODIFIED reference produced.  All tests here need a B200 (``-m gpu``).
+
+Tolerance: |dev - ref| <= 1e-5 * max(|ref|, 1) for positions, velocities, observations, node
+features, adjacency and rewards (BASELINE.json north_star).  Bit-exact:
+goal assignments, adjacency given the device's own fp32 positions, edge lists, reset placements.
+"""
+import numpy as np
+import pytest
+
+from oracle.edges import process_adj as oracle_process_adj
+from oracle.lexifair import lexifair, lexifair_bruteforce_batched, lexifair_descent
+from oracle.make_golden import CONFIGS, load, state_from
+from oracle.navgraph import INFO_KEYS, NavConfig, NavGraphOracle
+from parity_util import (assert_close, assert_fairness_close, compare_step_outputs, device_state_to_nav,
+                         sim_config_from, state_to_device_dict, state_to_fp32)
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(cfg, B, **kw):
+    import fair_marl_b200 as fm
+    return fm.B200GraphVecEnv(sim_config_from(cfg, **kw.pop("sim", {})), num_envs=B, **kw)
+
+
+def _np(out):
+    return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+
+
+def _actions(a):
+    import torch
+    return torch.as_tensor(np.asarray(a), dtype=torch.int32, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_step_matches_oracle_on_golden_states(name):
+    """One step from every recorded reference state (rounded to fp32): device vs float64 oracle."""
+    cfg, g = load(name)
+    pre = state_to_fp32(state_from(g, "pre_"))
+    T = pre.pos.shape[0]
+    env = _env(cfg, T, sim=dict(auto_reset=False, info_every_step=True))
+    env.set_state(state_to_device_dict(pre))
+    out = _np(env.step_tensor(_actions(g["actions"])))
+    orc = NavGraphOracle(cfg, T)
+    orc.set_state(pre)
+    ref = orc.step(actions=g["actions"], autoreset=False)
+    out["adj"] = out["adj_env"]
+    compare_step_outputs(out, ref, cfg)
+    # post-step state
+    post = device_state_to_nav(env.get_state())
+    rpost = orc.get_state()
+    for f in ("pos", "vel", "p_dist", "dists_to_goal", "times_required", "dist_left_to_goal",
+              "dist_traveled_mean", "dist_traveled_stddev"):
+        assert_close(getattr(post, f), getattr(rpost, f), f)
+    for f in ("num_agent_collisions", "num_obstacle_collisions", "step", "goal_match"):
+        assert (getattr(post, f) == getattr(rpost, f)).all(), f
+    # info rows
+    info = out["info"]
+    for k, key in enumerate(INFO_KEYS):
+        if key in ("Mean_by_variance", "Time_mean_by_stddev"):
+            assert_fairness_close(info[..., k], ref["info"][key], key)
+        else:
+            assert_close(info[..., k], ref["info"][key], key)
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["n3_o3_fafr", "n7_o3_fafr", "n16_o3_fafr"])
+def test_step_matches_reference_golden_directly(name):
+    """Device outputs against the reference's own float64 outputs (inputs rounded to fp32 on the way
+    in, so smooth quantities only: obs[0:6], node_obs, adj)."""
+    cfg, g = load(name)
+    pre = state_to_fp32(state_from(g, "pre_"))
+    env = _env(cfg, pre.pos.shape[0], sim=dict(auto_reset=False))
+    env.set_state(state_to_device_dict(pre))
+    out = _np(env.step_tensor(_actions(g["actions"])))
+    assert_close(out["obs"][..., :6], g["out_obs"][..., :6], "obs", rtol=2e-5)
+    assert_close(out["node_obs"], g["out_node_obs"], "node_obs", rtol=2e-5)
+    assert_close(out["adj_env"], g["out_adj"], "adj", rtol=2e-5)
+    assert (out["done"] == g["out_done"]).all()
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["n3_o3_fafr", "n7_o3_fafr", "n5_o0_fafr", "n16_o3_fafr"])
+def test_adjacency_and_edges_bit_exact_on_device_positions(name):
+    """Stage 2 of the two-stage check: the oracle evaluated on the device's own
+    post-step fp32 positions gives bit-identical adj (float64 -> float32) and edge lists."""
+    import fair_marl_b200 as fm
+    cfg, g = load(name)
+    pre = state_to_fp32(state_from(g, "pre_"))
+    T = pre.pos.shape[0]
+    env = _env(cfg, T, sim=dict(auto_reset=False))
+    env.set_state(state_to_device_dict(pre))
+    out = env.step_tensor(_actions(g["actions"]))
+    adj_dev = out["adj_env"].cpu().numpy()
+    orc = NavGraphOracle(cfg, T)
+    orc.set_state(device_state_to_nav(env.get_state()))
+    adj_ref = orc.distance_matrix().astype(np.float32)
+    assert (adj_dev == adj_ref).all(), np.abs(adj_dev - adj_ref).max()
+    for repeat in (1, cfg.num_agents):
+        ei, ea = fm.process_adj(out["adj_env"], cfg.max_edge_dist, repeat=repeat)
+        rei, rea = oracle_process_adj(np.repeat(adj_ref, repeat, axis=0), cfg.max_edge_dist)
+        assert ei.dtype.is_floating_point is False and tuple(ei.shape) == rei.shape
+        assert (ei.cpu().numpy() == rei).all()
+        assert (ea.cpu().numpy() == rea).all()
+    ei, ea = fm.process_adj(out["adj_env"], cfg.max_edge_dist, inclusive=True)
+    rei, rea = oracle_process_adj(adj_ref, cfg.max_edge_dist, inclusive=True)
+    assert (ei.cpu().numpy() == rei).all() and (ea.cpu().numpy() == rea).all()
+    env.close()
+
+
+@pytest.mark.parametrize("N,O,B", [(3, 3, 512), (7, 3, 256), (5, 0, 200), (16, 3, 96), (4, 2, 130), (1, 1, 33), (2, 0, 31)])
+def test_reset_bit_exact_vs_oracle(N, O, B):
+    """Device reset == oracle reset (same Philox stream, same acceptance rules): positions and
+    assignments bit-exact; also the reference's rejection rules hold."""
+    cfg = NavConfig(num_agents=N, num_obstacles=O)
+    env = _env(cfg, B, seed=1234, env_offset=77)
+    out = _np(env.reset_tensor())
+    st = device_state_to_nav(env.get_state())
+    orc = NavGraphOracle(cfg, B, seed=1234, env_offset=77)
+    ref = orc.reset()
+    rs = orc.get_state()
+    assert (st.pos == rs.pos).all() and (st.landmark_pos == rs.landmark_pos).all()
+    assert (st.obstacle_pos == rs.obstacle_pos).all()
+    assert (st.goal_match == rs.goal_match).all()
+    assert (st.vel == 0).all() and (st.p_dist == 0).all() and (st.step == 0).all() and (st.episode == 1).all()
+    assert (st.dists_to_goal == -1).all() and (st.times_required == -1).all()
+    assert_close(out["obs"], ref["obs"], "reset obs")
+    assert_close(out["node_obs"], ref["node_obs"], "reset node_obs")
+    assert (out["adj_env"] == ref["adj"].astype(np.float32)).all()
+    # a-14 acceptance rules
+    dmin = 1.05 * (0.05 + 0.05)
+    for a in range(N):
+        for b in range(a + 1, N):
+            assert (np.linalg.norm(st.pos[:, a] - st.pos[:, b], axis=-1) >= dmin).all()
+            assert (np.linalg.norm(st.landmark_pos[:, a] - st.landmark_pos[:, b], axis=-1) >= dmin).all()
+        for k in range(O):
+            assert (np.linalg.norm(st.pos[:, a] - st.obstacle_pos[:, k], axis=-1) >= dmin).all()
+    assert (np.abs(st.pos) <= 1).all() and (np.abs(st.landmark_pos) <= 0.8).all()
+    # a second reset draws a different episode and still matches
+    env.reset_tensor()
+    orc.reset()
+    st2 = device_state_to_nav(env.get_state())
+    assert (st2.pos == orc.s.pos).all() and (st2.goal_match == orc.s.goal_match).all()
+    assert not (st2.pos == st.pos).all()
+    env.close()
+
+
+@pytest.mark.parametrize("N,O,B,steps", [(3, 3, 256, 60), (7, 3, 64, 30), (16, 3, 16, 27)])
+def test_rollout_with_autoreset_matches_oracle(N, O, B, steps):
+    """Random-action rollout across auto-resets.  Every step the oracle is re-synchronised to the
+    device state (single-step parity from identical states), then both step; on auto-reset steps the
+    new episode's placements and assignment must be bit-exact, reward / done stay terminal."""
+    cfg = NavConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0)
+    env = _env(cfg, B, seed=7)
+    orc = NavGraphOracle(cfg, B, seed=7)
+    env.reset_tensor()
+    rng = np.random.default_rng(0)
+    n_resets = 0
+    for t in range(steps):
+        orc.set_state(device_state_to_nav(env.get_state()))
+        a = rng.integers(0, 5, (B, N))
+        out = _np(env.step_tensor(_actions(a)))
+        ref = orc.step(actions=a, autoreset=True)
+        out["adj"] = out["adj_env"]
+        compare_step_outputs(out, ref, cfg)
+        post, rpost = device_state_to_nav(env.get_state()), orc.get_state()
+        if ref["reset"].any():
+            n_resets += 1
+            assert ref["reset"].all() and out["done"].all()
+            assert (post.pos == rpost.pos).all() and (post.goal_match == rpost.goal_match).all()
+            assert (post.step == 0).all() and (post.episode == rpost.episode).all()
+            assert_close(post.min_time, rpost.min_time, "min_time")
+        else:
+            assert_close(post.pos, rpost.pos, "pos")
+    assert n_resets == steps // cfg.episode_length
+    env.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 11, 16, 17, 25, 32])
+def test_assignment_bit_exact(n):
+    """Stand-alone kernel (d) vs the exact CPU solvers, incl. tie-heavy integer costs."""
+    import fair_marl_b200 as fm
+    rng = np.random.default_rng(n)
+    num = 600 if n <= 8 else 60
+    costs = rng.random((num, n, n))
+    costs[num // 2:] = rng.integers(0, 4, (num - num // 2, n, n))        # ties
+    got = fm.lexifair_batched(costs=costs)
+    want = lexifair_bruteforce_batched(costs) if n <= 7 else np.stack([lexifair_descent(c) for c in costs])
+    assert got.dtype == np.int32 and (got == want).all()
+    # from positions (float64 cdist of float32 points)
+    ap = rng.uniform(-1, 1, (num, n, 2)).astype(np.float32)
+    gp = (0.8 * rng.uniform(-1, 1, (num, n, 2))).astype(np.float32)
+    d = ap.astype(np.float64)[:, :, None, :] - gp.astype(np.float64)[:, None, :, :]
+    c2 = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])
+    got2 = fm.lexifair_batched(agent_pos=ap, goal_pos=gp)
+    assert (got2 == lexifair(c2)).all()
+
+
+def test_assignment_reference_fixed_instance():
+    import fair_marl_b200 as fm
+    goals = np.array([[0., -0.5], [0.45, -0.5], [0.9, -0.5]])
+    agents = np.array([[-0.9, -0.9], [-0.9, 0.], [-0.9, 0.9]])
+    d = agents[:, None, :] - goals[None, :, :]
+    x, objs = fm.solve_fair_assignment(np.sqrt((d ** 2).sum(-1)))      # marl_fair_assign.py:63-70
+    assert (np.where(x == 1)[1] == [2, 1, 0]).all()
+    np.testing.assert_allclose(objs, [1.843909, 1.664332, 1.439618], atol=1e-6)
+
+
+def test_onehot_and_index_actions_agree():
+    import torch
+    cfg = NavConfig()
+    B = 300
+    e1, e2 = _env(cfg, B, seed=3), _env(cfg, B, seed=3)
+    e1.reset_tensor(); e2.reset_tensor()
+    a = np.random.default_rng(1).integers(0, 5, (B, 3))
+    o1 = _np(e1.step_tensor(_actions(a)))
+    o2 = _np(e2.step_tensor(torch.as_tensor(np.eye(5, dtype=np.float32)[a], device="cuda")))
+    for k in ("obs", "node_obs", "adj_env", "reward"):
+        assert (o1[k] == o2[k]).all(), k
+    e1.close(); e2.close()
+
+
+def test_shards_equal_one_batch_bitwise():
+    """results are independent of the sharding (RNG keyed by global env index)."""
+    cfg = NavConfig(num_agents=3, num_obstacles=3)
+    B, parts = 1000, [(0, 250), (250, 137), (387, 613)]
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, 5, (30, B, 3))
+    full = _env(cfg, B, seed=11)
+    shards = [_env(cfg, c, seed=11, env_offset=o) for o, c in parts]
+    outs_f = [_np(full.reset_tensor())]
+    outs_s = [[_np(s.reset_tensor()) for s in shards]]
+    for t in range(30):
+        outs_f.append(_np(full.step_tensor(_actions(acts[t]))))
+        outs_s.append([_np(s.step_tensor(_actions(acts[t, o:o + c]))) for s, (o, c) in zip(shards, parts)])
+    for f, ss in zip(outs_f, outs_s):
+        for k in ("obs", "node_obs", "adj_env") + (("reward", "done") if "reward" in f else ()):
+            assert (f[k] == np.concatenate([s[k] for s in ss])).all(), k
+    # statistics: the sum over shards equals the single batch (up to summation order)
+    sf = full.read_stats().cpu().numpy()
+    ss = sum(s.read_stats().cpu().numpy() for s in shards)
+    np.testing.assert_allclose(sf, ss, rtol=1e-9)
+    assert sf[15 * 3] == B and sf[15 * 3 + 1] == 30 * B
+    full.close()
+    [s.close() for s in shards]

@@ -1,0 +1,145 @@
+"""Boundary conformance of ``B200GraphVecEnv`` against the GraphSubprocVecEnv contract
+(env_wrappers.py:951-1025) and the host-buffer C-ABI path."""
+import numpy as np
+import pytest
+
+from oracle.navgraph import INFO_KEYS, NavConfig, NavGraphOracle
+from parity_util import assert_close, compare_step_outputs, device_state_to_nav, sim_config_from
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_api_shapes_dtypes_and_autoreset():
+    import fair_marl_b200 as fm
+    from argparse import Namespace
+    args = Namespace(num_agents=3, num_landmarks=3, num_obstacles=3, world_size=2, max_speed=2, collision_rew=30,
+                     goal_rew=30, min_dist_thresh=0.05, episode_length=25, fair_rew=1, zeroshift=5, max_edge_dist=1,
+                     collaborative=False, num_walls=0, graph_feat_type="relative", num_scripted_agents=0,
+                     scenario_name="navigation_graph", use_dones=False, fair_wt=1, n_rollout_threads=128, seed=1,
+                     env_name="GraphMPE")
+    env = fm.make_train_env(args)
+    B, N, E = 128, 3, 9
+    assert env.num_envs == B
+    assert env.observation_space[0].__class__.__name__ == "Box" and env.observation_space[0].shape == (7,)
+    assert env.share_observation_space[0].shape == (21,)
+    assert env.action_space[0].__class__.__name__ == "Discrete" and env.action_space[0].n == 5
+    assert env.node_observation_space[0].shape == (E, 11) and env.adj_observation_space[0].shape == (E, E)
+    assert env.edge_observation_space[0].shape == (1,) and env.agent_id_observation_space[0].shape == (1,)
+    assert env.share_agent_id_observation_space[0].shape == (N,)
+    obs, ag_id, node, adj = env.reset()
+    assert obs.shape == (B, N, 7) and ag_id.shape == (B, N, 1) and node.shape == (B, N, E, 11) and adj.shape == (B, N, E, E)
+    assert (ag_id[:, :, 0] == np.arange(N)).all()
+    assert (adj[:, 0] == adj[:, 1]).all() and (adj[:, 0] == np.swapaxes(adj[:, 0], 1, 2)).all()
+    rng = np.random.default_rng(0)
+    for t in range(25):
+        acts = np.eye(5)[rng.integers(0, 5, (B, N))]                 # graph_mpe_runner.py:429-431
+        obs, ag_id, node, adj, rew, done, infos = env.step(acts)
+        assert rew.shape == (B, N) and done.shape == (B, N) and done.dtype == bool
+        assert done.all() == (t == 24) and done.any() == (t == 24)
+    # terminal step: obs are the NEW episode's (velocity 0, fairness 0), infos are terminal
+    assert (obs[..., 0:2] == 0).all() and (obs[..., 6] == 0).all()
+    assert len(infos) == B and len(infos[0]) == N and set(infos[0][0]) == set(INFO_KEYS)
+    assert abs(infos[5][1]["Time_taken"] - 2.5) < 1e-5
+    assert infos[5][1]["individual_reward"] == pytest.approx(float(rew[5, 1]))
+    st = env.get_state()
+    assert (st["step"].cpu().numpy() == 0).all() and (st["episode"].cpu().numpy() == 2).all()
+    env.close()
+
+
+def test_host_api_equals_tensor_api_and_oracle():
+    import fair_marl_b200 as fm
+    cfg = NavConfig(num_agents=4, num_obstacles=2)
+    B = 200
+    e_host = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=9)
+    e_dev = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=9)
+    orc = NavGraphOracle(cfg, B, seed=9)
+    o_h = e_host.reset()
+    o_d = e_dev.reset_tensor()
+    assert (o_h[0] == o_d["obs"].cpu().numpy()).all() and (o_h[3] == o_d["adj"].cpu().numpy()).all()
+    rng = np.random.default_rng(2)
+    import torch
+    for t in range(28):
+        orc.set_state(device_state_to_nav(e_dev.get_state()))
+        a = rng.integers(0, 5, (B, 4))
+        obs, ag, node, adj, rew, done, infos = e_host.step(np.eye(5)[a])
+        d = e_dev.step_tensor(torch.as_tensor(a, dtype=torch.int32, device="cuda"))
+        assert (obs == d["obs"].cpu().numpy()).all() and (node == d["node_obs"].cpu().numpy()).all()
+        assert (adj == d["adj"].cpu().numpy()).all() and (rew == d["reward"].cpu().numpy()).all()
+        assert (done == d["done"].cpu().numpy()).all()
+        ref = orc.step(actions=a)
+        compare_step_outputs(dict(obs=obs, node_obs=node, adj=adj[:, 0], reward=rew, done=done), ref, cfg)
+        if done.all():
+            rows = infos.as_array()
+            for k, key in enumerate(INFO_KEYS):
+                if "by" not in key:
+                    assert_close(rows[..., k], ref["info"][key], key)
+    e_host.close(); e_dev.close()
+
+
+def test_episode_statistics_match_oracle_sums():
+    import fair_marl_b200 as fm
+    import torch
+    cfg = NavConfig(num_agents=3, num_obstacles=3)
+    B = 333
+    env = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=4)
+    orc = NavGraphOracle(cfg, B, seed=4)
+    env.reset_tensor()
+    rng = np.random.default_rng(3)
+    rew_sum = np.zeros(3)
+    info_sum = np.zeros((3, 14))
+    for t in range(50):
+        orc.set_state(device_state_to_nav(env.get_state()))
+        a = rng.integers(0, 5, (B, 3))
+        env.step_tensor(torch.as_tensor(a, dtype=torch.int32, device="cuda"))
+        ref = orc.step(actions=a)
+        rew_sum += ref["reward"].sum(0)
+        if ref["reset"].all():
+            for k, key in enumerate(INFO_KEYS):
+                info_sum[:, k] += ref["info"][key].sum(0)
+    v = env.read_stats(clear=True).cpu().numpy()
+    np.testing.assert_allclose(v[0:3], rew_sum, rtol=1e-5)
+    got = v[3:45].reshape(3, 14)
+    for k, key in enumerate(INFO_KEYS):
+        if "by" in key:
+            continue
+        np.testing.assert_allclose(got[:, k], info_sum[:, k], rtol=2e-5, atol=1e-3, err_msg=key)
+    assert v[45] == 2 * B and v[46] == 50 * B
+    assert (env.read_stats().cpu().numpy() == 0).all()
+    s = fm.EpisodeStats(3, device=torch.device("cuda", 0))
+    s.all_reduce_async(torch.as_tensor(v, device="cuda"))
+    summ = s.summary()
+    assert summ["episodes"] == 2 * B and len(summ["Dist_to_goal"]) == 3
+    env.close()
+
+
+def test_errors_are_python_exceptions():
+    import fair_marl_b200 as fm
+    from fair_marl_b200._lib import FairMarlError
+    with pytest.raises(FairMarlError):
+        fm.B200GraphVecEnv(fm.SimConfig(num_agents=40), num_envs=8)
+    env = fm.B200GraphVecEnv(fm.SimConfig(), num_envs=8)
+    with pytest.raises(ValueError):
+        env.step(np.zeros((8, 3, 4)))
+    with pytest.raises(NotImplementedError):
+        env.render()
+    env.close()
+
+
+@pytest.mark.parametrize("B", [1, 7, 8, 9, 31, 33])
+def test_ragged_batch_sizes(B):
+    """Batches that do not fill a warp / are not multiples of 4 take the unaligned store path."""
+    import fair_marl_b200 as fm
+    import torch
+    for N, O in [(3, 3), (7, 3), (9, 2), (16, 3)]:
+        cfg = NavConfig(num_agents=N, num_obstacles=O)
+        env = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=21)
+        orc = NavGraphOracle(cfg, B, seed=21)
+        env.reset_tensor()
+        a = np.random.default_rng(B).integers(0, 5, (B, N))
+        orc.set_state(device_state_to_nav(env.get_state()))
+        out = env.step_tensor(torch.as_tensor(a, dtype=torch.int32, device="cuda"))
+        ref = orc.step(actions=a)
+        o = {k: v.cpu().numpy() for k, v in out.items() if hasattr(v, "cpu")}
+        o["adj"] = o["adj_env"]
+        compare_step_outputs(o, ref, cfg)
+        env.close()
