@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
 
   // ---- World.step: forces (core.py:277-316, :370-404) from the positions at step entry --------
   // (== the reference's end-of-previous-step distance cache), partners in ascending entity index.
-  float Fx = ux, Fy = uy;                        // mass(1.0) * u + noise(0.0), core.py:291-293
+  double Fx = (double)ux, Fy = (double)uy;       // mass(1.0) * u + noise(0.0), core.py:291-293
   for (int j = 0; j < N; ++j) {
     const float qx = __shfl_sync(FULL, px, gl + j), qy = __shfl_sync(FULL, py, gl + j);
     if (act && j != i) contact_force(p, px, py, qx, qy, Fx, Fy);
@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
   }
   // ---- integrate_state (core.py:338-356), float64 so that p_dist keeps its low bits for the
   // ill-conditioned mean/std fairness ratio; state is stored rounded to fp32.
-  double v64x = (double)vx * p.damping_keep + (double)Fx * p.dt;
-  double v64y = (double)vy * p.damping_keep + (double)Fy * p.dt;
+  double v64x = (double)vx * p.damping_keep + Fx * p.dt;
+  double v64y = (double)vy * p.damping_keep + Fy * p.dt;
   if (p.has_max_speed) {
     const double speed = sqrt(v64x * v64x + v64y * v64y);
     if (speed > p.max_speed) { v64x = v64x / speed * p.max_speed; v64y = v64y / speed * p.max_speed; }
