@@ -216,6 +216,17 @@ int fm_step_onehot(FmHandle* h, const float* onehot, const FmOutputs* out, void*
   return step_common(h, nullptr, onehot, out, stream);
 }
 
+int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const FmOutputs* outs, void* stream) {
+  if (!h || !actions || !outs) return fail(FM_ERR_INVALID_ARG, "fm_step_many: null argument");
+  if (num_steps < 0) return fail(FM_ERR_INVALID_ARG, "fm_step_many: num_steps < 0");
+  const size_t stride = (size_t)h->p.B * h->p.N;
+  for (int t = 0; t < num_steps; ++t) {
+    int rc = step_common(h, actions + (size_t)t * stride, nullptr, outs + t, stream);
+    if (rc) return rc;
+  }
+  return FM_OK;
+}
+
 static int ensure_staging(FmHandle* h) {
   if (h->staging) return FM_OK;
   const size_t B = h->p.B, N = h->p.N, E = h->p.E;

@@ -122,6 +122,7 @@ class B200GraphVecEnv:
         self._step_version = 0
         self._pending_actions = None
         self._last_step_api = None
+        self._plans = {}
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
@@ -220,6 +221,40 @@ class B200GraphVecEnv:
         _lib.check(rc, "fm_step")
         self._step_version += 1
         self._last_step_api = "tensor"
+        return self._package(slot, with_step=True)
+
+    def rollout_tensor(self, actions) -> List[int]:
+        """``T`` consecutive steps from one host call (``fm_step_many``): ``actions`` int32 CUDA tensor
+        [T, B, N].  Step t writes slab slot (slot + 1 + t) % num_slots; returns the slot of every step.
+        Asynchronous; no per-step Python or ctypes overhead."""
+        t = self.torch
+        s = self._ensure_slabs()
+        B, N = self.num_envs, self.num_agents
+        if actions.dtype != t.int32 or not actions.is_contiguous() or actions.dim() != 3 or actions.shape[1:] != (B, N):
+            raise ValueError("actions must be a contiguous int32 CUDA tensor [T, B, N]")
+        T = int(actions.shape[0])
+        key = (T, self._slot)
+        plan = self._plans.get(key)
+        if plan is None:
+            arr = (_lib.FmOutputs * T)()
+            slots = []
+            for k in range(T):
+                slot = (self._slot + 1 + k) % self.num_slots
+                views = {name: s[name][slot] for name in ("obs", "node_obs", "adj", "reward", "done")}
+                views["info"] = s["info"]
+                arr[k] = self._outputs_struct(views, with_step=True)
+                slots.append(slot)
+            plan = self._plans[key] = (arr, slots)
+        arr, slots = plan
+        _lib.check(self.lib.fm_step_many(self._h, actions.data_ptr(), T, arr, self._stream()), "fm_step_many")
+        self._slot = slots[-1] if slots else self._slot
+        self._step_version += T
+        self._last_step_api = "tensor"
+        return slots
+
+    def slot_outputs(self, slot: int) -> Dict[str, Any]:
+        """Views of rollout slab ``slot`` (as returned by ``step_tensor``)."""
+        self._ensure_slabs()
         return self._package(slot, with_step=True)
 
     # ------------------------------------------------------------------ reference (numpy) API

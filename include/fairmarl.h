@@ -127,6 +127,11 @@ int fm_step(FmHandle* h, const int32_t* actions, const FmOutputs* out, void* str
  * (graph_mpe_runner.py:429-431; decode environment.py:301-311). */
 int fm_step_onehot(FmHandle* h, const float* onehot, const FmOutputs* out, void* stream);
 
+/* num_steps consecutive fm_step calls from one host call (rollout inner loop without per-step host
+ * overhead): step t uses actions + t*B*N and writes outs[t].  `outs` is a HOST array of structs
+ * holding DEVICE pointers. */
+int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const FmOutputs* outs, void* stream);
+
 /* Host-buffer form of fm_step_onehot: `onehot` and every member of `out` are HOST pointers
  * (pinned for full speed).  Copies actions in, steps, copies the requested outputs back and
  * synchronises `stream`.  This is the call a ShareVecEnv.step() drop-in makes. */
