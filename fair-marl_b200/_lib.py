@@ -24,7 +24,7 @@ class FmConfig(C.Structure):
         ("goal_rew", C.c_double), ("min_dist_thresh", C.c_double), ("fair_rew", C.c_double),
         ("zeroshift", C.c_double), ("max_edge_dist", C.c_double),
         ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32),
-        ("info_every_step", C.c_int32),
+        ("info_every_step", C.c_int32), ("mapping", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -82,6 +82,7 @@ def load():
         "fm_edge_list": ([C.c_int, vp, i32, i32, C.c_double, i32, i32, i64, vp, vp, vp, vp, vp], C.c_int),
         "fm_stats_read": ([vp, vp, i32, vp], C.c_int),
         "fm_num_entities": ([vp], C.c_int),
+        "fm_mapping": ([vp], C.c_int),
         "fm_algorithmic_bytes_per_step": ([vp], i64),
         "fm_kernel_launches": ([vp, C.POINTER(i64)], C.c_int),
     }
@@ -95,7 +96,7 @@ def load():
 EXPORTED_SYMBOLS = (
     "fm_abi_version", "fm_last_error", "fm_stats_len", "fm_create", "fm_destroy", "fm_reset", "fm_step",
     "fm_step_onehot", "fm_step_many", "fm_step_host", "fm_reset_host", "fm_read_info_host", "fm_set_state", "fm_get_state",
-    "fm_assign_costs", "fm_assign_positions", "fm_edge_list", "fm_stats_read", "fm_num_entities",
+    "fm_assign_costs", "fm_assign_positions", "fm_edge_list", "fm_stats_read", "fm_num_entities", "fm_mapping",
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",
 )
 

@@ -24,6 +24,9 @@ class SimConfig:
     fairness_reward: bool = True
     auto_reset: bool = True
     info_every_step: bool = False
+    # kernel mapping: 'auto' | 'group' (group-per-env) | 'thread' (thread-per-env) | 'tile' (env-tile); the last
+    # two exist for the small (N, O) they are compiled for; results are identical across mappings
+    mapping: str = "auto"
 
     @property
     def num_entities(self) -> int:

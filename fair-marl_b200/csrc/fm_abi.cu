@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "fm_device.cuh"
 #include "fm_launch.h"
@@ -31,6 +32,7 @@ struct FmHandle {
   int device;
   DevParams p;
   void* state_block;
+  void* luts;
   double* stats;
   int stats_rows, K;
   long long launches;
@@ -65,6 +67,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > 64)
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_obstacles must be in 0..64 (got %d)", cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_create: episode_length must be >= 1");
+  if (cfg->mapping < 0 || cfg->mapping > 3) return fail(FM_ERR_INVALID_ARG, "fm_create: mapping must be 0..3 (got %d)", cfg->mapping);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -127,6 +130,29 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.seed_hi = (uint32_t)(cfg->seed >> 32);
   p.env_offset = cfg->env_offset;
 
+  // Kernel mapping (cfg->mapping: 0 auto = env-tile where compiled for (N, O), else group-per-env;
+  // 1 group-per-env; 2 thread-per-env; 3 env-tile).  All mappings produce identical results.
+  if (cfg->mapping == 2 && !fm::tpe_supported(N, O)) {
+    cudaFree(h->state_block); delete h;
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: thread-per-env kernels are not compiled for N=%d O=%d", N, O);
+  }
+  if (cfg->mapping == 3 && !fm::tile_supported(N, O)) {
+    cudaFree(h->state_block); delete h;
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: env-tile kernels are not compiled for N=%d O=%d", N, O);
+  }
+  p.mapping = cfg->mapping == 1 ? 0 : (cfg->mapping == 2 ? 1 : ((cfg->mapping == 3 || fm::tile_supported(N, O)) ? 2 : 0));
+  if (p.mapping == 2) {
+    std::vector<uint32_t> lo, ln, la;
+    fm::tile_build_luts(N, O, lo, ln, la);
+    const size_t nw = lo.size() + ln.size() + la.size();
+    e = cudaMalloc(&h->luts, nw * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc luts: %s", cudaGetErrorString(e)); }
+    uint32_t* d = (uint32_t*)h->luts;
+    cudaMemcpy(d, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + lo.size(), ln.data(), ln.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + lo.size() + ln.size(), la.data(), la.size() * 4, cudaMemcpyHostToDevice);
+    p.lut_obs = d; p.lut_node = d + lo.size(); p.lut_adj = d + lo.size() + ln.size();
+  }
   const int G = fm::group_size(N), EPW = 32 / G;
   p.sm_cost = round4(2LL * EPW * N * N);
   p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
@@ -135,21 +161,21 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.sm_obs = round4((long long)EPW * N * fm::OBS_F);
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_stage + p.sm_obs + p.sm_asg;
-  if ((size_t)p.sm_per_warp * 4 * 4 > 227 * 1024) {
-    cudaFree(h->state_block); delete h;
+  if (p.mapping == 0 && (size_t)p.sm_per_warp * 4 * 4 > 227 * 1024) {
+    cudaFree(h->luts); cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: N=%d O=%d needs %d B of shared memory per CTA", N, O, p.sm_per_warp * 16);
   }
   h->K = fm_stats_len(N);
-  h->stats_rows = fm::num_warps(B, N);
+  h->stats_rows = p.mapping == 2 ? fm::tile_num_ctas(B) : (p.mapping == 1 ? fm::tpe_num_warps(B) : fm::num_warps(B, N));
   e = cudaMalloc(&h->stats, (size_t)h->stats_rows * h->K * sizeof(double));
-  if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc stats: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc stats: %s", cudaGetErrorString(e)); }
   cudaMemset(h->stats, 0, (size_t)h->stats_rows * h->K * sizeof(double));
   p.stats = h->stats;
   e = fm::prepare_kernels(p);
-  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
   e = fm::launch_state_init(p, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
   h->launches = 1;
   *out = h;
   return FM_OK;
@@ -168,6 +194,7 @@ int fm_destroy(FmHandle* h) {
   use_device(h->device);
   free_staging(h);
   cudaFree(h->stats);
+  cudaFree(h->luts);
   cudaFree(h->state_block);
   delete h;
   return FM_OK;
@@ -375,6 +402,7 @@ int fm_stats_read(FmHandle* h, double* out_dev, int32_t clear, void* stream) {
 }
 
 int fm_num_entities(const FmHandle* h) { return h ? h->p.E : 0; }
+int fm_mapping(const FmHandle* h) { return h ? h->p.mapping + 1 : 0; }
 
 int64_t fm_algorithmic_bytes_per_step(const FmHandle* h) {
   if (!h) return 0;

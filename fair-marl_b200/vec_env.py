@@ -97,7 +97,8 @@ class B200GraphVecEnv:
             collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
             fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
             fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative),
-            auto_reset=int(cfg.auto_reset), info_every_step=int(cfg.info_every_step))
+            auto_reset=int(cfg.auto_reset), info_every_step=int(cfg.info_every_step),
+            mapping={"auto": 0, "group": 1, "thread": 2, "tile": 3}[cfg.mapping])
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_create")
 
@@ -378,6 +379,11 @@ class B200GraphVecEnv:
         out = t.empty(self.lib.fm_stats_len(self.num_agents), dtype=t.float64, device=self.device)
         _lib.check(self.lib.fm_stats_read(self._h, out.data_ptr(), int(clear), self._stream()), "fm_stats_read")
         return out
+
+    @property
+    def mapping(self) -> str:
+        """Kernel mapping in use: 'group' (group-per-env), 'thread' (thread-per-env) or 'tile' (env-tile)."""
+        return {1: "group", 2: "thread", 3: "tile"}[int(self.lib.fm_mapping(self._h))]
 
     @property
     def kernel_launches(self) -> int:

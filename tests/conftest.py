@@ -6,11 +6,27 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs under both kernel mappings: 'auto' (thread-per-env where compiled, i.e. the
+    product default) and 'group' (group-per-env kernels forced)."""
+    if metafunc.definition.get_closest_marker("gpu") and "kernel_mapping" in metafunc.fixturenames:
+        metafunc.parametrize("kernel_mapping", ["auto", "group"], indirect=True)
+
+
+@pytest.fixture(autouse=True)
+def kernel_mapping(request):
+    import parity_util
+    parity_util.MAPPING = getattr(request, "param", "auto")
+    yield parity_util.MAPPING
+    parity_util.MAPPING = "auto"
 
 
 def pytest_collection_modifyitems(config, items):

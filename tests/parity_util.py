@@ -5,6 +5,7 @@ import numpy as np
 
 from oracle.navgraph import NavConfig, NavGraphOracle, NavState
 
+MAPPING = "auto"   # kernel mapping under test (set per test by conftest.kernel_mapping)
 RTOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative in fp32"
 
 
@@ -39,7 +40,8 @@ def sim_config_from(cfg: NavConfig, **kw):
                      max_speed=cfg.max_speed, collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew,
                      min_dist_thresh=cfg.min_dist_thresh, episode_length=cfg.episode_length,
                      fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
-                     collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, **kw)
+                     collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward,
+                     **{"mapping": MAPPING, **kw})
 
 
 def state_to_fp32(st: NavState) -> NavState:

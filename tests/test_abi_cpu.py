@@ -33,15 +33,31 @@ def test_binding_covers_header(lib_path):
     from fair_marl_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.load()
-    assert lib.fm_abi_version() == 1
+    assert lib.fm_abi_version() == 2
     assert lib.fm_stats_len(3) == 47
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct as gcc lays out include/fairmarl.h == the ctypes mirror."""
+    import subprocess
     from fair_marl_b200 import _lib
-    assert ctypes.sizeof(_lib.FmConfig) == 4 * 4 + 8 + 8 + 8 * 8 + 4 * 4
-    assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8
-    assert ctypes.sizeof(_lib.FmState) == 16 * 8
+    structs = {"FmConfig": _lib.FmConfig, "FmOutputs": _lib.FmOutputs, "FmState": _lib.FmState}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fairmarl.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
+    assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8 and ctypes.sizeof(_lib.FmState) == 16 * 8
 
 
 def test_library_is_sm100a_only(lib_path):
