@@ -68,14 +68,14 @@ struct TileLayout {
   static constexpr int OFF_T = OFF_SD + 2 * SD_ROWS * 32;
   static constexpr int OFF_D = OFF_T + TW * 32;
   static constexpr int OFF_FL = OFF_D + DW * 32;
-  static constexpr int WORDS = OFF_FL + PAIRS * 8;     // PAIRS * 32 bytes
   static constexpr int OBS_W = N * OBS_F, NODE_W = N * E * NODE_F, ADJ_W = E * E;
+  static constexpr int LUT_W = OBS_W + NODE_W + ADJ_W;  // gather descriptors: obs | node | adj
+  static constexpr int OFF_LUT = OFF_FL + PAIRS * 8;   // FL: PAIRS * 32 bytes
+  static constexpr int WORDS = OFF_LUT + LUT_W;
 };
 
 struct TileLuts {
-  const uint32_t* obs;     // [7N]      s1 | s2 << 16 into T
-  const uint32_t* node;    // [11 N E]  s1 | s2 << 16 into T
-  const uint32_t* adj;     // [E E]     index into D
+  const uint32_t* all;     // obs [7N] | node [11 N E]: s1 | s2 << 16 into T;  adj [E E]: index into D
 };
 
 __host__ __device__ constexpr int tile_pair_index(int a, int b, int E) { return a * E - a * (a + 1) / 2 + (b - a - 1); }   // a < b
@@ -93,141 +93,106 @@ __device__ __forceinline__ int row_y(int e) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Compile-time loops: static_for<B, E, S>(f) calls f(std::integral_constant<int, i>) for i = B, B+S, ... < E,
-// so that every item index is a constant expression (immediate shared-memory offsets, no index math).
-template <int B, int S, int... I, class F>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
-  (f(std::integral_constant<int, B + S * I>{}), ...);
-}
-template <int B, int E, int S = 1, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  constexpr int count = (E > B) ? (E - B + S - 1) / S : 0;
-  static_for_impl<B, S>(static_cast<F&&>(f), std::make_integer_sequence<int, count>{});
-}
+// Item descriptors, passed by value in the kernel-parameter constant bank: shared-memory word offsets
+// (row * 32) so that an item needs no index arithmetic beyond `offset + lane`.
+template <int N, int O>
+struct TileTables {
+  using L = TileLayout<N, O>;
+  uint16_t pair[L::PAIRS][4];                    // x_a, y_a, x_b, y_b rows of distance pair q (a < b, row-major)
+  uint16_t force[L::NF > 0 ? L::NF : 1][4];      // x_i, y_i, x_partner, y_partner rows of force item f
+  uint16_t ent[L::E][2];                         // x, y rows of entity e
+  uint8_t every_step[L::NROWS];                  // 1: state row is written back every step; 0: only after a reset
+};
 
 // pair q (row-major over a < b) -> a, b
 __host__ __device__ constexpr int pair_a(int q, int E) { int a = 0; while (q >= E - 1 - a) { q -= E - 1 - a; ++a; } return a; }
 __host__ __device__ constexpr int pair_b(int q, int E) { int a = 0; while (q >= E - 1 - a) { q -= E - 1 - a; ++a; } return a + 1 + q; }
 
-// ---------------------------------------------------------------------------------------------
-// Phase: distances of the entity pairs q = W, W + 4, ... at the current positions (core.py:204-228)
-// + predicate bits.  W is the warp's role: all indices are compile-time constants.
-template <int N, int O, int W>
-__device__ __forceinline__ void tile_distances(const DevParams& p, const float* __restrict__ S, float* __restrict__ D,
-                                               uint8_t* __restrict__ FL, int lane) {
+// Phase: distances of the entity pairs q = warp, warp + 4, ... at the current positions
+// (core.py:204-228) + predicate bits.
+template <int N, int O>
+__device__ __forceinline__ void tile_distances(const DevParams& p, const TileTables<N, O>& tb, const float* __restrict__ S,
+                                               float* __restrict__ D, uint8_t* __restrict__ FL, int lane, int warp) {
   using L = TileLayout<N, O>;
-  constexpr int E = L::E;
-  static_for<W, L::PAIRS, TILE_WARPS>([&](auto qc) {
-    constexpr int q = decltype(qc)::value;
-    constexpr int a = pair_a(q, E), b = pair_b(q, E);
-    const double d = dist64(S[row_x<N, O>(a) * 32 + lane], S[row_y<N, O>(a) * 32 + lane],
-                            S[row_x<N, O>(b) * 32 + lane], S[row_y<N, O>(b) * 32 + lane]);
-    D[lane * L::DW + q] = (float)d;
-    FL[q * 32 + lane] = (uint8_t)(((d < p.dcoll) ? 1 : 0) | ((d < p.min_dist_thresh) ? 2 : 0));
-  });
-  if (W == 0) D[lane * L::DW + L::DZERO] = 0.0f;
+  const float* Sl = S + lane;
+  float* Dq = D + lane * L::DW + warp;
+  uint8_t* Fq = FL + warp * 32 + lane;
+#pragma unroll 3
+  for (int k = 0; k < (L::PAIRS + TILE_WARPS - 1) / TILE_WARPS; ++k) {
+    const int q = warp + TILE_WARPS * k;
+    if (q < L::PAIRS) {
+      const uint2 o = *reinterpret_cast<const uint2*>(tb.pair[q]);
+      const double d = dist64(Sl[o.x & 0xffffu], Sl[o.x >> 16], Sl[o.y & 0xffffu], Sl[o.y >> 16]);
+      Dq[TILE_WARPS * k] = (float)d;
+      Fq[TILE_WARPS * 32 * k] = (uint8_t)(((d < p.dcoll) ? 1 : 0) | ((d < p.min_dist_thresh) ? 2 : 0));
+    }
+  }
+  if (warp == 0) D[lane * L::DW + L::DZERO] = 0.0f;
 }
 
-// Phase: per-env gather table for the outputs (items it = W, W + 4, ...).
-template <int N, int O, int W>
-__device__ __forceinline__ void tile_fill_table(const float* __restrict__ S, float* __restrict__ T, int lane) {
+// Phase: per-env gather table for the outputs (items it = warp, warp + 4, ...).
+template <int N, int O>
+__device__ __forceinline__ void tile_fill_table(const TileTables<N, O>& tb, const float* __restrict__ S, float* __restrict__ T,
+                                                int lane, int warp) {
   using L = TileLayout<N, O>;
   constexpr int E = L::E;
   float* t = T + lane * L::TW;
-  static_for<W, E + N + 1, TILE_WARPS>([&](auto ic) {
-    constexpr int it = decltype(ic)::value;
-    if constexpr (it < E) {                         // position of entity `it`
-      t[L::TP + 2 * it] = S[row_x<N, O>(it) * 32 + lane];
-      t[L::TP + 2 * it + 1] = S[row_y<N, O>(it) * 32 + lane];
-    } else if constexpr (it < E + N) {              // velocity, goal (landmark goal_match[i]) and fairness obs of agent i
-      constexpr int i = it - E;
-      t[L::TV + 2 * i] = S[(L::VX + i) * 32 + lane];
-      t[L::TV + 2 * i + 1] = S[(L::VY + i) * 32 + lane];
-      const int g = __float_as_int(S[(L::GM + i) * 32 + lane]);
+  for (int it = warp; it < E + N + 1; it += TILE_WARPS) {
+    if (it < E) {                                   // position of entity `it`
+      const uint32_t o = *reinterpret_cast<const uint32_t*>(tb.ent[it]);
+      t[L::TP + 2 * it] = S[(o & 0xffffu) + lane];
+      t[L::TP + 2 * it + 1] = S[(o >> 16) + lane];
+    } else if (it < E + N) {                        // velocity, goal (landmark goal_match[i]) and fairness obs of agent i
+      const int i = it - E;
+      const float* Si = S + i * 32 + lane;
+      t[L::TV + 2 * i] = Si[L::VX * 32];
+      t[L::TV + 2 * i + 1] = Si[L::VY * 32];
+      const int g = __float_as_int(Si[L::GM * 32]);
       t[L::TG + 2 * i] = S[(L::LX + g) * 32 + lane];
       t[L::TG + 2 * i + 1] = S[(L::LY + g) * 32 + lane];
-      t[L::TF + i] = S[(L::FOBS + i) * 32 + lane];
+      t[L::TF + i] = Si[L::FOBS * 32];
     } else {
       t[L::TZERO] = 0.0f; t[L::TONE] = 1.0f; t[L::TTWO] = 2.0f;
     }
-  });
-}
-
-// Gather descriptors of this lane, fetched once at kernel entry (registers): word w = lane + 32 k.
-template <int N, int O>
-struct LaneLuts {
-  using L = TileLayout<N, O>;
-  static constexpr int KN = (L::NODE_W + 31) / 32, KA = (L::ADJ_W + 31) / 32, KO = (L::OBS_W + 31) / 32;
-  uint32_t node[KN], adj[KA], obs[KO];
-  __device__ __forceinline__ void load(const TileLuts& luts, int lane) {
-#pragma unroll
-    for (int k = 0; k < KN; ++k) node[k] = (lane + 32 * k < L::NODE_W) ? __ldg(luts.node + lane + 32 * k) : 0u;
-#pragma unroll
-    for (int k = 0; k < KA; ++k) adj[k] = (lane + 32 * k < L::ADJ_W) ? __ldg(luts.adj + lane + 32 * k) : 0u;
-#pragma unroll
-    for (int k = 0; k < KO; ++k) obs[k] = (lane + 32 * k < L::OBS_W) ? __ldg(luts.obs + lane + 32 * k) : 0u;
-  }
-};
-
-// Phase: emission.  out[(env0 + el) * W + w] = T[el][s1(w)] - T[el][s2(w)]; a warp emits TILE_EPW envs
-// that sit at compile-time offsets from each other (immediate offsets for loads and stores).
-template <int TW, int WORDS, int K>
-__device__ __forceinline__ void tile_gather_sub(float* __restrict__ out, const uint32_t (&lut)[K],
-                                                const float* __restrict__ T, int env0, int nenv, int lane, int warp) {
-  const int el0 = warp * TILE_EPW;
-  if (el0 >= nenv) return;
-  float* o = out + (size_t)(env0 + el0) * WORDS + lane;
-  const float* t = T + el0 * TW;
-  const int ne = min(TILE_EPW, nenv - el0);
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    if (lane + 32 * k < WORDS) {
-      const int s1 = (int)(lut[k] & 0xffffu), s2 = (int)(lut[k] >> 16);
-      if (ne == TILE_EPW) {
-        float v[TILE_EPW];
-#pragma unroll
-        for (int e = 0; e < TILE_EPW; ++e) v[e] = t[e * TW + s1] - t[e * TW + s2];
-#pragma unroll
-        for (int e = 0; e < TILE_EPW; ++e) __stcs(o + e * WORDS + 32 * k, v[e]);
-      } else {
-        for (int e = 0; e < ne; ++e) __stcs(o + e * WORDS + 32 * k, t[e * TW + s1] - t[e * TW + s2]);
-      }
-    }
   }
 }
 
-template <int DW, int WORDS, int K>
-__device__ __forceinline__ void tile_gather_adj(float* __restrict__ out, const uint32_t (&lut)[K],
-                                                const float* __restrict__ D, int env0, int nenv, int lane, int warp) {
+// Phase: emission.  out[(env0 + el) * WORDS + w] = T[el][s1(w)] - T[el][s2(w)] (SUB) or D[el][s(w)]; a warp
+// emits TILE_EPW envs that sit at compile-time offsets from each other (immediate offsets for loads and
+// stores); lane = output word, so every store instruction writes 128 contiguous bytes.
+template <int STRIDE, int WORDS, bool SUB>
+__device__ __forceinline__ void tile_gather(float* __restrict__ out, const uint32_t* __restrict__ lut,
+                                            const float* __restrict__ tab, int env0, int nenv, int lane, int warp) {
   const int el0 = warp * TILE_EPW;
   if (el0 >= nenv) return;
   float* o = out + (size_t)(env0 + el0) * WORDS + lane;
-  const float* d = D + el0 * DW;
+  const float* t = tab + el0 * STRIDE;
   const int ne = min(TILE_EPW, nenv - el0);
+  uint32_t u = lut[lane < WORDS ? lane : 0];
+#pragma unroll 1
+  for (int w = lane; w < WORDS; w += 32) {
+    const int s1 = (int)(u & 0xffffu), s2 = (int)(u >> 16);
+    u = lut[w + 32 < WORDS ? w + 32 : 0];          // descriptor of the next iteration
+    if (ne == TILE_EPW) {
+      float v[TILE_EPW];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    if (lane + 32 * k < WORDS) {
-      const int s = (int)lut[k];
-      if (ne == TILE_EPW) {
-        float v[TILE_EPW];
+      for (int e = 0; e < TILE_EPW; ++e) v[e] = SUB ? t[e * STRIDE + s1] - t[e * STRIDE + s2] : t[e * STRIDE + s1];
 #pragma unroll
-        for (int e = 0; e < TILE_EPW; ++e) v[e] = d[e * DW + s];
-#pragma unroll
-        for (int e = 0; e < TILE_EPW; ++e) __stcs(o + e * WORDS + 32 * k, v[e]);
-      } else {
-        for (int e = 0; e < ne; ++e) __stcs(o + e * WORDS + 32 * k, d[e * DW + s]);
-      }
+      for (int e = 0; e < TILE_EPW; ++e) __stcs(o + e * WORDS, v[e]);
+    } else {
+      for (int e = 0; e < ne; ++e) __stcs(o + e * WORDS, SUB ? t[e * STRIDE + s1] - t[e * STRIDE + s2] : t[e * STRIDE + s1]);
     }
+    o += 32;
   }
 }
 
 template <int N, int O>
-__device__ __forceinline__ void tile_emit(const DevParams& p, const LaneLuts<N, O>& ll, const float* __restrict__ T,
+__device__ __forceinline__ void tile_emit(const DevParams& p, const uint32_t* __restrict__ LUT, const float* __restrict__ T,
                                           const float* __restrict__ D, int env0, int nenv, int lane, int warp) {
   using L = TileLayout<N, O>;
-  if (p.o_node) tile_gather_sub<L::TW, L::NODE_W>(p.o_node, ll.node, T, env0, nenv, lane, warp);
-  if (p.o_adj) tile_gather_adj<L::DW, L::ADJ_W>(p.o_adj, ll.adj, D, env0, nenv, lane, warp);
-  if (p.o_obs) tile_gather_sub<L::TW, L::OBS_W>(p.o_obs, ll.obs, T, env0, nenv, lane, warp);
+  if (p.o_node) tile_gather<L::TW, L::NODE_W, true>(p.o_node, LUT + L::OBS_W, T, env0, nenv, lane, warp);
+  if (p.o_adj) tile_gather<L::DW, L::ADJ_W, false>(p.o_adj, LUT + L::OBS_W + L::NODE_W, D, env0, nenv, lane, warp);
+  if (p.o_obs) tile_gather<L::TW, L::OBS_W, true>(p.o_obs, LUT, T, env0, nenv, lane, warp);
 }
 
 // Randomised reset of env `lane` (navigation_graph.py:212-262, :264-570) + lexifair (:555-561), by
@@ -293,21 +258,24 @@ __device__ __forceinline__ void tile_reset_env(const DevParams& p, long long gen
 }
 
 // =============================================================================================
-// Body of the kernels for warp role W (the warp's index in the CTA): every phase handles the items
-// W, W + 4, W + 8, ... of that phase with compile-time indices.  All warps execute the same sequence
-// of barriers.
+// One code path for all warps (the binary stays ~4 k instructions: a role-specialised variant with
+// compile-time items per warp executed 40 % fewer instructions but was instruction-fetch bound).
 //   MODE 0: fused env step (MultiAgentGraphEnv.step, environment.py:816-877, + graphworker auto-reset,
 //           env_wrappers.py:859-865).   MODE 1: masked reset + observe (environment.py:882-898).
-template <int N, int O, int MODE, int W>
-__device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& luts, float* __restrict__ smem) {
+template <int N, int O, int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const __grid_constant__ DevParams p, const TileLuts luts,
+                                                            const __grid_constant__ TileTables<N, O> tb) {
   using L = TileLayout<N, O>;
   constexpr int E = L::E;
+  extern __shared__ __align__(16) float smem[];
   float* S = smem + L::OFF_S;
   double* SD = reinterpret_cast<double*>(smem + L::OFF_SD);
   float* T = smem + L::OFF_T;
   float* D = smem + L::OFF_D;
   uint8_t* FL = reinterpret_cast<uint8_t*>(smem + L::OFF_FL);
+  uint32_t* LUT = reinterpret_cast<uint32_t*>(smem + L::OFF_LUT);
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int env0 = blockIdx.x * 32;
   const int nenv = min(32, p.B - env0);
   const int env = env0 + lane;                   // < Bp: the state block is padded to a multiple of 32 envs
@@ -315,17 +283,20 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
   const size_t Bp = (size_t)p.Bp;
   float* gstate = p.px + env;                    // [NROWS][Bp], rows in TileLayout order
   const long long genv = p.env_offset + env;
+  float* Sl = S + lane;
 
   // ---- A: state block -> S (one coalesced line per row; all loads in flight before the first store),
-  // gather descriptors -> registers, action decode ------------------------------------------------
+  // gather descriptors -> smem, action decode -----------------------------------------------------
   {
-    constexpr int NR = (L::NROWS - W + TILE_WARPS - 1) / TILE_WARPS;
-    float tmp[NR];
+    constexpr int NRK = (L::NROWS + TILE_WARPS - 1) / TILE_WARPS;
+    float tmp[NRK];
+    const float* gw = gstate + (size_t)warp * Bp;
 #pragma unroll
-    for (int k = 0; k < NR; ++k) tmp[k] = __ldcg(gstate + (size_t)(W + TILE_WARPS * k) * Bp);
+    for (int k = 0; k < NRK; ++k)
+      if (TILE_WARPS * k + TILE_WARPS <= L::NROWS || warp + TILE_WARPS * k < L::NROWS) tmp[k] = __ldcg(gw + (size_t)(TILE_WARPS * k) * Bp);
+    for (int w = threadIdx.x; w < L::LUT_W; w += TILE_THREADS) LUT[w] = __ldg(luts.all + w);
     if (MODE == 0) {
-      static_for<W, N, TILE_WARPS>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
+      for (int i = warp; i < N; i += TILE_WARPS) {
         float ux = 0.f, uy = 0.f;
         if (venv) {                              // environment.py:301-311: u = [a1 - a2, a3 - a4] * sensitivity (5.0)
           if (p.act_idx) {
@@ -339,121 +310,115 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
           }
           ux *= 5.0f; uy *= 5.0f;
         }
-        S[(L::UX + i) * 32 + lane] = ux; S[(L::UY + i) * 32 + lane] = uy;
-      });
+        Sl[(L::UX + i) * 32] = ux; Sl[(L::UY + i) * 32] = uy;
+      }
     }
+    float* Sw = Sl + warp * 32;
 #pragma unroll
-    for (int k = 0; k < NR; ++k) S[(W + TILE_WARPS * k) * 32 + lane] = tmp[k];
+    for (int k = 0; k < NRK; ++k)
+      if (TILE_WARPS * k + TILE_WARPS <= L::NROWS || warp + TILE_WARPS * k < L::NROWS) Sw[TILE_WARPS * k * 32] = tmp[k];
   }
-  LaneLuts<N, O> ll;
-  ll.load(luts, lane);
   __syncthreads();
 
   if (MODE == 1) {
     // ---- reset() / observe --------------------------------------------------------------------
     const bool do_reset = venv && (p.reset_mask ? (p.reset_mask[env] != 0) : true);
     const bool any_reset = __syncthreads_or(do_reset) != 0;
-    if (W == 0) {
-      S[L::RFLAG * 32 + lane] = __int_as_float(do_reset ? 1 : 0);
+    if (warp == 0) {
+      Sl[L::RFLAG * 32] = __int_as_float(do_reset ? 1 : 0);
       if (do_reset) {
-        tile_reset_env<N, O>(p, genv, (uint32_t)__float_as_int(S[L::EPIS * 32 + lane]), S, lane);
+        tile_reset_env<N, O>(p, genv, (uint32_t)__float_as_int(Sl[L::EPIS * 32]), S, lane);
       } else {
         // observation() on the current state (navigation_graph.py:826-857, :849-853)
         double sum_p = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j) sum_p += (double)S[(L::PD + j) * 32 + lane];
+        for (int j = 0; j < N; ++j) sum_p += (double)Sl[(L::PD + j) * 32];
         const double mean_p = sum_p / N;
         double q_p = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j) { const double dd = (double)S[(L::PD + j) * 32 + lane] - mean_p; q_p += dd * dd; }
+        for (int j = 0; j < N; ++j) { const double dd = (double)Sl[(L::PD + j) * 32] - mean_p; q_p += dd * dd; }
         const double std_p = sqrt(q_p / N);
-        const double dm = (double)S[L::DMEAN * 32 + lane], ds = (double)S[L::DSTD * 32 + lane];
+        const double dm = (double)Sl[L::DMEAN * 32], ds = (double)Sl[L::DSTD * 32];
 #pragma unroll
         for (int i = 0; i < N; ++i)
-          S[(L::FOBS + i) * 32 + lane] =
-              (float)((S[(L::DTG + i) * 32 + lane] == -1.0f) ? mean_p / (std_p + 0.0001) : dm / (ds + 0.0001));
+          Sl[(L::FOBS + i) * 32] = (float)((Sl[(L::DTG + i) * 32] == -1.0f) ? mean_p / (std_p + 0.0001) : dm / (ds + 0.0001));
       }
     }
     __syncthreads();
-    tile_distances<N, O, W>(p, S, D, FL, lane);
-    tile_fill_table<N, O, W>(S, T, lane);
-    if (any_reset && venv && __float_as_int(S[L::RFLAG * 32 + lane])) {   // rows a reset changes -> state block
-      static_for<W, L::NROWS, TILE_WARPS>([&](auto rc) {
-        constexpr int r = decltype(rc)::value;
-        if constexpr (r != L::DMEAN && r != L::DSTD) gstate[(size_t)r * Bp] = S[r * 32 + lane];
-      });
+    tile_distances<N, O>(p, tb, S, D, FL, lane, warp);
+    tile_fill_table<N, O>(tb, S, T, lane, warp);
+    if (any_reset && venv && __float_as_int(Sl[L::RFLAG * 32])) {   // rows a reset changes -> state block
+      for (int r = warp; r < L::NROWS; r += TILE_WARPS)
+        if (r != L::DMEAN && r != L::DSTD) gstate[(size_t)r * Bp] = Sl[r * 32];
     }
     __syncthreads();
-    tile_emit<N, O>(p, ll, T, D, env0, nenv, lane, W);
+    tile_emit<N, O>(p, LUT, T, D, env0, nenv, lane, warp);
     return;
   }
 
   // ---- B: force terms (core.py:277-316, :370-404) from the positions at step entry -------------
   // item f < NAA: agent pair (i, j), i < j;  item NAA + i * O + k: agent i vs obstacle k.  fp32 terms as
   // contact_force() (fm_device.cuh); the ordered fp64 accumulation happens in C.
-  static_for<W, L::NF, TILE_WARPS>([&](auto fc) {
-    constexpr int f = decltype(fc)::value;
-    constexpr bool aa = f < L::NAA;
-    constexpr int i = aa ? pair_a(f, N) : (f - L::NAA) / (O > 0 ? O : 1);
-    constexpr int rbx = aa ? L::PX + pair_b(aa ? f : 0, N) : L::OX + (f - L::NAA) - i * O;
-    constexpr int rby = aa ? L::PY + pair_b(aa ? f : 0, N) : L::OY + (f - L::NAA) - i * O;
-    const float dx = S[(L::PX + i) * 32 + lane] - S[rbx * 32 + lane], dy = S[(L::PY + i) * 32 + lane] - S[rby * 32 + lane];
-    const float dist = sqrtf(dx * dx + dy * dy);
-    const float pen = softplusf(-(dist - p.dist_min) / p.contact_margin) * p.contact_margin;
-    S[(L::FT + 2 * f) * 32 + lane] = p.contact_force * dx / dist * pen;
-    S[(L::FT + 2 * f + 1) * 32 + lane] = p.contact_force * dy / dist * pen;
-  });
+#pragma unroll 3
+  for (int k = 0; k < (L::NF + TILE_WARPS - 1) / TILE_WARPS; ++k) {
+    const int f = warp + TILE_WARPS * k;
+    if (f < L::NF) {
+      const uint2 o = *reinterpret_cast<const uint2*>(tb.force[f]);
+      const float dx = Sl[o.x & 0xffffu] - Sl[o.y & 0xffffu], dy = Sl[o.x >> 16] - Sl[o.y >> 16];
+      const float dist = sqrtf(dx * dx + dy * dy);
+      const float pen = softplusf(-(dist - p.dist_min) / p.contact_margin) * p.contact_margin;
+      Sl[(L::FT + 2 * f) * 32] = p.contact_force * dx / dist * pen;
+      Sl[(L::FT + 2 * f + 1) * 32] = p.contact_force * dy / dist * pen;
+    }
+  }
   __syncthreads();
 
   // ---- C: ordered force sum + integrate_state (core.py:338-356), float64; state rounded to fp32 ---
-  static_for<W, N, TILE_WARPS>([&](auto ic) {
-    constexpr int i = decltype(ic)::value;
-    double Fx = (double)S[(L::UX + i) * 32 + lane], Fy = (double)S[(L::UY + i) * 32 + lane];   // mass(1.0) * u + noise(0.0)
-    static_for<0, N>([&](auto jc) {              // partners in ascending entity index (core.py:311-316)
-      constexpr int j = decltype(jc)::value;
-      if constexpr (j != i) {
-        constexpr int f = tile_pair_index(j < i ? j : i, j < i ? i : j, N);
-        float tx = S[(L::FT + 2 * f) * 32 + lane], ty = S[(L::FT + 2 * f + 1) * 32 + lane];
+  for (int i = warp; i < N; i += TILE_WARPS) {
+    float* Si = Sl + i * 32;
+    double Fx = (double)Si[L::UX * 32], Fy = (double)Si[L::UY * 32];   // mass(1.0) * u + noise(0.0)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {                // partners in ascending entity index (core.py:311-316)
+      if (j != i) {
+        const int f = j < i ? tile_pair_index(j, i, N) : tile_pair_index(i, j, N);
+        float tx = Sl[(L::FT + 2 * f) * 32], ty = Sl[(L::FT + 2 * f + 1) * 32];
         if (j < i) { tx = -tx; ty = -ty; }       // agent i is the `b` of pair (j, i): -force
         Fx = (double)tx + Fx; Fy = (double)ty + Fy;
       }
-    });
-#pragma unroll
-    for (int k = 0; k < O; ++k) {
-      Fx = (double)S[(L::FT + 2 * (L::NAA + i * O + k)) * 32 + lane] + Fx;
-      Fy = (double)S[(L::FT + 2 * (L::NAA + i * O + k) + 1) * 32 + lane] + Fy;
     }
-    double v64x = (double)S[(L::VX + i) * 32 + lane] * p.damping_keep + Fx * p.dt;
-    double v64y = (double)S[(L::VY + i) * 32 + lane] * p.damping_keep + Fy * p.dt;
+    const float* Fo = Sl + (L::FT + 2 * (L::NAA + i * O)) * 32;
+#pragma unroll
+    for (int k = 0; k < O; ++k) { Fx = (double)Fo[2 * k * 32] + Fx; Fy = (double)Fo[(2 * k + 1) * 32] + Fy; }
+    double v64x = (double)Si[L::VX * 32] * p.damping_keep + Fx * p.dt;
+    double v64y = (double)Si[L::VY * 32] * p.damping_keep + Fy * p.dt;
     if (p.has_max_speed) {
       const double speed = sqrt(v64x * v64x + v64y * v64y);
       if (speed > p.max_speed) { v64x = v64x / speed * p.max_speed; v64y = v64y / speed * p.max_speed; }
     }
     const double sx = v64x * p.dt, sy = v64y * p.dt;
-    const double pd64 = (double)S[(L::PD + i) * 32 + lane] + sqrt(sx * sx + sy * sy);
+    const double pd64 = (double)Si[L::PD * 32] + sqrt(sx * sx + sy * sy);
     SD[(L::PD64 + i) * 32 + lane] = pd64;
-    S[(L::PX + i) * 32 + lane] = (float)((double)S[(L::PX + i) * 32 + lane] + sx);
-    S[(L::PY + i) * 32 + lane] = (float)((double)S[(L::PY + i) * 32 + lane] + sy);
-    S[(L::VX + i) * 32 + lane] = (float)v64x; S[(L::VY + i) * 32 + lane] = (float)v64y;
-    S[(L::PD + i) * 32 + lane] = (float)pd64;
-  });
+    Si[L::PX * 32] = (float)((double)Si[L::PX * 32] + sx);
+    Si[L::PY * 32] = (float)((double)Si[L::PY * 32] + sy);
+    Si[L::VX * 32] = (float)v64x; Si[L::VY * 32] = (float)v64y;
+    Si[L::PD * 32] = (float)pd64;
+  }
   __syncthreads();
 
   // ---- D: calculate_distances (core.py:204-228) at the new positions --------------------------
-  tile_distances<N, O, W>(p, S, D, FL, lane);
+  tile_distances<N, O>(p, tb, S, D, FL, lane, warp);
 
   // ---- E: statistic sets.  k = 0: mean / std of the new travelled distances; k = 1..N: mean / std of
   // world.dists_to_goal as left by agent k-1's info_callback, i.e. over [new_0..new_{k-1}, prev_k..]
   // (navigation_graph.py:587-598, :617-618).  Independent of D, so no barrier in between.
-  static_for<W, N + 1, TILE_WARPS>([&](auto kc) {
-    constexpr int k = decltype(kc)::value;
+  for (int k = warp; k <= N; k += TILE_WARPS) {
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const double pj = SD[(L::PD64 + j) * 32 + lane];
-      if (k == 0) v[j] = pj;
-      else if (j < k) v[j] = (S[(L::TREQ + j) * 32 + lane] != -1.0f) ? (double)S[(L::DTG + j) * 32 + lane] : pj;
-      else v[j] = (double)S[(L::DTG + j) * 32 + lane];
+      const double dj = (double)Sl[(L::DTG + j) * 32];
+      const bool latched = Sl[(L::TREQ + j) * 32] != -1.0f;
+      v[j] = (k == 0) ? pj : ((j < k && !latched) ? pj : dj);
     }
     double s = 0.0;
 #pragma unroll
@@ -464,38 +429,38 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
     for (int j = 0; j < N; ++j) { const double dd = v[j] - m; q += dd * dd; }
     SD[(L::VM + k) * 32 + lane] = m;
     SD[(L::VS + k) * 32 + lane] = sqrt(q / N);
-  });
+  }
   __syncthreads();
 
   // ---- F: per-agent observation scalar, reward, latches (environment.py:832-864) ----------------
-  const int nstep = __float_as_int(S[L::STEP * 32 + lane]) + 1;      // environment.py:819, :823
+  const int nstep = __float_as_int(Sl[L::STEP * 32]) + 1;            // environment.py:819, :823
   const bool done = nstep >= p.episode_length;   // environment.py:237-247 (agent.status is never set)
   const bool do_reset = venv && done && (p.auto_reset != 0);
   const bool want_info = venv && (p.o_info != nullptr || p.stats != nullptr) && (done || p.info_every_step);
   double* stats_row = p.stats ? p.stats + (size_t)blockIdx.x * (15 * N + 2) : nullptr;
-  static_for<W, N, TILE_WARPS>([&](auto ic) {
-    constexpr int i = decltype(ic)::value;
-    const float dtg = S[(L::DTG + i) * 32 + lane], treq = S[(L::TREQ + i) * 32 + lane];
-    const int gmi = __float_as_int(S[(L::GM + i) * 32 + lane]);
-    const int qg = tile_pair_index(i, N, E) + gmi;                   // pair (i, N + gm)
+  for (int i = warp; i < N; i += TILE_WARPS) {
+    float* Si = Sl + i * 32;
+    const float dtg = Si[L::DTG * 32], treq = Si[L::TREQ * 32];
+    const int gmi = __float_as_int(Si[L::GM * 32]);
+    const int qi = tile_pair_index(i, i + 1, E);                     // first pair of row i: (i, i + 1)
+    const int qg = qi + (N - i - 1) + gmi;                           // pair (i, N + gm)
     const float dgoal_f = D[lane * L::DW + qg];                      // (float)dgoal
     const bool reached = (FL[qg * 32 + lane] & 2) != 0;              // dgoal < min_dist_thresh (float64 compare)
     int ncoll = 0;
-    static_for<0, N>([&](auto jc) {
-      constexpr int j = decltype(jc)::value;
-      if constexpr (j != i) ncoll += FL[tile_pair_index(j < i ? j : i, j < i ? i : j, E) * 32 + lane] & 1;
-    });
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j != i) ncoll += FL[(j < i ? tile_pair_index(j, i, E) : tile_pair_index(i, j, E)) * 32 + lane] & 1;
     bool ocoll = false;
 #pragma unroll
-    for (int k = 0; k < O; ++k) ocoll = ocoll || ((FL[tile_pair_index(i, 2 * N + k, E) * 32 + lane] & 1) != 0);
+    for (int k = 0; k < O; ++k) ocoll = ocoll || ((FL[(qi + (2 * N - i - 1) + k) * 32 + lane] & 1) != 0);
     const bool latched = treq != -1.0f;
     const double pd64 = SD[(L::PD64 + i) * 32 + lane];
     const double dtg_new = latched ? (double)dtg : pd64;
     const double treq_new = (!latched && reached) ? (double)nstep * p.dt : (double)treq;   // :588
-    const float dleft_new = latched ? S[(L::DLEFT + i) * 32 + lane] : dgoal_f;
+    const float dleft_new = latched ? Si[L::DLEFT * 32] : dgoal_f;
     double fparam;                               // navigation_graph.py:764-769 / :849-853
     if (dtg == -1.0f) fparam = SD[(L::VM + 0) * 32 + lane] / (SD[(L::VS + 0) * 32 + lane] + 0.0001);
-    else if (i == 0) fparam = (double)S[L::DMEAN * 32 + lane] / ((double)S[L::DSTD * 32 + lane] + 0.0001);
+    else if (i == 0) fparam = (double)Sl[L::DMEAN * 32] / ((double)Sl[L::DSTD * 32] + 0.0001);
     else fparam = SD[(L::VM + i) * 32 + lane] / (SD[(L::VS + i) * 32 + lane] + 0.0001);
     float rw = reached ? p.goal_rew : -dgoal_f;  // navigation_graph.py:760-824
     rw -= p.coll_rew * (float)ncoll;
@@ -506,31 +471,30 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
       rw += fair;
     }
     rw = fminf(fmaxf(rw, p.clip_lo), p.clip_hi);
-    const int nac = __float_as_int(S[(L::NAC + i) * 32 + lane]) + ncoll;          // :604-613
-    const int noc = __float_as_int(S[(L::NOC + i) * 32 + lane]) + (ocoll ? 1 : 0); // :602-603
-    S[(L::OWN + i) * 32 + lane] = rw;
-    S[(L::FOBS + i) * 32 + lane] = (float)fparam;
-    S[(L::DTG + i) * 32 + lane] = (float)dtg_new;
-    S[(L::NTREQ + i) * 32 + lane] = (float)treq_new;   // TREQ keeps the old value for the info pass (G)
-    S[(L::DLEFT + i) * 32 + lane] = dleft_new;
-    S[(L::NAC + i) * 32 + lane] = __int_as_float(nac);
-    S[(L::NOC + i) * 32 + lane] = __int_as_float(noc);
+    const int nac = __float_as_int(Si[L::NAC * 32]) + ncoll;          // :604-613
+    const int noc = __float_as_int(Si[L::NOC * 32]) + (ocoll ? 1 : 0); // :602-603
+    Si[L::OWN * 32] = rw;
+    Si[L::FOBS * 32] = (float)fparam;
+    Si[L::DTG * 32] = (float)dtg_new;
+    Si[L::NTREQ * 32] = (float)treq_new;         // TREQ keeps the old value for the info pass (G)
+    Si[L::DLEFT * 32] = dleft_new;
+    Si[L::NAC * 32] = __int_as_float(nac);
+    Si[L::NOC * 32] = __int_as_float(noc);
     if (i == N - 1) {                            // world.dist_traveled_mean / stddev after the last info_callback
-      S[L::NDMEAN * 32 + lane] = (float)SD[(L::VM + N) * 32 + lane];
-      S[L::NDSTD * 32 + lane] = (float)SD[(L::VS + N) * 32 + lane];
+      Sl[L::NDMEAN * 32] = (float)SD[(L::VM + N) * 32 + lane];
+      Sl[L::NDSTD * 32] = (float)SD[(L::VS + N) * 32 + lane];
     }
     if (venv && p.o_done) p.o_done[(size_t)env * N + i] = done ? 1 : 0;
-  });
+  }
   __syncthreads();
 
   // ---- G: collaborative sum, reward output, episode statistics, info rows -----------------------
-  static_for<W, N, TILE_WARPS>([&](auto ic) {
-    constexpr int i = decltype(ic)::value;
-    float rew = S[(L::OWN + i) * 32 + lane];
+  for (int i = warp; i < N; i += TILE_WARPS) {
+    float rew = Sl[(L::OWN + i) * 32];
     if (p.collaborative) {                       // environment.py:866-870
       float tot = 0.f;
 #pragma unroll
-      for (int j = 0; j < N; ++j) tot += S[(L::OWN + j) * 32 + lane];
+      for (int j = 0; j < N; ++j) tot += Sl[(L::OWN + j) * 32];
       rew = tot;
     }
     if (venv && p.o_rew) p.o_rew[(size_t)env * N + i] = rew;
@@ -540,14 +504,13 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
       if (lane == 0) stats_row[i] += v;
     }
-  });
-  if (stats_row && W == TILE_WARPS - 1) {
+  }
+  if (stats_row && warp == TILE_WARPS - 1) {
     const unsigned termb = __ballot_sync(FULL, venv && done);
     if (lane == 0) { stats_row[15 * N] += (double)__popc(termb); stats_row[15 * N + 1] += (double)nenv; }
   }
   if (__syncthreads_or(want_info)) {
-    static_for<W, N, TILE_WARPS>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
+    for (int i = warp; i < N; i += TILE_WARPS) {
       // world-level time statistics right after agent i's own info_callback: new values of agents
       // j <= i, previous values of j > i (navigation_graph.py:620-621)
       double tacc = 0.0;                         // entity.state.time += dt per step (core.py:355)
@@ -555,8 +518,8 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
       double tv[N];                              // times_required as float64: a latch of THIS step is nstep * dt unrounded
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        const float told = S[(L::TREQ + j) * 32 + lane];
-        const bool fresh = j <= i && told == -1.0f && S[(L::NTREQ + j) * 32 + lane] != -1.0f;
+        const float told = Sl[(L::TREQ + j) * 32];
+        const bool fresh = j <= i && told == -1.0f && Sl[(L::NTREQ + j) * 32] != -1.0f;
         tv[j] = fresh ? (double)nstep * p.dt : (double)told;
       }
       double st = 0.0;
@@ -568,12 +531,13 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
       for (int j = 0; j < N; ++j) { const double dd = tv[j] - mt; qt += dd * dd; }
       const double stv = sqrt(qt / N);
       const double md = SD[(L::VM + i + 1) * 32 + lane], sdv = SD[(L::VS + i + 1) * 32 + lane];
+      const float* Si = Sl + i * 32;
       float info[INFO_F];
-      info[0] = S[(L::OWN + i) * 32 + lane]; info[1] = S[(L::DLEFT + i) * 32 + lane]; info[2] = S[(L::NTREQ + i) * 32 + lane];
-      info[3] = (float)__float_as_int(S[(L::NAC + i) * 32 + lane]); info[4] = (float)__float_as_int(S[(L::NOC + i) * 32 + lane]);
+      info[0] = Si[L::OWN * 32]; info[1] = Si[L::DLEFT * 32]; info[2] = Si[L::NTREQ * 32];
+      info[3] = (float)__float_as_int(Si[L::NAC * 32]); info[4] = (float)__float_as_int(Si[L::NOC * 32]);
       info[5] = (float)md; info[6] = (float)sdv; info[7] = (float)(md / (sdv + 0.0001));
-      info[8] = S[(L::DTG + i) * 32 + lane]; info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv;
-      info[12] = (float)(mt / (stv + 0.0001)); info[13] = S[(L::MINT + i) * 32 + lane];
+      info[8] = Si[L::DTG * 32]; info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv;
+      info[12] = (float)(mt / (stv + 0.0001)); info[13] = Si[L::MINT * 32];
       if (want_info && p.o_info) {
         float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
 #pragma unroll
@@ -588,47 +552,39 @@ __device__ __forceinline__ void tile_role(const DevParams& p, const TileLuts& lu
           if (lane == 0) stats_row[N + i * INFO_F + k] += v;
         }
       }
-    });
+    }
   }
 
   // ---- auto-reset (env_wrappers.py:859-865): obs / node_obs / adj come from the new episode, reward /
   // done / info stay terminal --------------------------------------------------------------------
   const bool any_reset = __syncthreads_or(do_reset) != 0;
-  if (W == 0) {
-    S[L::RFLAG * 32 + lane] = __int_as_float(do_reset ? 1 : 0);
-    if (!do_reset) S[L::STEP * 32 + lane] = __int_as_float(nstep);
+  if (warp == 0) {
+    Sl[L::RFLAG * 32] = __int_as_float(do_reset ? 1 : 0);
+    if (!do_reset) Sl[L::STEP * 32] = __int_as_float(nstep);
 #pragma unroll
-    for (int i = 0; i < N; ++i) S[(L::TREQ + i) * 32 + lane] = S[(L::NTREQ + i) * 32 + lane];
-    S[L::DMEAN * 32 + lane] = S[L::NDMEAN * 32 + lane];
-    S[L::DSTD * 32 + lane] = S[L::NDSTD * 32 + lane];
-    if (do_reset) tile_reset_env<N, O>(p, genv, (uint32_t)__float_as_int(S[L::EPIS * 32 + lane]), S, lane);
+    for (int i = 0; i < N; ++i) Sl[(L::TREQ + i) * 32] = Sl[(L::NTREQ + i) * 32];
+    Sl[L::DMEAN * 32] = Sl[L::NDMEAN * 32];
+    Sl[L::DSTD * 32] = Sl[L::NDSTD * 32];
+    if (do_reset) tile_reset_env<N, O>(p, genv, (uint32_t)__float_as_int(Sl[L::EPIS * 32]), S, lane);
   }
   __syncthreads();
-  if (any_reset) tile_distances<N, O, W>(p, S, D, FL, lane);
-  tile_fill_table<N, O, W>(S, T, lane);
+  if (any_reset) tile_distances<N, O>(p, tb, S, D, FL, lane, warp);
+  tile_fill_table<N, O>(tb, S, T, lane, warp);
   // ---- I: state block write-back (rows that change every step; the rest only for envs that reset) ----
   if (venv) {
-    const bool was_reset = any_reset && __float_as_int(S[L::RFLAG * 32 + lane]);
-    static_for<W, L::NROWS, TILE_WARPS>([&](auto rc) {
-      constexpr int r = decltype(rc)::value;
-      constexpr bool every_step = r < L::MINT || (r >= L::NAC && r < L::LX) || r == L::DMEAN || r == L::DSTD || r == L::STEP;
-      if (every_step || was_reset) gstate[(size_t)r * Bp] = S[r * 32 + lane];
-    });
+    const bool was_reset = any_reset && __float_as_int(Sl[L::RFLAG * 32]);
+    constexpr int NRK = (L::NROWS + TILE_WARPS - 1) / TILE_WARPS;
+    float* gw = gstate + (size_t)warp * Bp;
+    const float* Sw = Sl + warp * 32;
+#pragma unroll
+    for (int k = 0; k < NRK; ++k) {
+      const int r = warp + TILE_WARPS * k;
+      if ((TILE_WARPS * k + TILE_WARPS <= L::NROWS || r < L::NROWS) && (tb.every_step[r] || was_reset))
+        gw[(size_t)(TILE_WARPS * k) * Bp] = Sw[TILE_WARPS * k * 32];
+    }
   }
   __syncthreads();
-  tile_emit<N, O>(p, ll, T, D, env0, nenv, lane, W);
-}
-
-template <int N, int O, int MODE>
-__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const __grid_constant__ DevParams p, const TileLuts luts) {
-  extern __shared__ __align__(16) float smem[];
-  static_assert(TILE_WARPS == 4, "role dispatch below is written for 4 warps");
-  switch (threadIdx.x >> 5) {                    // warp role: compile-time item indices per role
-    case 0: tile_role<N, O, MODE, 0>(p, luts, smem); break;
-    case 1: tile_role<N, O, MODE, 1>(p, luts, smem); break;
-    case 2: tile_role<N, O, MODE, 2>(p, luts, smem); break;
-    default: tile_role<N, O, MODE, 3>(p, luts, smem); break;
-  }
+  tile_emit<N, O>(p, LUT, T, D, env0, nenv, lane, warp);
 }
 
 // =============================================================================================
@@ -665,12 +621,38 @@ static void tile_build_luts_no(std::vector<uint32_t>& obs, std::vector<uint32_t>
 }
 
 template <int N, int O>
+static TileTables<N, O> tile_make_tables() {
+  using L = TileLayout<N, O>;
+  constexpr int E = L::E;
+  TileTables<N, O> tb{};
+  auto rx = [](int e) { return e < N ? L::PX + e : (e < 2 * N ? L::LX + (e - N) : L::OX + (e - 2 * N)); };
+  auto ry = [](int e) { return e < N ? L::PY + e : (e < 2 * N ? L::LY + (e - N) : L::OY + (e - 2 * N)); };
+  for (int q = 0; q < L::PAIRS; ++q) {
+    const int a = pair_a(q, E), b = pair_b(q, E);
+    tb.pair[q][0] = (uint16_t)(rx(a) * 32); tb.pair[q][1] = (uint16_t)(ry(a) * 32);
+    tb.pair[q][2] = (uint16_t)(rx(b) * 32); tb.pair[q][3] = (uint16_t)(ry(b) * 32);
+  }
+  for (int f = 0; f < L::NF; ++f) {
+    int i, partner;
+    if (f < L::NAA) { i = pair_a(f, N); partner = pair_b(f, N); }
+    else { i = (f - L::NAA) / (O > 0 ? O : 1); partner = 2 * N + (f - L::NAA) - i * O; }
+    tb.force[f][0] = (uint16_t)(rx(i) * 32); tb.force[f][1] = (uint16_t)(ry(i) * 32);
+    tb.force[f][2] = (uint16_t)(rx(partner) * 32); tb.force[f][3] = (uint16_t)(ry(partner) * 32);
+  }
+  for (int e = 0; e < E; ++e) { tb.ent[e][0] = (uint16_t)(rx(e) * 32); tb.ent[e][1] = (uint16_t)(ry(e) * 32); }
+  for (int r = 0; r < L::NROWS; ++r)
+    tb.every_step[r] = (r < L::MINT || (r >= L::NAC && r < L::LX) || r == L::DMEAN || r == L::DSTD || r == L::STEP) ? 1 : 0;
+  return tb;
+}
+
+template <int N, int O>
 static cudaError_t tile_launch_no(const DevParams& p, const TileLuts& luts, cudaStream_t st, bool is_reset) {
   using L = TileLayout<N, O>;
+  static const TileTables<N, O> tb = tile_make_tables<N, O>();
   const int blocks = (p.B + 31) / 32;
   const size_t smem = (size_t)L::WORDS * sizeof(float);
-  if (is_reset) tile_kernel<N, O, 1><<<blocks, TILE_THREADS, smem, st>>>(p, luts);
-  else tile_kernel<N, O, 0><<<blocks, TILE_THREADS, smem, st>>>(p, luts);
+  if (is_reset) tile_kernel<N, O, 1><<<blocks, TILE_THREADS, smem, st>>>(p, luts, tb);
+  else tile_kernel<N, O, 0><<<blocks, TILE_THREADS, smem, st>>>(p, luts, tb);
   return cudaGetLastError();
 }
 
@@ -709,7 +691,7 @@ void tile_build_luts(int N, int O, std::vector<uint32_t>& obs, std::vector<uint3
 }
 
 cudaError_t tile_launch(const DevParams& p, cudaStream_t st, bool is_reset) {
-  TileLuts luts{p.lut_obs, p.lut_node, p.lut_adj};
+  TileLuts luts{p.lut_obs};   // obs | node | adj are contiguous (fm_abi.cu)
 #define X(n, o) if (p.N == n && p.O == o) return tile_launch_no<n, o>(p, luts, st, is_reset);
   FM_TILE_CASES(X)
 #undef X
