@@ -68,6 +68,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_obstacles must be in 0..64 (got %d)", cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_create: episode_length must be >= 1");
   if (cfg->mapping < 0 || cfg->mapping > 3) return fail(FM_ERR_INVALID_ARG, "fm_create: mapping must be 0..3 (got %d)", cfg->mapping);
+  if (cfg->aw_halves < 0 || cfg->aw_halves > 2) return fail(FM_ERR_INVALID_ARG, "fm_create: aw_halves must be 0, 1 or 2 (got %d)", cfg->aw_halves);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -85,9 +86,10 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   DevParams& p = h->p;
   const int B = cfg->num_envs, N = cfg->num_agents, O = cfg->num_obstacles, E = 2 * N + O;
   p.B = B; p.N = N; p.O = O; p.E = E;
-  p.Bp = (B + 31) & ~31;
+  p.Bp = (B + 63) & ~63;
   const size_t Bp = (size_t)p.Bp;
-  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4);
+  const int SP = (N + O) * (N + O - 1) / 2;
+  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4 + SP);
   cudaError_t e = cudaMalloc(&h->state_block, words * 4);
   if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc(%zu B): %s", words * 4, cudaGetErrorString(e)); }
   cudaMemset(h->state_block, 0, words * 4);
@@ -99,6 +101,8 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.lx = take(Bp * N); p.ly = take(Bp * N);
   p.ox = take(Bp * O); p.oy = take(Bp * O);
   p.dmean = take(Bp); p.dstd = take(Bp); p.step = (int*)take(Bp); p.episode = (int*)take(Bp);
+  p.sdist = take(Bp * SP);
+  p.aw_halves = cfg->aw_halves == 2 ? 2 : 1;
 
   // config -> device constants.  Collision threshold exactly as the reference spells it:
   // 1.05*(size + size) (navigation_graph.py:655, :704); cached min_dist = size + size (core.py:215).
@@ -130,18 +134,18 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.seed_hi = (uint32_t)(cfg->seed >> 32);
   p.env_offset = cfg->env_offset;
 
-  // Kernel mapping (cfg->mapping: 0 auto = env-tile where compiled for (N, O), else group-per-env;
-  // 1 group-per-env; 2 thread-per-env; 3 env-tile).  All mappings produce identical results.
-  if (cfg->mapping == 2 && !fm::tpe_supported(N, O)) {
-    cudaFree(h->state_block); delete h;
-    return fail(FM_ERR_UNSUPPORTED, "fm_create: thread-per-env kernels are not compiled for N=%d O=%d", N, O);
-  }
-  if (cfg->mapping == 3 && !fm::tile_supported(N, O)) {
+  // Kernel mapping (cfg->mapping: 0 auto = agent-warp where compiled for (N, O), else group-per-env;
+  // 1 group-per-env; 2 env-tile; 3 agent-warp).  All mappings produce identical results.
+  if (cfg->mapping == 2 && !fm::tile_supported(N, O)) {
     cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: env-tile kernels are not compiled for N=%d O=%d", N, O);
   }
-  p.mapping = cfg->mapping == 1 ? 0 : (cfg->mapping == 2 ? 1 : ((cfg->mapping == 3 || fm::tile_supported(N, O)) ? 2 : 0));
-  if (p.mapping == 2) {
+  if (cfg->mapping == 3 && !fm::aw_supported(N, O)) {
+    cudaFree(h->state_block); delete h;
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: agent-warp kernels are not compiled for N=%d O=%d", N, O);
+  }
+  p.mapping = cfg->mapping == 1 ? 0 : (cfg->mapping == 2 ? 1 : ((cfg->mapping == 3 || fm::aw_supported(N, O)) ? 2 : 0));
+  if (p.mapping == 1) {
     std::vector<uint32_t> lo, ln, la;
     fm::tile_build_luts(N, O, lo, ln, la);
     const size_t nw = lo.size() + ln.size() + la.size();
@@ -166,7 +170,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     return fail(FM_ERR_UNSUPPORTED, "fm_create: N=%d O=%d needs %d B of shared memory per CTA", N, O, p.sm_per_warp * 16);
   }
   h->K = fm_stats_len(N);
-  h->stats_rows = p.mapping == 2 ? fm::tile_num_ctas(B) : (p.mapping == 1 ? fm::tpe_num_warps(B) : fm::num_warps(B, N));
+  h->stats_rows = p.mapping == 2 ? fm::aw_stats_rows(B, p.aw_halves) : (p.mapping == 1 ? fm::tile_num_ctas(B) : fm::num_warps(B, N));
   e = cudaMalloc(&h->stats, (size_t)h->stats_rows * h->K * sizeof(double));
   if (e != cudaSuccess) { cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc stats: %s", cudaGetErrorString(e)); }
   cudaMemset(h->stats, 0, (size_t)h->stats_rows * h->K * sizeof(double));
@@ -338,6 +342,10 @@ int fm_set_state(FmHandle* h, const FmState* st, void* stream) {
   if (rc) return rc;
   FM_CUDA(fm::launch_state_io(h->p, *st, 1, (cudaStream_t)stream));
   h->launches += 1;
+  if (h->p.mapping == 2 && (st->landmark_pos || st->obstacle_pos)) {      // cached static distances follow the positions
+    FM_CUDA(fm::launch_static_dists(h->p, (cudaStream_t)stream));
+    h->launches += 1;
+  }
   return FM_OK;
 }
 

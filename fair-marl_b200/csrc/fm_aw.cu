@@ -1,0 +1,716 @@
+// Agent-warp kernels: one CTA owns a tile of 32*H consecutive envs; lane <-> env, WARP <-> AGENT.
+// Thread (env, agent i) keeps agent i's whole state in registers from the first global load to the
+// write-back: forces on agent i, integration, agent i's row of the distance matrix, its observation
+// scalar, reward, goal latches and counters never touch shared memory.  One extra "env warp" per 32 envs
+// owns what belongs to the env rather than to an agent: static entity positions, the landmark/obstacle
+// block of the distance matrix, step / done / auto-reset (placement + lexifair), episode statistics.
+// Specialised at compile time on (N, O, H); N <= 4 (lexifair by enumeration, whole-tile output staging).
+//
+// Why this mapping (measured on B200, C2 = 65 536 envs x 3 agents, profiles/):
+//   * env-tile (fm_tile.cu) spreads fine-grained work items over the warps of a CTA through shared
+//     memory: 19.2 M warp instructions per step, 30 % of them in the gather-style output emission,
+//     issue slots 53 % busy, 38 us per step (49 % of the HBM roofline).
+//   * here the compute phases are register resident (no item descriptors, no smem round trips), the
+//     distances between static entities are computed once per episode and kept in the state block,
+//     and the outputs are written lane = env into a shared-memory image of the API layout (odd strides:
+//     conflict free), which the whole CTA then streams out with 16-byte st.global.cs -- the tile's
+//     slice of every output array is one contiguous range.
+//
+// Shared memory per CTA: a small table block (new positions / velocities / goals of the tile, the
+// per-agent values the sequential-agent statistics need) and ONE staging region that is used twice:
+// first for adj + obs + reward + done of all 32*H envs, then for node_obs, 32 envs at a time.
+//
+// Arithmetic is operation for operation that of step_kernel<G> / reset_kernel<G> (fm_kernels.cu);
+// tests/test_gpu_parity.py checks the mappings against each other bit for bit.
+#include <utility>
+
+#include "fm_device.cuh"
+#include "fm_launch.h"
+#include "fm_small.cuh"
+
+namespace fm {
+
+template <int N, int O, int H>
+struct AwLayout {
+  static constexpr int E = 2 * N + O, M = N + O, SP = M * (M - 1) / 2;
+  static constexpr int WPH = N + 1, WARPS = H * WPH, THREADS = 32 * WARPS, ENVS = 32 * H, RW = ENVS;
+  // ---- global state rows ([row][Bp], fm_abi.cu fm_create order)
+  static constexpr int PX = 0, PY = PX + N, VX = PY + N, VY = VX + N, PD = VY + N, DTG = PD + N, TREQ = DTG + N,
+                       DLEFT = TREQ + N, MINT = DLEFT + N, GM = MINT + N, NAC = GM + N, NOC = NAC + N, LX = NOC + N,
+                       LY = LX + N, OX = LY + N, OY = OX + O, DMEAN = OY + O, DSTD = DMEAN + 1, STEP = DSTD + 1,
+                       EPIS = STEP + 1, SDIST = EPIS + 1;
+  // ---- shared tables, rows of RW floats
+  static constexpr int TP = 0,                 // [E][2] positions after the step (after the reset for envs that reset)
+                       TV = TP + 2 * E,        // [N][2] velocities
+                       TG = TV + 2 * N,        // [N][2] goal (assigned landmark) of agent i
+                       DTGO = TG + 2 * N,      // [N] world.dists_to_goal at step entry
+                       TREQO = DTGO + N,       // [N] world.times_required at step entry
+                       NTREQ = TREQO + N,      // [N] ... after agent i's info_callback
+                       OWN = NTREQ + N,        // [N] agent i's own reward
+                       GMO = OWN + N,          // [N] goal_match at step entry (int bits)
+                       RGM = GMO + N,          // [N] goal_match after a reset (int bits)
+                       RMINT = RGM + N,        // [N] min_time after a reset
+                       F_ROWS = RMINT + N;
+  static constexpr int PD64 = 0, SETM = PD64 + N, SETS = SETM + N + 1, D_ROWS = SETS + N + 1;   // rows of RW doubles
+  static constexpr int OFF_D = (F_ROWS * RW + 1) & ~1;
+  static constexpr int OFF_STAGE = (OFF_D + 2 * D_ROWS * RW + 3) & ~3;
+  static constexpr int OBS_W = N * OBS_F, NODE_W = N * E * NODE_F, ADJ_W = E * E;
+  // staging, use 1 (all ENVS envs): adj | obs | reward | done (bytes)
+  static constexpr int S_ADJ = 0, S_OBS = S_ADJ + ENVS * ADJ_W, S_REW = S_OBS + ENVS * OBS_W, S_DONE = S_REW + ENVS * N,
+                       SMALL_W = S_DONE + (ENVS * N + 3) / 4;
+  // staging, use 2 (32 envs at a time): node_obs
+  static constexpr int STAGE_NODE = 32 * NODE_W;
+  static constexpr int STAGE_W = ((STAGE_NODE > SMALL_W ? STAGE_NODE : SMALL_W) + 3) & ~3;
+  static constexpr int WORDS = OFF_STAGE + STAGE_W;
+};
+
+// static pair (a, b), a < b < M, row-major  ->  SDIST row
+__host__ __device__ constexpr int aw_spair(int a, int b, int M) { return a * M - a * (a + 1) / 2 + (b - a - 1); }
+
+// float64 distance with one point already converted (same bits as dist64: the conversions are exact).
+__device__ __forceinline__ double dist64_d(double ax, double ay, float bx, float by) {
+  const double dx = __dsub_rn(ax, (double)bx);
+  const double dy = __dsub_rn(ay, (double)by);
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+// CTA-wide copy of `nwords` floats from the staging image to global memory, 16-byte vectorised when
+// the destination is 16-byte aligned (it is whenever the slab starts 16-byte aligned: tiles are 32 envs).
+template <int THREADS>
+__device__ __forceinline__ void cta_copy_out(float* __restrict__ dst, const float* __restrict__ src, int nwords, int tid) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const int n4 = nwords >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+    for (int k = tid; k < n4; k += THREADS) __stcs(d4 + k, s4[k]);
+    for (int k = (n4 << 2) + tid; k < nwords; k += THREADS) __stcs(dst + k, src[k]);
+  } else {
+    for (int k = tid; k < nwords; k += THREADS) __stcs(dst + k, src[k]);
+  }
+}
+
+// Randomised reset of env column `col` by one thread of the env warp (navigation_graph.py:212-262,
+// :264-570) + lexifair (:555-561).  Same Philox stream, draw order and acceptance rules as
+// reset_group<G> (fm_device.cuh).  New positions go to the TP table, goal_match / min_time to RGM /
+// RMINT; the distances between static entities are returned in sd[] (float).
+template <int N, int O, int H>
+__device__ __forceinline__ void aw_reset_env(const DevParams& p, long long genv, uint32_t episode, float* __restrict__ Tc,
+                                             float (&sd)[AwLayout<N, O, H>::SP > 0 ? AwLayout<N, O, H>::SP : 1]) {
+  using L = AwLayout<N, O, H>;
+  constexpr int RW = L::RW, M = L::M;
+  auto PXY = [&](int e, int c) -> float& { return Tc[(L::TP + 2 * e + c) * RW]; };
+#pragma unroll 1
+  for (int k = 0; k < O; ++k) {            // obstacles: 0.8 * U(-ws/2, ws/2)^2, draws 0..O-1 (:271-275)
+    float x, y;
+    draw_uniform2(p, genv, episode, (uint32_t)k, x, y);
+    PXY(2 * N + k, 0) = __fmul_rn(0.8f, x);
+    PXY(2 * N + k, 1) = __fmul_rn(0.8f, y);
+  }
+  uint32_t d = (uint32_t)O;
+#pragma unroll 1
+  for (int slot = 0; slot < 2 * N; ++slot) {   // agents (:389-456) then goals (:472-535); entity index == slot
+    const bool goal = slot >= N;
+    const int base = goal ? N : 0;
+    float x, y;
+    while (true) {
+      draw_uniform2(p, genv, episode, d, x, y);
+      ++d;
+      if (goal) { x = __fmul_rn(0.8f, x); y = __fmul_rn(0.8f, y); }
+      bool bad = false;
+#pragma unroll 1
+      for (int k = 0; k < O; ++k) bad = bad || (dist64(PXY(2 * N + k, 0), PXY(2 * N + k, 1), x, y) < p.dcoll);
+#pragma unroll 1
+      for (int j = base; j < slot; ++j) bad = bad || (dist64(PXY(j, 0), PXY(j, 1), x, y) < p.dcoll);
+      if (!bad || d >= (uint32_t)MAX_DRAWS) break;
+    }
+    PXY(slot, 0) = x;
+    PXY(slot, 1) = y;
+  }
+  double cost[N * N];
+  int gm[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float ax = PXY(i, 0), ay = PXY(i, 1);
+    if (p.has_max_speed) {                 // min_time with the PREVIOUS goal_match (:545-547, :719-728)
+      const int og = __float_as_int(Tc[(L::GMO + i) * RW]);
+      Tc[(L::RMINT + i) * RW] = (float)(dist64(ax, ay, PXY(N + og, 0), PXY(N + og, 1)) / p.max_speed);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) cost[i * N + j] = dist64(ax, ay, PXY(N + j, 0), PXY(N + j, 1));   // cdist (:555)
+  }
+  lexifair_small<N>(cost, gm);
+#pragma unroll
+  for (int i = 0; i < N; ++i) Tc[(L::RGM + i) * RW] = __int_as_float(gm[i]);
+#pragma unroll
+  for (int a = 0; a < M; ++a)
+#pragma unroll
+    for (int b = a + 1; b < M; ++b)
+      sd[aw_spair(a, b, M)] = (float)dist64(PXY(N + a, 0), PXY(N + a, 1), PXY(N + b, 0), PXY(N + b, 1));
+}
+
+// =============================================================================================
+//   MODE 0: fused env step (MultiAgentGraphEnv.step, environment.py:816-877, + graphworker auto-reset,
+//           env_wrappers.py:859-865).   MODE 1: masked reset + observe (environment.py:882-898).
+template <int N, int O, int H, int MODE>
+__global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __grid_constant__ DevParams p) {
+  using L = AwLayout<N, O, H>;
+  constexpr int E = L::E, M = L::M, RW = L::RW, SP = L::SP;
+  constexpr int SPA = SP > 0 ? SP : 1;
+  extern __shared__ __align__(16) float smem[];
+  float* ST = smem + L::OFF_STAGE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = warp / L::WPH, role = warp - h * L::WPH;   // role < N: agent `role`;  role == N: env warp
+  const int col = h * 32 + lane;
+  const int env0 = blockIdx.x * L::ENVS;
+  const int nenv = min(L::ENVS, p.B - env0);
+  const int env = env0 + col;                    // < Bp: the state block is padded to a multiple of 64 envs
+  const bool venv = col < nenv;
+  const size_t Bp = (size_t)p.Bp;
+  float* gs = p.px + env;                        // state row r of this env: gs[r * Bp]
+  float* Tc = smem + col;                        // table row r of this env: Tc[r * RW]
+  double* Dc = reinterpret_cast<double*>(smem + L::OFF_D) + col;
+  const long long genv = p.env_offset + env;
+  const bool is_agent = role < N;
+  const int i = role;
+
+  // ---- registers of thread (env, agent i) ------------------------------------------------------
+  float px = 0.f, py = 0.f, vx = 0.f, vy = 0.f, pd = 0.f, dtg = 0.f, treq = 0.f, dleft = 0.f, fobs = 0.f;
+  int gm = 0, nac = 0, noc = 0;
+  float d[E];                                    // row i of the distance matrix (float), d[i] = 0
+  unsigned collbits = 0, reachbits = 0;          // bit e: float64 d(i, e) < collision distance / < goal threshold
+  float own_rew = 0.f;
+  // ---- registers of the env warp ---------------------------------------------------------------
+  float sd[SPA];                                 // distances between static entities
+  int step = 0, epis = 0;
+  bool do_reset = false, done = false;
+  int nstep = 0;
+
+  // Row i of the distance matrix at the positions in TP (core.py:204-228) + predicate bits.
+  auto agent_distances = [&]() {
+    const double ax = (double)px, ay = (double)py;
+    collbits = 0; reachbits = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const double dd = dist64_d(ax, ay, Tc[(L::TP + 2 * e) * RW], Tc[(L::TP + 2 * e + 1) * RW]);
+      const bool self = (e == i);
+      d[e] = self ? 0.0f : (float)dd;
+      collbits |= (!self && dd < p.dcoll) ? (1u << e) : 0u;
+      reachbits |= (dd < p.min_dist_thresh) ? (1u << e) : 0u;
+    }
+  };
+
+  if (MODE == 0) {
+    // =========================================================================================
+    double pd64 = 0.0;
+    float dmean0 = 0.f, dstd0 = 0.f;
+    if (is_agent) {
+      // ---- P0: own state + what the forces need, straight from the SoA state block --------------
+      const float* gi = gs + (size_t)i * Bp;
+      px = __ldcg(gi + (size_t)L::PX * Bp); py = __ldcg(gi + (size_t)L::PY * Bp);
+      vx = __ldcg(gi + (size_t)L::VX * Bp); vy = __ldcg(gi + (size_t)L::VY * Bp);
+      pd = __ldcg(gi + (size_t)L::PD * Bp); dtg = __ldcg(gi + (size_t)L::DTG * Bp);
+      treq = __ldcg(gi + (size_t)L::TREQ * Bp); dleft = __ldcg(gi + (size_t)L::DLEFT * Bp);
+      gm = __float_as_int(__ldcg(gi + (size_t)L::GM * Bp));
+      nac = __float_as_int(__ldcg(gi + (size_t)L::NAC * Bp));
+      noc = __float_as_int(__ldcg(gi + (size_t)L::NOC * Bp));
+      step = __float_as_int(__ldcg(gs + (size_t)L::STEP * Bp));
+      float qx[N + O], qy[N + O];              // partners: agents (own slot unused), obstacles
+#pragma unroll
+      for (int j = 0; j < N; ++j) { qx[j] = __ldcg(gs + (size_t)(L::PX + j) * Bp); qy[j] = __ldcg(gs + (size_t)(L::PY + j) * Bp); }
+#pragma unroll
+      for (int k = 0; k < O; ++k) { qx[N + k] = __ldcg(gs + (size_t)(L::OX + k) * Bp); qy[N + k] = __ldcg(gs + (size_t)(L::OY + k) * Bp); }
+      if (i == 0) { dmean0 = __ldcg(gs + (size_t)L::DMEAN * Bp); dstd0 = __ldcg(gs + (size_t)L::DSTD * Bp); }
+      float ux = 0.f, uy = 0.f;
+      if (venv) {                                // environment.py:301-311: u = [a1 - a2, a3 - a4] * sensitivity (5.0)
+        if (p.act_idx) {
+          const int a = __ldg(p.act_idx + (size_t)env * N + i);
+          ux = ((a == 1) ? 1.f : 0.f) - ((a == 2) ? 1.f : 0.f);
+          uy = ((a == 3) ? 1.f : 0.f) - ((a == 4) ? 1.f : 0.f);
+        } else {
+          const float* oh = p.act_onehot + ((size_t)env * N + i) * 5;
+          ux = __ldg(oh + 1) - __ldg(oh + 2);
+          uy = __ldg(oh + 3) - __ldg(oh + 4);
+        }
+        ux *= 5.0f; uy *= 5.0f;
+      }
+      // ---- P1: forces on agent i (core.py:277-316, :370-404), partners in ascending entity index;
+      // a pair (j, i), j < i, contributes -f(j, i) = f computed from agent i's side (IEEE sign symmetry).
+      double Fx = (double)ux, Fy = (double)uy;     // mass(1.0) * u + noise(0.0)
+#pragma unroll
+      for (int q = 0; q < N + O; ++q) {
+        if (q != i) {
+          const float dx = px - qx[q], dy = py - qy[q];
+          const float dist = sqrtf(dx * dx + dy * dy);
+          const float pen = softplusf(-(dist - p.dist_min) / p.contact_margin) * p.contact_margin;
+          const float tx = p.contact_force * dx / dist * pen;
+          const float ty = p.contact_force * dy / dist * pen;
+          Fx = (double)tx + Fx; Fy = (double)ty + Fy;
+        }
+      }
+      // integrate_state (core.py:338-356), float64; state rounded to fp32
+      double v64x, v64y, sx, sy;
+      integrate64(p, vx, vy, Fx, Fy, pd, v64x, v64y, sx, sy, pd64);
+      px = (float)__dadd_rn((double)px, sx); py = (float)__dadd_rn((double)py, sy);
+      vx = (float)v64x; vy = (float)v64y; pd = (float)pd64;
+      Tc[(L::TP + 2 * i) * RW] = px; Tc[(L::TP + 2 * i + 1) * RW] = py;
+      Tc[(L::TV + 2 * i) * RW] = vx; Tc[(L::TV + 2 * i + 1) * RW] = vy;
+      Tc[(L::DTGO + i) * RW] = dtg; Tc[(L::TREQO + i) * RW] = treq;
+      Tc[(L::GMO + i) * RW] = __int_as_float(gm);
+      Dc[(L::PD64 + i) * RW] = pd64;
+    } else {
+      // ---- env warp: static entities -> TP, cached static distances, step ------------------------
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        Tc[(L::TP + 2 * (N + j)) * RW] = __ldcg(gs + (size_t)(L::LX + j) * Bp);
+        Tc[(L::TP + 2 * (N + j) + 1) * RW] = __ldcg(gs + (size_t)(L::LY + j) * Bp);
+      }
+#pragma unroll
+      for (int k = 0; k < O; ++k) {
+        Tc[(L::TP + 2 * (2 * N + k)) * RW] = __ldcg(gs + (size_t)(L::OX + k) * Bp);
+        Tc[(L::TP + 2 * (2 * N + k) + 1) * RW] = __ldcg(gs + (size_t)(L::OY + k) * Bp);
+      }
+#pragma unroll
+      for (int q = 0; q < SP; ++q) sd[q] = __ldcg(gs + (size_t)(L::SDIST + q) * Bp);
+      step = __float_as_int(__ldcg(gs + (size_t)L::STEP * Bp));
+      epis = __float_as_int(__ldcg(gs + (size_t)L::EPIS * Bp));
+    }
+    __syncthreads();                              // #1: new agent positions, static positions (env warp) visible
+    nstep = step + 1;                              // environment.py:819, :823
+    done = nstep >= p.episode_length;              // environment.py:237-247 (agent.status is never set)
+    do_reset = venv && done && (p.auto_reset != 0);
+    if (is_agent) {
+      // ---- P2: distances, statistic sets, observation scalar, reward, latches ---------------------
+      const float gx = Tc[(L::TP + 2 * (N + gm)) * RW], gy = Tc[(L::TP + 2 * (N + gm) + 1) * RW];
+      Tc[(L::TG + 2 * i) * RW] = gx; Tc[(L::TG + 2 * i + 1) * RW] = gy;
+      agent_distances();
+      // world.dists_to_goal as left by the previous agent's info_callback: set k over
+      // [new_0..new_{k-1}, prev_k..] (navigation_graph.py:587-598, :617-618).  Agent i >= 1 needs set i;
+      // agent 0 reads last step's value from the state and computes set N (the value after this step).
+      const int kset = (i == 0) ? N : i;
+      double pj[N], dj[N];
+      bool lat[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        pj[j] = Dc[(L::PD64 + j) * RW];
+        dj[j] = (double)Tc[(L::DTGO + j) * RW];
+        lat[j] = Tc[(L::TREQO + j) * RW] != -1.0f;
+      }
+      double mk, sk;
+      {
+        double v[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = (j < kset && !lat[j]) ? pj[j] : dj[j];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += v[j];
+        mk = s / N;
+        double q = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { const double dd = v[j] - mk; q = sq_acc(q, dd); }
+        sk = sqrt(q / N);
+      }
+      Dc[(L::SETM + kset) * RW] = mk; Dc[(L::SETS + kset) * RW] = sk;
+      double fparam;                               // navigation_graph.py:764-769 / :849-853
+      if (dtg == -1.0f) {                          // first step of the episode: mean / std of the new travelled distances
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += pj[j];
+        const double m0 = s / N;
+        double q = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { const double dd = pj[j] - m0; q = sq_acc(q, dd); }
+        fparam = m0 / (sqrt(q / N) + 0.0001);
+      } else if (i == 0) {
+        fparam = (double)dmean0 / ((double)dstd0 + 0.0001);
+      } else {
+        fparam = mk / (sk + 0.0001);
+      }
+      float dgoal_f = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) dgoal_f = (gm == j) ? d[N + j] : dgoal_f;
+      const bool reached = ((reachbits >> (N + gm)) & 1u) != 0;      // dgoal < min_dist_thresh (float64 compare)
+      const int ncoll = __popc(collbits & ((1u << N) - 1u));
+      const bool ocoll = (collbits >> (2 * N)) != 0;
+      const bool latched = treq != -1.0f;
+      const double dtg_new = latched ? (double)dtg : pd64;
+      const double treq_new = (!latched && reached) ? (double)nstep * p.dt : (double)treq;   // :588
+      const float dleft_new = latched ? dleft : dgoal_f;
+      float rw = reached ? p.goal_rew : -dgoal_f;  // navigation_graph.py:760-824
+      rw -= p.coll_rew * (float)ncoll;
+      if (ocoll) rw -= p.coll_rew;
+      if (p.fairness_reward) {
+        float fair = p.fair_rew * tanhf((float)(fparam - p.zeroshift));
+        if (fair < -2.0f) fair = -2.0f;
+        rw += fair;
+      }
+      rw = fminf(fmaxf(rw, p.clip_lo), p.clip_hi);
+      nac += ncoll;                                // :604-613
+      noc += ocoll ? 1 : 0;                        // :602-603
+      own_rew = rw;
+      fobs = (float)fparam;
+      dtg = (float)dtg_new;
+      dleft = dleft_new;
+      Tc[(L::OWN + i) * RW] = rw;
+      Tc[(L::NTREQ + i) * RW] = (float)treq_new;   // `treq` keeps the old value for the info pass
+      if (i == 0 && venv) {                        // world.dist_traveled_mean / stddev after the last info_callback
+        gs[(size_t)L::DMEAN * Bp] = (float)mk;
+        gs[(size_t)L::DSTD * Bp] = (float)sk;
+      }
+    }
+    const bool want_info = venv && (p.o_info != nullptr || p.stats != nullptr) && (done || p.info_every_step);
+    double* stats_row = p.stats ? p.stats + ((size_t)blockIdx.x * H + h) * (15 * N + 2) : nullptr;
+    const bool any_done = __syncthreads_or(venv && done) != 0;   // #2: OWN / NTREQ / SETM / SETS / TG visible
+    const bool any_reset = any_done && (p.auto_reset != 0);
+    const bool any_info = (p.o_info != nullptr || p.stats != nullptr) && (any_done || p.info_every_step);
+
+    // ---- collaborative sum, episode statistics, info rows -------------------------------------------
+    float rew_out = own_rew;
+    if (is_agent) {
+      if (p.collaborative) {                       // environment.py:866-870
+        float tot = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) tot += Tc[(L::OWN + j) * RW];
+        rew_out = tot;
+      }
+      if (stats_row) {
+        double v = venv ? (double)rew_out : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+        if (lane == 0) stats_row[i] += v;
+      }
+      if (any_info) {
+        // world-level time statistics right after agent i's own info_callback: new values of agents
+        // j <= i, previous values of j > i (navigation_graph.py:620-621)
+        double tacc = 0.0;                         // entity.state.time += dt per step (core.py:355)
+        for (int k = 0; k < nstep; ++k) tacc += p.dt;
+        double tv[N];                              // times_required as float64: a latch of THIS step is nstep * dt unrounded
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float told = Tc[(L::TREQO + j) * RW];
+          const bool fresh = j <= i && told == -1.0f && Tc[(L::NTREQ + j) * RW] != -1.0f;
+          tv[j] = fresh ? (double)nstep * p.dt : (double)told;
+        }
+        double st = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) st += tv[j];
+        const double mt = st / N;
+        double qt = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { const double dd = tv[j] - mt; qt = sq_acc(qt, dd); }
+        const double stv = sqrt(qt / N);
+        const double md = Dc[(L::SETM + i + 1) * RW], sdv = Dc[(L::SETS + i + 1) * RW];
+        const float mint = __ldcg(gs + (size_t)(L::MINT + i) * Bp);
+        float info[INFO_F];
+        info[0] = own_rew; info[1] = dleft; info[2] = Tc[(L::NTREQ + i) * RW];
+        info[3] = (float)nac; info[4] = (float)noc;
+        info[5] = (float)md; info[6] = (float)sdv; info[7] = (float)(md / (sdv + 0.0001));
+        info[8] = dtg; info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv;
+        info[12] = (float)(mt / (stv + 0.0001)); info[13] = mint;
+        if (want_info && p.o_info) {
+          float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
+#pragma unroll
+          for (int k = 0; k < INFO_F; ++k) o[k] = info[k];
+        }
+        if (stats_row && __any_sync(FULL, venv && done)) {
+#pragma unroll
+          for (int k = 0; k < INFO_F; ++k) {
+            double v = (venv && done) ? (double)info[k] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+            if (lane == 0) stats_row[N + i * INFO_F + k] += v;
+          }
+        }
+      }
+      treq = Tc[(L::NTREQ + i) * RW];
+    } else if (stats_row) {
+      const unsigned termb = __ballot_sync(FULL, venv && done);
+      const unsigned validb = __ballot_sync(FULL, venv);
+      if (lane == 0) { stats_row[15 * N] += (double)__popc(termb); stats_row[15 * N + 1] += (double)__popc(validb); }
+    }
+
+    // ---- auto-reset (env_wrappers.py:859-865): obs / node_obs / adj come from the new episode, reward /
+    // done / info stay terminal ------------------------------------------------------------------------
+    if (any_reset) {
+      if (!is_agent) {
+        if (do_reset) {
+          aw_reset_env<N, O, H>(p, genv, (uint32_t)epis, Tc, sd);
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];
+            gs[(size_t)(L::LY + j) * Bp] = Tc[(L::TP + 2 * (N + j) + 1) * RW];
+          }
+#pragma unroll
+          for (int k = 0; k < O; ++k) {
+            gs[(size_t)(L::OX + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k)) * RW];
+            gs[(size_t)(L::OY + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k) + 1) * RW];
+          }
+#pragma unroll
+          for (int q = 0; q < SP; ++q) gs[(size_t)(L::SDIST + q) * Bp] = sd[q];
+          gs[(size_t)L::EPIS * Bp] = __int_as_float(epis + 1);
+        }
+      }
+      __syncthreads();                            // new positions / goal_match of the envs that reset
+      if (is_agent) {
+        if (do_reset) {
+          px = Tc[(L::TP + 2 * i) * RW]; py = Tc[(L::TP + 2 * i + 1) * RW];
+          vx = 0.f; vy = 0.f; pd = 0.f; dtg = -1.f; treq = -1.f; dleft = -1.f; nac = 0; noc = 0; fobs = 0.f;
+          gm = __float_as_int(Tc[(L::RGM + i) * RW]);
+          Tc[(L::TV + 2 * i) * RW] = 0.f; Tc[(L::TV + 2 * i + 1) * RW] = 0.f;
+          Tc[(L::TG + 2 * i) * RW] = Tc[(L::TP + 2 * (N + gm)) * RW];
+          Tc[(L::TG + 2 * i + 1) * RW] = Tc[(L::TP + 2 * (N + gm) + 1) * RW];
+          if (venv) {
+            gs[(size_t)(L::GM + i) * Bp] = __int_as_float(gm);
+            if (p.has_max_speed) gs[(size_t)(L::MINT + i) * Bp] = Tc[(L::RMINT + i) * RW];
+          }
+        }
+        agent_distances();
+      }
+    }
+    // ---- state write-back: agent rows from registers, one coalesced line per row --------------------
+    if (venv) {
+      if (is_agent) {
+        float* gi = gs + (size_t)i * Bp;
+        gi[(size_t)L::PX * Bp] = px; gi[(size_t)L::PY * Bp] = py;
+        gi[(size_t)L::VX * Bp] = vx; gi[(size_t)L::VY * Bp] = vy;
+        gi[(size_t)L::PD * Bp] = pd; gi[(size_t)L::DTG * Bp] = dtg;
+        gi[(size_t)L::TREQ * Bp] = treq; gi[(size_t)L::DLEFT * Bp] = dleft;
+        gi[(size_t)L::NAC * Bp] = __int_as_float(nac); gi[(size_t)L::NOC * Bp] = __int_as_float(noc);
+      } else {
+        gs[(size_t)L::STEP * Bp] = __int_as_float(do_reset ? 0 : nstep);
+      }
+    }
+    // ---- small outputs -> staging image (lane = env: odd strides, conflict free) ----------------------
+    if (is_agent) {
+      ST[L::S_REW + col * N + i] = rew_out;
+      reinterpret_cast<uint8_t*>(ST + L::S_DONE)[col * N + i] = done ? 1 : 0;
+    }
+  } else {
+    // =========================================================================================
+    // MODE 1: reset() / observe
+    do_reset = venv && (p.reset_mask ? (p.reset_mask[env] != 0) : true);
+    float dmean0 = 0.f, dstd0 = 0.f;
+    float pdj[N];
+    if (is_agent) {
+      const float* gi = gs + (size_t)i * Bp;
+      px = __ldcg(gi + (size_t)L::PX * Bp); py = __ldcg(gi + (size_t)L::PY * Bp);
+      vx = __ldcg(gi + (size_t)L::VX * Bp); vy = __ldcg(gi + (size_t)L::VY * Bp);
+      dtg = __ldcg(gi + (size_t)L::DTG * Bp);
+      gm = __float_as_int(__ldcg(gi + (size_t)L::GM * Bp));
+#pragma unroll
+      for (int j = 0; j < N; ++j) pdj[j] = __ldcg(gs + (size_t)(L::PD + j) * Bp);
+      dmean0 = __ldcg(gs + (size_t)L::DMEAN * Bp); dstd0 = __ldcg(gs + (size_t)L::DSTD * Bp);
+      Tc[(L::TP + 2 * i) * RW] = px; Tc[(L::TP + 2 * i + 1) * RW] = py;
+      Tc[(L::TV + 2 * i) * RW] = vx; Tc[(L::TV + 2 * i + 1) * RW] = vy;
+      Tc[(L::GMO + i) * RW] = __int_as_float(gm);
+      // observation() on the current state (navigation_graph.py:826-857, :849-853)
+      double sum_p = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) sum_p += (double)pdj[j];
+      const double mean_p = sum_p / N;
+      double q_p = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) { const double dd = (double)pdj[j] - mean_p; q_p = sq_acc(q_p, dd); }
+      const double std_p = sqrt(q_p / N);
+      fobs = (float)((dtg == -1.0f) ? mean_p / (std_p + 0.0001) : (double)dmean0 / ((double)dstd0 + 0.0001));
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        Tc[(L::TP + 2 * (N + j)) * RW] = __ldcg(gs + (size_t)(L::LX + j) * Bp);
+        Tc[(L::TP + 2 * (N + j) + 1) * RW] = __ldcg(gs + (size_t)(L::LY + j) * Bp);
+      }
+#pragma unroll
+      for (int k = 0; k < O; ++k) {
+        Tc[(L::TP + 2 * (2 * N + k)) * RW] = __ldcg(gs + (size_t)(L::OX + k) * Bp);
+        Tc[(L::TP + 2 * (2 * N + k) + 1) * RW] = __ldcg(gs + (size_t)(L::OY + k) * Bp);
+      }
+#pragma unroll
+      for (int q = 0; q < SP; ++q) sd[q] = __ldcg(gs + (size_t)(L::SDIST + q) * Bp);
+      epis = __float_as_int(__ldcg(gs + (size_t)L::EPIS * Bp));
+    }
+    const bool any_reset = __syncthreads_or(do_reset) != 0;
+    if (any_reset) {
+      if (!is_agent && do_reset) {
+        aw_reset_env<N, O, H>(p, genv, (uint32_t)epis, Tc, sd);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];
+          gs[(size_t)(L::LY + j) * Bp] = Tc[(L::TP + 2 * (N + j) + 1) * RW];
+        }
+#pragma unroll
+        for (int k = 0; k < O; ++k) {
+          gs[(size_t)(L::OX + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k)) * RW];
+          gs[(size_t)(L::OY + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k) + 1) * RW];
+        }
+#pragma unroll
+        for (int q = 0; q < SP; ++q) gs[(size_t)(L::SDIST + q) * Bp] = sd[q];
+        gs[(size_t)L::EPIS * Bp] = __int_as_float(epis + 1);
+        gs[(size_t)L::STEP * Bp] = __int_as_float(0);
+      }
+      __syncthreads();
+      if (is_agent && do_reset) {
+        px = Tc[(L::TP + 2 * i) * RW]; py = Tc[(L::TP + 2 * i + 1) * RW];
+        vx = 0.f; vy = 0.f; fobs = 0.f;           // mean(p_dist = 0) / (std + 1e-4)
+        gm = __float_as_int(Tc[(L::RGM + i) * RW]);
+        Tc[(L::TV + 2 * i) * RW] = 0.f; Tc[(L::TV + 2 * i + 1) * RW] = 0.f;
+        float* gi = gs + (size_t)i * Bp;
+        gi[(size_t)L::PX * Bp] = px; gi[(size_t)L::PY * Bp] = py;
+        gi[(size_t)L::VX * Bp] = 0.f; gi[(size_t)L::VY * Bp] = 0.f; gi[(size_t)L::PD * Bp] = 0.f;
+        gi[(size_t)L::DTG * Bp] = -1.f; gi[(size_t)L::TREQ * Bp] = -1.f; gi[(size_t)L::DLEFT * Bp] = -1.f;
+        gi[(size_t)L::NAC * Bp] = __int_as_float(0); gi[(size_t)L::NOC * Bp] = __int_as_float(0);
+        gi[(size_t)L::GM * Bp] = __int_as_float(gm);
+        if (p.has_max_speed) gi[(size_t)L::MINT * Bp] = Tc[(L::RMINT + i) * RW];
+      }
+    } else {
+      __syncthreads();                            // static positions (env warp) visible
+    }
+    if (is_agent) {
+      Tc[(L::TG + 2 * i) * RW] = Tc[(L::TP + 2 * (N + gm)) * RW];
+      Tc[(L::TG + 2 * i + 1) * RW] = Tc[(L::TP + 2 * (N + gm) + 1) * RW];
+      agent_distances();
+    }
+  }
+
+  // =============================================================================================
+  // Emission, use 1 of the staging region: adj | obs (| reward | done already placed in MODE 0).
+  if (is_agent) {
+    float* a = ST + L::S_ADJ + col * L::ADJ_W;
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[i * E + e] = d[e];             // row i
+#pragma unroll
+    for (int e = N; e < E; ++e) a[e * E + i] = d[e];             // column i below the agent block
+    float* o = ST + L::S_OBS + col * L::OBS_W + i * OBS_F;       // navigation_graph.py:826-857
+    const float gx = Tc[(L::TG + 2 * i) * RW], gy = Tc[(L::TG + 2 * i + 1) * RW];
+    o[0] = vx; o[1] = vy; o[2] = px; o[3] = py; o[4] = gx - px; o[5] = gy - py; o[6] = fobs;
+  } else {
+    float* a = ST + L::S_ADJ + col * L::ADJ_W;
+#pragma unroll
+    for (int x = 0; x < M; ++x) {
+      a[(N + x) * E + (N + x)] = 0.0f;
+#pragma unroll
+      for (int y = x + 1; y < M; ++y) {
+        const float v = sd[aw_spair(x, y, M)];
+        a[(N + x) * E + (N + y)] = v;
+        a[(N + y) * E + (N + x)] = v;
+      }
+    }
+  }
+  __syncthreads();                                // staging image of the small outputs + TP / TV / TG complete
+  if (p.o_adj) cta_copy_out<L::THREADS>(p.o_adj + (size_t)env0 * L::ADJ_W, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
+  if (p.o_obs) cta_copy_out<L::THREADS>(p.o_obs + (size_t)env0 * L::OBS_W, ST + L::S_OBS, nenv * L::OBS_W, tid);
+  if (MODE == 0) {
+    if (p.o_rew) cta_copy_out<L::THREADS>(p.o_rew + (size_t)env0 * N, ST + L::S_REW, nenv * N, tid);
+    if (p.o_done) {
+      const uint8_t* sdone = reinterpret_cast<const uint8_t*>(ST + L::S_DONE);
+      uint8_t* gdone = p.o_done + (size_t)env0 * N;
+      for (int k = tid; k < nenv * N; k += L::THREADS) gdone[k] = sdone[k];
+    }
+  }
+  if (!p.o_node) return;
+  // ---- use 2: node_obs, 32 envs at a time (navigation_graph.py:1079-1124, relative features): for ego
+  // agent a and entity e  [v_e - v_a (2), p_e - p_a (2), goal_e - p_a (2), p_e - p_a (2), p_e - p_a (2), type]
+  // with goal_e = assigned landmark for agents and = p_e otherwise, v_e = 0 for non-agents.  Work items
+  // (a, e) are spread over all warps; lane = env, so table reads and staging writes are conflict free.
+#pragma unroll 1
+  for (int hh = 0; hh < H; ++hh) {
+    __syncthreads();                              // previous use of the staging region fully read
+    if (hh * 32 < nenv) {
+      const float* Th = smem + hh * 32 + lane;
+      float* sn = ST + lane * L::NODE_W;
+#pragma unroll 1
+      for (int it = warp; it < N * E; it += L::WARPS) {
+        const int a = it / E, e = it - a * E;
+        const float pax = Th[(L::TP + 2 * a) * RW], pay = Th[(L::TP + 2 * a + 1) * RW];
+        const float vax = Th[(L::TV + 2 * a) * RW], vay = Th[(L::TV + 2 * a + 1) * RW];
+        const float pex = Th[(L::TP + 2 * e) * RW], pey = Th[(L::TP + 2 * e + 1) * RW];
+        const float rpx = pex - pax, rpy = pey - pay;
+        float vex = 0.f, vey = 0.f, rgx = rpx, rgy = rpy, type = (e < 2 * N) ? 1.0f : 2.0f;
+        if (e < N) {
+          vex = Th[(L::TV + 2 * e) * RW]; vey = Th[(L::TV + 2 * e + 1) * RW];
+          rgx = Th[(L::TG + 2 * e) * RW] - pax; rgy = Th[(L::TG + 2 * e + 1) * RW] - pay;
+          type = 0.0f;
+        }
+        float* o = sn + it * NODE_F;
+        o[0] = vex - vax; o[1] = vey - vay; o[2] = rpx; o[3] = rpy; o[4] = rgx; o[5] = rgy;
+        o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy; o[10] = type;
+      }
+    }
+    __syncthreads();
+    const int ne = min(32, nenv - hh * 32);
+    if (ne > 0) cta_copy_out<L::THREADS>(p.o_node + (size_t)(env0 + hh * 32) * L::NODE_W, ST, ne * L::NODE_W, tid);
+  }
+}
+
+// =============================================================================================
+// Distances between static entities from the SoA state (after fm_set_state injected positions).
+__global__ void aw_static_kernel(const DevParams p, float* __restrict__ sdist) {
+  const int M = p.N + p.O, SP = M * (M - 1) / 2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)p.Bp * SP) return;
+  const int q = (int)(t / p.Bp), env = (int)(t % p.Bp);
+  int a = 0, rem = q;
+  while (rem >= M - 1 - a) { rem -= M - 1 - a; ++a; }
+  const int b = a + 1 + rem;
+  auto X = [&](int s) { return s < p.N ? p.lx[(size_t)s * p.Bp + env] : p.ox[(size_t)(s - p.N) * p.Bp + env]; };
+  auto Y = [&](int s) { return s < p.N ? p.ly[(size_t)s * p.Bp + env] : p.oy[(size_t)(s - p.N) * p.Bp + env]; };
+  sdist[(size_t)q * p.Bp + env] = (float)dist64(X(a), Y(a), X(b), Y(b));
+}
+
+// =============================================================================================
+// Host side.
+template <int N, int O, int H>
+static cudaError_t aw_launch_noh(const DevParams& p, cudaStream_t st, bool is_reset) {
+  using L = AwLayout<N, O, H>;
+  const int blocks = (p.B + L::ENVS - 1) / L::ENVS;
+  const size_t smem = (size_t)L::WORDS * sizeof(float);
+  if (is_reset) aw_kernel<N, O, H, 1><<<blocks, L::THREADS, smem, st>>>(p);
+  else aw_kernel<N, O, H, 0><<<blocks, L::THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int N, int O, int H>
+static cudaError_t aw_prepare_noh() {
+  using L = AwLayout<N, O, H>;
+  const int smem = L::WORDS * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(aw_kernel<N, O, H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(aw_kernel<N, O, H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+// The (N, O) pairs compiled for this mapping.  Everything else runs the group-per-env kernels.
+#define FM_AW_CASES(X) X(1, 1) X(2, 0) X(3, 0) X(3, 3) X(4, 2)
+
+bool aw_supported(int N, int O) {
+#define X(n, o) if (N == n && O == o) return true;
+  FM_AW_CASES(X)
+#undef X
+  return false;
+}
+
+int aw_halves(const DevParams& p) { return p.aw_halves == 2 ? 2 : 1; }
+int aw_stats_rows(int B, int halves) { return ((B + 32 * halves - 1) / (32 * halves)) * halves; }
+
+cudaError_t aw_prepare(const DevParams& p) {
+#define X(n, o) if (p.N == n && p.O == o) return aw_halves(p) == 2 ? aw_prepare_noh<n, o, 2>() : aw_prepare_noh<n, o, 1>();
+  FM_AW_CASES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset) {
+#define X(n, o) \
+  if (p.N == n && p.O == o) return aw_halves(p) == 2 ? aw_launch_noh<n, o, 2>(p, st, is_reset) : aw_launch_noh<n, o, 1>(p, st, is_reset);
+  FM_AW_CASES(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_static_dists(const DevParams& p, cudaStream_t st) {
+  const int M = p.N + p.O, SP = M * (M - 1) / 2;
+  if (SP == 0 || !p.sdist) return cudaSuccess;
+  const long long total = (long long)p.Bp * SP;
+  aw_static_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(p, p.sdist);
+  return cudaGetLastError();
+}
+
+}  // namespace fm

@@ -90,15 +90,9 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
   }
   // ---- integrate_state (core.py:338-356), float64 so that p_dist keeps its low bits for the
   // ill-conditioned mean/std fairness ratio; state is stored rounded to fp32.
-  double v64x = (double)vx * p.damping_keep + Fx * p.dt;
-  double v64y = (double)vy * p.damping_keep + Fy * p.dt;
-  if (p.has_max_speed) {
-    const double speed = sqrt(v64x * v64x + v64y * v64y);
-    if (speed > p.max_speed) { v64x = v64x / speed * p.max_speed; v64y = v64y / speed * p.max_speed; }
-  }
-  const double sx = v64x * p.dt, sy = v64y * p.dt;
-  const double pd64 = (double)pd + sqrt(sx * sx + sy * sy);
-  const float npx0 = (float)((double)px + sx), npy0 = (float)((double)py + sy);
+  double v64x, v64y, sx, sy, pd64;
+  integrate64(p, vx, vy, Fx, Fy, pd, v64x, v64y, sx, sy, pd64);
+  const float npx0 = (float)__dadd_rn((double)px, sx), npy0 = (float)__dadd_rn((double)py, sy);
   float npx = npx0, npy = npy0;
   float nvx = (float)v64x, nvy = (float)v64y;
   float npd = (float)pd64;
@@ -140,7 +134,7 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
     const double aj = __shfl_sync(FULL, dtg_new, gl + j);
     const double bj = __shfl_sync(FULL, dtg_prev, gl + j);
     const double dp = pj - mean_p, da = aj - mean_a, dv = ((j < i) ? aj : bj) - mean_v;
-    q_p += dp * dp; q_a += da * da; q_v += dv * dv;
+    q_p = sq_acc(q_p, dp); q_a = sq_acc(q_a, da); q_v = sq_acc(q_v, dv);
   }
   const double std_p = sqrt(q_p / N), std_v = sqrt(q_v / N), std_a = sqrt(q_a / N);
   double fparam;                                 // navigation_graph.py:764-769 / :849-853
@@ -186,7 +180,7 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
       const double aj = __shfl_sync(FULL, dtg_new, gl + j), bj = __shfl_sync(FULL, dtg_prev, gl + j);
       const double tj = __shfl_sync(FULL, treq_new, gl + j), uj = __shfl_sync(FULL, treq_prev, gl + j);
       const double dd = ((j <= i) ? aj : bj) - md, dtt = ((j <= i) ? tj : uj) - mt;
-      qd += dd * dd; qt += dtt * dtt;
+      qd = sq_acc(qd, dd); qt = sq_acc(qt, dtt);
     }
     const double sdv = sqrt(qd / N), stv = sqrt(qt / N);
     double tacc = 0.0;                           // entity.state.time += dt per step (core.py:355)
@@ -330,7 +324,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   for (int j = 0; j < N; ++j) sum_p += __shfl_sync(FULL, pd64, gl + j);
   const double mean_p = sum_p / N;
   double q_p = 0.0;
-  for (int j = 0; j < N; ++j) { const double d = __shfl_sync(FULL, pd64, gl + j) - mean_p; q_p += d * d; }
+  for (int j = 0; j < N; ++j) { const double d = __shfl_sync(FULL, pd64, gl + j) - mean_p; q_p = sq_acc(q_p, d); }
   const double std_p = sqrt(q_p / N);
   const double fparam = (dtg == -1.0f) ? mean_p / (std_p + 0.0001) : (double)dmean / ((double)dstd + 0.0001);
   double dgoal; int ncoll; bool ocoll;
@@ -549,8 +543,8 @@ int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); 
 int num_warps(int B, int N) { const int epw = 32 / group_size(N); return (B + epw - 1) / epw; }
 
 cudaError_t prepare_kernels(const DevParams& p) {
-  if (p.mapping == 2) return tile_prepare(p);
-  if (p.mapping == 1) return tpe_prepare(p);
+  if (p.mapping == 2) return aw_prepare(p);
+  if (p.mapping == 1) return tile_prepare(p);
   switch (group_size(p.N)) {
     case 4: return prepare_g<4>(p);
     case 8: return prepare_g<8>(p);
@@ -560,8 +554,8 @@ cudaError_t prepare_kernels(const DevParams& p) {
 }
 
 cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset) {
-  if (p.mapping == 2) return tile_launch(p, st, is_reset);
-  if (p.mapping == 1) return tpe_launch(p, st, is_reset);
+  if (p.mapping == 2) return aw_launch(p, st, is_reset);
+  if (p.mapping == 1) return tile_launch(p, st, is_reset);
   switch (group_size(p.N)) {
     case 4: return launch_step_g<4>(p, st, is_reset);
     case 8: return launch_step_g<8>(p, st, is_reset);

@@ -1,4 +1,4 @@
-// Small-team helpers shared by the thread-per-env (fm_tpe.cu) and env-tile (fm_tile.cu) kernels:
+// Small-team helpers shared by the env-tile (fm_tile.cu) and agent-warp (fm_aw.cu) kernels:
 // lexifair assignment by enumeration for N <= 4, entirely in registers.
 #pragma once
 #include <utility>

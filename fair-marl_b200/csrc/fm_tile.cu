@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const __grid_constan
         const double mean_p = sum_p / N;
         double q_p = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j) { const double dd = (double)Sl[(L::PD + j) * 32] - mean_p; q_p += dd * dd; }
+        for (int j = 0; j < N; ++j) { const double dd = (double)Sl[(L::PD + j) * 32] - mean_p; q_p = sq_acc(q_p, dd); }
         const double std_p = sqrt(q_p / N);
         const double dm = (double)Sl[L::DMEAN * 32], ds = (double)Sl[L::DSTD * 32];
 #pragma unroll
@@ -389,17 +389,11 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const __grid_constan
     const float* Fo = Sl + (L::FT + 2 * (L::NAA + i * O)) * 32;
 #pragma unroll
     for (int k = 0; k < O; ++k) { Fx = (double)Fo[2 * k * 32] + Fx; Fy = (double)Fo[(2 * k + 1) * 32] + Fy; }
-    double v64x = (double)Si[L::VX * 32] * p.damping_keep + Fx * p.dt;
-    double v64y = (double)Si[L::VY * 32] * p.damping_keep + Fy * p.dt;
-    if (p.has_max_speed) {
-      const double speed = sqrt(v64x * v64x + v64y * v64y);
-      if (speed > p.max_speed) { v64x = v64x / speed * p.max_speed; v64y = v64y / speed * p.max_speed; }
-    }
-    const double sx = v64x * p.dt, sy = v64y * p.dt;
-    const double pd64 = (double)Si[L::PD * 32] + sqrt(sx * sx + sy * sy);
+    double v64x, v64y, sx, sy, pd64;
+    integrate64(p, Si[L::VX * 32], Si[L::VY * 32], Fx, Fy, Si[L::PD * 32], v64x, v64y, sx, sy, pd64);
     SD[(L::PD64 + i) * 32 + lane] = pd64;
-    Si[L::PX * 32] = (float)((double)Si[L::PX * 32] + sx);
-    Si[L::PY * 32] = (float)((double)Si[L::PY * 32] + sy);
+    Si[L::PX * 32] = (float)__dadd_rn((double)Si[L::PX * 32], sx);
+    Si[L::PY * 32] = (float)__dadd_rn((double)Si[L::PY * 32], sy);
     Si[L::VX * 32] = (float)v64x; Si[L::VY * 32] = (float)v64y;
     Si[L::PD * 32] = (float)pd64;
   }
@@ -426,7 +420,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const __grid_constan
     const double m = s / N;
     double q = 0.0;
 #pragma unroll
-    for (int j = 0; j < N; ++j) { const double dd = v[j] - m; q += dd * dd; }
+    for (int j = 0; j < N; ++j) { const double dd = v[j] - m; q = sq_acc(q, dd); }
     SD[(L::VM + k) * 32 + lane] = m;
     SD[(L::VS + k) * 32 + lane] = sqrt(q / N);
   }
@@ -528,7 +522,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(const __grid_constan
       const double mt = st / N;
       double qt = 0.0;
 #pragma unroll
-      for (int j = 0; j < N; ++j) { const double dd = tv[j] - mt; qt += dd * dd; }
+      for (int j = 0; j < N; ++j) { const double dd = tv[j] - mt; qt = sq_acc(qt, dd); }
       const double stv = sqrt(qt / N);
       const double md = SD[(L::VM + i + 1) * 32 + lane], sdv = SD[(L::VS + i + 1) * 32 + lane];
       const float* Si = Sl + i * 32;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FM_ABI_VERSION 2
+#define FM_ABI_VERSION 3
 #define FM_OBS_DIM 7         /* navigation_graph.py:826-857 */
 #define FM_NODE_FEAT_DIM 11  /* navigation_graph.py:1079-1124 (relative features) */
 #define FM_INFO_DIM 14       /* navigation_graph.py:625-647 + environment.py:857 */
@@ -64,9 +64,9 @@ typedef struct FmConfig {
   int32_t collaborative;   /* environment.py:867-870 */
   int32_t auto_reset;      /* env_wrappers.py:859-865 (graphworker) */
   int32_t info_every_step; /* 0: info rows are written on terminal steps only */
-  int32_t mapping;         /* kernel mapping: 0 auto (env-tile when compiled for (N, O), else group-per-env),
-                              1 group-per-env, 2 thread-per-env, 3 env-tile.  Results are identical. */
-  int32_t reserved_;
+  int32_t mapping;         /* kernel mapping: 0 auto (agent-warp when compiled for (N, O), else group-per-env),
+                              1 group-per-env, 2 env-tile, 3 agent-warp.  Results are identical. */
+  int32_t aw_halves;       /* agent-warp only: 32-env halves per CTA, 1 (0 = default) or 2 */
 } FmConfig;
 
 /* Per-step outputs, API layout (what GraphSubprocVecEnv.step_wait stacks, env_wrappers.py:988-996). */
@@ -183,7 +183,7 @@ int fm_stats_read(FmHandle* h, double* out_dev, int32_t clear, void* stream);
 
 /* Introspection. */
 int fm_num_entities(const FmHandle* h);
-int fm_mapping(const FmHandle* h);                        /* 1 group-per-env, 2 thread-per-env, 3 env-tile */
+int fm_mapping(const FmHandle* h);                        /* 1 group-per-env, 2 env-tile, 3 agent-warp */
 int64_t fm_algorithmic_bytes_per_step(const FmHandle* h); /* W * 4 * B */
 int fm_kernel_launches(const FmHandle* h, int64_t* out);   /* kernels launched by this handle so far */
 int fm_abi_version(void);

@@ -15,7 +15,7 @@ def pytest_configure(config):
 
 
 def pytest_generate_tests(metafunc):
-    """Every GPU test runs under both kernel mappings: 'auto' (thread-per-env where compiled, i.e. the
+    """Every GPU test runs under both kernel mappings: 'auto' (agent-warp where compiled, i.e. the
     product default) and 'group' (group-per-env kernels forced)."""
     if metafunc.definition.get_closest_marker("gpu") and "kernel_mapping" in metafunc.fixturenames:
         metafunc.parametrize("kernel_mapping", ["auto", "group"], indirect=True)

@@ -33,7 +33,7 @@ def test_binding_covers_header(lib_path):
     from fair_marl_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.load()
-    assert lib.fm_abi_version() == 2
+    assert lib.fm_abi_version() == 3
     assert lib.fm_stats_len(3) == 47
 
 
