@@ -182,7 +182,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.init_process_group("nccl", device_id=dev)
     B = args.envs
     K, W = args.steps, args.warmup
-    cfg = fm.SimConfig(**sim_kwargs(), mapping=args.mapping, aw_halves=args.aw_halves)
+    cfg = fm.SimConfig(**sim_kwargs(), mapping=args.mapping)
     env = fm.B200GraphVecEnv(cfg, num_envs=B, device=local_rank, seed=0, env_offset=rank * B, num_slots=EPISODE)
     E = cfg.num_entities
     stats = fm.EpisodeStats(N_AGENTS, device=dev)
@@ -237,8 +237,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env.algorithmic_bytes_per_step
-    kernel_name = {"aw": f"fm::aw_kernel<{N_AGENTS},{N_OBST},{args.aw_halves},0> (agent-warp)",
-                   "tile": f"fm::tile_kernel<{N_AGENTS},{N_OBST},0> (env-tile)",
+    kernel_name = {"aw": f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)",
                    "group": "fm::step_kernel<G> (group-per-env)"}[env.mapping]
     step_kernel_ms = elapsed_ms / K              # rank-max; one step kernel per step dominates the region
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
@@ -312,8 +311,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mapping", default="auto", choices=["auto", "group", "tile", "aw"], help="kernel mapping (diagnostic)")
-    ap.add_argument("--aw-halves", type=int, default=1, choices=[1, 2], help="agent-warp: 32-env halves per CTA (diagnostic)")
+    ap.add_argument("--mapping", default="auto", choices=["auto", "group", "aw"], help="kernel mapping (diagnostic)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

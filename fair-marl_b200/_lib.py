@@ -24,7 +24,7 @@ class FmConfig(C.Structure):
         ("goal_rew", C.c_double), ("min_dist_thresh", C.c_double), ("fair_rew", C.c_double),
         ("zeroshift", C.c_double), ("max_edge_dist", C.c_double),
         ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32),
-        ("info_every_step", C.c_int32), ("mapping", C.c_int32), ("aw_halves", C.c_int32),
+        ("info_every_step", C.c_int32), ("mapping", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

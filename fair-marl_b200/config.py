@@ -24,11 +24,9 @@ class SimConfig:
     fairness_reward: bool = True
     auto_reset: bool = True
     info_every_step: bool = False
-    # kernel mapping: 'auto' | 'group' (group-per-env) | 'tile' (env-tile) | 'aw' (agent-warp); the last
-    # two exist for the small (N, O) they are compiled for; results are
-    # identical across mappings.  aw_halves: 32-env halves per CTA of the agent-warp kernels (1 or 2).
+    # kernel mapping: 'auto' | 'group' (group-per-env) | 'aw' (agent-warp, compiled for small (N, O));
+    # results are identical across mappings
     mapping: str = "auto"
-    aw_halves: int = 1
 
     @property
     def num_entities(self) -> int:

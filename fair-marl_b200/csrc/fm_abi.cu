@@ -32,7 +32,6 @@ struct FmHandle {
   int device;
   DevParams p;
   void* state_block;
-  void* luts;
   double* stats;
   int stats_rows, K;
   long long launches;
@@ -67,8 +66,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > 64)
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_obstacles must be in 0..64 (got %d)", cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_create: episode_length must be >= 1");
-  if (cfg->mapping < 0 || cfg->mapping > 3) return fail(FM_ERR_INVALID_ARG, "fm_create: mapping must be 0..3 (got %d)", cfg->mapping);
-  if (cfg->aw_halves < 0 || cfg->aw_halves > 2) return fail(FM_ERR_INVALID_ARG, "fm_create: aw_halves must be 0, 1 or 2 (got %d)", cfg->aw_halves);
+  if (cfg->mapping < 0 || cfg->mapping > 2) return fail(FM_ERR_INVALID_ARG, "fm_create: mapping must be 0..2 (got %d)", cfg->mapping);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -102,7 +100,6 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.ox = take(Bp * O); p.oy = take(Bp * O);
   p.dmean = take(Bp); p.dstd = take(Bp); p.step = (int*)take(Bp); p.episode = (int*)take(Bp);
   p.sdist = take(Bp * SP);
-  p.aw_halves = cfg->aw_halves == 2 ? 2 : 1;
 
   // config -> device constants.  Collision threshold exactly as the reference spells it:
   // 1.05*(size + size) (navigation_graph.py:655, :704); cached min_dist = size + size (core.py:215).
@@ -135,28 +132,12 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.env_offset = cfg->env_offset;
 
   // Kernel mapping (cfg->mapping: 0 auto = agent-warp where compiled for (N, O), else group-per-env;
-  // 1 group-per-env; 2 env-tile; 3 agent-warp).  All mappings produce identical results.
-  if (cfg->mapping == 2 && !fm::tile_supported(N, O)) {
-    cudaFree(h->state_block); delete h;
-    return fail(FM_ERR_UNSUPPORTED, "fm_create: env-tile kernels are not compiled for N=%d O=%d", N, O);
-  }
-  if (cfg->mapping == 3 && !fm::aw_supported(N, O)) {
+  // 1 group-per-env; 2 agent-warp).  Both mappings produce identical results.
+  if (cfg->mapping == 2 && !fm::aw_supported(N, O)) {
     cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: agent-warp kernels are not compiled for N=%d O=%d", N, O);
   }
-  p.mapping = cfg->mapping == 1 ? 0 : (cfg->mapping == 2 ? 1 : ((cfg->mapping == 3 || fm::aw_supported(N, O)) ? 2 : 0));
-  if (p.mapping == 1) {
-    std::vector<uint32_t> lo, ln, la;
-    fm::tile_build_luts(N, O, lo, ln, la);
-    const size_t nw = lo.size() + ln.size() + la.size();
-    e = cudaMalloc(&h->luts, nw * sizeof(uint32_t));
-    if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc luts: %s", cudaGetErrorString(e)); }
-    uint32_t* d = (uint32_t*)h->luts;
-    cudaMemcpy(d, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(d + lo.size(), ln.data(), ln.size() * 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(d + lo.size() + ln.size(), la.data(), la.size() * 4, cudaMemcpyHostToDevice);
-    p.lut_obs = d; p.lut_node = d + lo.size(); p.lut_adj = d + lo.size() + ln.size();
-  }
+  p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || fm::aw_supported(N, O)) ? 1 : 0);
   const int G = fm::group_size(N), EPW = 32 / G;
   p.sm_cost = round4(2LL * EPW * N * N);
   p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
@@ -166,20 +147,20 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_stage + p.sm_obs + p.sm_asg;
   if (p.mapping == 0 && (size_t)p.sm_per_warp * 4 * 4 > 227 * 1024) {
-    cudaFree(h->luts); cudaFree(h->state_block); delete h;
+    cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: N=%d O=%d needs %d B of shared memory per CTA", N, O, p.sm_per_warp * 16);
   }
   h->K = fm_stats_len(N);
-  h->stats_rows = p.mapping == 2 ? fm::aw_stats_rows(B, p.aw_halves) : (p.mapping == 1 ? fm::tile_num_ctas(B) : fm::num_warps(B, N));
+  h->stats_rows = p.mapping == 1 ? fm::aw_stats_rows(B) : fm::num_warps(B, N);
   e = cudaMalloc(&h->stats, (size_t)h->stats_rows * h->K * sizeof(double));
-  if (e != cudaSuccess) { cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc stats: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc stats: %s", cudaGetErrorString(e)); }
   cudaMemset(h->stats, 0, (size_t)h->stats_rows * h->K * sizeof(double));
   p.stats = h->stats;
   e = fm::prepare_kernels(p);
-  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
   e = fm::launch_state_init(p, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->luts); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
   h->launches = 1;
   *out = h;
   return FM_OK;
@@ -198,7 +179,6 @@ int fm_destroy(FmHandle* h) {
   use_device(h->device);
   free_staging(h);
   cudaFree(h->stats);
-  cudaFree(h->luts);
   cudaFree(h->state_block);
   delete h;
   return FM_OK;
@@ -342,7 +322,7 @@ int fm_set_state(FmHandle* h, const FmState* st, void* stream) {
   if (rc) return rc;
   FM_CUDA(fm::launch_state_io(h->p, *st, 1, (cudaStream_t)stream));
   h->launches += 1;
-  if (h->p.mapping == 2 && (st->landmark_pos || st->obstacle_pos)) {      // cached static distances follow the positions
+  if (h->p.mapping == 1 && (st->landmark_pos || st->obstacle_pos)) {      // cached static distances follow the positions
     FM_CUDA(fm::launch_static_dists(h->p, (cudaStream_t)stream));
     h->launches += 1;
   }

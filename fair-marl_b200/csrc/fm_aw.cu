@@ -1,27 +1,31 @@
-// Agent-warp kernels: one CTA owns a tile of 32*H consecutive envs; lane <-> env, WARP <-> AGENT.
+// Agent-warp kernels: one CTA owns a tile of 32 consecutive envs; lane <-> env, WARP <-> AGENT.
 // Thread (env, agent i) keeps agent i's whole state in registers from the first global load to the
 // write-back: forces on agent i, integration, agent i's row of the distance matrix, its observation
-// scalar, reward, goal latches and counters never touch shared memory.  One extra "env warp" per 32 envs
-// owns what belongs to the env rather than to an agent: static entity positions, the landmark/obstacle
-// block of the distance matrix, step / done / auto-reset (placement + lexifair), episode statistics.
-// Specialised at compile time on (N, O, H); N <= 4 (lexifair by enumeration, whole-tile output staging).
+// scalar, reward, goal latches and counters never leave the thread.  One extra "env warp" owns what
+// belongs to the env rather than to an agent: static entity positions, the landmark/obstacle block of
+// the distance matrix, auto-reset (placement + lexifair), episode counters.
+// Specialised at compile time on (N, O); N <= 4 (lexifair by enumeration, whole-tile output staging).
 //
 // Why this mapping (measured on B200, C2 = 65 536 envs x 3 agents, profiles/):
-//   * env-tile (fm_tile.cu) spreads fine-grained work items over the warps of a CTA through shared
-//     memory: 19.2 M warp instructions per step, 30 % of them in the gather-style output emission,
-//     issue slots 53 % busy, 38 us per step (49 % of the HBM roofline).
+//   * group-per-env (fm_kernels.cu, G lanes per env, runtime N): 35 M warp instructions per step,
+//     issue bound, 55 us / step (34 % of the HBM roofline).
+//   * env-tile (round-1 experiment, removed): fine-grained work items spread over the warps of a CTA
+//     through shared memory; 19.2 M warp instructions, 30 % of them in a gather-style output
+//     emission, 38 us / step (49 %).
 //   * here the compute phases are register resident (no item descriptors, no smem round trips), the
 //     distances between static entities are computed once per episode and kept in the state block,
-//     and the outputs are written lane = env into a shared-memory image of the API layout (odd strides:
-//     conflict free), which the whole CTA then streams out with 16-byte st.global.cs -- the tile's
-//     slice of every output array is one contiguous range.
+//     and every output is written lane = env into a shared-memory IMAGE of the API layout (odd strides:
+//     conflict free) which the whole CTA then streams out with 16-byte st.global.cs -- the tile's
+//     slice of every output array is one contiguous, 16-byte aligned range.
 //
-// Shared memory per CTA: a small table block (new positions / velocities / goals of the tile, the
-// per-agent values the sequential-agent statistics need) and ONE staging region that is used twice:
-// first for adj + obs + reward + done of all 32*H envs, then for node_obs, 32 envs at a time.
+// Shared memory per CTA (41.8 KB at N = 3, O = 3 -> 5 CTAs / SM):
+//   tables   TP / TV / TG  positions, velocities, goals of the tile after the step ([row][32], lane = env)
+//   staging  one region used twice: (1) adj | obs | reward | done of the 32 envs, with the scratch rows
+//            the sequential-agent statistics exchange placed behind them; (2) node_obs of the 32 envs.
 //
-// Arithmetic is operation for operation that of step_kernel<G> / reset_kernel<G> (fm_kernels.cu);
-// tests/test_gpu_parity.py checks the mappings against each other bit for bit.
+// Arithmetic is operation for operation that of step_kernel<G> / reset_kernel<G> (fm_kernels.cu,
+// shared helpers in fm_device.cuh); tests/test_gpu_parity.py checks the mappings against each other
+// bit for bit.
 #include <utility>
 
 #include "fm_device.cuh"
@@ -30,38 +34,42 @@
 
 namespace fm {
 
-template <int N, int O, int H>
+template <int N, int O>
 struct AwLayout {
   static constexpr int E = 2 * N + O, M = N + O, SP = M * (M - 1) / 2;
-  static constexpr int WPH = N + 1, WARPS = H * WPH, THREADS = 32 * WARPS, ENVS = 32 * H, RW = ENVS;
+  static constexpr int WARPS = N + 1, THREADS = 32 * WARPS, ENVS = 32, RW = 32;
   // ---- global state rows ([row][Bp], fm_abi.cu fm_create order)
   static constexpr int PX = 0, PY = PX + N, VX = PY + N, VY = VX + N, PD = VY + N, DTG = PD + N, TREQ = DTG + N,
                        DLEFT = TREQ + N, MINT = DLEFT + N, GM = MINT + N, NAC = GM + N, NOC = NAC + N, LX = NOC + N,
                        LY = LX + N, OX = LY + N, OY = OX + O, DMEAN = OY + O, DSTD = DMEAN + 1, STEP = DSTD + 1,
                        EPIS = STEP + 1, SDIST = EPIS + 1;
-  // ---- shared tables, rows of RW floats
+  // ---- tables that live until the node_obs emission, rows of RW floats
   static constexpr int TP = 0,                 // [E][2] positions after the step (after the reset for envs that reset)
                        TV = TP + 2 * E,        // [N][2] velocities
                        TG = TV + 2 * N,        // [N][2] goal (assigned landmark) of agent i
-                       DTGO = TG + 2 * N,      // [N] world.dists_to_goal at step entry
+                       T_ROWS = TG + 2 * N;
+  static constexpr int OFF_STAGE = T_ROWS * RW;                       // multiple of 32 floats
+  static constexpr int OBS_W = N * OBS_F, NODE_W = N * E * NODE_F, ADJ_W = E * E;
+  // ---- staging, use 1: adj | obs | reward | done (bytes) | scratch
+  static constexpr int S_ADJ = 0, S_OBS = S_ADJ + ENVS * ADJ_W, S_REW = S_OBS + ENVS * OBS_W, S_DONE = S_REW + ENVS * N,
+                       SMALL_W = (S_DONE + (ENVS * N + 3) / 4 + 3) & ~3;
+  // scratch rows (dead before the node_obs emission), RW floats each, relative to staging + SMALL_W
+  static constexpr int DTGO = 0,               // [N] world.dists_to_goal at step entry
                        TREQO = DTGO + N,       // [N] world.times_required at step entry
                        NTREQ = TREQO + N,      // [N] ... after agent i's info_callback
                        OWN = NTREQ + N,        // [N] agent i's own reward
                        GMO = OWN + N,          // [N] goal_match at step entry (int bits)
                        RGM = GMO + N,          // [N] goal_match after a reset (int bits)
                        RMINT = RGM + N,        // [N] min_time after a reset
-                       F_ROWS = RMINT + N;
+                       F_ROWS = (RMINT + N + 1) & ~1;
   static constexpr int PD64 = 0, SETM = PD64 + N, SETS = SETM + N + 1, D_ROWS = SETS + N + 1;   // rows of RW doubles
-  static constexpr int OFF_D = (F_ROWS * RW + 1) & ~1;
-  static constexpr int OFF_STAGE = (OFF_D + 2 * D_ROWS * RW + 3) & ~3;
-  static constexpr int OBS_W = N * OBS_F, NODE_W = N * E * NODE_F, ADJ_W = E * E;
-  // staging, use 1 (all ENVS envs): adj | obs | reward | done (bytes)
-  static constexpr int S_ADJ = 0, S_OBS = S_ADJ + ENVS * ADJ_W, S_REW = S_OBS + ENVS * OBS_W, S_DONE = S_REW + ENVS * N,
-                       SMALL_W = S_DONE + (ENVS * N + 3) / 4;
-  // staging, use 2 (32 envs at a time): node_obs
-  static constexpr int STAGE_NODE = 32 * NODE_W;
-  static constexpr int STAGE_W = ((STAGE_NODE > SMALL_W ? STAGE_NODE : SMALL_W) + 3) & ~3;
+  static constexpr int OFF_SCR = SMALL_W, OFF_SCRD = OFF_SCR + F_ROWS * RW, SCR_END = OFF_SCRD + 2 * D_ROWS * RW;
+  // ---- staging, use 2: node_obs
+  static constexpr int STAGE_NODE = ENVS * NODE_W;
+  static constexpr int STAGE_W = ((STAGE_NODE > SCR_END ? STAGE_NODE : SCR_END) + 3) & ~3;
   static constexpr int WORDS = OFF_STAGE + STAGE_W;
+  static constexpr int FIT = (227 * 1024) / (WORDS * 4 + 1024);
+  static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT > 5 ? 5 : FIT);   // 5 x 128 threads -> up to 102 registers
 };
 
 // static pair (a, b), a < b < M, row-major  ->  SDIST row
@@ -74,30 +82,46 @@ __device__ __forceinline__ double dist64_d(double ax, double ay, float bx, float
   return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
-// CTA-wide copy of `nwords` floats from the staging image to global memory, 16-byte vectorised when
-// the destination is 16-byte aligned (it is whenever the slab starts 16-byte aligned: tiles are 32 envs).
-template <int THREADS>
+// CTA-wide copy of the staging image to global memory, 16-byte vectorised.  When the tile has all 32
+// envs the trip count is a compile-time constant and the loads of 8 iterations are in flight before
+// the first store; otherwise `nwords` is a runtime count.  The destination is 16-byte aligned whenever
+// the output array is (tiles are 32 envs).
+template <int THREADS, int WORDS_FULL>
 __device__ __forceinline__ void cta_copy_out(float* __restrict__ dst, const float* __restrict__ src, int nwords, int tid) {
   if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-    const int n4 = nwords >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll 4
-    for (int k = tid; k < n4; k += THREADS) __stcs(d4 + k, s4[k]);
-    for (int k = (n4 << 2) + tid; k < nwords; k += THREADS) __stcs(dst + k, src[k]);
+    if (nwords == WORDS_FULL) {
+      constexpr int N4 = WORDS_FULL >> 2;
+      constexpr int IT = (N4 + THREADS - 1) / THREADS;
+      constexpr int U = IT < 8 ? IT : 8;
+#pragma unroll 1
+      for (int k0 = 0; k0 < IT; k0 += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int k = (k0 + u) * THREADS + tid; if (k < N4) v[u] = s4[k]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int k = (k0 + u) * THREADS + tid; if (k < N4) __stcs(d4 + k, v[u]); }
+      }
+      for (int k = (N4 << 2) + tid; k < WORDS_FULL; k += THREADS) __stcs(dst + k, src[k]);
+    } else {
+      const int n4 = nwords >> 2;
+      for (int k = tid; k < n4; k += THREADS) __stcs(d4 + k, s4[k]);
+      for (int k = (n4 << 2) + tid; k < nwords; k += THREADS) __stcs(dst + k, src[k]);
+    }
   } else {
     for (int k = tid; k < nwords; k += THREADS) __stcs(dst + k, src[k]);
   }
 }
 
-// Randomised reset of env column `col` by one thread of the env warp (navigation_graph.py:212-262,
+// Randomised reset of env `lane` by one thread of the env warp (navigation_graph.py:212-262,
 // :264-570) + lexifair (:555-561).  Same Philox stream, draw order and acceptance rules as
-// reset_group<G> (fm_device.cuh).  New positions go to the TP table, goal_match / min_time to RGM /
-// RMINT; the distances between static entities are returned in sd[] (float).
-template <int N, int O, int H>
-__device__ __forceinline__ void aw_reset_env(const DevParams& p, long long genv, uint32_t episode, float* __restrict__ Tc,
-                                             float (&sd)[AwLayout<N, O, H>::SP > 0 ? AwLayout<N, O, H>::SP : 1]) {
-  using L = AwLayout<N, O, H>;
+// reset_group<G> (fm_device.cuh).  New positions go to the TP table, goal_match / min_time to the
+// RGM / RMINT scratch rows; the distances between static entities are returned in sd[] (float).
+template <int N, int O>
+__device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, uint32_t episode, float* __restrict__ Tc,
+                                          float* __restrict__ Sc, float* __restrict__ sd) {
+  using L = AwLayout<N, O>;
   constexpr int RW = L::RW, M = L::M;
   auto PXY = [&](int e, int c) -> float& { return Tc[(L::TP + 2 * e + c) * RW]; };
 #pragma unroll 1
@@ -133,18 +157,18 @@ __device__ __forceinline__ void aw_reset_env(const DevParams& p, long long genv,
   for (int i = 0; i < N; ++i) {
     const float ax = PXY(i, 0), ay = PXY(i, 1);
     if (p.has_max_speed) {                 // min_time with the PREVIOUS goal_match (:545-547, :719-728)
-      const int og = __float_as_int(Tc[(L::GMO + i) * RW]);
-      Tc[(L::RMINT + i) * RW] = (float)(dist64(ax, ay, PXY(N + og, 0), PXY(N + og, 1)) / p.max_speed);
+      const int og = __float_as_int(Sc[(L::GMO + i) * RW]);
+      Sc[(L::RMINT + i) * RW] = (float)(dist64(ax, ay, PXY(N + og, 0), PXY(N + og, 1)) / p.max_speed);
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) cost[i * N + j] = dist64(ax, ay, PXY(N + j, 0), PXY(N + j, 1));   // cdist (:555)
   }
   lexifair_small<N>(cost, gm);
 #pragma unroll
-  for (int i = 0; i < N; ++i) Tc[(L::RGM + i) * RW] = __int_as_float(gm[i]);
-#pragma unroll
+  for (int i = 0; i < N; ++i) Sc[(L::RGM + i) * RW] = __int_as_float(gm[i]);
+#pragma unroll 1
   for (int a = 0; a < M; ++a)
-#pragma unroll
+#pragma unroll 1
     for (int b = a + 1; b < M; ++b)
       sd[aw_spair(a, b, M)] = (float)dist64(PXY(N + a, 0), PXY(N + a, 1), PXY(N + b, 0), PXY(N + b, 1));
 }
@@ -152,24 +176,24 @@ __device__ __forceinline__ void aw_reset_env(const DevParams& p, long long genv,
 // =============================================================================================
 //   MODE 0: fused env step (MultiAgentGraphEnv.step, environment.py:816-877, + graphworker auto-reset,
 //           env_wrappers.py:859-865).   MODE 1: masked reset + observe (environment.py:882-898).
-template <int N, int O, int H, int MODE>
-__global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __grid_constant__ DevParams p) {
-  using L = AwLayout<N, O, H>;
+template <int N, int O, int MODE>
+__global__ void __launch_bounds__(AwLayout<N, O>::THREADS, AwLayout<N, O>::MIN_CTAS)
+aw_kernel(const __grid_constant__ DevParams p) {
+  using L = AwLayout<N, O>;
   constexpr int E = L::E, M = L::M, RW = L::RW, SP = L::SP;
-  constexpr int SPA = SP > 0 ? SP : 1;
   extern __shared__ __align__(16) float smem[];
   float* ST = smem + L::OFF_STAGE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int h = warp / L::WPH, role = warp - h * L::WPH;   // role < N: agent `role`;  role == N: env warp
-  const int col = h * 32 + lane;
-  const int env0 = blockIdx.x * L::ENVS;
-  const int nenv = min(L::ENVS, p.B - env0);
-  const int env = env0 + col;                    // < Bp: the state block is padded to a multiple of 64 envs
-  const bool venv = col < nenv;
+  const int tid = threadIdx.x, lane = tid & 31, role = tid >> 5;   // role < N: agent `role`;  role == N: env warp
+  const int env0 = blockIdx.x * 32;
+  const int nenv = min(32, p.B - env0);
+  const int env = env0 + lane;                   // < Bp: the state block is padded to a multiple of 64 envs
+  const bool venv = lane < nenv;
   const size_t Bp = (size_t)p.Bp;
   float* gs = p.px + env;                        // state row r of this env: gs[r * Bp]
-  float* Tc = smem + col;                        // table row r of this env: Tc[r * RW]
-  double* Dc = reinterpret_cast<double*>(smem + L::OFF_D) + col;
+  float* Tc = smem + lane;                       // table row r of this env: Tc[r * RW]
+  float* Sc = ST + L::OFF_SCR + lane;            // scratch row r: Sc[r * RW]
+  double* Dc = reinterpret_cast<double*>(ST + L::OFF_SCRD) + lane;
+  float* adj = ST + L::S_ADJ + lane * L::ADJ_W;  // this env's adj image
   const long long genv = p.env_offset + env;
   const bool is_agent = role < N;
   const int i = role;
@@ -177,27 +201,75 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
   // ---- registers of thread (env, agent i) ------------------------------------------------------
   float px = 0.f, py = 0.f, vx = 0.f, vy = 0.f, pd = 0.f, dtg = 0.f, treq = 0.f, dleft = 0.f, fobs = 0.f;
   int gm = 0, nac = 0, noc = 0;
-  float d[E];                                    // row i of the distance matrix (float), d[i] = 0
   unsigned collbits = 0, reachbits = 0;          // bit e: float64 d(i, e) < collision distance / < goal threshold
-  float own_rew = 0.f;
-  // ---- registers of the env warp ---------------------------------------------------------------
-  float sd[SPA];                                 // distances between static entities
-  int step = 0, epis = 0;
+  float dgoal_f = 0.f, own_rew = 0.f, rew_out = 0.f;
+  // ---- env warp / common ---------------------------------------------------------------------------
+  int step = 0, epis = 0, nstep = 0;
   bool do_reset = false, done = false;
-  int nstep = 0;
 
-  // Row i of the distance matrix at the positions in TP (core.py:204-228) + predicate bits.
+  // Row (and column) i of the distance matrix at the positions in TP (core.py:204-228), written straight
+  // into the adj image, + the predicate bits and the distance to the assigned goal.
   auto agent_distances = [&]() {
     const double ax = (double)px, ay = (double)py;
     collbits = 0; reachbits = 0;
-#pragma unroll
+    const int eg = N + gm;
+#pragma unroll 3
     for (int e = 0; e < E; ++e) {
       const double dd = dist64_d(ax, ay, Tc[(L::TP + 2 * e) * RW], Tc[(L::TP + 2 * e + 1) * RW]);
       const bool self = (e == i);
-      d[e] = self ? 0.0f : (float)dd;
+      const float df = self ? 0.0f : (float)dd;
+      adj[i * E + e] = df;
+      if (e >= N) adj[e * E + i] = df;
       collbits |= (!self && dd < p.dcoll) ? (1u << e) : 0u;
       reachbits |= (dd < p.min_dist_thresh) ? (1u << e) : 0u;
+      dgoal_f = (e == eg) ? df : dgoal_f;
     }
+  };
+  // Landmark/obstacle block of the adj image from the cached static distances (env warp).
+  auto static_block = [&](const float* sd) {
+#pragma unroll
+    for (int x = 0; x < M; ++x) {
+      adj[(N + x) * E + (N + x)] = 0.0f;
+#pragma unroll
+      for (int y = x + 1; y < M; ++y) {
+        const float v = sd[aw_spair(x, y, M)];
+        adj[(N + x) * E + (N + y)] = v;
+        adj[(N + y) * E + (N + x)] = v;
+      }
+    }
+  };
+  // Static entities: state block -> TP table and adj image (env warp).
+  auto load_static = [&](float* sd) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      Tc[(L::TP + 2 * (N + j)) * RW] = __ldcg(gs + (size_t)(L::LX + j) * Bp);
+      Tc[(L::TP + 2 * (N + j) + 1) * RW] = __ldcg(gs + (size_t)(L::LY + j) * Bp);
+    }
+#pragma unroll
+    for (int k = 0; k < O; ++k) {
+      Tc[(L::TP + 2 * (2 * N + k)) * RW] = __ldcg(gs + (size_t)(L::OX + k) * Bp);
+      Tc[(L::TP + 2 * (2 * N + k) + 1) * RW] = __ldcg(gs + (size_t)(L::OY + k) * Bp);
+    }
+#pragma unroll
+    for (int q = 0; q < SP; ++q) sd[q] = __ldcg(gs + (size_t)(L::SDIST + q) * Bp);
+  };
+  // Reset of this env by its env-warp thread: new placement -> tables, scratch and the state block.
+  auto reset_static = [&](float* sd) {
+    aw_reset_env<N, O>(p, genv, (uint32_t)epis, Tc, Sc, sd);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];
+      gs[(size_t)(L::LY + j) * Bp] = Tc[(L::TP + 2 * (N + j) + 1) * RW];
+    }
+#pragma unroll
+    for (int k = 0; k < O; ++k) {
+      gs[(size_t)(L::OX + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k)) * RW];
+      gs[(size_t)(L::OY + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k) + 1) * RW];
+    }
+#pragma unroll
+    for (int q = 0; q < SP; ++q) gs[(size_t)(L::SDIST + q) * Bp] = sd[q];
+    gs[(size_t)L::EPIS * Bp] = __int_as_float(epis + 1);
+    static_block(sd);
   };
 
   if (MODE == 0) {
@@ -238,42 +310,23 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
       // a pair (j, i), j < i, contributes -f(j, i) = f computed from agent i's side (IEEE sign symmetry).
       double Fx = (double)ux, Fy = (double)uy;     // mass(1.0) * u + noise(0.0)
 #pragma unroll
-      for (int q = 0; q < N + O; ++q) {
-        if (q != i) {
-          const float dx = px - qx[q], dy = py - qy[q];
-          const float dist = sqrtf(dx * dx + dy * dy);
-          const float pen = softplusf(-(dist - p.dist_min) / p.contact_margin) * p.contact_margin;
-          const float tx = p.contact_force * dx / dist * pen;
-          const float ty = p.contact_force * dy / dist * pen;
-          Fx = (double)tx + Fx; Fy = (double)ty + Fy;
-        }
-      }
-      // integrate_state (core.py:338-356), float64; state rounded to fp32
-      double v64x, v64y, sx, sy;
+      for (int q = 0; q < N + O; ++q)
+        if (q != i) contact_force(p, px, py, qx[q], qy[q], Fx, Fy);
+      double v64x, v64y, sx, sy;                   // integrate_state (core.py:338-356)
       integrate64(p, vx, vy, Fx, Fy, pd, v64x, v64y, sx, sy, pd64);
       px = (float)__dadd_rn((double)px, sx); py = (float)__dadd_rn((double)py, sy);
       vx = (float)v64x; vy = (float)v64y; pd = (float)pd64;
       Tc[(L::TP + 2 * i) * RW] = px; Tc[(L::TP + 2 * i + 1) * RW] = py;
       Tc[(L::TV + 2 * i) * RW] = vx; Tc[(L::TV + 2 * i + 1) * RW] = vy;
-      Tc[(L::DTGO + i) * RW] = dtg; Tc[(L::TREQO + i) * RW] = treq;
-      Tc[(L::GMO + i) * RW] = __int_as_float(gm);
+      Sc[(L::DTGO + i) * RW] = dtg; Sc[(L::TREQO + i) * RW] = treq;
+      Sc[(L::GMO + i) * RW] = __int_as_float(gm);
       Dc[(L::PD64 + i) * RW] = pd64;
     } else {
-      // ---- env warp: static entities -> TP, cached static distances, step ------------------------
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        Tc[(L::TP + 2 * (N + j)) * RW] = __ldcg(gs + (size_t)(L::LX + j) * Bp);
-        Tc[(L::TP + 2 * (N + j) + 1) * RW] = __ldcg(gs + (size_t)(L::LY + j) * Bp);
-      }
-#pragma unroll
-      for (int k = 0; k < O; ++k) {
-        Tc[(L::TP + 2 * (2 * N + k)) * RW] = __ldcg(gs + (size_t)(L::OX + k) * Bp);
-        Tc[(L::TP + 2 * (2 * N + k) + 1) * RW] = __ldcg(gs + (size_t)(L::OY + k) * Bp);
-      }
-#pragma unroll
-      for (int q = 0; q < SP; ++q) sd[q] = __ldcg(gs + (size_t)(L::SDIST + q) * Bp);
+      float sd[SP > 0 ? SP : 1];
+      load_static(sd);
       step = __float_as_int(__ldcg(gs + (size_t)L::STEP * Bp));
       epis = __float_as_int(__ldcg(gs + (size_t)L::EPIS * Bp));
+      static_block(sd);
     }
     __syncthreads();                              // #1: new agent positions, static positions (env warp) visible
     nstep = step + 1;                              // environment.py:819, :823
@@ -281,61 +334,43 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
     do_reset = venv && done && (p.auto_reset != 0);
     if (is_agent) {
       // ---- P2: distances, statistic sets, observation scalar, reward, latches ---------------------
-      const float gx = Tc[(L::TP + 2 * (N + gm)) * RW], gy = Tc[(L::TP + 2 * (N + gm) + 1) * RW];
-      Tc[(L::TG + 2 * i) * RW] = gx; Tc[(L::TG + 2 * i + 1) * RW] = gy;
+      Tc[(L::TG + 2 * i) * RW] = Tc[(L::TP + 2 * (N + gm)) * RW];
+      Tc[(L::TG + 2 * i + 1) * RW] = Tc[(L::TP + 2 * (N + gm) + 1) * RW];
       agent_distances();
       // world.dists_to_goal as left by the previous agent's info_callback: set k over
       // [new_0..new_{k-1}, prev_k..] (navigation_graph.py:587-598, :617-618).  Agent i >= 1 needs set i;
       // agent 0 reads last step's value from the state and computes set N (the value after this step).
       const int kset = (i == 0) ? N : i;
-      double pj[N], dj[N];
-      bool lat[N];
+      const bool first = dtg == -1.0f;             // first step of the episode: statistics of the new travelled distances
+      double v[N];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        pj[j] = Dc[(L::PD64 + j) * RW];
-        dj[j] = (double)Tc[(L::DTGO + j) * RW];
-        lat[j] = Tc[(L::TREQO + j) * RW] != -1.0f;
+        const double pj = Dc[(L::PD64 + j) * RW];
+        const double dj = (double)Sc[(L::DTGO + j) * RW];
+        const bool lat = Sc[(L::TREQO + j) * RW] != -1.0f;
+        v[j] = (j < kset && !lat) ? pj : dj;
       }
       double mk, sk;
-      {
-        double v[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) v[j] = (j < kset && !lat[j]) ? pj[j] : dj[j];
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) s += v[j];
-        mk = s / N;
-        double q = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) { const double dd = v[j] - mk; q = sq_acc(q, dd); }
-        sk = sqrt(q / N);
-      }
+      mean_std<N>(v, mk, sk);
       Dc[(L::SETM + kset) * RW] = mk; Dc[(L::SETS + kset) * RW] = sk;
       double fparam;                               // navigation_graph.py:764-769 / :849-853
-      if (dtg == -1.0f) {                          // first step of the episode: mean / std of the new travelled distances
-        double s = 0.0;
+      if (first) {
+        double w[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) s += pj[j];
-        const double m0 = s / N;
-        double q = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) { const double dd = pj[j] - m0; q = sq_acc(q, dd); }
-        fparam = m0 / (sqrt(q / N) + 0.0001);
+        for (int j = 0; j < N; ++j) w[j] = Dc[(L::PD64 + j) * RW];
+        double m0, s0;
+        mean_std<N>(w, m0, s0);
+        fparam = m0 / (s0 + 0.0001);
       } else if (i == 0) {
         fparam = (double)dmean0 / ((double)dstd0 + 0.0001);
       } else {
         fparam = mk / (sk + 0.0001);
       }
-      float dgoal_f = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; ++j) dgoal_f = (gm == j) ? d[N + j] : dgoal_f;
       const bool reached = ((reachbits >> (N + gm)) & 1u) != 0;      // dgoal < min_dist_thresh (float64 compare)
       const int ncoll = __popc(collbits & ((1u << N) - 1u));
       const bool ocoll = (collbits >> (2 * N)) != 0;
       const bool latched = treq != -1.0f;
-      const double dtg_new = latched ? (double)dtg : pd64;
       const double treq_new = (!latched && reached) ? (double)nstep * p.dt : (double)treq;   // :588
-      const float dleft_new = latched ? dleft : dgoal_f;
       float rw = reached ? p.goal_rew : -dgoal_f;  // navigation_graph.py:760-824
       rw -= p.coll_rew * (float)ncoll;
       if (ocoll) rw -= p.coll_rew;
@@ -349,64 +384,58 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
       noc += ocoll ? 1 : 0;                        // :602-603
       own_rew = rw;
       fobs = (float)fparam;
-      dtg = (float)dtg_new;
-      dleft = dleft_new;
-      Tc[(L::OWN + i) * RW] = rw;
-      Tc[(L::NTREQ + i) * RW] = (float)treq_new;   // `treq` keeps the old value for the info pass
+      dtg = latched ? dtg : pd;                    // pd == (float)pd64
+      dleft = latched ? dleft : dgoal_f;
+      Sc[(L::OWN + i) * RW] = rw;
+      Sc[(L::NTREQ + i) * RW] = (float)treq_new;   // `treq` keeps the old value for the info pass
       if (i == 0 && venv) {                        // world.dist_traveled_mean / stddev after the last info_callback
         gs[(size_t)L::DMEAN * Bp] = (float)mk;
         gs[(size_t)L::DSTD * Bp] = (float)sk;
       }
     }
     const bool want_info = venv && (p.o_info != nullptr || p.stats != nullptr) && (done || p.info_every_step);
-    double* stats_row = p.stats ? p.stats + ((size_t)blockIdx.x * H + h) * (15 * N + 2) : nullptr;
+    double* stats_row = p.stats ? p.stats + (size_t)blockIdx.x * (15 * N + 2) : nullptr;
     const bool any_done = __syncthreads_or(venv && done) != 0;   // #2: OWN / NTREQ / SETM / SETS / TG visible
     const bool any_reset = any_done && (p.auto_reset != 0);
     const bool any_info = (p.o_info != nullptr || p.stats != nullptr) && (any_done || p.info_every_step);
 
     // ---- collaborative sum, episode statistics, info rows -------------------------------------------
-    float rew_out = own_rew;
+    rew_out = own_rew;
     if (is_agent) {
       if (p.collaborative) {                       // environment.py:866-870
         float tot = 0.f;
 #pragma unroll
-        for (int j = 0; j < N; ++j) tot += Tc[(L::OWN + j) * RW];
+        for (int j = 0; j < N; ++j) tot += Sc[(L::OWN + j) * RW];
         rew_out = tot;
       }
       if (stats_row) {
-        double v = venv ? (double)rew_out : 0.0;
+        double s = venv ? (double)rew_out : 0.0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-        if (lane == 0) stats_row[i] += v;
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+        if (lane == 0) atomicAdd(stats_row + i, s);                  // one add per (row, step): order is fixed
       }
       if (any_info) {
         // world-level time statistics right after agent i's own info_callback: new values of agents
         // j <= i, previous values of j > i (navigation_graph.py:620-621)
         double tacc = 0.0;                         // entity.state.time += dt per step (core.py:355)
+#pragma unroll 1
         for (int k = 0; k < nstep; ++k) tacc += p.dt;
         double tv[N];                              // times_required as float64: a latch of THIS step is nstep * dt unrounded
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          const float told = Tc[(L::TREQO + j) * RW];
-          const bool fresh = j <= i && told == -1.0f && Tc[(L::NTREQ + j) * RW] != -1.0f;
+          const float told = Sc[(L::TREQO + j) * RW];
+          const bool fresh = j <= i && told == -1.0f && Sc[(L::NTREQ + j) * RW] != -1.0f;
           tv[j] = fresh ? (double)nstep * p.dt : (double)told;
         }
-        double st = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) st += tv[j];
-        const double mt = st / N;
-        double qt = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) { const double dd = tv[j] - mt; qt = sq_acc(qt, dd); }
-        const double stv = sqrt(qt / N);
+        double mt, stv;
+        mean_std<N>(tv, mt, stv);
         const double md = Dc[(L::SETM + i + 1) * RW], sdv = Dc[(L::SETS + i + 1) * RW];
-        const float mint = __ldcg(gs + (size_t)(L::MINT + i) * Bp);
         float info[INFO_F];
-        info[0] = own_rew; info[1] = dleft; info[2] = Tc[(L::NTREQ + i) * RW];
+        info[0] = own_rew; info[1] = dleft; info[2] = Sc[(L::NTREQ + i) * RW];
         info[3] = (float)nac; info[4] = (float)noc;
         info[5] = (float)md; info[6] = (float)sdv; info[7] = (float)(md / (sdv + 0.0001));
         info[8] = dtg; info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv;
-        info[12] = (float)(mt / (stv + 0.0001)); info[13] = mint;
+        info[12] = (float)(mt / (stv + 0.0001)); info[13] = __ldcg(gs + (size_t)(L::MINT + i) * Bp);
         if (want_info && p.o_info) {
           float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
 #pragma unroll
@@ -415,54 +444,37 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
         if (stats_row && __any_sync(FULL, venv && done)) {
 #pragma unroll
           for (int k = 0; k < INFO_F; ++k) {
-            double v = (venv && done) ? (double)info[k] : 0.0;
+            double s = (venv && done) ? (double)info[k] : 0.0;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-            if (lane == 0) stats_row[N + i * INFO_F + k] += v;
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+            if (lane == 0) atomicAdd(stats_row + N + i * INFO_F + k, s);
           }
         }
       }
-      treq = Tc[(L::NTREQ + i) * RW];
+      treq = Sc[(L::NTREQ + i) * RW];
     } else if (stats_row) {
       const unsigned termb = __ballot_sync(FULL, venv && done);
-      const unsigned validb = __ballot_sync(FULL, venv);
-      if (lane == 0) { stats_row[15 * N] += (double)__popc(termb); stats_row[15 * N + 1] += (double)__popc(validb); }
+      if (lane == 0) { atomicAdd(stats_row + 15 * N, (double)__popc(termb)); atomicAdd(stats_row + 15 * N + 1, (double)nenv); }
     }
 
     // ---- auto-reset (env_wrappers.py:859-865): obs / node_obs / adj come from the new episode, reward /
     // done / info stay terminal ------------------------------------------------------------------------
     if (any_reset) {
-      if (!is_agent) {
-        if (do_reset) {
-          aw_reset_env<N, O, H>(p, genv, (uint32_t)epis, Tc, sd);
-#pragma unroll
-          for (int j = 0; j < N; ++j) {
-            gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];
-            gs[(size_t)(L::LY + j) * Bp] = Tc[(L::TP + 2 * (N + j) + 1) * RW];
-          }
-#pragma unroll
-          for (int k = 0; k < O; ++k) {
-            gs[(size_t)(L::OX + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k)) * RW];
-            gs[(size_t)(L::OY + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k) + 1) * RW];
-          }
-#pragma unroll
-          for (int q = 0; q < SP; ++q) gs[(size_t)(L::SDIST + q) * Bp] = sd[q];
-          gs[(size_t)L::EPIS * Bp] = __int_as_float(epis + 1);
-        }
+      if (!is_agent && do_reset) {
+        float sd[SP > 0 ? SP : 1];
+        reset_static(sd);
       }
       __syncthreads();                            // new positions / goal_match of the envs that reset
       if (is_agent) {
         if (do_reset) {
           px = Tc[(L::TP + 2 * i) * RW]; py = Tc[(L::TP + 2 * i + 1) * RW];
           vx = 0.f; vy = 0.f; pd = 0.f; dtg = -1.f; treq = -1.f; dleft = -1.f; nac = 0; noc = 0; fobs = 0.f;
-          gm = __float_as_int(Tc[(L::RGM + i) * RW]);
+          gm = __float_as_int(Sc[(L::RGM + i) * RW]);
           Tc[(L::TV + 2 * i) * RW] = 0.f; Tc[(L::TV + 2 * i + 1) * RW] = 0.f;
           Tc[(L::TG + 2 * i) * RW] = Tc[(L::TP + 2 * (N + gm)) * RW];
           Tc[(L::TG + 2 * i + 1) * RW] = Tc[(L::TP + 2 * (N + gm) + 1) * RW];
-          if (venv) {
-            gs[(size_t)(L::GM + i) * Bp] = __int_as_float(gm);
-            if (p.has_max_speed) gs[(size_t)(L::MINT + i) * Bp] = Tc[(L::RMINT + i) * RW];
-          }
+          gs[(size_t)(L::GM + i) * Bp] = __int_as_float(gm);
+          if (p.has_max_speed) gs[(size_t)(L::MINT + i) * Bp] = Sc[(L::RMINT + i) * RW];
         }
         agent_distances();
       }
@@ -480,78 +492,49 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
         gs[(size_t)L::STEP * Bp] = __int_as_float(do_reset ? 0 : nstep);
       }
     }
-    // ---- small outputs -> staging image (lane = env: odd strides, conflict free) ----------------------
     if (is_agent) {
-      ST[L::S_REW + col * N + i] = rew_out;
-      reinterpret_cast<uint8_t*>(ST + L::S_DONE)[col * N + i] = done ? 1 : 0;
+      ST[L::S_REW + lane * N + i] = rew_out;
+      reinterpret_cast<uint8_t*>(ST + L::S_DONE)[lane * N + i] = done ? 1 : 0;
     }
   } else {
     // =========================================================================================
     // MODE 1: reset() / observe
     do_reset = venv && (p.reset_mask ? (p.reset_mask[env] != 0) : true);
-    float dmean0 = 0.f, dstd0 = 0.f;
-    float pdj[N];
     if (is_agent) {
       const float* gi = gs + (size_t)i * Bp;
       px = __ldcg(gi + (size_t)L::PX * Bp); py = __ldcg(gi + (size_t)L::PY * Bp);
       vx = __ldcg(gi + (size_t)L::VX * Bp); vy = __ldcg(gi + (size_t)L::VY * Bp);
       dtg = __ldcg(gi + (size_t)L::DTG * Bp);
       gm = __float_as_int(__ldcg(gi + (size_t)L::GM * Bp));
+      double w[N];
 #pragma unroll
-      for (int j = 0; j < N; ++j) pdj[j] = __ldcg(gs + (size_t)(L::PD + j) * Bp);
-      dmean0 = __ldcg(gs + (size_t)L::DMEAN * Bp); dstd0 = __ldcg(gs + (size_t)L::DSTD * Bp);
+      for (int j = 0; j < N; ++j) w[j] = (double)__ldcg(gs + (size_t)(L::PD + j) * Bp);
+      const float dmean0 = __ldcg(gs + (size_t)L::DMEAN * Bp), dstd0 = __ldcg(gs + (size_t)L::DSTD * Bp);
       Tc[(L::TP + 2 * i) * RW] = px; Tc[(L::TP + 2 * i + 1) * RW] = py;
       Tc[(L::TV + 2 * i) * RW] = vx; Tc[(L::TV + 2 * i + 1) * RW] = vy;
-      Tc[(L::GMO + i) * RW] = __int_as_float(gm);
+      Sc[(L::GMO + i) * RW] = __int_as_float(gm);
       // observation() on the current state (navigation_graph.py:826-857, :849-853)
-      double sum_p = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; ++j) sum_p += (double)pdj[j];
-      const double mean_p = sum_p / N;
-      double q_p = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; ++j) { const double dd = (double)pdj[j] - mean_p; q_p = sq_acc(q_p, dd); }
-      const double std_p = sqrt(q_p / N);
+      double mean_p, std_p;
+      mean_std<N>(w, mean_p, std_p);
       fobs = (float)((dtg == -1.0f) ? mean_p / (std_p + 0.0001) : (double)dmean0 / ((double)dstd0 + 0.0001));
     } else {
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        Tc[(L::TP + 2 * (N + j)) * RW] = __ldcg(gs + (size_t)(L::LX + j) * Bp);
-        Tc[(L::TP + 2 * (N + j) + 1) * RW] = __ldcg(gs + (size_t)(L::LY + j) * Bp);
-      }
-#pragma unroll
-      for (int k = 0; k < O; ++k) {
-        Tc[(L::TP + 2 * (2 * N + k)) * RW] = __ldcg(gs + (size_t)(L::OX + k) * Bp);
-        Tc[(L::TP + 2 * (2 * N + k) + 1) * RW] = __ldcg(gs + (size_t)(L::OY + k) * Bp);
-      }
-#pragma unroll
-      for (int q = 0; q < SP; ++q) sd[q] = __ldcg(gs + (size_t)(L::SDIST + q) * Bp);
+      float sd[SP > 0 ? SP : 1];
+      load_static(sd);
       epis = __float_as_int(__ldcg(gs + (size_t)L::EPIS * Bp));
+      static_block(sd);
     }
-    const bool any_reset = __syncthreads_or(do_reset) != 0;
+    const bool any_reset = __syncthreads_or(do_reset) != 0;      // static positions / GMO visible
     if (any_reset) {
       if (!is_agent && do_reset) {
-        aw_reset_env<N, O, H>(p, genv, (uint32_t)epis, Tc, sd);
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];
-          gs[(size_t)(L::LY + j) * Bp] = Tc[(L::TP + 2 * (N + j) + 1) * RW];
-        }
-#pragma unroll
-        for (int k = 0; k < O; ++k) {
-          gs[(size_t)(L::OX + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k)) * RW];
-          gs[(size_t)(L::OY + k) * Bp] = Tc[(L::TP + 2 * (2 * N + k) + 1) * RW];
-        }
-#pragma unroll
-        for (int q = 0; q < SP; ++q) gs[(size_t)(L::SDIST + q) * Bp] = sd[q];
-        gs[(size_t)L::EPIS * Bp] = __int_as_float(epis + 1);
+        float sd[SP > 0 ? SP : 1];
+        reset_static(sd);
         gs[(size_t)L::STEP * Bp] = __int_as_float(0);
       }
       __syncthreads();
       if (is_agent && do_reset) {
         px = Tc[(L::TP + 2 * i) * RW]; py = Tc[(L::TP + 2 * i + 1) * RW];
         vx = 0.f; vy = 0.f; fobs = 0.f;           // mean(p_dist = 0) / (std + 1e-4)
-        gm = __float_as_int(Tc[(L::RGM + i) * RW]);
+        gm = __float_as_int(Sc[(L::RGM + i) * RW]);
         Tc[(L::TV + 2 * i) * RW] = 0.f; Tc[(L::TV + 2 * i + 1) * RW] = 0.f;
         float* gi = gs + (size_t)i * Bp;
         gi[(size_t)L::PX * Bp] = px; gi[(size_t)L::PY * Bp] = py;
@@ -559,10 +542,8 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
         gi[(size_t)L::DTG * Bp] = -1.f; gi[(size_t)L::TREQ * Bp] = -1.f; gi[(size_t)L::DLEFT * Bp] = -1.f;
         gi[(size_t)L::NAC * Bp] = __int_as_float(0); gi[(size_t)L::NOC * Bp] = __int_as_float(0);
         gi[(size_t)L::GM * Bp] = __int_as_float(gm);
-        if (p.has_max_speed) gi[(size_t)L::MINT * Bp] = Tc[(L::RMINT + i) * RW];
+        if (p.has_max_speed) gi[(size_t)L::MINT * Bp] = Sc[(L::RMINT + i) * RW];
       }
-    } else {
-      __syncthreads();                            // static positions (env warp) visible
     }
     if (is_agent) {
       Tc[(L::TG + 2 * i) * RW] = Tc[(L::TP + 2 * (N + gm)) * RW];
@@ -572,34 +553,17 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
   }
 
   // =============================================================================================
-  // Emission, use 1 of the staging region: adj | obs (| reward | done already placed in MODE 0).
+  // Emission, use 1 of the staging region: adj (already in place) | obs | reward | done.
   if (is_agent) {
-    float* a = ST + L::S_ADJ + col * L::ADJ_W;
-#pragma unroll
-    for (int e = 0; e < E; ++e) a[i * E + e] = d[e];             // row i
-#pragma unroll
-    for (int e = N; e < E; ++e) a[e * E + i] = d[e];             // column i below the agent block
-    float* o = ST + L::S_OBS + col * L::OBS_W + i * OBS_F;       // navigation_graph.py:826-857
+    float* o = ST + L::S_OBS + lane * L::OBS_W + i * OBS_F;       // navigation_graph.py:826-857
     const float gx = Tc[(L::TG + 2 * i) * RW], gy = Tc[(L::TG + 2 * i + 1) * RW];
     o[0] = vx; o[1] = vy; o[2] = px; o[3] = py; o[4] = gx - px; o[5] = gy - py; o[6] = fobs;
-  } else {
-    float* a = ST + L::S_ADJ + col * L::ADJ_W;
-#pragma unroll
-    for (int x = 0; x < M; ++x) {
-      a[(N + x) * E + (N + x)] = 0.0f;
-#pragma unroll
-      for (int y = x + 1; y < M; ++y) {
-        const float v = sd[aw_spair(x, y, M)];
-        a[(N + x) * E + (N + y)] = v;
-        a[(N + y) * E + (N + x)] = v;
-      }
-    }
   }
-  __syncthreads();                                // staging image of the small outputs + TP / TV / TG complete
-  if (p.o_adj) cta_copy_out<L::THREADS>(p.o_adj + (size_t)env0 * L::ADJ_W, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
-  if (p.o_obs) cta_copy_out<L::THREADS>(p.o_obs + (size_t)env0 * L::OBS_W, ST + L::S_OBS, nenv * L::OBS_W, tid);
+  __syncthreads();                                // #3: image of the small outputs + TP / TV / TG complete
+  if (p.o_adj) cta_copy_out<L::THREADS, 32 * L::ADJ_W>(p.o_adj + (size_t)env0 * L::ADJ_W, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
+  if (p.o_obs) cta_copy_out<L::THREADS, 32 * L::OBS_W>(p.o_obs + (size_t)env0 * L::OBS_W, ST + L::S_OBS, nenv * L::OBS_W, tid);
   if (MODE == 0) {
-    if (p.o_rew) cta_copy_out<L::THREADS>(p.o_rew + (size_t)env0 * N, ST + L::S_REW, nenv * N, tid);
+    if (p.o_rew) cta_copy_out<L::THREADS, 32 * N>(p.o_rew + (size_t)env0 * N, ST + L::S_REW, nenv * N, tid);
     if (p.o_done) {
       const uint8_t* sdone = reinterpret_cast<const uint8_t*>(ST + L::S_DONE);
       uint8_t* gdone = p.o_done + (size_t)env0 * N;
@@ -607,38 +571,30 @@ __global__ void __launch_bounds__(AwLayout<N, O, H>::THREADS) aw_kernel(const __
     }
   }
   if (!p.o_node) return;
-  // ---- use 2: node_obs, 32 envs at a time (navigation_graph.py:1079-1124, relative features): for ego
-  // agent a and entity e  [v_e - v_a (2), p_e - p_a (2), goal_e - p_a (2), p_e - p_a (2), p_e - p_a (2), type]
-  // with goal_e = assigned landmark for agents and = p_e otherwise, v_e = 0 for non-agents.  Work items
-  // (a, e) are spread over all warps; lane = env, so table reads and staging writes are conflict free.
-#pragma unroll 1
-  for (int hh = 0; hh < H; ++hh) {
-    __syncthreads();                              // previous use of the staging region fully read
-    if (hh * 32 < nenv) {
-      const float* Th = smem + hh * 32 + lane;
-      float* sn = ST + lane * L::NODE_W;
-#pragma unroll 1
-      for (int it = warp; it < N * E; it += L::WARPS) {
-        const int a = it / E, e = it - a * E;
-        const float pax = Th[(L::TP + 2 * a) * RW], pay = Th[(L::TP + 2 * a + 1) * RW];
-        const float vax = Th[(L::TV + 2 * a) * RW], vay = Th[(L::TV + 2 * a + 1) * RW];
-        const float pex = Th[(L::TP + 2 * e) * RW], pey = Th[(L::TP + 2 * e + 1) * RW];
-        const float rpx = pex - pax, rpy = pey - pay;
-        float vex = 0.f, vey = 0.f, rgx = rpx, rgy = rpy, type = (e < 2 * N) ? 1.0f : 2.0f;
-        if (e < N) {
-          vex = Th[(L::TV + 2 * e) * RW]; vey = Th[(L::TV + 2 * e + 1) * RW];
-          rgx = Th[(L::TG + 2 * e) * RW] - pax; rgy = Th[(L::TG + 2 * e + 1) * RW] - pay;
-          type = 0.0f;
-        }
-        float* o = sn + it * NODE_F;
-        o[0] = vex - vax; o[1] = vey - vay; o[2] = rpx; o[3] = rpy; o[4] = rgx; o[5] = rgy;
-        o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy; o[10] = type;
+  __syncthreads();                                // #4: staging region fully read
+  // ---- use 2: node_obs (navigation_graph.py:1079-1124, relative features): for ego agent i and entity e
+  //   [v_e - v_i (2), p_e - p_i (2), goal_e - p_i (2), p_e - p_i (2), p_e - p_i (2), type]
+  // with goal_e = assigned landmark for agents and = p_e otherwise, v_e = 0 for non-agents.  Agent warp i
+  // writes ego i's E rows from its registers and the tables; lane = env, stride NODE_W (odd): conflict free.
+  if (is_agent) {
+    float* o = ST + lane * L::NODE_W + i * E * NODE_F;
+    const float nvx = 0.f - vx, nvy = 0.f - vy;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float rpx = Tc[(L::TP + 2 * e) * RW] - px, rpy = Tc[(L::TP + 2 * e + 1) * RW] - py;
+      float rvx = nvx, rvy = nvy, rgx = rpx, rgy = rpy;
+      if (e < N) {
+        rvx = Tc[(L::TV + 2 * e) * RW] - vx; rvy = Tc[(L::TV + 2 * e + 1) * RW] - vy;
+        rgx = Tc[(L::TG + 2 * e) * RW] - px; rgy = Tc[(L::TG + 2 * e + 1) * RW] - py;
       }
+      o[0] = rvx; o[1] = rvy; o[2] = rpx; o[3] = rpy; o[4] = rgx; o[5] = rgy;
+      o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy;
+      o[10] = (e < N) ? 0.0f : ((e < 2 * N) ? 1.0f : 2.0f);
+      o += NODE_F;
     }
-    __syncthreads();
-    const int ne = min(32, nenv - hh * 32);
-    if (ne > 0) cta_copy_out<L::THREADS>(p.o_node + (size_t)(env0 + hh * 32) * L::NODE_W, ST, ne * L::NODE_W, tid);
   }
+  __syncthreads();                                // #5
+  cta_copy_out<L::THREADS, 32 * L::NODE_W>(p.o_node + (size_t)env0 * L::NODE_W, ST, nenv * L::NODE_W, tid);
 }
 
 // =============================================================================================
@@ -658,23 +614,23 @@ __global__ void aw_static_kernel(const DevParams p, float* __restrict__ sdist) {
 
 // =============================================================================================
 // Host side.
-template <int N, int O, int H>
-static cudaError_t aw_launch_noh(const DevParams& p, cudaStream_t st, bool is_reset) {
-  using L = AwLayout<N, O, H>;
-  const int blocks = (p.B + L::ENVS - 1) / L::ENVS;
+template <int N, int O>
+static cudaError_t aw_launch_no(const DevParams& p, cudaStream_t st, bool is_reset) {
+  using L = AwLayout<N, O>;
+  const int blocks = (p.B + 31) / 32;
   const size_t smem = (size_t)L::WORDS * sizeof(float);
-  if (is_reset) aw_kernel<N, O, H, 1><<<blocks, L::THREADS, smem, st>>>(p);
-  else aw_kernel<N, O, H, 0><<<blocks, L::THREADS, smem, st>>>(p);
+  if (is_reset) aw_kernel<N, O, 1><<<blocks, L::THREADS, smem, st>>>(p);
+  else aw_kernel<N, O, 0><<<blocks, L::THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
-template <int N, int O, int H>
-static cudaError_t aw_prepare_noh() {
-  using L = AwLayout<N, O, H>;
+template <int N, int O>
+static cudaError_t aw_prepare_no() {
+  using L = AwLayout<N, O>;
   const int smem = L::WORDS * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(aw_kernel<N, O, H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(aw_kernel<N, O, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(aw_kernel<N, O, H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return cudaFuncSetAttribute(aw_kernel<N, O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 // The (N, O) pairs compiled for this mapping.  Everything else runs the group-per-env kernels.
@@ -687,19 +643,17 @@ bool aw_supported(int N, int O) {
   return false;
 }
 
-int aw_halves(const DevParams& p) { return p.aw_halves == 2 ? 2 : 1; }
-int aw_stats_rows(int B, int halves) { return ((B + 32 * halves - 1) / (32 * halves)) * halves; }
+int aw_stats_rows(int B) { return (B + 31) / 32; }
 
 cudaError_t aw_prepare(const DevParams& p) {
-#define X(n, o) if (p.N == n && p.O == o) return aw_halves(p) == 2 ? aw_prepare_noh<n, o, 2>() : aw_prepare_noh<n, o, 1>();
+#define X(n, o) if (p.N == n && p.O == o) return aw_prepare_no<n, o>();
   FM_AW_CASES(X)
 #undef X
   return cudaErrorInvalidValue;
 }
 
 cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset) {
-#define X(n, o) \
-  if (p.N == n && p.O == o) return aw_halves(p) == 2 ? aw_launch_noh<n, o, 2>(p, st, is_reset) : aw_launch_noh<n, o, 1>(p, st, is_reset);
+#define X(n, o) if (p.N == n && p.O == o) return aw_launch_no<n, o>(p, st, is_reset);
   FM_AW_CASES(X)
 #undef X
   return cudaErrorInvalidValue;

@@ -543,8 +543,7 @@ int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); 
 int num_warps(int B, int N) { const int epw = 32 / group_size(N); return (B + epw - 1) / epw; }
 
 cudaError_t prepare_kernels(const DevParams& p) {
-  if (p.mapping == 2) return aw_prepare(p);
-  if (p.mapping == 1) return tile_prepare(p);
+  if (p.mapping == 1) return aw_prepare(p);
   switch (group_size(p.N)) {
     case 4: return prepare_g<4>(p);
     case 8: return prepare_g<8>(p);
@@ -554,8 +553,7 @@ cudaError_t prepare_kernels(const DevParams& p) {
 }
 
 cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset) {
-  if (p.mapping == 2) return aw_launch(p, st, is_reset);
-  if (p.mapping == 1) return tile_launch(p, st, is_reset);
+  if (p.mapping == 1) return aw_launch(p, st, is_reset);
   switch (group_size(p.N)) {
     case 4: return launch_step_g<4>(p, st, is_reset);
     case 8: return launch_step_g<8>(p, st, is_reset);

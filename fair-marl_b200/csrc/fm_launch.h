@@ -13,15 +13,9 @@ typedef FmState HostState;   // API-layout device pointers
 
 int group_size(int n);
 int num_warps(int B, int N);
-// env-tile mapping (fm_tile.cu): compiled for a fixed list of small (N, O)
-bool tile_supported(int N, int O);
-int tile_num_ctas(int B);
-cudaError_t tile_prepare(const DevParams& p);
-void tile_build_luts(int N, int O, std::vector<uint32_t>& obs, std::vector<uint32_t>& node, std::vector<uint32_t>& adj);
-cudaError_t tile_launch(const DevParams& p, cudaStream_t st, bool is_reset);
 // agent-warp mapping (fm_aw.cu): compiled for a fixed list of small (N, O)
 bool aw_supported(int N, int O);
-int aw_stats_rows(int B, int halves);
+int aw_stats_rows(int B);
 cudaError_t aw_prepare(const DevParams& p);
 cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset);
 cudaError_t launch_static_dists(const DevParams& p, cudaStream_t st);   // recompute p.sdist from the static positions

@@ -98,8 +98,7 @@ class B200GraphVecEnv:
             fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
             fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative),
             auto_reset=int(cfg.auto_reset), info_every_step=int(cfg.info_every_step),
-            mapping={"auto": 0, "group": 1, "tile": 2, "aw": 3}[cfg.mapping],
-            aw_halves=int(cfg.aw_halves))
+            mapping={"auto": 0, "group": 1, "aw": 2}[cfg.mapping])
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_create")
 
@@ -383,8 +382,8 @@ class B200GraphVecEnv:
 
     @property
     def mapping(self) -> str:
-        """Kernel mapping in use: 'group' (group-per-env), 'tile' (env-tile) or 'aw' (agent-warp)."""
-        return {1: "group", 2: "tile", 3: "aw"}[int(self.lib.fm_mapping(self._h))]
+        """Kernel mapping in use: 'group' (group-per-env) or 'aw' (agent-warp)."""
+        return {1: "group", 2: "aw"}[int(self.lib.fm_mapping(self._h))]
 
     @property
     def kernel_launches(self) -> int:

@@ -65,8 +65,8 @@ typedef struct FmConfig {
   int32_t auto_reset;      /* env_wrappers.py:859-865 (graphworker) */
   int32_t info_every_step; /* 0: info rows are written on terminal steps only */
   int32_t mapping;         /* kernel mapping: 0 auto (agent-warp when compiled for (N, O), else group-per-env),
-                              1 group-per-env, 2 env-tile, 3 agent-warp.  Results are identical. */
-  int32_t aw_halves;       /* agent-warp only: 32-env halves per CTA, 1 (0 = default) or 2 */
+                              1 group-per-env, 2 agent-warp.  Results are identical. */
+  int32_t reserved_;
 } FmConfig;
 
 /* Per-step outputs, API layout (what GraphSubprocVecEnv.step_wait stacks, env_wrappers.py:988-996). */
@@ -183,7 +183,7 @@ int fm_stats_read(FmHandle* h, double* out_dev, int32_t clear, void* stream);
 
 /* Introspection. */
 int fm_num_entities(const FmHandle* h);
-int fm_mapping(const FmHandle* h);                        /* 1 group-per-env, 2 env-tile, 3 agent-warp */
+int fm_mapping(const FmHandle* h);                        /* 1 group-per-env, 2 agent-warp */
 int64_t fm_algorithmic_bytes_per_step(const FmHandle* h); /* W * 4 * B */
 int fm_kernel_launches(const FmHandle* h, int64_t* out);   /* kernels launched by this handle so far */
 int fm_abi_version(void);

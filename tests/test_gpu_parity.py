@@ -246,15 +246,14 @@ def test_shards_equal_one_batch_bitwise():
     [s.close() for s in shards]
 
 
-@pytest.mark.parametrize("other", ["aw", "aw2", "tile"])
+@pytest.mark.parametrize("other", ["aw"])
 @pytest.mark.parametrize("N,O,B", [(3, 3, 1000), (4, 2, 333), (2, 0, 65), (1, 1, 40), (3, 0, 129)])
 def test_mappings_bitwise_equal(N, O, B, other):
-    """The agent-warp kernels (fm_aw.cu; 'aw2' = two 32-env halves per CTA), the env-tile kernels
-    (fm_tile.cu) and the group-per-env kernels (fm_kernels.cu)
-    perform the same arithmetic: every output, the state and the statistics agree bit for bit over a
-    rollout with auto-resets, goal latches and info rows."""
+    """The agent-warp kernels (fm_aw.cu) and the group-per-env kernels (fm_kernels.cu) perform the same
+    arithmetic: every output, the state and the statistics agree bit for bit over a rollout with
+    auto-resets, goal latches and info rows."""
     cfg = NavConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=7)
-    osim = dict(mapping="aw", aw_halves=2) if other == "aw2" else dict(mapping=other)
+    osim = dict(mapping=other)
     e_t = _env(cfg, B, seed=5, env_offset=11, sim=dict(info_every_step=True, **osim))
     e_g = _env(cfg, B, seed=5, env_offset=11, sim=dict(mapping="group", info_every_step=True))
     assert e_t.mapping == osim["mapping"] and e_g.mapping == "group"
@@ -287,7 +286,7 @@ def torch_mask(B):
     return torch.as_tensor((np.arange(B) % 3 == 1).astype(np.uint8), device="cuda")
 
 
-@pytest.mark.parametrize("mapping", ["tile", "aw"])
+@pytest.mark.parametrize("mapping", ["aw"])
 def test_mapping_unavailable_raises(mapping):
     import fair_marl_b200 as fm
     with pytest.raises(fm._lib.FairMarlError, match="not compiled"):

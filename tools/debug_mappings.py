@@ -8,7 +8,7 @@ N, O, B = 3, 3, 1000
 a_map = sys.argv[1] if len(sys.argv) > 1 else "aw"
 halves = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 kw = dict(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=7, info_every_step=True)
-e1 = fm.B200GraphVecEnv(fm.SimConfig(mapping=a_map, aw_halves=halves, **kw), num_envs=B, seed=5, env_offset=11)
+e1 = fm.B200GraphVecEnv(fm.SimConfig(mapping=a_map, **kw), num_envs=B, seed=5, env_offset=11)
 e2 = fm.B200GraphVecEnv(fm.SimConfig(mapping="group", **kw), num_envs=B, seed=5, env_offset=11)
 e1.reset_tensor(); e2.reset_tensor()
 rng = np.random.default_rng(2)
