@@ -1,5 +1,6 @@
 // C ABI of libfairmarl.so (include/fairmarl.h): handle management, argument checking, launches.
 // No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -111,6 +112,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.dt = 0.1;
   p.damping_keep = 1 - 0.25;
   p.zeroshift = cfg->zeroshift;
+  p.zeroshift_f = (float)cfg->zeroshift;
   p.fair_rew_d = cfg->fair_rew;
   p.goal_rew = (float)cfg->goal_rew;
   p.coll_rew = (float)cfg->collision_rew;
@@ -122,6 +124,16 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.contact_force = 3e2f;                                    // core.py:153-160
   p.contact_margin = 2e-2f;
   p.dist_min = (float)(size + size);
+  p.inv_margin = 1.0f / p.contact_margin;
+  p.cf_margin = p.contact_force * p.contact_margin;
+  {                                                          // largest double whose sqrt is <= max_speed
+    double t = cfg->max_speed * cfg->max_speed;
+    if (p.has_max_speed) {
+      while (sqrt(t) > cfg->max_speed) t = nextafter(t, 0.0);
+      while (sqrt(nextafter(t, INFINITY)) <= cfg->max_speed) t = nextafter(t, INFINITY);
+    }
+    p.speed2_max = t;
+  }
   p.episode_length = cfg->episode_length;
   p.fairness_reward = cfg->fairness_reward;
   p.collaborative = cfg->collaborative;

@@ -93,16 +93,19 @@ __device__ __forceinline__ void cta_copy_out(float* __restrict__ dst, const floa
     float4* d4 = reinterpret_cast<float4*>(dst);
     if (nwords == WORDS_FULL) {
       constexpr int N4 = WORDS_FULL >> 2;
-      constexpr int IT = (N4 + THREADS - 1) / THREADS;
-      constexpr int U = IT < 8 ? IT : 8;
-#pragma unroll 1
-      for (int k0 = 0; k0 < IT; k0 += U) {
+      constexpr int FI = N4 / THREADS;               // iterations in which every thread moves 16 bytes
+      constexpr int U = 6;
+      const float4* sp = s4 + tid;
+      float4* dp = d4 + tid;
+#pragma unroll
+      for (int k0 = 0; k0 < FI; k0 += U) {           // compile-time trip count: immediate offsets, no predicates
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int k = (k0 + u) * THREADS + tid; if (k < N4) v[u] = s4[k]; }
+        for (int u = 0; u < U; ++u) if (k0 + u < FI) v[u] = sp[(k0 + u) * THREADS];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int k = (k0 + u) * THREADS + tid; if (k < N4) __stcs(d4 + k, v[u]); }
+        for (int u = 0; u < U; ++u) if (k0 + u < FI) __stcs(dp + (k0 + u) * THREADS, v[u]);
       }
+      if (tid < N4 - FI * THREADS) __stcs(dp + FI * THREADS, sp[FI * THREADS]);
       for (int k = (N4 << 2) + tid; k < WORDS_FULL; k += THREADS) __stcs(dst + k, src[k]);
     } else {
       const int n4 = nwords >> 2;
@@ -213,14 +216,15 @@ aw_kernel(const __grid_constant__ DevParams p) {
     const double ax = (double)px, ay = (double)py;
     collbits = 0; reachbits = 0;
     const int eg = N + gm;
-#pragma unroll 3
-    for (int e = 0; e < E; ++e) {
+    adj[i * E + i] = 0.0f;
+#pragma unroll 4
+    for (int k = 1; k < E; ++k) {                  // the E - 1 other entities, ascending from i + 1 (wrapping)
+      const int e = (i + k >= E) ? i + k - E : i + k;
       const double dd = dist64_d(ax, ay, Tc[(L::TP + 2 * e) * RW], Tc[(L::TP + 2 * e + 1) * RW]);
-      const bool self = (e == i);
-      const float df = self ? 0.0f : (float)dd;
+      const float df = (float)dd;
       adj[i * E + e] = df;
       if (e >= N) adj[e * E + i] = df;
-      collbits |= (!self && dd < p.dcoll) ? (1u << e) : 0u;
+      collbits |= (dd < p.dcoll) ? (1u << e) : 0u;
       reachbits |= (dd < p.min_dist_thresh) ? (1u << e) : 0u;
       dgoal_f = (e == eg) ? df : dgoal_f;
     }
@@ -308,10 +312,11 @@ aw_kernel(const __grid_constant__ DevParams p) {
       }
       // ---- P1: forces on agent i (core.py:277-316, :370-404), partners in ascending entity index;
       // a pair (j, i), j < i, contributes -f(j, i) = f computed from agent i's side (IEEE sign symmetry).
-      double Fx = (double)ux, Fy = (double)uy;     // mass(1.0) * u + noise(0.0)
+      float cfx = 0.f, cfy = 0.f;
 #pragma unroll
       for (int q = 0; q < N + O; ++q)
-        if (q != i) contact_force(p, px, py, qx[q], qy[q], Fx, Fy);
+        if (q != i) contact_force(p, px, py, qx[q], qy[q], cfx, cfy);
+      const double Fx = __dadd_rn((double)ux, (double)cfx), Fy = __dadd_rn((double)uy, (double)cfy);   // mass(1.0) * u + contact
       double v64x, v64y, sx, sy;                   // integrate_state (core.py:338-356)
       integrate64(p, vx, vy, Fx, Fy, pd, v64x, v64y, sx, sy, pd64);
       px = (float)__dadd_rn((double)px, sx); py = (float)__dadd_rn((double)py, sy);
@@ -350,21 +355,23 @@ aw_kernel(const __grid_constant__ DevParams p) {
         const bool lat = Sc[(L::TREQO + j) * RW] != -1.0f;
         v[j] = (j < kset && !lat) ? pj : dj;
       }
-      double mk, sk;
+      double mk;
+      float sk;
       mean_std<N>(v, mk, sk);
-      Dc[(L::SETM + kset) * RW] = mk; Dc[(L::SETS + kset) * RW] = sk;
-      double fparam;                               // navigation_graph.py:764-769 / :849-853
+      Dc[(L::SETM + kset) * RW] = mk; Dc[(L::SETS + kset) * RW] = (double)sk;
+      float fparam;                                // navigation_graph.py:764-769 / :849-853
       if (first) {
         double w[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) w[j] = Dc[(L::PD64 + j) * RW];
-        double m0, s0;
+        double m0;
+        float s0;
         mean_std<N>(w, m0, s0);
-        fparam = m0 / (s0 + 0.0001);
+        fparam = ratio_eps((float)m0, s0);
       } else if (i == 0) {
-        fparam = (double)dmean0 / ((double)dstd0 + 0.0001);
+        fparam = ratio_eps(dmean0, dstd0);
       } else {
-        fparam = mk / (sk + 0.0001);
+        fparam = ratio_eps((float)mk, sk);
       }
       const bool reached = ((reachbits >> (N + gm)) & 1u) != 0;      // dgoal < min_dist_thresh (float64 compare)
       const int ncoll = __popc(collbits & ((1u << N) - 1u));
@@ -375,7 +382,7 @@ aw_kernel(const __grid_constant__ DevParams p) {
       rw -= p.coll_rew * (float)ncoll;
       if (ocoll) rw -= p.coll_rew;
       if (p.fairness_reward) {
-        float fair = p.fair_rew * tanhf((float)(fparam - p.zeroshift));
+        float fair = p.fair_rew * tanhf(fparam - p.zeroshift_f);
         if (fair < -2.0f) fair = -2.0f;
         rw += fair;
       }
@@ -383,14 +390,14 @@ aw_kernel(const __grid_constant__ DevParams p) {
       nac += ncoll;                                // :604-613
       noc += ocoll ? 1 : 0;                        // :602-603
       own_rew = rw;
-      fobs = (float)fparam;
+      fobs = fparam;
       dtg = latched ? dtg : pd;                    // pd == (float)pd64
       dleft = latched ? dleft : dgoal_f;
       Sc[(L::OWN + i) * RW] = rw;
       Sc[(L::NTREQ + i) * RW] = (float)treq_new;   // `treq` keeps the old value for the info pass
       if (i == 0 && venv) {                        // world.dist_traveled_mean / stddev after the last info_callback
         gs[(size_t)L::DMEAN * Bp] = (float)mk;
-        gs[(size_t)L::DSTD * Bp] = (float)sk;
+        gs[(size_t)L::DSTD * Bp] = sk;
       }
     }
     const bool want_info = venv && (p.o_info != nullptr || p.stats != nullptr) && (done || p.info_every_step);
@@ -427,15 +434,17 @@ aw_kernel(const __grid_constant__ DevParams p) {
           const bool fresh = j <= i && told == -1.0f && Sc[(L::NTREQ + j) * RW] != -1.0f;
           tv[j] = fresh ? (double)nstep * p.dt : (double)told;
         }
-        double mt, stv;
+        double mt;
+        float stv;
         mean_std<N>(tv, mt, stv);
-        const double md = Dc[(L::SETM + i + 1) * RW], sdv = Dc[(L::SETS + i + 1) * RW];
+        const double md = Dc[(L::SETM + i + 1) * RW];
+        const float sdv = (float)Dc[(L::SETS + i + 1) * RW];
         float info[INFO_F];
         info[0] = own_rew; info[1] = dleft; info[2] = Sc[(L::NTREQ + i) * RW];
         info[3] = (float)nac; info[4] = (float)noc;
-        info[5] = (float)md; info[6] = (float)sdv; info[7] = (float)(md / (sdv + 0.0001));
-        info[8] = dtg; info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv;
-        info[12] = (float)(mt / (stv + 0.0001)); info[13] = __ldcg(gs + (size_t)(L::MINT + i) * Bp);
+        info[5] = (float)md; info[6] = sdv; info[7] = ratio_eps((float)md, sdv);
+        info[8] = dtg; info[9] = (float)tacc; info[10] = (float)mt; info[11] = stv;
+        info[12] = ratio_eps((float)mt, stv); info[13] = __ldcg(gs + (size_t)(L::MINT + i) * Bp);
         if (want_info && p.o_info) {
           float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
 #pragma unroll
@@ -514,9 +523,10 @@ aw_kernel(const __grid_constant__ DevParams p) {
       Tc[(L::TV + 2 * i) * RW] = vx; Tc[(L::TV + 2 * i + 1) * RW] = vy;
       Sc[(L::GMO + i) * RW] = __int_as_float(gm);
       // observation() on the current state (navigation_graph.py:826-857, :849-853)
-      double mean_p, std_p;
+      double mean_p;
+      float std_p;
       mean_std<N>(w, mean_p, std_p);
-      fobs = (float)((dtg == -1.0f) ? mean_p / (std_p + 0.0001) : (double)dmean0 / ((double)dstd0 + 0.0001));
+      fobs = (dtg == -1.0f) ? ratio_eps((float)mean_p, std_p) : ratio_eps(dmean0, dstd0);
     } else {
       float sd[SP > 0 ? SP : 1];
       load_static(sd);

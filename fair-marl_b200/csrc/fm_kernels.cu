@@ -77,17 +77,18 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
 
   // ---- World.step: forces (core.py:277-316, :370-404) from the positions at step entry --------
   // (== the reference's end-of-previous-step distance cache), partners in ascending entity index.
-  double Fx = (double)ux, Fy = (double)uy;       // mass(1.0) * u + noise(0.0), core.py:291-293
+  float cfx = 0.f, cfy = 0.f;
   for (int j = 0; j < N; ++j) {
     const float qx = __shfl_sync(FULL, px, gl + j), qy = __shfl_sync(FULL, py, gl + j);
-    if (act && j != i) contact_force(p, px, py, qx, qy, Fx, Fy);
+    if (act && j != i) contact_force(p, px, py, qx, qy, cfx, cfy);
   }
   if (act) {
     for (int k = 0; k < O; ++k) {
       const float* o = ent + (2 * N + k) * ENT_STRIDE;
-      contact_force(p, px, py, o[0], o[1], Fx, Fy);
+      contact_force(p, px, py, o[0], o[1], cfx, cfy);
     }
   }
+  const double Fx = __dadd_rn((double)ux, (double)cfx), Fy = __dadd_rn((double)uy, (double)cfy);   // mass(1.0) * u + contact
   // ---- integrate_state (core.py:338-356), float64 so that p_dist keeps its low bits for the
   // ill-conditioned mean/std fairness ratio; state is stored rounded to fp32.
   double v64x, v64y, sx, sy, pd64;
@@ -125,29 +126,30 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
     const double pj = __shfl_sync(FULL, pd64, gl + j);
     const double aj = __shfl_sync(FULL, dtg_new, gl + j);
     const double bj = __shfl_sync(FULL, dtg_prev, gl + j);
-    sum_p += pj; sum_a += aj; sum_v += (j < i) ? aj : bj;
+    sum_p = __dadd_rn(sum_p, pj); sum_a = __dadd_rn(sum_a, aj); sum_v = __dadd_rn(sum_v, (j < i) ? aj : bj);
   }
-  const double mean_p = sum_p / N, mean_v = sum_v / N, mean_a = sum_a / N;
+  const double inv_n = 1.0 / N;
+  const double mean_p = __dmul_rn(sum_p, inv_n), mean_v = __dmul_rn(sum_v, inv_n), mean_a = __dmul_rn(sum_a, inv_n);
   double q_p = 0.0, q_v = 0.0, q_a = 0.0;
   for (int j = 0; j < N; ++j) {
     const double pj = __shfl_sync(FULL, pd64, gl + j);
     const double aj = __shfl_sync(FULL, dtg_new, gl + j);
     const double bj = __shfl_sync(FULL, dtg_prev, gl + j);
-    const double dp = pj - mean_p, da = aj - mean_a, dv = ((j < i) ? aj : bj) - mean_v;
+    const double dp = __dsub_rn(pj, mean_p), da = __dsub_rn(aj, mean_a), dv = __dsub_rn((j < i) ? aj : bj, mean_v);
     q_p = sq_acc(q_p, dp); q_a = sq_acc(q_a, da); q_v = sq_acc(q_v, dv);
   }
-  const double std_p = sqrt(q_p / N), std_v = sqrt(q_v / N), std_a = sqrt(q_a / N);
-  double fparam;                                 // navigation_graph.py:764-769 / :849-853
-  if (dtg == -1.0f) fparam = mean_p / (std_p + 0.0001);
-  else if (i == 0) fparam = (double)dmean / ((double)dstd + 0.0001);
-  else fparam = mean_v / (std_v + 0.0001);
+  const float std_p = std_from_q(q_p, inv_n), std_v = std_from_q(q_v, inv_n), std_a = std_from_q(q_a, inv_n);
+  float fparam;                                  // navigation_graph.py:764-769 / :849-853
+  if (dtg == -1.0f) fparam = ratio_eps((float)mean_p, std_p);
+  else if (i == 0) fparam = ratio_eps(dmean, dstd);
+  else fparam = ratio_eps((float)mean_v, std_v);
 
   // reward (navigation_graph.py:760-824)
   float rew = reached ? p.goal_rew : -(float)dgoal;
   rew -= p.coll_rew * (float)ncoll;
   if (ocoll) rew -= p.coll_rew;
   if (p.fairness_reward) {
-    float fair = p.fair_rew * tanhf((float)(fparam - p.zeroshift));
+    float fair = p.fair_rew * tanhf(fparam - p.zeroshift_f);
     if (fair < -2.0f) fair = -2.0f;
     rew += fair;
   }
@@ -172,22 +174,22 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
     for (int j = 0; j < N; ++j) {
       const double aj = __shfl_sync(FULL, dtg_new, gl + j), bj = __shfl_sync(FULL, dtg_prev, gl + j);
       const double tj = __shfl_sync(FULL, treq_new, gl + j), uj = __shfl_sync(FULL, treq_prev, gl + j);
-      sd += (j <= i) ? aj : bj; st += (j <= i) ? tj : uj;
+      sd = __dadd_rn(sd, (j <= i) ? aj : bj); st = __dadd_rn(st, (j <= i) ? tj : uj);
     }
-    const double md = sd / N, mt = st / N;
+    const double md = __dmul_rn(sd, inv_n), mt = __dmul_rn(st, inv_n);
     double qd = 0.0, qt = 0.0;
     for (int j = 0; j < N; ++j) {
       const double aj = __shfl_sync(FULL, dtg_new, gl + j), bj = __shfl_sync(FULL, dtg_prev, gl + j);
       const double tj = __shfl_sync(FULL, treq_new, gl + j), uj = __shfl_sync(FULL, treq_prev, gl + j);
-      const double dd = ((j <= i) ? aj : bj) - md, dtt = ((j <= i) ? tj : uj) - mt;
+      const double dd = __dsub_rn((j <= i) ? aj : bj, md), dtt = __dsub_rn((j <= i) ? tj : uj, mt);
       qd = sq_acc(qd, dd); qt = sq_acc(qt, dtt);
     }
-    const double sdv = sqrt(qd / N), stv = sqrt(qt / N);
+    const float sdv = std_from_q(qd, inv_n), stv = std_from_q(qt, inv_n);
     double tacc = 0.0;                           // entity.state.time += dt per step (core.py:355)
     for (int k = 0; k < nstep; ++k) tacc += p.dt;
     info[0] = own_rew; info[1] = dleft_new; info[2] = (float)treq_new; info[3] = (float)nac; info[4] = (float)noc;
-    info[5] = (float)md; info[6] = (float)sdv; info[7] = (float)(md / (sdv + 0.0001)); info[8] = (float)dtg_new;
-    info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv; info[12] = (float)(mt / (stv + 0.0001));
+    info[5] = (float)md; info[6] = sdv; info[7] = ratio_eps((float)md, sdv); info[8] = (float)dtg_new;
+    info[9] = (float)tacc; info[10] = (float)mt; info[11] = stv; info[12] = ratio_eps((float)mt, stv);
     info[13] = mint = act ? p.mintime[idx] : 0.f;
     if (act && want_info && p.o_info) {
       float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
@@ -321,12 +323,13 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   // observation() on the current state (navigation_graph.py:826-857)
   double sum_p = 0.0;
   const double pd64 = (double)pd;
-  for (int j = 0; j < N; ++j) sum_p += __shfl_sync(FULL, pd64, gl + j);
-  const double mean_p = sum_p / N;
+  for (int j = 0; j < N; ++j) sum_p = __dadd_rn(sum_p, __shfl_sync(FULL, pd64, gl + j));
+  const double inv_n = 1.0 / N;
+  const double mean_p = __dmul_rn(sum_p, inv_n);
   double q_p = 0.0;
-  for (int j = 0; j < N; ++j) { const double d = __shfl_sync(FULL, pd64, gl + j) - mean_p; q_p = sq_acc(q_p, d); }
-  const double std_p = sqrt(q_p / N);
-  const double fparam = (dtg == -1.0f) ? mean_p / (std_p + 0.0001) : (double)dmean / ((double)dstd + 0.0001);
+  for (int j = 0; j < N; ++j) { const double d = __dsub_rn(__shfl_sync(FULL, pd64, gl + j), mean_p); q_p = sq_acc(q_p, d); }
+  const float std_p = std_from_q(q_p, inv_n);
+  const float fparam = (dtg == -1.0f) ? ratio_eps((float)mean_p, std_p) : ratio_eps(dmean, dstd);
   double dgoal; int ncoll; bool ocoll;
   if (venv) distance_tile<G>(p, ent, adj, i, act, gm, dgoal, ncoll, ocoll);
   if (act) {
