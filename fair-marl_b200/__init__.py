@@ -12,9 +12,9 @@ from fair_marl_b200.build import build_library, library_path            # noqa: 
 from fair_marl_b200.config import SimConfig                             # noqa: F401
 from fair_marl_b200.spaces import Box, Discrete                         # noqa: F401
 from fair_marl_b200.vec_env import B200GraphVecEnv, make_train_env      # noqa: F401
-from fair_marl_b200.assign import lexifair_batched, solve_fair_assignment  # noqa: F401
+from fair_marl_b200.assign import lexifair_batched, pair_dist, solve_fair_assignment  # noqa: F401
 from fair_marl_b200.edges import process_adj                            # noqa: F401
 from fair_marl_b200.sharding import shard_range, EpisodeStats           # noqa: F401
 
 __all__ = ["B200GraphVecEnv", "make_train_env", "SimConfig", "Box", "Discrete", "solve_fair_assignment",
-           "lexifair_batched", "process_adj", "shard_range", "EpisodeStats", "build_library", "library_path"]
+           "lexifair_batched", "pair_dist", "process_adj", "shard_range", "EpisodeStats", "build_library", "library_path"]

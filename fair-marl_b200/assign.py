@@ -53,3 +53,22 @@ def solve_fair_assignment(costs):
     x[np.arange(n), match] = 1
     objs = np.sort(np.sum(costs * x, axis=1))[::-1]
     return x, objs
+
+
+def pair_dist(a, b, device: int = 0):
+    """float64 ``||a[k] - b[k]||`` for float32 points ``a``, ``b`` [num, 2] with the kernels' distance
+    primitive (``fm_pair_dist``): bit-identical to ``np.linalg.norm(a64 - b64, axis=1)`` evaluated as
+    sqrt(dx*dx + dy*dy) in float64 (core.py:204-228, navigation_graph.py:555)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+    as_numpy = isinstance(a, np.ndarray)
+    with torch.cuda.device(dev):
+        ta = torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
+        tb = torch.as_tensor(b, dtype=torch.float32, device=dev).contiguous()
+        if ta.shape != tb.shape or ta.dim() != 2 or ta.shape[1] != 2:
+            raise ValueError("a / b must both be [num, 2]")
+        out = torch.empty(ta.shape[0], dtype=torch.float64, device=dev)
+        _lib.check(lib.fm_pair_dist(device, ta.data_ptr(), tb.data_ptr(), int(ta.shape[0]), out.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream), "fm_pair_dist")
+    return out.cpu().numpy() if as_numpy else out

@@ -371,6 +371,15 @@ int fm_assign_positions(int device, const float* agent_pos, const float* goal_po
   return FM_OK;
 }
 
+int fm_pair_dist(int device, const float* a, const float* b, int64_t num, double* out, void* stream) {
+  if (!a || !b || !out) return fail(FM_ERR_INVALID_ARG, "fm_pair_dist: null argument");
+  if (num < 0) return fail(FM_ERR_INVALID_ARG, "fm_pair_dist: num < 0");
+  int rc = use_device(device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_pair_dist(a, b, (long long)num, out, (cudaStream_t)stream));
+  return FM_OK;
+}
+
 int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, double max_edge_dist, int32_t inclusive,
                  int32_t repeat, int64_t capacity, int64_t* graph_offsets, int64_t* edge_index, float* edge_attr,
                  int64_t* nnz_out, void* stream) {

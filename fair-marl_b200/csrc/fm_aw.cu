@@ -79,7 +79,7 @@ __host__ __device__ constexpr int aw_spair(int a, int b, int M) { return a * M -
 __device__ __forceinline__ double dist64_d(double ax, double ay, float bx, float by) {
   const double dx = __dsub_rn(ax, (double)bx);
   const double dy = __dsub_rn(ay, (double)by);
-  return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  return dsqrt_fast(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
 // CTA-wide copy of the staging image to global memory, 16-byte vectorised.  When the tile has all 32

@@ -617,6 +617,17 @@ cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr,
   return cudaGetLastError();
 }
 
+__global__ void pair_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, long long num, double* __restrict__ out) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < num) out[k] = dist64(a[2 * k], a[2 * k + 1], b[2 * k], b[2 * k + 1]);
+}
+
+cudaError_t launch_pair_dist(const float* a, const float* b, long long num, double* out, cudaStream_t st) {
+  if (num <= 0) return cudaSuccess;
+  pair_dist_kernel<<<(int)((num + 255) / 256), 256, 0, st>>>(a, b, num, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st) {
   stats_reduce_kernel<<<K, 256, 0, st>>>(partial, rows, K, out, clear);
   return cudaGetLastError();

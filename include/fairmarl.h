@@ -159,6 +159,11 @@ int fm_assign_costs(int device, const double* costs, int32_t num, int32_t n, int
 int fm_assign_positions(int device, const float* agent_pos, const float* goal_pos, int32_t num,
                         int32_t n, int32_t* out, void* stream);
 
+/* Float64 Euclidean distances of `num` pairs of float [.,2] points, out[k] = ||a[k] - b[k]||: the kernels'
+ * distance primitive (np.linalg.norm in World.calculate_distances, core.py:204-228; cdist at
+ * navigation_graph.py:555), exposed so that its bit-exactness against numpy can be tested directly. */
+int fm_pair_dist(int device, const float* a, const float* b, int64_t num, double* out, void* stream);
+
 /* Policy-side edge list, TransformerConvNet.process_adj (onpolicy/algorithms/utils/gnn_new.py:381-413)
  * on adj float [num_graphs, E, E]: mask (adj < max_edge_dist) & (adj > 0) (inclusive != 0: <=, the
  * env-side Scenario.update_graph rule, navigation_graph.py:1037-1056), edges in (b, i, j) order.

@@ -207,6 +207,27 @@ def test_assignment_reference_fixed_instance():
     np.testing.assert_allclose(objs, [1.843909, 1.664332, 1.439618], atol=1e-6)
 
 
+def test_pair_dist_bit_exact():
+    """The branch-free float64 square root behind every distance (dsqrt_fast, fm_device.cuh) is
+    correctly rounded: fm_pair_dist == numpy's float64 sqrt(dx*dx + dy*dy) bit for bit, over random
+    points, coincident points, tiny and large separations and exact squares."""
+    import fair_marl_b200 as fm
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    a = rng.uniform(-1.5, 1.5, (n, 2)).astype(np.float32)
+    b = rng.uniform(-1.5, 1.5, (n, 2)).astype(np.float32)
+    b[:1000] = a[:1000]                                                     # coincident -> 0
+    b[1000:3000] = a[1000:3000] + rng.uniform(-1e-6, 1e-6, (2000, 2)).astype(np.float32)
+    a[3000:4000] *= np.float32(1e-20); b[3000:4000] *= np.float32(1e-20)    # tiny magnitudes
+    a[4000:5000] *= np.float32(1e15); b[4000:5000] *= np.float32(1e15)      # large magnitudes
+    a[5000:6000] = 0; b[5000:6000, 0] = rng.integers(1, 2000, 1000); b[5000:6000, 1] = 0   # exact squares
+    a[6000:7000] = 0; b[6000:7000, 0] = 3 * rng.integers(1, 500, 1000); b[6000:7000, 1] = 4 * (b[6000:7000, 0] / 3)
+    dev = fm.pair_dist(a, b)
+    d = a.astype(np.float64) - b.astype(np.float64)
+    ref = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+    assert dev.dtype == np.float64 and np.array_equal(dev.view(np.uint64), ref.view(np.uint64))
+
+
 def test_onehot_and_index_actions_agree():
     import torch
     cfg = NavConfig()
