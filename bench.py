@@ -37,11 +37,33 @@ ENVS_PER_GPU = 65536
 METRIC = "agent-steps/sec, navigation_graph step+obs+reward"
 WORKLOAD = ("navigation_graph 3 agents / 3 goals / 3 obstacles, FA+FR reward, goal_rew=collision_rew=30, "
             "episode_length 25 with auto-reset + lexifair assignment, random actions")
+GOAL_REW = COLL_REW = 30.0
+FAIRNESS = True
+
+# BASELINE.json configs (the headline line is c2; the others are diagnostic runs: --config c1|c3|c4)
+CONFIGS = {
+    "c1": dict(agents=3, obstacles=3, envs=128, rew=5.0, fairness=False,
+               workload="navigation_graph 3 agents / 3 goals / 3 obstacles, FA (no fairness reward), 128 envs, random actions"),
+    "c2": dict(agents=3, obstacles=3, envs=65536, rew=30.0, fairness=True, workload=WORKLOAD),
+    "c3": dict(agents=7, obstacles=3, envs=262144, rew=5.0, fairness=True,
+               workload="navigation_graph 7 agents / 7 goals / 3 obstacles, FA+FR, 262144 envs, random actions"),
+    "c4": dict(agents=16, obstacles=3, envs=131072, rew=5.0, fairness=True,
+               workload="navigation_graph 16 agents / 16 goals / 3 obstacles, FA+FR, 131072 envs per GPU (1M over 8), random actions"),
+}
+
+
+def select_config(name: str, envs: int | None):
+    global N_AGENTS, N_OBST, ENVS_PER_GPU, WORKLOAD, GOAL_REW, COLL_REW, FAIRNESS
+    c = CONFIGS[name]
+    N_AGENTS, N_OBST, WORKLOAD = c["agents"], c["obstacles"], c["workload"]
+    GOAL_REW = COLL_REW = c["rew"]
+    FAIRNESS = c["fairness"]
+    ENVS_PER_GPU = envs if envs else c["envs"]
 
 
 def sim_kwargs():
-    return dict(num_agents=N_AGENTS, num_obstacles=N_OBST, goal_rew=30.0, collision_rew=30.0,
-                episode_length=EPISODE, fairness_reward=True)
+    return dict(num_agents=N_AGENTS, num_obstacles=N_OBST, goal_rew=GOAL_REW, collision_rew=COLL_REW,
+                episode_length=EPISODE, fairness_reward=FAIRNESS)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -116,7 +138,8 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """One host process: B envs of the numpy oracle, `steps` steps with auto-reset."""
-    seed, B, steps, warm = args
+    seed, B, steps, warm, config = args
+    select_config(config, None)
     import numpy as np
     from oracle.navgraph import NavConfig, NavGraphOracle
     cfg = NavConfig(**sim_kwargs())
@@ -132,14 +155,14 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_port_throughput(steps: int, warm: int, envs_per_proc: int = 2048):
+def cpu_port_throughput(steps: int, warm: int, envs_per_proc: int = 2048, config: str = "c2"):
     """agent-steps/s of the oracle port on all host cores (one process per core, env-sharded)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(r, envs_per_proc, steps, warm) for r in range(cores)])
+        times = pool.map(_cpu_worker, [(r, envs_per_proc, steps, warm, config) for r in range(cores)])
     wall = time.perf_counter() - t0
     worst = max(times)
     value = cores * envs_per_proc * N_AGENTS * steps / worst
@@ -153,7 +176,7 @@ def run_reference(args, rank: int, world: int):
         return
     steps = max(1, min(args.steps, 200))
     warm = max(1, min(args.warmup, 25))
-    value, cores, sample, ms = cpu_port_throughput(steps, warm)
+    value, cores, sample, ms = cpu_port_throughput(steps, warm, config=args.config)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -183,8 +206,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     B = args.envs
     K, W = args.steps, args.warmup
     cfg = fm.SimConfig(**sim_kwargs(), mapping=args.mapping)
-    env = fm.B200GraphVecEnv(cfg, num_envs=B, device=local_rank, seed=0, env_offset=rank * B, num_slots=EPISODE)
     E = cfg.num_entities
+    out_bytes = B * (N_AGENTS * 7 + N_AGENTS * E * 11 + E * E + N_AGENTS) * 4 + B * N_AGENTS
+    slots = max(2, min(EPISODE, int(12e9 // out_bytes)))        # ring > L2, bounded to ~12 GB of HBM
+    slab_gb = slots * out_bytes / 1e9
+    env = fm.B200GraphVecEnv(cfg, num_envs=B, device=local_rank, seed=0, env_offset=rank * B, num_slots=slots)
     stats = fm.EpisodeStats(N_AGENTS, device=dev)
 
     # synthetic random actions for one episode, resident in HBM before the timed region
@@ -238,7 +264,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env.algorithmic_bytes_per_step
     kernel_name = {"aw": f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)",
-                   "group": "fm::step_kernel<G> (group-per-env)"}[env.mapping]
+                   "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}> (group-per-env)"}[env.mapping]
     step_kernel_ms = elapsed_ms / K              # rank-max; one step kernel per step dominates the region
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
     traffic = None
@@ -280,7 +306,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_port_throughput(100, 5)
+        per_proc = 2048 if N_AGENTS <= 4 else (512 if N_AGENTS <= 8 else 128)
+        v, cores, sample, _ = cpu_port_throughput(100, 5, envs_per_proc=per_proc, config=args.config)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
@@ -290,7 +317,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": B, "envs_total": B * world, "agents": N_AGENTS,
                        "entities": E, "sharding": f"env-index x{world}" if world > 1 else "single GPU",
-                       "l2": "outputs cycle through a 25-slot slab ring (3.1 GB per GPU > 126 MB L2); the 15 MB SoA "
+                       "l2": f"outputs cycle through a {slots}-slot slab ring ({slab_gb:.1f} GB per GPU > 126 MB L2); the SoA "
                              "state is read+written every step",
                        "stats_allreduce": "per episode (25 steps), side stream" if world > 1 else "local reduce per episode"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -308,7 +335,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the config's)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (headline: c2)")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mapping", default="auto", choices=["auto", "group", "aw"], help="kernel mapping (diagnostic)")
@@ -316,6 +344,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    select_config(args.config, args.envs)
+    args.envs = ENVS_PER_GPU
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
