@@ -151,10 +151,10 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   }
   p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || fm::aw_supported(N, O)) ? 1 : 0);
   const int G = fm::group_size(N), EPW = 32 / G;
-  p.sm_cost = round4(2LL * EPW * N * N);
+  p.sm_cost = 0;                                   // the reset's cost matrix lives inside the adj tile
   p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
   p.sm_adj = round4((long long)EPW * E * E);
-  p.sm_stage = 32 * fm::NODE_F;
+  p.sm_stage = fm::STAGE_ROWS * fm::NODE_F;
   p.sm_obs = round4((long long)EPW * N * fm::OBS_F);
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_stage + p.sm_obs + p.sm_asg;
@@ -334,7 +334,7 @@ int fm_set_state(FmHandle* h, const FmState* st, void* stream) {
   if (rc) return rc;
   FM_CUDA(fm::launch_state_io(h->p, *st, 1, (cudaStream_t)stream));
   h->launches += 1;
-  if (h->p.mapping == 1 && (st->landmark_pos || st->obstacle_pos)) {      // cached static distances follow the positions
+  if (st->landmark_pos || st->obstacle_pos) {                              // cached static distances follow the positions
     FM_CUDA(fm::launch_static_dists(h->p, (cudaStream_t)stream));
     h->launches += 1;
   }

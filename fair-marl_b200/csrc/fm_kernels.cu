@@ -16,6 +16,9 @@ namespace fm {
 
 constexpr int THREADS = 128;   // 4 warps per CTA; no block-level barrier is used
 
+// shared memory of one assign_kernel problem, in floats (even): n^2 doubles | n^2 uint16 | 5n + 1 ints
+__host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + ((n * n + 1) >> 1) + 5 * n + 1 + 1) & ~1; }
+
 // =============================================================================================
 // The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
 template <int G>
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
 
   // ---- calculate_distances (core.py:204-228) at the new positions -----------------------------
   double dgoal; int ncoll; bool ocoll;
-  if (venv) distance_tile<G>(p, ent, adj, i, act, gm, dgoal, ncoll, ocoll);
+  if (venv) distance_tile<G>(p, ent, adj, env, false, i, act, gm, dgoal, ncoll, ocoll);
   else { dgoal = 0.0; ncoll = 0; ocoll = false; }
 
   // ---- per-agent loop of MultiAgentGraphEnv.step (environment.py:832-864): agent i's observation
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ D
       fobs = 0.f;                                // mean(p_dist = 0) / (std + 1e-4)
       if (act) p.mintime[idx] = rmint;
       double d2; int c2; bool o2;
-      distance_tile<G>(p, ent, adj, i, act, gm, d2, c2, o2);
+      distance_tile<G>(p, ent, adj, env, true, i, act, gm, d2, c2, o2);
     }
   }
   if (act) {
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   const float std_p = std_from_q(q_p, inv_n);
   const float fparam = (dtg == -1.0f) ? ratio_eps((float)mean_p, std_p) : ratio_eps(dmean, dstd);
   double dgoal; int ncoll; bool ocoll;
-  if (venv) distance_tile<G>(p, ent, adj, i, act, gm, dgoal, ncoll, ocoll);
+  if (venv) distance_tile<G>(p, ent, adj, env, do_reset, i, act, gm, dgoal, ncoll, ocoll);
   if (act) {
     const float gx = ent[i * ENT_STRIDE + 4], gy = ent[i * ENT_STRIDE + 5];
     obs[i * OBS_F + 0] = vx; obs[i * OBS_F + 1] = vy; obs[i * OBS_F + 2] = px; obs[i * OBS_F + 3] = py;
@@ -354,10 +357,11 @@ __global__ void __launch_bounds__(THREADS) assign_kernel(const double* __restric
   const int el = lane / G, i = lane % G;
   const int prob = gw * EPW + el;
   const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
-  const int per_group = 2 * n * n + ((5 * n + 1 + 1) & ~1);      // floats: cost (doubles) + int scratch, even
+  const int per_group = assign_smem_floats(n);                   // cost (doubles) | sort permutation (uint16) | int scratch
   float* base = smem + (size_t)(wib * EPW + el) * per_group;
   double* cost = reinterpret_cast<double*>(base);
-  int* asg = reinterpret_cast<int*>(base + 2 * n * n);
+  uint16_t* ord = reinterpret_cast<uint16_t*>(base + 2 * n * n);
+  int* asg = reinterpret_cast<int*>(base + 2 * n * n + ((n * n + 1) >> 1));
   if (prob >= num) return;                                        // group-uniform; only group syncs below
   if (i < n) {
     for (int j = 0; j < n; ++j) {
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(THREADS) assign_kernel(const double* __restric
     }
   }
   __syncwarp(gmask);
-  const int g = lexifair_group<G>(cost, asg, n, i, gmask, 0);
+  const int g = lexifair_group<G>(cost, ord, asg, n, i, gmask);
   if (i < n) out[(size_t)prob * n + i] = g;
 }
 
@@ -571,7 +575,7 @@ static cudaError_t launch_assign_g(const double* costs, const float* apos, const
   constexpr int EPW = 32 / G;
   const int warps = (num + EPW - 1) / EPW;
   const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
-  const int per_group = 2 * n * n + ((5 * n + 1 + 1) & ~1);
+  const int per_group = assign_smem_floats(n);
   const size_t smem = (size_t)per_group * EPW * (THREADS / 32) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(assign_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void perm_all(const int (&rank)[N * N], unsigned& bes
 // Lexifair assignment by enumeration (marl_fair_assign.py:16-55; oracle/lexifair.py
 // lexifair_bruteforce_batched): rank every entry in the total order (cost, i, j), then take the
 // permutation whose descending-sorted rank vector is lexicographically smallest.  Equals the
-// threshold descent of lexifair_group<G> (fm_device.cuh) entry for entry, ties included.
+// sorted threshold descent of lexifair_group<G> (fm_device.cuh) entry for entry, ties included.
 template <int N>
 __device__ __forceinline__ void lexifair_small(const double (&c)[N * N], int (&out)[N]) {
   int rank[N * N];
