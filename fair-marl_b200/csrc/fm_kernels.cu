@@ -22,7 +22,7 @@ __host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + (
 // =============================================================================================
 // The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
 template <int G>
-__global__ void __launch_bounds__(THREADS) step_kernel(const __grid_constant__ DevParams p) {
+__global__ void __launch_bounds__(THREADS, 5) step_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EPW = 32 / G;
   const int lane = threadIdx.x & 31;
