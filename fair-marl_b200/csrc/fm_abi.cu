@@ -28,6 +28,8 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(FM_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+#define FM_MAX_LANES 4
+
 struct FmHandle {
   FmConfig cfg;
   int device;
@@ -36,6 +38,11 @@ struct FmHandle {
   double* stats;
   int stats_rows, K;
   long long launches;
+  // fm_step_many: env-range lanes on side streams, so that the partial last wave and the launch gap of
+  // one range are filled by the kernels of the others (created on first use)
+  cudaStream_t lane_stream[FM_MAX_LANES];
+  cudaEvent_t lane_fork, lane_join[FM_MAX_LANES];
+  int lanes_ready;
   // device staging for the *_host entry points (allocated on first use)
   float* st_onehot;
   uint8_t* st_mask;
@@ -85,6 +92,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   DevParams& p = h->p;
   const int B = cfg->num_envs, N = cfg->num_agents, O = cfg->num_obstacles, E = 2 * N + O;
   p.B = B; p.N = N; p.O = O; p.E = E;
+  p.env_begin = 0; p.env_end = B;
   p.Bp = (B + 63) & ~63;
   const size_t Bp = (size_t)p.Bp;
   const int SP = (N + O) * (N + O - 1) / 2;
@@ -190,6 +198,10 @@ int fm_destroy(FmHandle* h) {
   if (!h) return FM_OK;
   use_device(h->device);
   free_staging(h);
+  if (h->lanes_ready) {
+    for (int k = 1; k < FM_MAX_LANES; ++k) { cudaStreamDestroy(h->lane_stream[k]); cudaEventDestroy(h->lane_join[k]); }
+    cudaEventDestroy(h->lane_fork);
+  }
   cudaFree(h->stats);
   cudaFree(h->state_block);
   delete h;
@@ -242,10 +254,48 @@ int fm_step_onehot(FmHandle* h, const float* onehot, const FmOutputs* out, void*
 int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const FmOutputs* outs, void* stream) {
   if (!h || !actions || !outs) return fail(FM_ERR_INVALID_ARG, "fm_step_many: null argument");
   if (num_steps < 0) return fail(FM_ERR_INVALID_ARG, "fm_step_many: num_steps < 0");
+  int rc = use_device(h->device);
+  if (rc) return rc;
   const size_t stride = (size_t)h->p.B * h->p.N;
+  // Envs are independent, so a rollout of T steps is T x L independent kernel chains, one per env-range
+  // lane.  Lane 0 runs on the caller's stream, the others on side streams forked from / joined to it; the
+  // GPU then always has runnable CTAs of another lane while one lane's last wave drains or its next
+  // launch is in flight.  Small batches (less than two waves of CTAs per lane) stay on one stream.
+  const int B = h->p.B;
+  int lanes = 1;
+  if (num_steps > 1 && B >= 32768) lanes = FM_MAX_LANES;
+  if (lanes > 1 && !h->lanes_ready) {
+    h->lane_stream[0] = nullptr;
+    for (int k = 1; k < FM_MAX_LANES; ++k) {
+      FM_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
+      FM_CUDA(cudaEventCreateWithFlags(&h->lane_join[k], cudaEventDisableTiming));
+    }
+    FM_CUDA(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
+    h->lanes_ready = 1;
+  }
+  cudaStream_t user = (cudaStream_t)stream;
+  if (lanes > 1) {
+    FM_CUDA(cudaEventRecord(h->lane_fork, user));
+    for (int k = 1; k < lanes; ++k) FM_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->lane_fork, 0));
+  }
+  const int per_lane = (((B + lanes - 1) / lanes) + 127) & ~127;      // lane boundaries at multiples of 128 envs
   for (int t = 0; t < num_steps; ++t) {
-    int rc = step_common(h, actions + (size_t)t * stride, nullptr, outs + t, stream);
-    if (rc) return rc;
+    for (int k = 0; k < lanes; ++k) {
+      DevParams p = h->p;
+      set_outputs(p, outs + t);
+      p.act_idx = actions + (size_t)t * stride; p.act_onehot = nullptr; p.reset_mask = nullptr;
+      p.env_begin = k * per_lane < B ? k * per_lane : B;
+      p.env_end = (k + 1) * per_lane < B ? (k + 1) * per_lane : B;
+      if (p.env_begin >= p.env_end) continue;
+      FM_CUDA(fm::launch_step(p, k == 0 ? user : h->lane_stream[k], false));
+      h->launches += 1;
+    }
+  }
+  if (lanes > 1) {
+    for (int k = 1; k < lanes; ++k) {
+      FM_CUDA(cudaEventRecord(h->lane_join[k], h->lane_stream[k]));
+      FM_CUDA(cudaStreamWaitEvent(user, h->lane_join[k], 0));
+    }
   }
   return FM_OK;
 }

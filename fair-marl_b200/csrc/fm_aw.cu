@@ -187,8 +187,8 @@ aw_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   float* ST = smem + L::OFF_STAGE;
   const int tid = threadIdx.x, lane = tid & 31, role = tid >> 5;   // role < N: agent `role`;  role == N: env warp
-  const int env0 = blockIdx.x * 32;
-  const int nenv = min(32, p.B - env0);
+  const int env0 = p.env_begin + blockIdx.x * 32;
+  const int nenv = min(32, p.env_end - env0);
   const int env = env0 + lane;                   // < Bp: the state block is padded to a multiple of 64 envs
   const bool venv = lane < nenv;
   const size_t Bp = (size_t)p.Bp;
@@ -401,7 +401,7 @@ aw_kernel(const __grid_constant__ DevParams p) {
       }
     }
     const bool want_info = venv && (p.o_info != nullptr || p.stats != nullptr) && (done || p.info_every_step);
-    double* stats_row = p.stats ? p.stats + (size_t)blockIdx.x * (15 * N + 2) : nullptr;
+    double* stats_row = p.stats ? p.stats + (size_t)(env0 >> 5) * (15 * N + 2) : nullptr;
     const bool any_done = __syncthreads_or(venv && done) != 0;   // #2: OWN / NTREQ / SETM / SETS / TG visible
     const bool any_reset = any_done && (p.auto_reset != 0);
     const bool any_info = (p.o_info != nullptr || p.stats != nullptr) && (any_done || p.info_every_step);
@@ -627,7 +627,8 @@ __global__ void aw_static_kernel(const DevParams p, float* __restrict__ sdist) {
 template <int N, int O>
 static cudaError_t aw_launch_no(const DevParams& p, cudaStream_t st, bool is_reset) {
   using L = AwLayout<N, O>;
-  const int blocks = (p.B + 31) / 32;
+  const int blocks = (p.env_end - p.env_begin + 31) / 32;
+  if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)L::WORDS * sizeof(float);
   if (is_reset) aw_kernel<N, O, 1><<<blocks, L::THREADS, smem, st>>>(p);
   else aw_kernel<N, O, 0><<<blocks, L::THREADS, smem, st>>>(p);

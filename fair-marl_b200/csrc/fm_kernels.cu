@@ -27,10 +27,10 @@ __global__ void __launch_bounds__(THREADS, 5) step_kernel(const __grid_constant_
   constexpr int EPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (THREADS / 32) + wib;
-  const int env0 = gw * EPW;
-  if (env0 >= p.B) return;                       // warp-uniform
-  const int nenv = min(EPW, p.B - env0);
+  const int env0 = p.env_begin + (blockIdx.x * (THREADS / 32) + wib) * EPW;
+  if (env0 >= p.env_end) return;                 // warp-uniform
+  const int gw = env0 / EPW;                     // global warp index (statistics row)
+  const int nenv = min(EPW, p.env_end - env0);
   const int el = lane / G, i = lane % G;
   const int env = env0 + el;
   const int N = p.N, O = p.O, E = p.E;
@@ -269,10 +269,9 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   constexpr int EPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (THREADS / 32) + wib;
-  const int env0 = gw * EPW;
-  if (env0 >= p.B) return;
-  const int nenv = min(EPW, p.B - env0);
+  const int env0 = p.env_begin + (blockIdx.x * (THREADS / 32) + wib) * EPW;
+  if (env0 >= p.env_end) return;
+  const int nenv = min(EPW, p.env_end - env0);
   const int el = lane / G, i = lane % G;
   const int env = env0 + el;
   const int N = p.N, O = p.O, E = p.E;
@@ -529,8 +528,9 @@ __global__ void stats_reduce_kernel(double* __restrict__ partial, int rows, int 
 template <int G>
 static cudaError_t launch_step_g(const DevParams& p, cudaStream_t st, bool is_reset) {
   constexpr int EPW = 32 / G;
-  const int warps = (p.B + EPW - 1) / EPW;
+  const int warps = (p.env_end - p.env_begin + EPW - 1) / EPW;
   const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
+  if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)p.sm_per_warp * (THREADS / 32) * sizeof(float);
   if (is_reset) reset_kernel<G><<<blocks, THREADS, smem, st>>>(p);
   else step_kernel<G><<<blocks, THREADS, smem, st>>>(p);
