@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -28,7 +29,7 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(FM_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
-#define FM_MAX_LANES 4
+#define FM_MAX_LANES 8
 
 struct FmHandle {
   FmConfig cfg;
@@ -263,7 +264,11 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
   // launch is in flight.  Small batches (less than two waves of CTAs per lane) stay on one stream.
   const int B = h->p.B;
   int lanes = 1;
-  if (num_steps > 1 && B >= 32768) lanes = FM_MAX_LANES;
+  if (num_steps > 1 && B >= 32768) lanes = 2;           // 2, 3, 4 lanes measure the same at C2; 8 is launch bound
+  if (const char* ev = getenv("FM_LANES")) {                          // diagnostic override
+    const int v = atoi(ev);
+    if (v >= 1 && v <= FM_MAX_LANES) lanes = v;
+  }
   if (lanes > 1 && !h->lanes_ready) {
     h->lane_stream[0] = nullptr;
     for (int k = 1; k < FM_MAX_LANES; ++k) {

@@ -117,6 +117,28 @@ __device__ __forceinline__ void cta_copy_out(float* __restrict__ dst, const floa
   }
 }
 
+// TMA bulk store of a contiguous shared-memory image to global memory (cp.async.bulk, shared::cta -> global):
+// one thread issues it, the copy engine streams it out; evict-first L2 policy (the outputs are not re-read
+// by this kernel).  Destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(s), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (after the CTA barrier that ordered them)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// all bulk stores issued by this thread have finished READING shared memory (it may be overwritten / released)
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
 // Randomised reset of env `lane` by one thread of the env warp (navigation_graph.py:212-262,
 // :264-570) + lexifair (:555-561).  Same Philox stream, draw order and acceptance rules as
 // reset_group<G> (fm_device.cuh).  New positions go to the TP table, goal_match / min_time to the
@@ -570,17 +592,35 @@ aw_kernel(const __grid_constant__ DevParams p) {
     o[0] = vx; o[1] = vy; o[2] = px; o[3] = py; o[4] = gx - px; o[5] = gy - py; o[6] = fobs;
   }
   __syncthreads();                                // #3: image of the small outputs + TP / TV / TG complete
-  if (p.o_adj) cta_copy_out<L::THREADS, 32 * L::ADJ_W>(p.o_adj + (size_t)env0 * L::ADJ_W, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
-  if (p.o_obs) cta_copy_out<L::THREADS, 32 * L::OBS_W>(p.o_obs + (size_t)env0 * L::OBS_W, ST + L::S_OBS, nenv * L::OBS_W, tid);
-  if (MODE == 0) {
-    if (p.o_rew) cta_copy_out<L::THREADS, 32 * N>(p.o_rew + (size_t)env0 * N, ST + L::S_REW, nenv * N, tid);
-    if (p.o_done) {
+  // A full tile whose slices of the output arrays are 16-byte aligned (always, when the arrays are) goes out
+  // as TMA bulk stores issued by one thread; ragged or unaligned tiles use vectorised st.global.cs.
+  float* g_adj = p.o_adj ? p.o_adj + (size_t)env0 * L::ADJ_W : nullptr;
+  float* g_obs = p.o_obs ? p.o_obs + (size_t)env0 * L::OBS_W : nullptr;
+  float* g_rew = (MODE == 0 && p.o_rew) ? p.o_rew + (size_t)env0 * N : nullptr;
+  uint8_t* g_done = (MODE == 0 && p.o_done) ? p.o_done + (size_t)env0 * N : nullptr;
+  float* g_node = p.o_node ? p.o_node + (size_t)env0 * L::NODE_W : nullptr;
+  const bool bulk = nenv == 32 && aligned16(g_adj) && aligned16(g_obs) && aligned16(g_rew) && aligned16(g_done) &&
+                    aligned16(g_node) && (32 * N) % 16 == 0;
+  if (bulk) {
+    if (tid == 0) {
+      const uint64_t pol = evict_first_policy();
+      fence_async_smem();
+      if (g_adj) bulk_store(g_adj, ST + L::S_ADJ, 32 * L::ADJ_W * 4, pol);
+      if (g_obs) bulk_store(g_obs, ST + L::S_OBS, 32 * L::OBS_W * 4, pol);
+      if (g_rew) bulk_store(g_rew, ST + L::S_REW, 32 * N * 4, pol);
+      if (g_done) bulk_store(g_done, ST + L::S_DONE, 32 * N, pol);
+      bulk_commit_wait_read();
+    }
+  } else {
+    if (g_adj) cta_copy_out<L::THREADS, 32 * L::ADJ_W>(g_adj, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
+    if (g_obs) cta_copy_out<L::THREADS, 32 * L::OBS_W>(g_obs, ST + L::S_OBS, nenv * L::OBS_W, tid);
+    if (g_rew) cta_copy_out<L::THREADS, 32 * N>(g_rew, ST + L::S_REW, nenv * N, tid);
+    if (g_done) {
       const uint8_t* sdone = reinterpret_cast<const uint8_t*>(ST + L::S_DONE);
-      uint8_t* gdone = p.o_done + (size_t)env0 * N;
-      for (int k = tid; k < nenv * N; k += L::THREADS) gdone[k] = sdone[k];
+      for (int k = tid; k < nenv * N; k += L::THREADS) g_done[k] = sdone[k];
     }
   }
-  if (!p.o_node) return;
+  if (!g_node) return;
   __syncthreads();                                // #4: staging region fully read
   // ---- use 2: node_obs (navigation_graph.py:1079-1124, relative features): for ego agent i and entity e
   //   [v_e - v_i (2), p_e - p_i (2), goal_e - p_i (2), p_e - p_i (2), p_e - p_i (2), type]
@@ -604,7 +644,15 @@ aw_kernel(const __grid_constant__ DevParams p) {
     }
   }
   __syncthreads();                                // #5
-  cta_copy_out<L::THREADS, 32 * L::NODE_W>(p.o_node + (size_t)env0 * L::NODE_W, ST, nenv * L::NODE_W, tid);
+  if (bulk) {
+    if (tid == 0) {
+      fence_async_smem();
+      bulk_store(g_node, ST, 32 * L::NODE_W * 4, evict_first_policy());
+      bulk_commit_wait_read();                    // the image must stay valid until the copy engine has read it
+    }
+  } else {
+    cta_copy_out<L::THREADS, 32 * L::NODE_W>(g_node, ST, nenv * L::NODE_W, tid);
+  }
 }
 
 // =============================================================================================
