@@ -265,7 +265,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     alg_bytes = env.algorithmic_bytes_per_step
     kernel_name = {"aw": f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)",
                    "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}> (group-per-env)"}[env.mapping]
-    step_kernel_ms = elapsed_ms / K              # rank-max; one step kernel per step dominates the region
+    # One step = the step kernel over the whole batch (fm_step_many issues it as `launches / K` concurrent
+    # env-range launches on side streams); the kernel is > 99 % of the timed region (profiles/: launch list),
+    # so bytes per step / time per step is the kernel's achieved algorithmic bandwidth.
+    step_kernel_ms = elapsed_ms / K              # rank-max
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
@@ -275,8 +278,30 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src}
+                "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_step": alg_bytes,
+                "launches_per_step": launches / K, "peak_source": peak_src,
+                "note": "the SoA state (14 % of the algorithmic bytes) is L2-resident between steps; the outputs "
+                        "(86 %) stream to HBM through a slab ring larger than L2"}
+
+    # closed loop: one fm_step per call (what a policy-in-the-loop rollout does), no host sync in between
+    cl_steps = min(K, 1000)
+    for k in range(3):
+        env.step_tensor(actions[k])
+    torch.cuda.synchronize(dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for k in range(cl_steps):
+        env.step_tensor(actions[k % EPISODE])
+    c1.record()
+    torch.cuda.synchronize(dev)
+    cl_ms = c0.elapsed_time(c1)
+    if world > 1:
+        tt = torch.tensor([cl_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cl_ms = float(tt.item())
+    closed_loop = {"value": B * world * N_AGENTS * cl_steps / (cl_ms * 1e-3), "unit": "agent-steps/s",
+                   "ms_per_step": cl_ms / cl_steps, "steps": cl_steps,
+                   "api": "B200GraphVecEnv.step_tensor -> fm_step, one launch per step, device tensors"}
 
     # e2e through the reference-facing API with host buffers
     e2e_steps = max(3, min(args.e2e_steps, K))
@@ -320,7 +345,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "l2": f"outputs cycle through a {slots}-slot slab ring ({slab_gb:.1f} GB per GPU > 126 MB L2); the SoA "
                              "state is read+written every step",
                        "stats_allreduce": "per episode (25 steps), side stream" if world > 1 else "local reduce per episode"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "closed_loop": closed_loop,
+            "gpu_launches": launches, "clocks": clocks,
             "episode_stats": {"episodes": total_stats["episodes"], "env_steps": total_stats["env_steps"]},
         }
         print(json.dumps(line), flush=True)

@@ -178,7 +178,7 @@ class B200GraphVecEnv:
                "adj": s["adj"][slot][:, None].expand(B, N, E, E),      # written once per env
                "adj_env": s["adj"][slot], "agent_id": self._agent_id_dev, "slot": slot}
         if with_step:
-            out.update(reward=s["reward"][slot], done=s["done"][slot].bool(), info=s["info"])
+            out.update(reward=s["reward"][slot], done=s["done"][slot].view(self.torch.bool), info=s["info"])   # zero-copy
         return out
 
     # ------------------------------------------------------------------ tensor fast path
