@@ -1,5 +1,6 @@
 // C ABI of libfairmarl.so (include/fairmarl.h): handle management, argument checking, launches.
 // No torch types, no exceptions across the boundary, no CPU fallback.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -162,11 +163,14 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   const int G = fm::group_size(N), EPW = 32 / G;
   p.sm_cost = 0;                                   // the reset's cost matrix lives inside the adj tile
   p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
-  p.sm_adj = round4((long long)EPW * E * E);
-  p.sm_stage = fm::STAGE_ROWS * fm::NODE_F;
-  p.sm_obs = round4((long long)EPW * N * fm::OBS_F);
+  // adj / obs images sit at the 16-byte phase of their destinations (<= 3 words of slack); the adj region is
+  // reused as two node_obs staging buffers of stage_k x 32 rows (+ phase slack) each, so it holds at least 2 x 1.
+  const int stage_words = fm::STAGE_SUB * fm::NODE_F;                  // 352
+  p.sm_adj = round4(std::max((long long)EPW * E * E + 3, 2LL * (stage_words + 4)));
+  p.stage_k = std::min(4, (((p.sm_adj >> 1) & ~3) - 3) / stage_words);
+  p.sm_obs = round4((long long)EPW * N * fm::OBS_F + 3);
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
-  p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_stage + p.sm_obs + p.sm_asg;
+  p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_obs + p.sm_asg;
   if (p.mapping == 0 && (size_t)p.sm_per_warp * 4 * 4 > 227 * 1024) {
     cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: N=%d O=%d needs %d B of shared memory per CTA", N, O, p.sm_per_warp * 16);

@@ -117,28 +117,6 @@ __device__ __forceinline__ void cta_copy_out(float* __restrict__ dst, const floa
   }
 }
 
-// TMA bulk store of a contiguous shared-memory image to global memory (cp.async.bulk, shared::cta -> global):
-// one thread issues it, the copy engine streams it out; evict-first L2 policy (the outputs are not re-read
-// by this kernel).  Destination and size must be multiples of 16 bytes.
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-               :: "l"(gdst), "r"(s), "r"(bytes), "l"(policy) : "memory");
-}
-__device__ __forceinline__ uint64_t evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-// generic-proxy writes to shared memory -> visible to the async proxy (after the CTA barrier that ordered them)
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// all bulk stores issued by this thread have finished READING shared memory (it may be overwritten / released)
-__device__ __forceinline__ void bulk_commit_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
-
 // Randomised reset of env `lane` by one thread of the env warp (navigation_graph.py:212-262,
 // :264-570) + lexifair (:555-561).  Same Philox stream, draw order and acceptance rules as
 // reset_group<G> (fm_device.cuh).  New positions go to the TP table, goal_match / min_time to the

@@ -22,7 +22,7 @@ __host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + (
 // =============================================================================================
 // The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
 template <int G>
-__global__ void __launch_bounds__(THREADS, 5) step_kernel(const __grid_constant__ DevParams p) {
+__global__ void __launch_bounds__(THREADS, G == 8 ? 7 : (G == 4 ? 5 : (G == 16 ? 4 : 3))) step_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EPW = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(THREADS, 5) step_kernel(const __grid_constant_
   const bool act = venv && i < N;
   const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
   const int gl = el * G;                         // first lane of my group
-  const WarpSmem s = carve(p, smem, wib);
+  const WarpSmem s = carve(p, smem, wib, env0);
   float* ent = s.ent + (size_t)el * E * ENT_STRIDE;
   float* adj = s.adj + (size_t)el * E * E;
   float* obs = s.obs + (size_t)el * N * OBS_F;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   const bool act = venv && i < N;
   const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
   const int gl = el * G;
-  const WarpSmem s = carve(p, smem, wib);
+  const WarpSmem s = carve(p, smem, wib, env0);
   float* ent = s.ent + (size_t)el * E * ENT_STRIDE;
   float* adj = s.adj + (size_t)el * E * E;
   float* obs = s.obs + (size_t)el * N * OBS_F;
