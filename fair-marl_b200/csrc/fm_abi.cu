@@ -98,7 +98,8 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.Bp = (B + 63) & ~63;
   const size_t Bp = (size_t)p.Bp;
   const int SP = (N + O) * (N + O - 1) / 2;
-  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4 + SP);
+  const int SPp = (SP + 3) & ~3;                   // per-env row of the group mapping's layout
+  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4 + SPp);
   cudaError_t e = cudaMalloc(&h->state_block, words * 4);
   if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc(%zu B): %s", words * 4, cudaGetErrorString(e)); }
   cudaMemset(h->state_block, 0, words * 4);
@@ -110,7 +111,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.lx = take(Bp * N); p.ly = take(Bp * N);
   p.ox = take(Bp * O); p.oy = take(Bp * O);
   p.dmean = take(Bp); p.dstd = take(Bp); p.step = (int*)take(Bp); p.episode = (int*)take(Bp);
-  p.sdist = take(Bp * SP);
+  p.sdist = take(Bp * SPp);
 
   // config -> device constants.  Collision threshold exactly as the reference spells it:
   // 1.05*(size + size) (navigation_graph.py:655, :704); cached min_dist = size + size (core.py:215).
@@ -160,14 +161,17 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     return fail(FM_ERR_UNSUPPORTED, "fm_create: agent-warp kernels are not compiled for N=%d O=%d", N, O);
   }
   p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || fm::aw_supported(N, O)) ? 1 : 0);
+  p.sd_env_stride = p.mapping == 0 ? SPp : 0;      // group mapping: [env][SPp];  agent-warp mapping: [pair][Bp]
   const int G = fm::group_size(N), EPW = 32 / G;
   p.sm_cost = 0;                                   // the reset's cost matrix lives inside the adj tile
   p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
   // adj / obs images sit at the 16-byte phase of their destinations (<= 3 words of slack); the adj region is
   // reused as two node_obs staging buffers of stage_k x 32 rows (+ phase slack) each, so it holds at least 2 x 1.
   const int stage_words = fm::STAGE_SUB * fm::NODE_F;                  // 352
-  p.sm_adj = round4(std::max((long long)EPW * E * E + 3, 2LL * (stage_words + 4)));
-  p.stage_k = std::min(4, (((p.sm_adj >> 1) & ~3) - 3) / stage_words);
+  int want_k = 1;
+  if (const char* ev = getenv("FM_STAGE_K")) want_k = atoi(ev) >= 3 ? 3 : 1;   // diagnostic: force 96-row chunks
+  p.sm_adj = round4(std::max((long long)EPW * E * E + 3, 2LL * (want_k * stage_words + 4)));
+  p.stage_k = (((p.sm_adj >> 1) & ~3) - 3) / stage_words >= 3 ? 3 : 1;          // 32 or 96 rows per chunk
   p.sm_obs = round4((long long)EPW * N * fm::OBS_F + 3);
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_obs + p.sm_asg;

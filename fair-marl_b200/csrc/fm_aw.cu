@@ -645,7 +645,8 @@ __global__ void aw_static_kernel(const DevParams p, float* __restrict__ sdist) {
   const int b = a + 1 + rem;
   auto X = [&](int s) { return s < p.N ? p.lx[(size_t)s * p.Bp + env] : p.ox[(size_t)(s - p.N) * p.Bp + env]; };
   auto Y = [&](int s) { return s < p.N ? p.ly[(size_t)s * p.Bp + env] : p.oy[(size_t)(s - p.N) * p.Bp + env]; };
-  sdist[(size_t)q * p.Bp + env] = (float)dist64(X(a), Y(a), X(b), Y(b));
+  const size_t at = p.sd_env_stride ? (size_t)env * p.sd_env_stride + q : (size_t)q * p.Bp + env;
+  sdist[at] = (float)dist64(X(a), Y(a), X(b), Y(b));
 }
 
 // =============================================================================================

@@ -64,16 +64,14 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 7 : (G == 4 ? 5 : (G == 16 ?
     }
     ux *= 5.0f; uy *= 5.0f;
     const float lxx = p.lx[idx], lyy = p.ly[idx];
-    float* l = ent + (N + i) * ENT_STRIDE;
-    l[0] = lxx; l[1] = lyy; l[2] = 0.f; l[3] = 0.f; l[4] = lxx; l[5] = lyy;
+    ent_write(ent + (N + i) * ENT_STRIDE, lxx, lyy, 0.f, 0.f, lxx, lyy, 1.0f);
   }
   int step = 0; uint32_t episode = 0; float dmean = 0.f, dstd = 0.f;
   if (venv) {
     step = p.step[env]; episode = (uint32_t)p.episode[env]; dmean = p.dmean[env]; dstd = p.dstd[env];
     for (int k = i; k < O; k += G) {
       const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
-      float* o = ent + (2 * N + k) * ENT_STRIDE;
-      o[0] = x; o[1] = y; o[2] = 0.f; o[3] = 0.f; o[4] = x; o[5] = y;
+      ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
     }
   }
   __syncwarp();
@@ -102,9 +100,8 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 7 : (G == 4 ? 5 : (G == 16 ?
   float npd = (float)pd64;
   const int nstep = step + 1;                    // environment.py:819, :823
   if (act) {
-    float* a = ent + i * ENT_STRIDE;
     const float* g = ent + (N + gm) * ENT_STRIDE;
-    a[0] = npx; a[1] = npy; a[2] = nvx; a[3] = nvy; a[4] = g[0]; a[5] = g[1];
+    ent_write(ent + i * ENT_STRIDE, npx, npy, nvx, nvy, g[0], g[1], 0.0f);
   }
   __syncwarp();
 
@@ -291,8 +288,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
     px = p.px[idx]; py = p.py[idx]; vx = p.vx[idx]; vy = p.vy[idx]; pd = p.pdist[idx]; dtg = p.dtg[idx];
     gm = p.gm[idx]; mint = p.mintime[idx];
     const float lxx = p.lx[idx], lyy = p.ly[idx];
-    float* l = ent + (N + i) * ENT_STRIDE;
-    l[0] = lxx; l[1] = lyy; l[2] = 0.f; l[3] = 0.f; l[4] = lxx; l[5] = lyy;
+    ent_write(ent + (N + i) * ENT_STRIDE, lxx, lyy, 0.f, 0.f, lxx, lyy, 1.0f);
   }
   uint32_t episode = 0; float dmean = 0.f, dstd = 0.f;
   bool do_reset = false;
@@ -301,15 +297,13 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
     do_reset = p.reset_mask ? (p.reset_mask[env] != 0) : true;
     for (int k = i; k < O; k += G) {
       const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
-      float* o = ent + (2 * N + k) * ENT_STRIDE;
-      o[0] = x; o[1] = y; o[2] = 0.f; o[3] = 0.f; o[4] = x; o[5] = y;
+      ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
     }
   }
   __syncwarp();
   if (act) {
-    float* a = ent + i * ENT_STRIDE;
     const float* g = ent + (N + gm) * ENT_STRIDE;
-    a[0] = px; a[1] = py; a[2] = vx; a[3] = vy; a[4] = g[0]; a[5] = g[1];
+    ent_write(ent + i * ENT_STRIDE, px, py, vx, vy, g[0], g[1], 0.0f);
   }
   __syncwarp();
   if (__any_sync(FULL, do_reset)) {
