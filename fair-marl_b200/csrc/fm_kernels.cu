@@ -22,7 +22,7 @@ __host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + (
 // =============================================================================================
 // The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
 template <int G>
-__global__ void __launch_bounds__(THREADS, G == 8 ? 7 : (G == 4 ? 5 : (G == 16 ? 4 : 3))) step_kernel(const __grid_constant__ DevParams p) {
+__global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ? 4 : 3))) step_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EPW = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -201,23 +201,23 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 7 : (G == 4 ? 5 : (G == 16 ?
     for (int k = 0; k < INFO_F; ++k) info[k] = 0.f;
   }
 
-  // ---- episode statistics: per-warp partial sums, fixed order, no atomics ----------------------
+  // ---- episode statistics: per-warp partial sums (one row per warp, so the order of the adds is fixed) ----
   if (p.stats) {
     double* row = p.stats + (size_t)gw * (15 * N + 2);
     double r = act ? (double)rew : 0.0;
     for (int off = G; off < 32; off <<= 1) r += __shfl_xor_sync(FULL, r, off);
-    if (el == 0 && i < N) row[i] += r;
+    if (el == 0 && i < N) atomicAdd(row + i, r);                    // RED: one add per (row, step), order fixed
     const bool term = venv && done;
     if (__any_sync(FULL, term)) {
 #pragma unroll
       for (int k = 0; k < INFO_F; ++k) {
         double v = (act && done) ? (double)info[k] : 0.0;
         for (int off = G; off < 32; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
-        if (el == 0 && i < N) row[N + i * INFO_F + k] += v;
+        if (el == 0 && i < N) atomicAdd(row + N + i * INFO_F + k, v);
       }
     }
     const unsigned termb = __ballot_sync(FULL, term && i == 0);
-    if (lane == 0) { row[15 * N] += (double)__popc(termb); row[15 * N + 1] += (double)nenv; }
+    if (lane == 0) { atomicAdd(row + 15 * N, (double)__popc(termb)); atomicAdd(row + 15 * N + 1, (double)nenv); }
   }
 
   // ---- write back state; observation row --------------------------------------------------------
