@@ -49,6 +49,10 @@ CONFIGS = {
                workload="navigation_graph 7 agents / 7 goals / 3 obstacles, FA+FR, 262144 envs, random actions"),
     "c4": dict(agents=16, obstacles=3, envs=131072, rew=5.0, fairness=True,
                workload="navigation_graph 16 agents / 16 goals / 3 obstacles, FA+FR, 131072 envs per GPU (1M over 8), random actions"),
+    # config 5: the rollout loop (policy forward in torch + simulator step + buffer insert), all on the device
+    "c5": dict(agents=3, obstacles=3, envs=65536, rew=30.0, fairness=True,
+               workload="rmappo rollout loop at 3 agents: dense GNN actor + critic forward (torch) -> fused simulator step writing "
+                        "the device-resident rollout buffer -> insert; sampled actions"),
 }
 
 
@@ -191,6 +195,100 @@ def run_reference(args, rank: int, world: int):
 
 
 # ----------------------------------------------------------------------------------------------
+def run_rollout(args, rank: int, local_rank: int, world: int):
+    """BASELINE config 5 (diagnostic line, not the headline): GMPERunner's collect -> step -> insert loop with the
+    dense torch policy and the device-resident rollout buffer.  A step = one env step of the whole batch including
+    the actor + critic forward that produced its actions.  Envs are sharded over ranks (weak scaling), policy
+    parameters are replicated; there is no collective on this path."""
+    import torch
+    import torch.distributed as dist
+    import fair_marl_b200 as fm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.envs
+    cfg = fm.SimConfig(**sim_kwargs(), mapping=args.mapping)
+    env = fm.B200GraphVecEnv(cfg, num_envs=B, device=local_rank, seed=0, env_offset=rank * B)
+    pc = fm.PolicyConfig(num_agents=N_AGENTS)
+    torch.manual_seed(0)
+    actor, critic = fm.DenseGraphActor(pc).to(dev).eval(), fm.DenseGraphCritic(pc).to(dev).eval()
+    col = fm.RolloutCollector(env, actor, critic, max_graphs=args.max_graphs,
+                              generator=torch.Generator(device=dev).manual_seed(1234 + rank))
+    col.warmup()
+    episodes = max(1, args.steps // EPISODE)
+    K = episodes * EPISODE
+    col.run()                                       # warm-up episode (allocator, library handles)
+    col.buffer.after_update()
+    graph = "eager"
+    if not args.no_graph:
+        try:
+            col.capture()
+            col.run()                                   # one replay before timing
+            col.buffer.after_update()
+            graph = "one CUDA graph per episode"
+        except Exception as exc:                        # noqa: BLE001 -- report and time the eager loop
+            graph = f"eager (capture failed: {type(exc).__name__}: {exc})"[:200]
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.05)
+    if world > 1:
+        dist.barrier()
+    launches0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(episodes):
+        col.run()
+        col.buffer.after_update()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    # the simulator's share: the same number of steps without the policy (same buffer slabs, recorded actions)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(episodes):
+        for t in range(EPISODE):
+            env.step_tensor(col.buffer.actions_env[t], out=col.buffer.env_views(t + 1))
+    s1.record()
+    torch.cuda.synchronize(dev)
+    sim_ms = s0.elapsed_time(s1)
+    launches = env.kernel_launches - launches0
+    clocks = sampler.summary(t0, t1)
+    sampler.stop()
+    if world > 1:
+        tt = torch.tensor([elapsed_ms, sim_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms, sim_ms = float(tt[0].item()), float(tt[1].item())
+    if rank == 0:
+        value = B * world * N_AGENTS * K / (elapsed_ms * 1e-3)
+        line = {
+            "metric": "agent-steps/sec, rollout loop (policy forward + navigation_graph step + buffer insert)", "value": value,
+            "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": EPISODE, "ms_per_step": elapsed_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": B, "envs_total": B * world, "agents": N_AGENTS,
+                       "policy": "DenseGraphActor + DenseGraphCritic (EmbedConv 16 -> 3 x TransformerConv 3 heads x 16 -> MLP 64 -> GRU 64), "
+                                 "random init, sampled actions", "policy_chunk_graphs": args.max_graphs,
+                       "buffer": f"DeviceRolloutBuffer, {EPISODE + 1} slabs written in place by the step kernel",
+                       "launch": graph},
+            "simulator_share": {"ms_per_step": sim_ms / K, "frac_of_step": sim_ms / elapsed_ms,
+                                "api": "step_tensor(out=buffer slab): one launch per step"},
+            "gpu_launches": launches, "clocks": clocks,
+            "mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import numpy as np
     import torch
@@ -366,6 +464,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mapping", default="auto", choices=["auto", "group", "aw"], help="kernel mapping (diagnostic)")
+    ap.add_argument("--max-graphs", type=int, default=1 << 17, help="c5: graphs per policy forward chunk")
+    ap.add_argument("--no-graph", action="store_true", help="c5: time the eager loop instead of the captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -377,6 +477,9 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus}")
+    if args.config == "c5":
+        run_rollout(args, rank, local_rank, world)
+        return
     run_ours(args, rank, local_rank, world)
 
 

@@ -182,32 +182,64 @@ class B200GraphVecEnv:
         return out
 
     # ------------------------------------------------------------------ tensor fast path
-    def reset_tensor(self, mask=None) -> Dict[str, Any]:
+    def _check_out(self, out: Dict[str, Any], with_step: bool) -> Dict[str, Any]:
+        """Validate caller-owned output arrays (e.g. slabs of a ``DeviceRolloutBuffer``): contiguous CUDA tensors of the
+        API shapes; ``adj`` is ``[B, E, E]`` (one matrix per env)."""
+        t, B, N, E = self.torch, self.num_envs, self.num_agents, self.num_entities
+        want = {"obs": ((B, N, _lib.OBS_DIM), t.float32), "node_obs": ((B, N, E, _lib.NODE_FEAT_DIM), t.float32),
+                "adj": ((B, E, E), t.float32)}
+        if with_step:
+            want.update(reward=((B, N), t.float32), done=((B, N), t.uint8))
+        views = {}
+        for name, (shape, dt) in want.items():
+            x = out.get(name)
+            if x is None or tuple(x.shape) != shape or x.dtype != dt or not x.is_contiguous() or x.device != self.device:
+                raise ValueError(f"out[{name!r}] must be a contiguous {dt} tensor of shape {shape} on {self.device}")
+            views[name] = x
+        return views
+
+    def _package_out(self, views: Dict[str, Any], with_step: bool) -> Dict[str, Any]:
+        B, N, E = self.num_envs, self.num_agents, self.num_entities
+        self._ensure_slabs()
+        res = {"obs": views["obs"], "node_obs": views["node_obs"], "adj": views["adj"][:, None].expand(B, N, E, E),
+               "adj_env": views["adj"], "agent_id": self._agent_id_dev, "slot": None}
+        if with_step:
+            res.update(reward=views["reward"], done=views["done"].view(self.torch.bool), info=self._slabs["info"])
+        return res
+
+    def reset_tensor(self, mask=None, out: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
         """Reset envs (all, or those with ``mask`` != 0: uint8 CUDA tensor [B]); returns device tensors
-        ``obs [B,N,7]``, ``node_obs [B,N,E,11]``, ``adj [B,N,E,E]`` (stride-0 view), ``agent_id``."""
+        ``obs [B,N,7]``, ``node_obs [B,N,E,11]``, ``adj [B,N,E,E]`` (stride-0 view), ``agent_id``.
+        ``out``: caller-owned arrays to write into instead of the env's slab ring (see ``_check_out``)."""
         s = self._ensure_slabs()
         slot = self._slot
-        views = {k: s[k][slot] for k in ("obs", "node_obs", "adj")}
+        views = self._check_out(out, with_step=False) if out is not None else {k: s[k][slot] for k in ("obs", "node_obs", "adj")}
         o = self._outputs_struct(views, with_step=False)
         mptr = None
         if mask is not None:
             mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
             mptr = mask.data_ptr()
         _lib.check(self.lib.fm_reset(self._h, mptr, C.byref(o), self._stream()), "fm_reset")
-        return self._package(slot, with_step=False)
+        return self._package_out(views, with_step=False) if out is not None else self._package(slot, with_step=False)
 
     def observe_tensor(self) -> Dict[str, Any]:
         """Observation of the current state without stepping or resetting."""
         z = self.torch.zeros(self.num_envs, dtype=self.torch.uint8, device=self.device)
         return self.reset_tensor(mask=z)
 
-    def step_tensor(self, actions) -> Dict[str, Any]:
+    def step_tensor(self, actions, out: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
         """One env step.  ``actions``: int32 CUDA tensor [B, N] in {0..4}, or float32 [B, N, 5] one-hot.
-        Asynchronous on the current stream; the returned tensors are views of slab ``slot``."""
+        Asynchronous on the current stream; the returned tensors are views of slab ``slot``, or of ``out`` when the
+        caller passes its own arrays (``obs``, ``node_obs``, ``adj [B,E,E]``, ``reward``, ``done``: e.g. slab t + 1 of a
+        ``DeviceRolloutBuffer``, so that the step kernel writes the rollout buffer directly)."""
         t = self.torch
         s = self._ensure_slabs()
-        self._slot = slot = (self._slot + 1) % self.num_slots
-        views = {k: s[k][slot] for k in ("obs", "node_obs", "adj", "reward", "done")}
+        if out is not None:
+            views = self._check_out(out, with_step=True)
+            slot = None
+        else:
+            self._slot = slot = (self._slot + 1) % self.num_slots
+            views = {k: s[k][slot] for k in ("obs", "node_obs", "adj", "reward", "done")}
         views["info"] = s["info"]
         o = self._outputs_struct(views, with_step=True)
         B, N = self.num_envs, self.num_agents
@@ -222,7 +254,7 @@ class B200GraphVecEnv:
         _lib.check(rc, "fm_step")
         self._step_version += 1
         self._last_step_api = "tensor"
-        return self._package(slot, with_step=True)
+        return self._package_out(views, with_step=True) if out is not None else self._package(slot, with_step=True)
 
     def rollout_tensor(self, actions) -> List[int]:
         """``T`` consecutive steps from one host call (``fm_step_many``): ``actions`` int32 CUDA tensor
