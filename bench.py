@@ -401,6 +401,40 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "ms_per_step": cl_ms / cl_steps, "steps": cl_steps,
                    "api": "B200GraphVecEnv.step_tensor -> fm_step, one launch per step, device tensors"}
 
+    # policy-side edge list (a-7, process_adj) emitted after every step: SURVEY 8(d) asks for it at config 3
+    edge_list = None
+    if args.edge_list or args.config == "c3":
+        import ctypes as C
+        from fair_marl_b200 import _lib
+        lib = _lib.load()
+        cap = B * E * (E - 1)
+        offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        eidx = torch.empty((2, cap), dtype=torch.int64, device=dev)
+        eattr = torch.empty(cap, dtype=torch.float32, device=dev)
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def step_and_edges(k):
+            o = env.step_tensor(actions[k % EPISODE])
+            _lib.check(lib.fm_edge_list(local_rank, o["adj_env"].data_ptr(), B, E, float(cfg.max_edge_dist), 0, 1, cap,
+                                        offsets.data_ptr(), eidx.data_ptr(), eattr.data_ptr(), nnz.data_ptr(), stream), "fm_edge_list")
+        el_steps = min(K, 100)
+        for k in range(3):
+            step_and_edges(k)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(el_steps):
+            step_and_edges(k)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        el_ms = g0.elapsed_time(g1) / el_steps
+        n_edges = int(nnz.item())
+        edge_list = {"ms_per_step_with_edge_list": el_ms, "ms_per_step_closed_loop": closed_loop["ms_per_step"],
+                     "edges_per_step": n_edges, "edge_bytes_per_step": n_edges * 20,
+                     "value": B * N_AGENTS / (el_ms * 1e-3), "unit": "agent-steps/s",
+                     "api": "step_tensor + fm_edge_list (count / scan / emit, one graph per env, int64 edge_index + fp32 attr)"}
+
     # e2e through the reference-facing API with host buffers
     e2e_steps = max(3, min(args.e2e_steps, K))
     rng = np.random.default_rng(rank)
@@ -443,7 +477,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "l2": f"outputs cycle through a {slots}-slot slab ring ({slab_gb:.1f} GB per GPU > 126 MB L2); the SoA "
                              "state is read+written every step",
                        "stats_allreduce": "per episode (25 steps), side stream" if world > 1 else "local reduce per episode"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "closed_loop": closed_loop,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "closed_loop": closed_loop, "edge_list": edge_list,
             "gpu_launches": launches, "clocks": clocks,
             "episode_stats": {"episodes": total_stats["episodes"], "env_steps": total_stats["env_steps"]},
         }
@@ -465,6 +499,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mapping", default="auto", choices=["auto", "group", "aw"], help="kernel mapping (diagnostic)")
     ap.add_argument("--max-graphs", type=int, default=1 << 17, help="c5: graphs per policy forward chunk")
+    ap.add_argument("--edge-list", action="store_true", help="also time step + policy-side edge list (default on for c3)")
     ap.add_argument("--no-graph", action="store_true", help="c5: time the eager loop instead of the captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -8,6 +8,7 @@ import os
 from fair_marl_b200.build import library_path
 
 OBS_DIM, NODE_FEAT_DIM, INFO_DIM = 7, 11, 14
+NODE_FEAT_DIM_GLOBAL = 7        # graph_feat_type = 'global'
 INFO_KEYS = (
     "individual_reward", "Dist_to_goal", "Time_req_to_goal", "Num_agent_collisions",
     "Num_obst_collisions", "Distance_mean", "Distance_variance", "Mean_by_variance",
@@ -24,7 +25,7 @@ class FmConfig(C.Structure):
         ("goal_rew", C.c_double), ("min_dist_thresh", C.c_double), ("fair_rew", C.c_double),
         ("zeroshift", C.c_double), ("max_edge_dist", C.c_double),
         ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32),
-        ("info_every_step", C.c_int32), ("mapping", C.c_int32), ("reserved_", C.c_int32),
+        ("info_every_step", C.c_int32), ("mapping", C.c_int32), ("graph_feat_global", C.c_int32),
     ]
 
 

@@ -22,6 +22,8 @@ class SimConfig:
     collaborative: bool = False
     # navigation_graph.py (FA+FR) vs nav_graph_goalassign_noFair.py (FA)
     fairness_reward: bool = True
+    # 'relative' (11 ego-relative node features) or 'global' (7 absolute ones), navigation_graph.py:941-1035
+    graph_feat_type: str = "relative"
     auto_reset: bool = True
     info_every_step: bool = False
     # kernel mapping: 'auto' | 'group' (group-per-env) | 'aw' (agent-warp, compiled for small (N, O));
@@ -31,6 +33,10 @@ class SimConfig:
     @property
     def num_entities(self) -> int:
         return 2 * self.num_agents + self.num_obstacles
+
+    @property
+    def node_feat_dim(self) -> int:
+        return 11 if self.graph_feat_type == "relative" else 7
 
     @classmethod
     def from_args(cls, args: Any, **overrides) -> "SimConfig":
@@ -44,8 +50,8 @@ class SimConfig:
                              f"(got {args.num_landmarks} vs {kw.get('num_agents')})")
         if getattr(args, "num_walls", 0):
             raise NotImplementedError("num_walls > 0 is not supported (SURVEY.md row N4)")
-        if getattr(args, "graph_feat_type", "relative") != "relative":
-            raise NotImplementedError("graph_feat_type='global' is not supported (SURVEY.md row N4)")
+        if getattr(args, "graph_feat_type", "relative") not in ("relative", "global"):
+            raise ValueError(f"graph_feat_type must be 'relative' or 'global' (got {args.graph_feat_type!r})")
         if getattr(args, "num_scripted_agents", 0):
             raise NotImplementedError("scripted agents are not supported")
         scen = getattr(args, "scenario_name", "navigation_graph")

@@ -150,6 +150,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.collaborative = cfg->collaborative;
   p.auto_reset = cfg->auto_reset;
   p.info_every_step = cfg->info_every_step;
+  p.feat_global = cfg->graph_feat_global ? 1 : 0;
   p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull);
   p.seed_hi = (uint32_t)(cfg->seed >> 32);
   p.env_offset = cfg->env_offset;
@@ -333,7 +334,7 @@ static int copy_outputs_to_host(FmHandle* h, const FmOutputs* out_host, bool wit
   const size_t B = h->p.B, N = h->p.N, E = h->p.E;
   if (!out_host) return FM_OK;
   if (out_host->obs) FM_CUDA(cudaMemcpyAsync(out_host->obs, h->st_out.obs, B * N * fm::OBS_F * 4, cudaMemcpyDeviceToHost, st));
-  if (out_host->node_obs) FM_CUDA(cudaMemcpyAsync(out_host->node_obs, h->st_out.node_obs, B * N * E * fm::NODE_F * 4, cudaMemcpyDeviceToHost, st));
+  if (out_host->node_obs) FM_CUDA(cudaMemcpyAsync(out_host->node_obs, h->st_out.node_obs, B * N * E * (h->p.feat_global ? fm::NODE_F_GLOBAL : fm::NODE_F) * 4, cudaMemcpyDeviceToHost, st));
   if (out_host->adj) FM_CUDA(cudaMemcpyAsync(out_host->adj, h->st_out.adj, B * E * E * 4, cudaMemcpyDeviceToHost, st));
   if (with_step_outputs) {
     if (out_host->reward) FM_CUDA(cudaMemcpyAsync(out_host->reward, h->st_out.reward, B * N * 4, cudaMemcpyDeviceToHost, st));
@@ -479,7 +480,8 @@ int fm_mapping(const FmHandle* h) { return h ? h->p.mapping + 1 : 0; }
 int64_t fm_algorithmic_bytes_per_step(const FmHandle* h) {
   if (!h) return 0;
   const int64_t N = h->p.N, O = h->p.O, E = h->p.E;
-  return (30 * N + 2 * O + 5 + 11 * N * E + E * E) * 4 * (int64_t)h->p.B;
+  const int64_t nf = h->p.feat_global ? fm::NODE_F_GLOBAL : fm::NODE_F;
+  return (30 * N + 2 * O + 5 + nf * N * E + E * E) * 4 * (int64_t)h->p.B;
 }
 
 int fm_kernel_launches(const FmHandle* h, int64_t* out) {

@@ -179,11 +179,13 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
 // =============================================================================================
 //   MODE 0: fused env step (MultiAgentGraphEnv.step, environment.py:816-877, + graphworker auto-reset,
 //           env_wrappers.py:859-865).   MODE 1: masked reset + observe (environment.py:882-898).
-template <int N, int O, int MODE>
+// NF: node feature width, NODE_F (relative, 11) or NODE_F_GLOBAL (graph_feat_type = 'global', 7).
+template <int N, int O, int MODE, int NF>
 __global__ void __launch_bounds__(AwLayout<N, O>::THREADS, AwLayout<N, O>::MIN_CTAS)
 aw_kernel(const __grid_constant__ DevParams p) {
   using L = AwLayout<N, O>;
   constexpr int E = L::E, M = L::M, RW = L::RW, SP = L::SP;
+  constexpr int NW = N * E * NF;                   // node_obs words per env (the staging region is sized for NF = 11)
   extern __shared__ __align__(16) float smem[];
   float* ST = smem + L::OFF_STAGE;
   const int tid = threadIdx.x, lane = tid & 31, role = tid >> 5;   // role < N: agent `role`;  role == N: env warp
@@ -576,7 +578,7 @@ aw_kernel(const __grid_constant__ DevParams p) {
   float* g_obs = p.o_obs ? p.o_obs + (size_t)env0 * L::OBS_W : nullptr;
   float* g_rew = (MODE == 0 && p.o_rew) ? p.o_rew + (size_t)env0 * N : nullptr;
   uint8_t* g_done = (MODE == 0 && p.o_done) ? p.o_done + (size_t)env0 * N : nullptr;
-  float* g_node = p.o_node ? p.o_node + (size_t)env0 * L::NODE_W : nullptr;
+  float* g_node = p.o_node ? p.o_node + (size_t)env0 * NW : nullptr;
   const bool bulk = nenv == 32 && aligned16(g_adj) && aligned16(g_obs) && aligned16(g_rew) && aligned16(g_done) &&
                     aligned16(g_node) && (32 * N) % 16 == 0;
   if (bulk) {
@@ -605,31 +607,42 @@ aw_kernel(const __grid_constant__ DevParams p) {
   // with goal_e = assigned landmark for agents and = p_e otherwise, v_e = 0 for non-agents.  Agent warp i
   // writes ego i's E rows from its registers and the tables; lane = env, stride NODE_W (odd): conflict free.
   if (is_agent) {
-    float* o = ST + lane * L::NODE_W + i * E * NODE_F;
+    float* o = ST + lane * NW + i * E * NF;
     const float nvx = 0.f - vx, nvy = 0.f - vy;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const float rpx = Tc[(L::TP + 2 * e) * RW] - px, rpy = Tc[(L::TP + 2 * e + 1) * RW] - py;
-      float rvx = nvx, rvy = nvy, rgx = rpx, rgy = rpy;
-      if (e < N) {
-        rvx = Tc[(L::TV + 2 * e) * RW] - vx; rvy = Tc[(L::TV + 2 * e + 1) * RW] - vy;
-        rgx = Tc[(L::TG + 2 * e) * RW] - px; rgy = Tc[(L::TG + 2 * e + 1) * RW] - py;
+      const float epx = Tc[(L::TP + 2 * e) * RW], epy = Tc[(L::TP + 2 * e + 1) * RW];
+      const float ty = (e < N) ? 0.0f : ((e < 2 * N) ? 1.0f : 2.0f);
+      if (NF == NODE_F_GLOBAL) {                    // [vel, pos, goal, type] in world coordinates, same rows for every ego agent
+        float evx = 0.f, evy = 0.f, egx = epx, egy = epy;
+        if (e < N) {
+          evx = Tc[(L::TV + 2 * e) * RW]; evy = Tc[(L::TV + 2 * e + 1) * RW];
+          egx = Tc[(L::TG + 2 * e) * RW]; egy = Tc[(L::TG + 2 * e + 1) * RW];
+        }
+        o[0] = evx; o[1] = evy; o[2] = epx; o[3] = epy; o[4] = egx; o[5] = egy; o[6] = ty;
+      } else {
+        const float rpx = epx - px, rpy = epy - py;
+        float rvx = nvx, rvy = nvy, rgx = rpx, rgy = rpy;
+        if (e < N) {
+          rvx = Tc[(L::TV + 2 * e) * RW] - vx; rvy = Tc[(L::TV + 2 * e + 1) * RW] - vy;
+          rgx = Tc[(L::TG + 2 * e) * RW] - px; rgy = Tc[(L::TG + 2 * e + 1) * RW] - py;
+        }
+        o[0] = rvx; o[1] = rvy; o[2] = rpx; o[3] = rpy; o[4] = rgx; o[5] = rgy;
+        o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy;
+        o[10] = ty;
       }
-      o[0] = rvx; o[1] = rvy; o[2] = rpx; o[3] = rpy; o[4] = rgx; o[5] = rgy;
-      o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy;
-      o[10] = (e < N) ? 0.0f : ((e < 2 * N) ? 1.0f : 2.0f);
-      o += NODE_F;
+      o += NF;
     }
   }
   __syncthreads();                                // #5
   if (bulk) {
     if (tid == 0) {
       fence_async_smem();
-      bulk_store(g_node, ST, 32 * L::NODE_W * 4, evict_first_policy());
+      bulk_store(g_node, ST, 32 * NW * 4, evict_first_policy());
       bulk_commit_wait_read();                    // the image must stay valid until the copy engine has read it
     }
   } else {
-    cta_copy_out<L::THREADS, 32 * L::NODE_W>(g_node, ST, nenv * L::NODE_W, tid);
+    cta_copy_out<L::THREADS, 32 * NW>(g_node, ST, nenv * NW, tid);
   }
 }
 
@@ -657,8 +670,13 @@ static cudaError_t aw_launch_no(const DevParams& p, cudaStream_t st, bool is_res
   const int blocks = (p.env_end - p.env_begin + 31) / 32;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)L::WORDS * sizeof(float);
-  if (is_reset) aw_kernel<N, O, 1><<<blocks, L::THREADS, smem, st>>>(p);
-  else aw_kernel<N, O, 0><<<blocks, L::THREADS, smem, st>>>(p);
+  if (p.feat_global) {
+    if (is_reset) aw_kernel<N, O, 1, NODE_F_GLOBAL><<<blocks, L::THREADS, smem, st>>>(p);
+    else aw_kernel<N, O, 0, NODE_F_GLOBAL><<<blocks, L::THREADS, smem, st>>>(p);
+  } else {
+    if (is_reset) aw_kernel<N, O, 1, NODE_F><<<blocks, L::THREADS, smem, st>>>(p);
+    else aw_kernel<N, O, 0, NODE_F><<<blocks, L::THREADS, smem, st>>>(p);
+  }
   return cudaGetLastError();
 }
 
@@ -666,9 +684,11 @@ template <int N, int O>
 static cudaError_t aw_prepare_no() {
   using L = AwLayout<N, O>;
   const int smem = L::WORDS * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(aw_kernel<N, O, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(aw_kernel<N, O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(aw_kernel<N, O, 0, NODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 1, NODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 0, NODE_F_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 1, NODE_F_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return e;
 }
 
 // The (N, O) pairs compiled for this mapping.  Everything else runs the group-per-env kernels.

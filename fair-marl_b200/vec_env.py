@@ -89,6 +89,7 @@ class B200GraphVecEnv:
         cfg = self.cfg
         N, E = cfg.num_agents, cfg.num_entities
         self.num_agents, self.num_entities = N, E
+        self.node_feat_dim = cfg.node_feat_dim
 
         c = _lib.FmConfig(
             num_envs=self.num_envs, num_agents=N, num_obstacles=cfg.num_obstacles,
@@ -98,7 +99,8 @@ class B200GraphVecEnv:
             fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
             fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative),
             auto_reset=int(cfg.auto_reset), info_every_step=int(cfg.info_every_step),
-            mapping={"auto": 0, "group": 1, "aw": 2}[cfg.mapping])
+            mapping={"auto": 0, "group": 1, "aw": 2}[cfg.mapping],
+            graph_feat_global=int(cfg.graph_feat_type == "global"))
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_create")
 
@@ -107,7 +109,7 @@ class B200GraphVecEnv:
         self.observation_space = [Box(-inf, inf, (_lib.OBS_DIM,)) for _ in range(N)]
         self.share_observation_space = [Box(-inf, inf, (_lib.OBS_DIM * N,)) for _ in range(N)]
         self.action_space = [Discrete(5) for _ in range(N)]
-        self.node_observation_space = [Box(-inf, inf, (E, _lib.NODE_FEAT_DIM)) for _ in range(N)]
+        self.node_observation_space = [Box(-inf, inf, (E, self.node_feat_dim)) for _ in range(N)]
         self.adj_observation_space = [Box(-inf, inf, (E, E)) for _ in range(N)]
         self.edge_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
         self.agent_id_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
@@ -136,7 +138,7 @@ class B200GraphVecEnv:
             self._host = {
                 "onehot": t.empty((B, N, 5), dtype=t.float32, **pin),
                 "obs": [t.empty((B, N, _lib.OBS_DIM), dtype=t.float32, **pin) for _ in range(2)],
-                "node_obs": [t.empty((B, N, E, _lib.NODE_FEAT_DIM), dtype=t.float32, **pin) for _ in range(2)],
+                "node_obs": [t.empty((B, N, E, self.node_feat_dim), dtype=t.float32, **pin) for _ in range(2)],
                 "adj": [t.empty((B, E, E), dtype=t.float32, **pin) for _ in range(2)],
                 "reward": [t.empty((B, N), dtype=t.float32, **pin) for _ in range(2)],
                 "done": [t.empty((B, N), dtype=t.uint8, **pin) for _ in range(2)],
@@ -151,7 +153,7 @@ class B200GraphVecEnv:
             kw = dict(device=self.device)
             self._slabs = {
                 "obs": t.empty((S, B, N, _lib.OBS_DIM), dtype=t.float32, **kw),
-                "node_obs": t.empty((S, B, N, E, _lib.NODE_FEAT_DIM), dtype=t.float32, **kw),
+                "node_obs": t.empty((S, B, N, E, self.node_feat_dim), dtype=t.float32, **kw),
                 "adj": t.empty((S, B, E, E), dtype=t.float32, **kw),
                 "reward": t.empty((S, B, N), dtype=t.float32, **kw),
                 "done": t.empty((S, B, N), dtype=t.uint8, **kw),
@@ -186,7 +188,7 @@ class B200GraphVecEnv:
         """Validate caller-owned output arrays (e.g. slabs of a ``DeviceRolloutBuffer``): contiguous CUDA tensors of the
         API shapes; ``adj`` is ``[B, E, E]`` (one matrix per env)."""
         t, B, N, E = self.torch, self.num_envs, self.num_agents, self.num_entities
-        want = {"obs": ((B, N, _lib.OBS_DIM), t.float32), "node_obs": ((B, N, E, _lib.NODE_FEAT_DIM), t.float32),
+        want = {"obs": ((B, N, _lib.OBS_DIM), t.float32), "node_obs": ((B, N, E, self.node_feat_dim), t.float32),
                 "adj": ((B, E, E), t.float32)}
         if with_step:
             want.update(reward=((B, N), t.float32), done=((B, N), t.uint8))

@@ -66,13 +66,14 @@ typedef struct FmConfig {
   int32_t info_every_step; /* 0: info rows are written on terminal steps only */
   int32_t mapping;         /* kernel mapping: 0 auto (agent-warp when compiled for (N, O), else group-per-env),
                               1 group-per-env, 2 agent-warp.  Results are identical. */
-  int32_t reserved_;
+  int32_t graph_feat_global; /* 0: graph_feat_type 'relative' (node_obs [B,N,E,11], navigation_graph.py:1079-1124);
+                                1: 'global' (node_obs [B,N,E,7] = [vel, pos, goal, type], :1058-1077) */
 } FmConfig;
 
 /* Per-step outputs, API layout (what GraphSubprocVecEnv.step_wait stacks, env_wrappers.py:988-996). */
 typedef struct FmOutputs {
   float* obs;        /* [B, N, 7] */
-  float* node_obs;   /* [B, N, E, 11] */
+  float* node_obs;   /* [B, N, E, 11]  ([B, N, E, 7] with graph_feat_global) */
   float* adj;        /* [B, E, E]   (identical for the N agents of an env: written once) */
   float* reward;     /* [B, N] */
   uint8_t* done;     /* [B, N] */

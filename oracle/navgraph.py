@@ -50,6 +50,8 @@ class NavConfig:
     # True  -> navigation_graph.py (FA+FR: tanh fairness term in the reward, :806-823)
     # False -> nav_graph_goalassign_noFair.py (FA: same file minus that term)
     fairness_reward: bool = True
+    # 'relative': ego-relative 11-dim node features (:1079-1124);  'global': 7-dim absolute features (:1058-1077)
+    graph_feat_type: str = "relative"
     dt: float = 0.1
     damping: float = 0.25
     contact_force: float = 3e2
@@ -61,6 +63,10 @@ class NavConfig:
     @property
     def num_entities(self) -> int:
         return 2 * self.num_agents + self.num_obstacles
+
+    @property
+    def node_feat_dim(self) -> int:
+        return 11 if self.graph_feat_type == "relative" else 7
 
 
 STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_match",
@@ -286,11 +292,18 @@ class NavGraphOracle:
         s.dist_traveled_stddev = np.std(s.dists_to_goal, axis=1)                  # :618
 
     def _node_obs(self, goal: np.ndarray) -> np.ndarray:
-        """navigation_graph.py:941-1035 + :1079-1124 (relative features) -> [B,N,E,11]."""
+        """navigation_graph.py:941-1035 + :1079-1124 (relative features) -> [B,N,E,11];
+        :1058-1077 (global features [vel, pos, goal, type], the same rows for every agent) -> [B,N,E,7]."""
         cfg, s = self.cfg, self.s
         N, O, E = cfg.num_agents, cfg.num_obstacles, cfg.num_entities
         ent_pos = self._entity_pos()
         ent_vel = np.concatenate([s.vel, np.zeros((self.B, N + O, 2))], axis=1)
+        if cfg.graph_feat_type == "global":
+            g = ent_pos.copy()
+            g[:, :N] = goal
+            typ = np.concatenate([np.zeros(N), np.ones(N), 2.0 * np.ones(O)])
+            rows = np.concatenate([ent_vel, ent_pos, g, np.broadcast_to(typ[None, :, None], (self.B, E, 1))], axis=2)
+            return np.broadcast_to(rows[:, None], (self.B, N, E, 7)).copy()
         out = np.zeros((self.B, N, E, 11))
         for a in range(N):
             rel_pos = ent_pos - s.pos[:, a:a + 1]

@@ -71,7 +71,7 @@ def args_from_config(cfg: NavConfig) -> Namespace:
         num_scripted_agents=0, num_obstacles=cfg.num_obstacles, collaborative=cfg.collaborative,
         max_speed=cfg.max_speed, collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew,
         min_dist_thresh=cfg.min_dist_thresh, use_dones=False, episode_length=cfg.episode_length,
-        max_edge_dist=cfg.max_edge_dist, graph_feat_type="relative", fair_wt=1, fair_rew=cfg.fair_rew,
+        max_edge_dist=cfg.max_edge_dist, graph_feat_type=cfg.graph_feat_type, fair_wt=1, fair_rew=cfg.fair_rew,
         num_walls=0, zeroshift=cfg.zeroshift, scenario_name="navigation_graph",
         algorithm_name="rmappo")
 

@@ -143,3 +143,29 @@ def test_ragged_batch_sizes(B):
         o["adj"] = o["adj_env"]
         compare_step_outputs(o, ref, cfg)
         env.close()
+
+
+def test_global_graph_features_through_the_reference_api():
+    """graph_feat_type='global' (navigation_graph.py:1058-1077): node_obs [B,N,E,7] = [vel, pos, goal, type] in world
+    coordinates, the same rows for every agent; checked against the oracle through the numpy API."""
+    import fair_marl_b200 as fm
+    cfg = NavConfig(num_agents=3, num_obstacles=3, graph_feat_type="global")
+    B, N, E = 70, 3, 9
+    env = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=4)
+    assert env.node_observation_space[0].shape == (E, 7)
+    orc = NavGraphOracle(cfg, B, seed=4)
+    obs, ag_id, node, adj = env.reset()
+    ref = orc.reset()
+    assert node.shape == (B, N, E, 7)
+    assert_close(node, ref["node_obs"], "reset node_obs (global)")
+    rng = np.random.default_rng(1)
+    for t in range(27):
+        orc.set_state(device_state_to_nav(env.get_state()))
+        a = rng.integers(0, 5, (B, N))
+        obs, ag_id, node, adj, rew, done, infos = env.step(a)
+        want = orc.step(actions=a)
+        assert node.shape == (B, N, E, 7) and (node[:, 0] == node[:, 1]).all()
+        assert_close(node, want["node_obs"], f"node_obs (global) step {t}")
+        assert (node[..., 6] == np.array([0, 0, 0, 1, 1, 1, 2, 2, 2], dtype=np.float32)).all()
+        assert_close(rew, want["reward"], f"reward step {t}")
+    env.close()
