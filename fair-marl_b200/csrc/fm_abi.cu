@@ -169,10 +169,19 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   // adj / obs images sit at the 16-byte phase of their destinations (<= 3 words of slack); the adj region is
   // reused as two node_obs staging buffers of stage_k x 32 rows (+ phase slack) each, so it holds at least 2 x 1.
   const int stage_words = fm::STAGE_SUB * fm::NODE_F;                  // 352
-  int want_k = 1;
-  if (const char* ev = getenv("FM_STAGE_K")) want_k = atoi(ev) >= 3 ? 3 : 1;   // diagnostic: force 96-row chunks
-  p.sm_adj = round4(std::max((long long)EPW * E * E + 3, 2LL * (want_k * stage_words + 4)));
-  p.stage_k = (((p.sm_adj >> 1) & ~3) - 3) / stage_words >= 3 ? 3 : 1;          // 32 or 96 rows per chunk
+  // node_obs staging inside the adj region: two buffers of 96 rows if they fit, else ONE buffer of 96 rows (refilled
+  // once the copy engine has read it: fewer, larger chunks beat double buffering when the region is small -- N = 7),
+  // else two buffers of 32 rows.  FM_STAGE=k3x2|k3x1|k1x2 forces a variant (diagnostic; may enlarge the region).
+  const char* force = getenv("FM_STAGE");
+  long long need = (long long)EPW * E * E + 3;
+  if (force && !strcmp(force, "k3x2")) need = std::max(need, 2LL * (3 * stage_words + 4));
+  p.sm_adj = round4(std::max(need, 2LL * (stage_words + 4)));
+  const int half = (p.sm_adj >> 1) & ~3;
+  if (half - 3 >= 3 * stage_words) { p.stage_k = 3; p.stage_bufs = 2; }
+  else if (p.sm_adj - 3 >= 3 * stage_words) { p.stage_k = 3; p.stage_bufs = 1; }
+  else { p.stage_k = 1; p.stage_bufs = 2; }
+  if (force && !strcmp(force, "k1x2")) { p.stage_k = 1; p.stage_bufs = 2; }
+  if (force && !strcmp(force, "k3x1") && p.sm_adj - 3 >= 3 * stage_words) { p.stage_k = 3; p.stage_bufs = 1; }
   p.sm_obs = round4((long long)EPW * N * fm::OBS_F + 3);
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_obs + p.sm_asg;
@@ -452,15 +461,18 @@ int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, do
   if (num_graphs > 0 && !adj) return fail(FM_ERR_INVALID_ARG, "fm_edge_list: null adj");
   int rc = use_device(device);
   if (rc) return rc;
-  // counts scratch lives at the tail of graph_offsets' own storage? No: keep the ABI honest and
-  // allocate it stream-ordered.
-  int* counts = nullptr;
+  // scratch (stream-ordered): per-CTA sums / offsets (int64) followed by the per-graph counts (int32)
+  const int nb = fm::edge_list_blocks(num_graphs);
   cudaStream_t st = (cudaStream_t)stream;
-  FM_CUDA(cudaMallocAsync((void**)&counts, sizeof(int) * (size_t)(num_graphs > 0 ? num_graphs : 1), st));
+  void* scratch = nullptr;
+  const size_t bs_bytes = sizeof(long long) * (size_t)(nb > 0 ? nb : 1);
+  FM_CUDA(cudaMallocAsync(&scratch, bs_bytes + sizeof(int) * (size_t)(num_graphs > 0 ? num_graphs : 1), st));
+  long long* blocksums = (long long*)scratch;
+  int* counts = (int*)((char*)scratch + bs_bytes);
   cudaError_t e = fm::launch_edge_list(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity,
-                                       counts, (long long*)graph_offsets, (long long*)edge_index, edge_attr,
+                                       counts, blocksums, (long long*)graph_offsets, (long long*)edge_index, edge_attr,
                                        (long long*)nnz_out, st);
-  cudaFreeAsync(counts, st);
+  cudaFreeAsync(scratch, st);
   if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_edge_list: %s", cudaGetErrorString(e));
   return FM_OK;
 }

@@ -419,65 +419,79 @@ __device__ __forceinline__ bool edge_pred(float d, float thr, int inclusive) {
   return (inclusive ? (d <= thr) : (d < thr)) && (d > 0.0f);
 }
 
+constexpr int EDGE_WPB = 8;          // graphs (warps) per CTA of the edge-list kernels
+
+// Pass 1: edges per graph (one warp per graph) and per CTA.
 __global__ void edge_count_kernel(const float* __restrict__ adj, int num_graphs, int EE, float thr, int inclusive,
-                                  int* __restrict__ counts) {
-  const int lane = threadIdx.x & 31;
-  const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (g >= num_graphs) return;
-  const float* a = adj + (size_t)g * EE;
+                                  int* __restrict__ counts, long long* __restrict__ blocksums) {
+  __shared__ int wc[EDGE_WPB];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = blockIdx.x * EDGE_WPB + w;
   int c = 0;
-  for (int q = lane; q < EE; q += 32) c += edge_pred(a[q], thr, inclusive) ? 1 : 0;
-  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(FULL, c, off);
-  if (lane == 0) counts[g] = c;
+  if (g < num_graphs) {
+    const float* a = adj + (size_t)g * EE;
+    for (int q = lane; q < EE; q += 32) c += edge_pred(__ldg(a + q), thr, inclusive) ? 1 : 0;
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(FULL, c, off);
+    if (lane == 0) counts[g] = c;
+  }
+  if (lane == 0) wc[w] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < EDGE_WPB; ++k) t += wc[k];
+    blocksums[blockIdx.x] = t;
+  }
 }
 
-// Exclusive scan of counts (as int64, each graph counted `repeat` times) by ONE block, sequential
-// over tiles: num_graphs is at most a few hundred thousand, so this is a few microseconds.
-__global__ void edge_scan_kernel(const int* __restrict__ counts, int num_graphs, int repeat,
-                                 long long* __restrict__ graph_offsets, long long* __restrict__ nnz_out) {
-  __shared__ long long wsum[32];
-  __shared__ long long carry;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
+// Pass 2: exclusive scan of the per-CTA sums by ONE block (in place; each thread owns a contiguous segment, the 1024
+// segment totals are scanned through shared memory), scaled by `repeat`.  num_blocks = num_graphs / 8: 32 K entries
+// at 262 144 graphs, a few microseconds.  Also writes the end sentinel of graph_offsets and nnz.
+__global__ void edge_scan_kernel(long long* __restrict__ blocksums, int num_blocks, int repeat, long long* __restrict__ sentinel,
+                                 long long* __restrict__ nnz_out) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (num_blocks + 1023) / 1024;
+  const int lo = min(num_blocks, t * per), hi = min(num_blocks, lo + per);
+  long long sum = 0;
+  for (int k = lo; k < hi; ++k) sum += blocksums[k];
+  part[t] = sum;
   __syncthreads();
-  for (int base = 0; base < num_graphs; base += blockDim.x) {
-    const int g = base + threadIdx.x;
-    const long long c = (g < num_graphs) ? (long long)counts[g] : 0;
-    long long v = c * repeat;
-    long long incl = v;
-    for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += o; }
-    if (lane == 31) wsum[w] = incl;
+  for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan of the segment totals
+    const long long v = (t >= off) ? part[t - off] : 0;
     __syncthreads();
-    if (w == 0) {
-      long long x = (lane < nw) ? wsum[lane] : 0, xi = x;
-      for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(FULL, xi, off); if (lane >= off) xi += o; }
-      wsum[lane] = xi - x;
-    }
-    __syncthreads();
-    const long long excl = carry + wsum[w] + incl - v;
-    if (g < num_graphs)
-      for (int a = 0; a < repeat; ++a) graph_offsets[(size_t)g * repeat + a] = excl + (long long)a * c;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    part[t] += v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { graph_offsets[(size_t)num_graphs * repeat] = carry; if (nnz_out) *nnz_out = carry; }
+  long long run = (part[t] - sum) * repeat;
+  for (int k = lo; k < hi; ++k) { const long long c = blocksums[k]; blocksums[k] = run; run += c * repeat; }
+  if (t == 1023) { *sentinel = part[1023] * repeat; if (nnz_out) *nnz_out = part[1023] * repeat; }
 }
 
+// Pass 3: graph offsets inside the CTA from the 8 counts, then ballot + popc compaction in (b, i, j) order.
 __global__ void edge_emit_kernel(const float* __restrict__ adj, int num_graphs, int E, float thr, int inclusive, int repeat,
-                                 long long capacity, const long long* __restrict__ graph_offsets,
-                                 long long* __restrict__ edge_index, float* __restrict__ edge_attr) {
-  const int lane = threadIdx.x & 31;
-  const int g = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+                                 long long capacity, const int* __restrict__ counts, const long long* __restrict__ blockoffs,
+                                 long long* __restrict__ graph_offsets, long long* __restrict__ edge_index,
+                                 float* __restrict__ edge_attr) {
+  __shared__ int wc[EDGE_WPB];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = blockIdx.x * EDGE_WPB + w;
+  const int cnt = (g < num_graphs) ? counts[g] : 0;
+  if (lane == 0) wc[w] = cnt;
+  __syncthreads();
   if (g >= num_graphs) return;
+  int before = 0;
+#pragma unroll
+  for (int k = 0; k < EDGE_WPB; ++k) before += (k < w) ? wc[k] : 0;
+  const long long base0 = blockoffs[blockIdx.x] + (long long)before * repeat;
+  if (lane < repeat) graph_offsets[(size_t)g * repeat + lane] = base0 + (long long)lane * cnt;
+  for (int cp = 32 + lane; cp < repeat; cp += 32) graph_offsets[(size_t)g * repeat + cp] = base0 + (long long)cp * cnt;
   const int EE = E * E;
   const float* a = adj + (size_t)g * EE;
-  const long long base0 = graph_offsets[(size_t)g * repeat];
-  const long long cnt = graph_offsets[(size_t)g * repeat + 1] - base0;   // per copy (offsets has +1 sentinel)
   int run = 0;
   for (int q0 = 0; q0 < EE; q0 += 32) {
     const int q = q0 + lane;
-    const float d = (q < EE) ? a[q] : 0.0f;
+    const float d = (q < EE) ? __ldg(a + q) : 0.0f;
     const bool pr = (q < EE) && edge_pred(d, thr, inclusive);
     const unsigned b = __ballot_sync(FULL, pr);
     if (pr) {
@@ -487,9 +501,9 @@ __global__ void edge_emit_kernel(const float* __restrict__ adj, int num_graphs, 
         const long long pos = base0 + (long long)cp * cnt + k;
         if (pos < capacity) {
           const long long node0 = ((long long)g * repeat + cp) * E;
-          edge_index[pos] = node0 + r;
-          edge_index[capacity + pos] = node0 + c;
-          edge_attr[pos] = d;
+          __stcs(edge_index + pos, node0 + r);
+          __stcs(edge_index + capacity + pos, node0 + c);
+          __stcs(edge_attr + pos, d);
         }
       }
     }
@@ -603,17 +617,18 @@ cudaError_t launch_state_init(const DevParams& p, cudaStream_t st) {
 }
 
 cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
-                             long long capacity, int* counts, long long* graph_offsets, long long* edge_index,
-                             float* edge_attr, long long* nnz_out, cudaStream_t st) {
-  const int wpb = 8;
-  const int blocks = (num_graphs + wpb - 1) / wpb;
-  if (num_graphs > 0) edge_count_kernel<<<blocks, wpb * 32, 0, st>>>(adj, num_graphs, E * E, thr, inclusive, counts);
-  edge_scan_kernel<<<1, 1024, 0, st>>>(counts, num_graphs, repeat, graph_offsets, nnz_out);
-  if (num_graphs > 0)
-    edge_emit_kernel<<<blocks, wpb * 32, 0, st>>>(adj, num_graphs, E, thr, inclusive, repeat, capacity, graph_offsets,
-                                                  edge_index, edge_attr);
+                             long long capacity, int* counts, long long* blocksums, long long* graph_offsets,
+                             long long* edge_index, float* edge_attr, long long* nnz_out, cudaStream_t st) {
+  const int blocks = (num_graphs + EDGE_WPB - 1) / EDGE_WPB;
+  if (blocks > 0) edge_count_kernel<<<blocks, EDGE_WPB * 32, 0, st>>>(adj, num_graphs, E * E, thr, inclusive, counts, blocksums);
+  edge_scan_kernel<<<1, 1024, 0, st>>>(blocksums, blocks, repeat, graph_offsets + (size_t)num_graphs * repeat, nnz_out);
+  if (blocks > 0)
+    edge_emit_kernel<<<blocks, EDGE_WPB * 32, 0, st>>>(adj, num_graphs, E, thr, inclusive, repeat, capacity, counts, blocksums,
+                                                      graph_offsets, edge_index, edge_attr);
   return cudaGetLastError();
 }
+
+int edge_list_blocks(int num_graphs) { return (num_graphs + EDGE_WPB - 1) / EDGE_WPB; }
 
 __global__ void pair_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, long long num, double* __restrict__ out) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;

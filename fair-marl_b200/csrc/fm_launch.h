@@ -25,9 +25,10 @@ cudaError_t launch_assign(const double* costs, const float* apos, const float* g
                           cudaStream_t st);
 cudaError_t launch_state_io(const DevParams& p, const HostState& hs, int to_internal, cudaStream_t st);
 cudaError_t launch_state_init(const DevParams& p, cudaStream_t st);
+int edge_list_blocks(int num_graphs);             // CTAs of the edge-list kernels (8 graphs each): size of `blocksums`
 cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
-                             long long capacity, int* counts, long long* graph_offsets, long long* edge_index,
-                             float* edge_attr, long long* nnz_out, cudaStream_t st);
+                             long long capacity, int* counts, long long* blocksums, long long* graph_offsets,
+                             long long* edge_index, float* edge_attr, long long* nnz_out, cudaStream_t st);
 cudaError_t launch_pair_dist(const float* a, const float* b, long long num, double* out, cudaStream_t st);
 cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st);
 }  // namespace fm
