@@ -430,6 +430,7 @@ __global__ void edge_count_kernel(const float* __restrict__ adj, int num_graphs,
   int c = 0;
   if (g < num_graphs) {
     const float* a = adj + (size_t)g * EE;
+#pragma unroll 8
     for (int q = lane; q < EE; q += 32) c += edge_pred(__ldg(a + q), thr, inclusive) ? 1 : 0;
     for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(FULL, c, off);
     if (lane == 0) counts[g] = c;
@@ -488,26 +489,36 @@ __global__ void edge_emit_kernel(const float* __restrict__ adj, int num_graphs, 
   for (int cp = 32 + lane; cp < repeat; cp += 32) graph_offsets[(size_t)g * repeat + cp] = base0 + (long long)cp * cnt;
   const int EE = E * E;
   const float* a = adj + (size_t)g * EE;
+  const unsigned magic = (E <= 100) ? ((1u << 20) + E - 1) / E : 0u;       // q / E == (q * magic) >> 20 for q < 2^20 / E
   int run = 0;
-  for (int q0 = 0; q0 < EE; q0 += 32) {
-    const int q = q0 + lane;
-    const float d = (q < EE) ? __ldg(a + q) : 0.0f;
-    const bool pr = (q < EE) && edge_pred(d, thr, inclusive);
-    const unsigned b = __ballot_sync(FULL, pr);
-    if (pr) {
-      const int k = run + __popc(b & ((1u << lane) - 1u));
-      const int r = q / E, c = q - r * E;
-      for (int cp = 0; cp < repeat; ++cp) {
-        const long long pos = base0 + (long long)cp * cnt + k;
-        if (pos < capacity) {
-          const long long node0 = ((long long)g * repeat + cp) * E;
-          __stcs(edge_index + pos, node0 + r);
-          __stcs(edge_index + capacity + pos, node0 + c);
-          __stcs(edge_attr + pos, d);
+  constexpr int U = 8;                               // 8 independent loads in flight per lane before the compaction
+  for (int q0 = 0; q0 < EE; q0 += 32 * U) {
+    float dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int q = q0 + u * 32 + lane; dv[u] = (q < EE) ? __ldg(a + q) : 0.0f; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32 + lane;
+      if (q0 + u * 32 >= EE) break;                  // warp-uniform
+      const float d = dv[u];
+      const bool pr = (q < EE) && edge_pred(d, thr, inclusive);
+      const unsigned b = __ballot_sync(FULL, pr);
+      if (pr) {
+        const int k = run + __popc(b & ((1u << lane) - 1u));
+        const int r = magic ? (int)(((unsigned)q * magic) >> 20) : q / E;
+        const int c = q - r * E;
+        for (int cp = 0; cp < repeat; ++cp) {
+          const long long pos = base0 + (long long)cp * cnt + k;
+          if (pos < capacity) {
+            const long long node0 = ((long long)g * repeat + cp) * E;
+            __stcs(edge_index + pos, node0 + r);
+            __stcs(edge_index + capacity + pos, node0 + c);
+            __stcs(edge_attr + pos, d);
+          }
         }
       }
+      run += __popc(b);
     }
-    run += __popc(b);
   }
 }
 
