@@ -249,6 +249,19 @@ int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* strea
   return FM_OK;
 }
 
+// Side streams + fork / join events shared by fm_step_many (env-range lanes) and the host-buffer copies.
+static int ensure_lanes(FmHandle* h) {
+  if (h->lanes_ready) return FM_OK;
+  h->lane_stream[0] = nullptr;
+  for (int k = 1; k < FM_MAX_LANES; ++k) {
+    FM_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
+    FM_CUDA(cudaEventCreateWithFlags(&h->lane_join[k], cudaEventDisableTiming));
+  }
+  FM_CUDA(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
+  h->lanes_ready = 1;
+  return FM_OK;
+}
+
 static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, const FmOutputs* out, void* stream) {
   if (!h) return fail(FM_ERR_INVALID_ARG, "fm_step: null handle");
   if (!idx && !onehot) return fail(FM_ERR_INVALID_ARG, "fm_step: null actions");
@@ -287,15 +300,7 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
     const int v = atoi(ev);
     if (v >= 1 && v <= FM_MAX_LANES) lanes = v;
   }
-  if (lanes > 1 && !h->lanes_ready) {
-    h->lane_stream[0] = nullptr;
-    for (int k = 1; k < FM_MAX_LANES; ++k) {
-      FM_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
-      FM_CUDA(cudaEventCreateWithFlags(&h->lane_join[k], cudaEventDisableTiming));
-    }
-    FM_CUDA(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
-    h->lanes_ready = 1;
-  }
+  if (lanes > 1) { rc = ensure_lanes(h); if (rc) return rc; }
   cudaStream_t user = (cudaStream_t)stream;
   if (lanes > 1) {
     FM_CUDA(cudaEventRecord(h->lane_fork, user));
@@ -339,16 +344,44 @@ static int ensure_staging(FmHandle* h) {
   return FM_OK;
 }
 
+// Device staging -> caller's host buffers.  One D2H stream reaches ~52 GB/s on this PCIe link, two concurrent ones
+// ~55 GB/s (two copy engines), so large results are split over the caller's stream and one side stream (about half
+// of the bytes each: the side stream takes adj and the tail of node_obs) and joined before returning.
 static int copy_outputs_to_host(FmHandle* h, const FmOutputs* out_host, bool with_step_outputs, cudaStream_t st) {
   const size_t B = h->p.B, N = h->p.N, E = h->p.E;
   if (!out_host) return FM_OK;
+  const size_t node_bytes = B * N * E * (h->p.feat_global ? fm::NODE_F_GLOBAL : fm::NODE_F) * 4, adj_bytes = B * E * E * 4;
+  const size_t small_bytes = B * N * (fm::OBS_F * 4 + 5);
+  size_t node_side = 0;                              // bytes of node_obs copied by the side stream
+  cudaStream_t side = st;
+  const bool split = out_host->node_obs && node_bytes + adj_bytes > (8u << 20);
+  if (split) {
+    int rc = ensure_lanes(h);
+    if (rc) return rc;
+    side = h->lane_stream[1];
+    const size_t total = node_bytes + (out_host->adj ? adj_bytes : 0) + small_bytes;
+    const size_t side_adj = out_host->adj ? adj_bytes : 0;
+    node_side = total / 2 > side_adj ? ((total / 2 - side_adj) & ~(size_t)15) : 0;
+    if (node_side > node_bytes) node_side = node_bytes;
+    FM_CUDA(cudaEventRecord(h->lane_fork, st));
+    FM_CUDA(cudaStreamWaitEvent(side, h->lane_fork, 0));
+  }
+  if (out_host->node_obs) {
+    FM_CUDA(cudaMemcpyAsync(out_host->node_obs, h->st_out.node_obs, node_bytes - node_side, cudaMemcpyDeviceToHost, st));
+    if (node_side)
+      FM_CUDA(cudaMemcpyAsync((char*)out_host->node_obs + (node_bytes - node_side), (char*)h->st_out.node_obs + (node_bytes - node_side),
+                              node_side, cudaMemcpyDeviceToHost, side));
+  }
+  if (out_host->adj) FM_CUDA(cudaMemcpyAsync(out_host->adj, h->st_out.adj, adj_bytes, cudaMemcpyDeviceToHost, side));
   if (out_host->obs) FM_CUDA(cudaMemcpyAsync(out_host->obs, h->st_out.obs, B * N * fm::OBS_F * 4, cudaMemcpyDeviceToHost, st));
-  if (out_host->node_obs) FM_CUDA(cudaMemcpyAsync(out_host->node_obs, h->st_out.node_obs, B * N * E * (h->p.feat_global ? fm::NODE_F_GLOBAL : fm::NODE_F) * 4, cudaMemcpyDeviceToHost, st));
-  if (out_host->adj) FM_CUDA(cudaMemcpyAsync(out_host->adj, h->st_out.adj, B * E * E * 4, cudaMemcpyDeviceToHost, st));
   if (with_step_outputs) {
     if (out_host->reward) FM_CUDA(cudaMemcpyAsync(out_host->reward, h->st_out.reward, B * N * 4, cudaMemcpyDeviceToHost, st));
     if (out_host->done) FM_CUDA(cudaMemcpyAsync(out_host->done, h->st_out.done, B * N, cudaMemcpyDeviceToHost, st));
     if (out_host->info) FM_CUDA(cudaMemcpyAsync(out_host->info, h->st_out.info, B * N * fm::INFO_F * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (split) {
+    FM_CUDA(cudaEventRecord(h->lane_join[1], side));
+    FM_CUDA(cudaStreamWaitEvent(st, h->lane_join[1], 0));
   }
   return FM_OK;
 }

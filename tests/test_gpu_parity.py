@@ -312,3 +312,30 @@ def test_mapping_unavailable_raises(mapping):
     import fair_marl_b200 as fm
     with pytest.raises(fm._lib.FairMarlError, match="not compiled"):
         fm.B200GraphVecEnv(fm.SimConfig(num_agents=7, mapping=mapping), num_envs=8)
+
+
+@pytest.mark.parametrize("variant", ["k1x2", "k3x1", "k3x2"])
+def test_group_kernel_staging_variants_are_bitwise_equal(variant, monkeypatch):
+    """The node_obs staging of the group kernel has three shapes (two 32-row buffers, one 96-row buffer, two 96-row
+    buffers; fm_create picks by what fits, FM_STAGE forces one).  All of them must produce the same bytes."""
+    import torch
+    cfg = NavConfig(num_agents=7, num_obstacles=3)
+    B = 37                                            # ragged: the last warp holds one env
+    outs = []
+    for force in (None, variant):
+        if force:
+            monkeypatch.setenv("FM_STAGE", force)
+        else:
+            monkeypatch.delenv("FM_STAGE", raising=False)
+        env = _env(cfg, B, seed=21, sim=dict(mapping="group"))
+        o = env.reset_tensor()
+        rec = [o["node_obs"].clone(), o["adj_env"].clone()]
+        g = torch.Generator(device="cuda").manual_seed(3)
+        for t in range(27):
+            a = torch.randint(0, 5, (B, 7), generator=g, device="cuda", dtype=torch.int32)
+            o = env.step_tensor(a)
+            rec += [o["node_obs"].clone(), o["adj_env"].clone(), o["obs"].clone(), o["reward"].clone()]
+        outs.append(rec)
+        env.close()
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
