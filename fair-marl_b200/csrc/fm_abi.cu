@@ -45,6 +45,13 @@ struct FmHandle {
   cudaStream_t lane_stream[FM_MAX_LANES];
   cudaEvent_t lane_fork, lane_join[FM_MAX_LANES];
   int lanes_ready;
+  // next-episode prefetch (group mapping): pending block, one side stream + events per lane, and the
+  // host's view of the episode phase (all envs share one step counter after a full reset: "lockstep")
+  void* pend_block;
+  int pf_on, pf_ready_made, pf_used[FM_MAX_LANES];
+  cudaStream_t pf_stream[FM_MAX_LANES];
+  cudaEvent_t pf_go[FM_MAX_LANES], pf_ready[FM_MAX_LANES];
+  int lockstep, host_step;
   // device staging for the *_host entry points (allocated on first use)
   float* st_onehot;
   uint8_t* st_mask;
@@ -163,6 +170,22 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   }
   p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || fm::aw_supported(N, O)) ? 1 : 0);
   p.sd_env_stride = p.mapping == 0 ? SPp : 0;      // group mapping: [env][SPp];  agent-warp mapping: [pair][Bp]
+  // pending block of the next-episode prefetch (group mapping with auto-reset; FM_PREFETCH=0 disables it)
+  h->lockstep = 1; h->host_step = 0;
+  {
+    const char* ev = getenv("FM_PREFETCH");
+    h->pf_on = p.mapping == 0 && cfg->auto_reset && !(ev && atoi(ev) == 0);
+  }
+  if (h->pf_on) {
+    const size_t rows = (size_t)(5 * N + 2 * O);
+    e = cudaMalloc(&h->pend_block, (rows * Bp + Bp) * 4);
+    if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc pending block: %s", cudaGetErrorString(e)); }
+    float* g = (float*)h->pend_block;
+    auto takeq = [&](size_t n) { float* r = g; g += n; return r; };
+    p.q_px = takeq(Bp * N); p.q_py = takeq(Bp * N); p.q_lx = takeq(Bp * N); p.q_ly = takeq(Bp * N);
+    p.q_ox = takeq(Bp * O); p.q_oy = takeq(Bp * O); p.q_gm = (int*)takeq(Bp * N); p.q_tag = (int*)takeq(Bp);
+    cudaMemset(p.q_tag, 0xff, Bp * 4);              // -1: no entry
+  }
   const int G = fm::group_size(N), EPW = 32 / G;
   p.sm_cost = 0;                                   // the reset's cost matrix lives inside the adj tile
   p.sm_ent = round4((long long)EPW * E * fm::ENT_STRIDE);
@@ -185,8 +208,10 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.sm_obs = round4((long long)EPW * N * fm::OBS_F + 3);
   p.sm_asg = round4((long long)EPW * (5 * N + 1));
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_obs + p.sm_asg;
+  p.sm_pf_cost = round4(2LL * N * N + (N * N + 1) / 2 + 2);          // float64 costs | uint16 permutation | alignment
+  p.sm_pf_per_warp = EPW * p.sm_pf_cost + p.sm_ent + p.sm_asg;
   if (p.mapping == 0 && (size_t)p.sm_per_warp * 4 * 4 > 227 * 1024) {
-    cudaFree(h->state_block); delete h;
+    cudaFree(h->pend_block); cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: N=%d O=%d needs %d B of shared memory per CTA", N, O, p.sm_per_warp * 16);
   }
   h->K = fm_stats_len(N);
@@ -196,10 +221,10 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   cudaMemset(h->stats, 0, (size_t)h->stats_rows * h->K * sizeof(double));
   p.stats = h->stats;
   e = fm::prepare_kernels(p);
-  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->pend_block); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
   e = fm::launch_state_init(p, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->pend_block); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
   h->launches = 1;
   *out = h;
   return FM_OK;
@@ -217,6 +242,10 @@ int fm_destroy(FmHandle* h) {
   if (!h) return FM_OK;
   use_device(h->device);
   free_staging(h);
+  if (h->pf_ready_made) {
+    for (int k = 0; k < FM_MAX_LANES; ++k) { cudaStreamDestroy(h->pf_stream[k]); cudaEventDestroy(h->pf_go[k]); cudaEventDestroy(h->pf_ready[k]); }
+  }
+  cudaFree(h->pend_block);
   if (h->lanes_ready) {
     for (int k = 1; k < FM_MAX_LANES; ++k) { cudaStreamDestroy(h->lane_stream[k]); cudaEventDestroy(h->lane_join[k]); }
     cudaEventDestroy(h->lane_fork);
@@ -236,6 +265,66 @@ static void set_outputs(DevParams& p, const FmOutputs* out) {
   p.o_info = out ? out->info : nullptr;
 }
 
+// ---- next-episode prefetch plumbing -----------------------------------------------------------------------------
+static bool stream_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+static int ensure_prefetch_streams(FmHandle* h) {
+  if (h->pf_ready_made) return FM_OK;
+  // Most urgent priority: the prefetch is a fixed amount of SM work that has to be done before the next terminal
+  // step either way; running it first (at 7+ CTAs/SM) measured slightly better than letting it trail behind the
+  // step kernels (C3 66 % vs 64 % of the roofline), and the terminal step never waits.  FM_PREFETCH_PRIO=0: least urgent.
+  int lo = 0, hi = 0;
+  FM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least urgent, hi = most urgent
+  int prio = hi;
+  if (const char* ev = getenv("FM_PREFETCH_PRIO")) { if (atoi(ev) == 0) prio = lo; }
+  for (int k = 0; k < FM_MAX_LANES; ++k) {
+    FM_CUDA(cudaStreamCreateWithPriority(&h->pf_stream[k], cudaStreamNonBlocking, prio));
+    FM_CUDA(cudaEventCreateWithFlags(&h->pf_go[k], cudaEventDisableTiming));
+    FM_CUDA(cudaEventCreateWithFlags(&h->pf_ready[k], cudaEventDisableTiming));
+  }
+  h->pf_ready_made = 1;
+  return FM_OK;
+}
+
+// Before a step launch on stream s: the kernel may consume pending entries only when the host knows the episode
+// phase (lockstep) and the stream is not being captured; a terminal step waits for every prefetch in flight.
+static int prefetch_before_step(FmHandle* h, DevParams& p, cudaStream_t s, bool terminal) {
+  if (!h->pf_on || !h->lockstep || stream_capturing(s)) { p.q_tag = nullptr; return FM_OK; }
+  if (terminal)
+    for (int k = 0; k < FM_MAX_LANES; ++k)
+      if (h->pf_used[k]) FM_CUDA(cudaStreamWaitEvent(s, h->pf_ready[k], 0));
+  return FM_OK;
+}
+
+// After a launch on stream s that advanced the episode counters of envs [env_begin, env_end): produce their next
+// placement + assignment on lane `lane`'s low-priority side stream.
+static int prefetch_after_reset(FmHandle* h, cudaStream_t s, int lane, int env_begin, int env_end) {
+  if (!h->pf_on || !h->lockstep || stream_capturing(s)) return FM_OK;
+  int rc = ensure_prefetch_streams(h);
+  if (rc) return rc;
+  FM_CUDA(cudaEventRecord(h->pf_go[lane], s));
+  FM_CUDA(cudaStreamWaitEvent(h->pf_stream[lane], h->pf_go[lane], 0));
+  DevParams p = h->p;
+  p.env_begin = env_begin; p.env_end = env_end;
+  FM_CUDA(fm::launch_prefetch(p, h->pf_stream[lane]));
+  FM_CUDA(cudaEventRecord(h->pf_ready[lane], h->pf_stream[lane]));
+  h->pf_used[lane] = 1;
+  h->launches += 1;
+  return FM_OK;
+}
+
+// Host view of the episode phase: returns whether the step about to be launched is terminal for every env.
+static bool step_is_terminal(const FmHandle* h) { return h->lockstep && h->host_step + 1 >= h->p.episode_length; }
+static void advance_phase(FmHandle* h, bool terminal) {
+  if (!h->lockstep) return;
+  if (!terminal) { h->host_step += 1; return; }
+  if (h->p.auto_reset) h->host_step = 0; else h->lockstep = 0;
+}
+
 int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* stream) {
   if (!h) return fail(FM_ERR_INVALID_ARG, "fm_reset: null handle");
   int rc = use_device(h->device);
@@ -246,7 +335,9 @@ int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* strea
   p.act_idx = nullptr; p.act_onehot = nullptr;
   FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, true));
   h->launches += 1;
-  return FM_OK;
+  if (mask) h->lockstep = 0;                         // envs are no longer in the same episode phase
+  else { h->lockstep = 1; h->host_step = 0; }
+  return prefetch_after_reset(h, (cudaStream_t)stream, 0, 0, h->p.B);
 }
 
 // Side streams + fork / join events shared by fm_step_many (env-range lanes) and the host-buffer copies.
@@ -270,8 +361,13 @@ static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, con
   DevParams p = h->p;
   set_outputs(p, out);
   p.act_idx = idx; p.act_onehot = onehot; p.reset_mask = nullptr;
+  const bool terminal = step_is_terminal(h);
+  rc = prefetch_before_step(h, p, (cudaStream_t)stream, terminal);
+  if (rc) return rc;
   FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, false));
   h->launches += 1;
+  advance_phase(h, terminal);
+  if (terminal && h->p.auto_reset) return prefetch_after_reset(h, (cudaStream_t)stream, 0, 0, h->p.B);
   return FM_OK;
 }
 
@@ -308,6 +404,7 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
   }
   const int per_lane = (((B + lanes - 1) / lanes) + 127) & ~127;      // lane boundaries at multiples of 128 envs
   for (int t = 0; t < num_steps; ++t) {
+    const bool terminal = step_is_terminal(h);
     for (int k = 0; k < lanes; ++k) {
       DevParams p = h->p;
       set_outputs(p, outs + t);
@@ -315,9 +412,14 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
       p.env_begin = k * per_lane < B ? k * per_lane : B;
       p.env_end = (k + 1) * per_lane < B ? (k + 1) * per_lane : B;
       if (p.env_begin >= p.env_end) continue;
-      FM_CUDA(fm::launch_step(p, k == 0 ? user : h->lane_stream[k], false));
+      cudaStream_t ls = k == 0 ? user : h->lane_stream[k];
+      rc = prefetch_before_step(h, p, ls, terminal);
+      if (rc) return rc;
+      FM_CUDA(fm::launch_step(p, ls, false));
       h->launches += 1;
+      if (terminal && h->p.auto_reset) { rc = prefetch_after_reset(h, ls, k, p.env_begin, p.env_end); if (rc) return rc; }
     }
+    advance_phase(h, terminal);
   }
   if (lanes > 1) {
     for (int k = 1; k < lanes; ++k) {
@@ -440,6 +542,7 @@ int fm_set_state(FmHandle* h, const FmState* st, void* stream) {
   if (rc) return rc;
   FM_CUDA(fm::launch_state_io(h->p, *st, 1, (cudaStream_t)stream));
   h->launches += 1;
+  if (st->step || st->episode) h->lockstep = 0;      // the host no longer knows the episode phase of every env
   if (st->landmark_pos || st->obstacle_pos) {                              // cached static distances follow the positions
     FM_CUDA(fm::launch_static_dists(h->p, (cudaStream_t)stream));
     h->launches += 1;

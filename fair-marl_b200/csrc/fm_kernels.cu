@@ -231,7 +231,36 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
     // episode; reward / done / info stay terminal.
     float rx = npx, ry = npy, rmint = act ? p.mintime[idx] : 0.f;
     int rgm = gm;
-    reset_group<G>(p, s, el, i, env, do_reset, gmask, episode, rgm, rx, ry, rmint);
+    // An entry of the pending block generated for this env's episode key (prefetch_kernel) replaces the rejection
+    // sampling and the lexifair solve: same Philox stream, same bits.
+    const bool use_pend = do_reset && p.q_tag != nullptr && p.q_tag[env] == (int)episode;
+    if (__any_sync(FULL, use_pend)) {
+      int pgm = 0;
+      if (use_pend) {
+        if (i < N) {
+          rx = p.q_px[idx]; ry = p.q_py[idx]; pgm = p.q_gm[idx];
+          const float lxx = p.q_lx[idx], lyy = p.q_ly[idx];
+          ent_write(ent + (N + i) * ENT_STRIDE, lxx, lyy, 0.f, 0.f, lxx, lyy, 1.0f);
+          p.lx[idx] = lxx; p.ly[idx] = lyy;
+        }
+        for (int k = i; k < O; k += G) {
+          const float x = p.q_ox[(size_t)k * p.Bp + env], y = p.q_oy[(size_t)k * p.Bp + env];
+          ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
+          p.ox[(size_t)k * p.Bp + env] = x; p.oy[(size_t)k * p.Bp + env] = y;
+        }
+      }
+      __syncwarp();
+      if (use_pend && i < N) {
+        const float* og = ent + (N + gm) * ENT_STRIDE;     // min_time with the previous episode's goal_match (:545-547)
+        if (p.has_max_speed) rmint = (float)(dist64(rx, ry, og[0], og[1]) / p.max_speed);
+        rgm = pgm;
+        const float* g = ent + (N + rgm) * ENT_STRIDE;
+        ent_write(ent + i * ENT_STRIDE, rx, ry, 0.f, 0.f, g[0], g[1], 0.0f);
+      }
+      __syncwarp();
+    }
+    if (__any_sync(FULL, do_reset && !use_pend))
+      reset_group<G>(p, s, el, i, env, do_reset && !use_pend, gmask, episode, rgm, rx, ry, rmint, p.lx, p.ly, p.ox, p.oy, true);
     if (do_reset) {
       gm = rgm; npx = rx; npy = ry; nvx = 0.f; nvy = 0.f; npd = 0.f;
       ndtg = -1.f; ntreq = -1.f; ndleft = -1.f; nac = 0; noc = 0; nstep_store = 0; nepisode = episode + 1;
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   }
   __syncwarp();
   if (__any_sync(FULL, do_reset)) {
-    reset_group<G>(p, s, el, i, env, do_reset, gmask, episode, gm, px, py, mint);
+    reset_group<G>(p, s, el, i, env, do_reset, gmask, episode, gm, px, py, mint, p.lx, p.ly, p.ox, p.oy, true);
     if (do_reset && act) {
       vx = 0.f; vy = 0.f; pd = 0.f; dtg = -1.f;
       p.px[idx] = px; p.py[idx] = py; p.vx[idx] = 0.f; p.vy[idx] = 0.f; p.pdist[idx] = 0.f;
@@ -335,6 +364,39 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   }
   __syncwarp();
   emit_tiles(p, s, env0, nenv, lane);
+}
+
+// =============================================================================================
+// Placement + lexifair assignment of every env's NEXT episode, ahead of time (navigation_graph.py:264-570; the draws
+// depend only on (seed, global env, episode key)).  Launched on a side stream right after the kernel that advanced
+// the episode counters; it overlaps the memory-bound regular steps of the episode, and the terminal step copies the
+// entry (step_kernel, `use_pend`).  Envs whose entry already carries the current key are skipped.
+template <int G>
+__global__ void __launch_bounds__(THREADS) prefetch_kernel(const __grid_constant__ DevParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int EPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int env0 = p.env_begin + (blockIdx.x * (THREADS / 32) + wib) * EPW;
+  if (env0 >= p.env_end) return;
+  const int nenv = min(EPW, p.env_end - env0);
+  const int el = lane / G, i = lane % G;
+  const int env = env0 + el;
+  const bool venv = el < nenv;
+  const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
+  const WarpSmem s = carve_prefetch(p, smem, wib);
+  const uint32_t episode = venv ? (uint32_t)p.episode[env] : 0u;
+  const bool need = venv && p.q_tag[env] != (int)episode;
+  if (!__any_sync(FULL, need)) return;
+  int gm = 0;
+  float x = 0.f, y = 0.f, mint = 0.f;
+  reset_group<G>(p, s, el, i, env, need, gmask, episode, gm, x, y, mint, p.q_lx, p.q_ly, p.q_ox, p.q_oy, false);
+  if (need && i < p.N) {
+    const size_t idx = (size_t)i * p.Bp + env;
+    p.q_px[idx] = x; p.q_py[idx] = y; p.q_gm[idx] = gm;
+  }
+  __syncwarp();
+  if (need && i == 0) p.q_tag[env] = (int)episode;
 }
 
 // =============================================================================================
@@ -557,9 +619,32 @@ static cudaError_t launch_step_g(const DevParams& p, cudaStream_t st, bool is_re
 }
 
 template <int G>
+static cudaError_t launch_prefetch_g(const DevParams& p, cudaStream_t st) {
+  constexpr int EPW = 32 / G;
+  const int warps = (p.env_end - p.env_begin + EPW - 1) / EPW;
+  const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
+  if (blocks <= 0) return cudaSuccess;
+  const size_t smem = (size_t)p.sm_pf_per_warp * (THREADS / 32) * sizeof(float);
+  prefetch_kernel<G><<<blocks, THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prefetch(const DevParams& p, cudaStream_t st) {
+  switch (group_size(p.N)) {
+    case 4: return launch_prefetch_g<4>(p, st);
+    case 8: return launch_prefetch_g<8>(p, st);
+    case 16: return launch_prefetch_g<16>(p, st);
+    default: return launch_prefetch_g<32>(p, st);
+  }
+}
+
+template <int G>
 static cudaError_t prepare_g(const DevParams& p) {
   const int smem = p.sm_per_warp * (THREADS / 32) * (int)sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(reset_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(prefetch_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           p.sm_pf_per_warp * (THREADS / 32) * (int)sizeof(float));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }

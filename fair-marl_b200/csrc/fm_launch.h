@@ -21,6 +21,7 @@ cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset);
 cudaError_t launch_static_dists(const DevParams& p, cudaStream_t st);   // recompute p.sdist from the static positions
 cudaError_t prepare_kernels(const DevParams& p);   // opt in to > 48 KB dynamic shared memory, once per handle
 cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset);
+cudaError_t launch_prefetch(const DevParams& p, cudaStream_t st);   // next-episode placement + assignment (group mapping)
 cudaError_t launch_assign(const double* costs, const float* apos, const float* gpos, int num, int n, int* out,
                           cudaStream_t st);
 cudaError_t launch_state_io(const DevParams& p, const HostState& hs, int to_internal, cudaStream_t st);

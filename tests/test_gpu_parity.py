@@ -339,3 +339,46 @@ def test_group_kernel_staging_variants_are_bitwise_equal(variant, monkeypatch):
         env.close()
     for x, y in zip(*outs):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("N,O,B,lanes", [(7, 3, 300, 1), (16, 3, 70, 1), (7, 3, 1024, 2), (5, 0, 33, 1)])
+def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, monkeypatch):
+    """The group mapping produces the placement + assignment of every env's next episode ahead of time on a side
+    stream (prefetch_kernel) and the terminal step copies it.  Same Philox stream, same bits: a run with the
+    prefetch disabled (FM_PREFETCH=0: every reset is computed inside the step kernel) must be identical, through
+    single steps, through fm_step_many with env-range lanes, and across a masked reset that breaks the lockstep."""
+    import torch
+    cfg = NavConfig(num_agents=N, num_obstacles=O, episode_length=6)
+    monkeypatch.setenv("FM_LANES", str(lanes))
+    runs = []
+    for pf in ("1", "0"):
+        monkeypatch.setenv("FM_PREFETCH", pf)
+        env = _env(cfg, B, seed=31, sim=dict(mapping="group"), num_slots=8)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        rec = []
+
+        def keep(o):
+            rec.extend([o["obs"].clone(), o["node_obs"].clone(), o["adj_env"].clone()])
+            if "reward" in o:
+                rec.extend([o["reward"].clone(), o["done"].clone()])
+
+        keep(env.reset_tensor())
+        for t in range(14):                                   # two auto-resets through single steps
+            keep(env.step_tensor(torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int32)))
+        acts = torch.randint(0, 5, (7, B, N), generator=g, device="cuda", dtype=torch.int32)
+        for slot in env.rollout_tensor(acts):                 # one more through fm_step_many (lanes)
+            keep(env.slot_outputs(slot))
+        mask = (torch.arange(B, device="cuda") % 3 == 0).to(torch.uint8)
+        keep(env.reset_tensor(mask=mask))                     # lockstep broken: inline resets from here on
+        for t in range(9):
+            keep(env.step_tensor(torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int32)))
+        keep(env.reset_tensor())                              # lockstep again
+        for t in range(8):
+            keep(env.step_tensor(torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int32)))
+        st = env.get_state()
+        rec.extend([st["goal_match"], st["landmark_pos"], st["obstacle_pos"], st["episode"], st["min_time"]])
+        runs.append(rec)
+        env.close()
+    assert len(runs[0]) == len(runs[1])
+    for k, (x, y) in enumerate(zip(*runs)):
+        assert torch.equal(x, y), k
