@@ -65,12 +65,16 @@ class B200GraphVecEnv:
     seed : base seed (default ``args.seed``); reset streams are keyed by (seed, global env index).
     env_offset : global index of local env 0 when the batch is sharded over ranks.
     num_slots : rollout slabs for the tensor path (``step_tensor`` writes slot (t+1) % num_slots).
+    dummy_vec_env : mirror ``GraphDummyVecEnv`` (env_wrappers.py:895-950) instead of ``GraphSubprocVecEnv``:
+        ``step()`` returns the 8-tuple ``(..., infos, reset_count)`` with ``reset_count = 1`` when an env finished
+        its episode in this step (the eval / render loops read it, graph_mpe_runner.py:684-685).
     """
 
     closed = False
 
     def __init__(self, args: Any = None, num_envs: Optional[int] = None, device: int = 0,
-                 seed: Optional[int] = None, env_offset: int = 0, num_slots: int = 2, **overrides):
+                 seed: Optional[int] = None, env_offset: int = 0, num_slots: int = 2, dummy_vec_env: bool = False,
+                 **overrides):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
@@ -126,6 +130,7 @@ class B200GraphVecEnv:
         self._pending_actions = None
         self._last_step_api = None
         self._plans = {}
+        self.dummy_vec_env = bool(dummy_vec_env)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
@@ -348,6 +353,9 @@ class B200GraphVecEnv:
         done = cur["done"].numpy().astype(bool)
         if copy:
             rew = rew.copy()
+        if self.dummy_vec_env:                                        # env_wrappers.py:917-928
+            reset_count = 1 if bool(done.all(axis=1).any()) else 0
+            return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version), reset_count
         return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version)
 
     def step(self, actions, copy: bool = False):

@@ -169,3 +169,18 @@ def test_global_graph_features_through_the_reference_api():
         assert (node[..., 6] == np.array([0, 0, 0, 1, 1, 1, 2, 2, 2], dtype=np.float32)).all()
         assert_close(rew, want["reward"], f"reward step {t}")
     env.close()
+
+
+def test_dummy_vec_env_returns_reset_count():
+    """GraphDummyVecEnv.step_wait (env_wrappers.py:911-928) appends ``reset_count``."""
+    import fair_marl_b200 as fm
+    cfg = NavConfig(num_agents=3, num_obstacles=3, episode_length=4)
+    env = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=1, seed=3, dummy_vec_env=True)
+    env.reset()
+    counts = []
+    for t in range(9):
+        out = env.step(np.zeros((1, 3), dtype=np.int64))
+        assert len(out) == 8
+        counts.append(out[7])
+    assert counts == [0, 0, 0, 1, 0, 0, 0, 1, 0]
+    env.close()
