@@ -263,6 +263,32 @@ class B200GraphVecEnv:
         self._last_step_api = "tensor"
         return self._package_out(views, with_step=True) if out is not None else self._package(slot, with_step=True)
 
+    def edge_list_tensor(self, adj_env, repeat: int = 1, inclusive: bool = False) -> Dict[str, Any]:
+        """Policy-side edge list of ``adj_env [B,E,E]`` (``process_adj``, gnn_new.py:381-413) WITHOUT a host sync:
+        buffers of worst-case capacity are allocated once and reused; ``nnz`` stays on the device.  Returns
+        ``edge_index [2, capacity]`` (int64, the first ``nnz`` columns are valid, (b, i, j) order, node ids offset by
+        ``b*E``), ``edge_attr [capacity]``, ``offsets [B*repeat + 1]`` and ``nnz [1]``.  ``repeat=N`` emits every
+        env's graph once per agent, i.e. the batch the policy sees.  ``fair_marl_b200.process_adj`` is the
+        synchronising variant that trims to ``nnz``."""
+        t, B, E = self.torch, self.num_envs, self.num_entities
+        if tuple(adj_env.shape) != (B, E, E) or adj_env.dtype != t.float32 or not adj_env.is_contiguous():
+            raise ValueError(f"adj_env must be a contiguous float32 tensor of shape {(B, E, E)}")
+        key = ("edges", repeat)
+        buf = self._plans.get(key)
+        if buf is None:
+            cap = B * repeat * E * (E - 1)
+            buf = self._plans[key] = {
+                "capacity": cap,
+                "offsets": t.empty(B * repeat + 1, dtype=t.int64, device=self.device),
+                "edge_index": t.empty((2, max(cap, 1)), dtype=t.int64, device=self.device),
+                "edge_attr": t.empty(max(cap, 1), dtype=t.float32, device=self.device),
+                "nnz": t.zeros(1, dtype=t.int64, device=self.device)}
+        _lib.check(self.lib.fm_edge_list(self.device_index, adj_env.data_ptr(), B, E, float(self.cfg.max_edge_dist),
+                                         int(inclusive), int(repeat), buf["capacity"], buf["offsets"].data_ptr(),
+                                         buf["edge_index"].data_ptr(), buf["edge_attr"].data_ptr(), buf["nnz"].data_ptr(),
+                                         self._stream()), "fm_edge_list")
+        return buf
+
     def rollout_tensor(self, actions) -> List[int]:
         """``T`` consecutive steps from one host call (``fm_step_many``): ``actions`` int32 CUDA tensor
         [T, B, N].  Step t writes slab slot (slot + 1 + t) % num_slots; returns the slot of every step.

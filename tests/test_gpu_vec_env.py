@@ -184,3 +184,23 @@ def test_dummy_vec_env_returns_reset_count():
         counts.append(out[7])
     assert counts == [0, 0, 0, 1, 0, 0, 0, 1, 0]
     env.close()
+
+
+def test_edge_list_tensor_matches_process_adj_without_sync():
+    import torch
+    import fair_marl_b200 as fm
+    from oracle.edges import process_adj as oracle_process_adj
+    cfg = NavConfig(num_agents=7, num_obstacles=3)
+    B, N, E = 50, 7, 17
+    env = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=6)
+    o = env.reset_tensor()
+    o = env.step_tensor(torch.zeros(B, N, dtype=torch.int32, device=env.device))
+    r = env.edge_list_tensor(o["adj_env"], repeat=N)
+    n = int(r["nnz"].item())
+    adj_policy = o["adj"].reshape(B * N, E, E).cpu().numpy()             # what the policy's process_adj would see
+    ei, ea = oracle_process_adj(adj_policy, cfg.max_edge_dist)
+    assert n == ei.shape[1]
+    assert np.array_equal(r["edge_index"][:, :n].cpu().numpy(), ei)
+    assert np.array_equal(r["edge_attr"][:n].cpu().numpy(), ea[:, 0].astype(np.float32))
+    assert int(r["offsets"][-1].item()) == n
+    env.close()
