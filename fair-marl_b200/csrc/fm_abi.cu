@@ -206,7 +206,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   if (force && !strcmp(force, "k1x2")) { p.stage_k = 1; p.stage_bufs = 2; }
   if (force && !strcmp(force, "k3x1") && p.sm_adj - 3 >= 3 * stage_words) { p.stage_k = 3; p.stage_bufs = 1; }
   p.sm_obs = round4((long long)EPW * N * fm::OBS_F + 3);
-  p.sm_asg = round4((long long)EPW * (5 * N + 1));
+  p.sm_asg = round4((long long)EPW * N);               // lexifair row masks (the matching lives in registers)
   p.sm_per_warp = p.sm_cost + p.sm_ent + p.sm_adj + p.sm_obs + p.sm_asg;
   p.sm_pf_cost = round4(2LL * N * N + (N * N + 1) / 2 + 2);          // float64 costs | uint16 permutation | alignment
   p.sm_pf_per_warp = EPW * p.sm_pf_cost + p.sm_ent + p.sm_asg;

@@ -17,7 +17,7 @@ namespace fm {
 constexpr int THREADS = 128;   // 4 warps per CTA; no block-level barrier is used
 
 // shared memory of one assign_kernel problem, in floats (even): n^2 doubles | n^2 uint16 | 5n + 1 ints
-__host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + ((n * n + 1) >> 1) + 5 * n + 1 + 1) & ~1; }
+__host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + ((n * n + 1) >> 1) + n + 1) & ~1; }
 
 // =============================================================================================
 // The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
