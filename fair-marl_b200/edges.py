@@ -25,7 +25,7 @@ def process_adj(adj, max_edge_dist: float, repeat: int = 1, inclusive: bool = Fa
     adj = adj.to(torch.float32).contiguous()
     G, E = int(adj.shape[0]), int(adj.shape[1])
     dev = adj.device
-    cap = G * repeat * E * (E - 1)
+    cap = G * repeat * E * E                    # a distance matrix has a zero diagonal, a general input may not
     with torch.cuda.device(dev):
         offsets = torch.empty(G * repeat + 1, dtype=torch.int64, device=dev)
         edge_index = torch.empty((2, max(cap, 1)), dtype=torch.int64, device=dev)

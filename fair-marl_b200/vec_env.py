@@ -276,7 +276,7 @@ class B200GraphVecEnv:
         key = ("edges", repeat)
         buf = self._plans.get(key)
         if buf is None:
-            cap = B * repeat * E * (E - 1)
+            cap = B * repeat * E * (E - 1)          # adj_env is a distance matrix: zero diagonal
             buf = self._plans[key] = {
                 "capacity": cap,
                 "offsets": t.empty(B * repeat + 1, dtype=t.int64, device=self.device),

@@ -172,7 +172,8 @@ int fm_pair_dist(int device, const float* a, const float* b, int64_t num, double
  * (b*repeat + a)*E): the [B*N, E, E] batch the policy sees repeats each env's adj N times.
  * graph_offsets: int64 [num_graphs*repeat + 1] exclusive prefix of edge counts (out);
  * edge_index: int64 [2, capacity]; edge_attr: float [capacity]; nnz_out: int64 [1] (device, may be NULL).
- * Edges beyond `capacity` are not written (capacity num_graphs*repeat*E*(E-1) always suffices). */
+ * Edges beyond `capacity` are not written, nnz_out still counts them (capacity num_graphs*repeat*E*E always suffices;
+ * num_graphs*repeat*E*(E-1) for distance matrices, whose diagonal is zero). */
 int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, double max_edge_dist,
                  int32_t inclusive, int32_t repeat, int64_t capacity, int64_t* graph_offsets,
                  int64_t* edge_index, float* edge_attr, int64_t* nnz_out, void* stream);

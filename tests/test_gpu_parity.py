@@ -382,3 +382,37 @@ def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, monkeypatch)
     assert len(runs[0]) == len(runs[1])
     for k, (x, y) in enumerate(zip(*runs)):
         assert torch.equal(x, y), k
+
+
+def test_edge_list_corner_cases():
+    """process_adj on shapes the simulator never produces by itself: no edges at all, every edge, a single graph (2-D
+    input), E = 35, more graph copies than lanes (repeat = 40), a graph count that is not a multiple of the 8 graphs
+    a CTA handles, and 70 000 graphs (more CTAs than one scan segment)."""
+    import torch
+    import fair_marl_b200 as fm
+    rng = np.random.default_rng(3)
+    dev = torch.device("cuda")
+
+    def check(adj, thr, **kw):
+        repeat = kw.get("repeat", 1)
+        ei, ea = fm.process_adj(torch.as_tensor(adj, device=dev), thr, **kw)
+        a3 = adj if adj.ndim == 3 else adj[None]
+        rei, rea = oracle_process_adj(np.repeat(a3, repeat, axis=0), thr, inclusive=kw.get("inclusive", False))
+        if adj.ndim == 2:
+            assert tuple(ei.shape) == (2, rei.shape[1])
+        assert (ei.cpu().numpy() == rei).all() and (ea.cpu().numpy() == rea).all()
+        return rei.shape[1]
+
+    assert check(np.zeros((5, 9, 9), np.float32), 1.0) == 0                         # nothing within reach
+    far = np.full((3, 9, 9), 7.0, np.float32)
+    assert check(far, 1.0) == 0
+    full = rng.random((11, 9, 9)).astype(np.float32) * 0.9 + 0.01                  # every off- AND on-diagonal entry is an edge
+    assert check(full, 1.0) == 11 * 81
+    assert check(full[0], 1.0) == 81                                               # 2-D input
+    big = rng.random((13, 35, 35)).astype(np.float32) * 2
+    check(big, 1.0)
+    check(big, 1.0, repeat=40)
+    check(big, 1.0, inclusive=True)
+    many = (rng.random((70001, 5, 5)) * 2).astype(np.float32)
+    check(many, 1.0)
+    check(many[:9], 1.0, repeat=3)
