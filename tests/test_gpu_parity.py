@@ -416,3 +416,53 @@ def test_edge_list_corner_cases():
     many = (rng.random((70001, 5, 5)) * 2).astype(np.float32)
     check(many, 1.0)
     check(many[:9], 1.0, repeat=3)
+
+
+@pytest.mark.parametrize("N,O,B", [(7, 3, 21), (16, 3, 9), (3, 3, 40), (5, 0, 13)])
+def test_outputs_at_any_alignment_and_partial_outputs(N, O, B):
+    """The emission goes through TMA bulk stores, which need 16-byte aligned global addresses: the group kernel builds
+    its images at the 16-byte phase of their destination and stores the <= 3 head / tail words by lanes, the
+    agent-warp kernel falls back to vector / scalar stores.  Output arrays that start 4, 8 or 12 bytes past a
+    16-byte boundary, and FmOutputs with null members (the ABI allows any subset), must give the same bytes."""
+    import torch
+    cfg = NavConfig(num_agents=N, num_obstacles=O, episode_length=5)
+    E = 2 * N + O
+    shapes = {"obs": (B, N, 7), "node_obs": (B, N, E, 11), "adj": (B, E, E), "reward": (B, N)}
+    g = torch.Generator(device="cuda").manual_seed(9)
+    acts = torch.randint(0, 5, (8, B, N), generator=g, device="cuda", dtype=torch.int32)
+
+    def run(offset, keep):
+        env = _env(cfg, B, seed=17)
+        env.reset_tensor()
+        rec = []
+        for t in range(8):
+            out = {}
+            for name, shp in shapes.items():
+                n = int(np.prod(shp))
+                flat = torch.full((n + 8,), float("nan"), device="cuda")
+                out[name] = flat[offset:offset + n].view(shp)
+            out["done"] = torch.zeros((B, N), dtype=torch.uint8, device="cuda")
+            if keep is None:
+                env.step_tensor(acts[t], out=out)
+            else:                                   # raw ABI call with null members
+                import ctypes as C
+                from fair_marl_b200 import _lib
+                o = _lib.FmOutputs()
+                for name in keep:
+                    setattr(o, name, out[name].data_ptr())
+                _lib.check(env.lib.fm_step(env._h, acts[t].data_ptr(), C.byref(o), env._stream()), "fm_step")
+            rec.append({k: v.clone() for k, v in out.items()})
+        env.close()
+        return rec
+
+    ref = run(0, None)
+    for offset in (1, 2, 3):
+        got = run(offset, None)
+        for a, b in zip(ref, got):
+            for k in a:
+                assert torch.equal(a[k], b[k]), (offset, k)
+    for keep in (("reward", "done"), ("node_obs",), ("adj", "obs"), ("obs", "reward")):
+        got = run(2, keep)
+        for a, b in zip(ref, got):
+            for k in keep:
+                assert torch.equal(a[k], b[k]), (keep, k)
