@@ -341,14 +341,14 @@ def test_group_kernel_staging_variants_are_bitwise_equal(variant, monkeypatch):
         assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("N,O,B,lanes", [(7, 3, 300, 1), (16, 3, 70, 1), (7, 3, 1024, 2), (5, 0, 33, 1)])
-def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, monkeypatch):
+@pytest.mark.parametrize("N,O,B,lanes,T", [(7, 3, 300, 1, 6), (16, 3, 70, 1, 6), (7, 3, 1024, 2, 6), (5, 0, 33, 1, 6), (7, 3, 64, 1, 1)])
+def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, T, monkeypatch):
     """The group mapping produces the placement + assignment of every env's next episode ahead of time on a side
     stream (prefetch_kernel) and the terminal step copies it.  Same Philox stream, same bits: a run with the
     prefetch disabled (FM_PREFETCH=0: every reset is computed inside the step kernel) must be identical, through
     single steps, through fm_step_many with env-range lanes, and across a masked reset that breaks the lockstep."""
     import torch
-    cfg = NavConfig(num_agents=N, num_obstacles=O, episode_length=6)
+    cfg = NavConfig(num_agents=N, num_obstacles=O, episode_length=T)    # T = 1: every step is terminal
     monkeypatch.setenv("FM_LANES", str(lanes))
     runs = []
     for pf in ("1", "0"):

@@ -69,8 +69,11 @@ def test_rollout_writes_buffer_in_place_and_replays_bitwise(N, O, B):
     env.close(); env2.close()
 
 
-def test_captured_graph_episode_equals_eager_episode():
-    cfg = NavConfig(num_agents=3, num_obstacles=3)
+@pytest.mark.parametrize("N", [3, 7])
+def test_captured_graph_episode_equals_eager_episode(N):
+    """N = 7 runs the group kernel: the eager loop consumes prefetched next-episode placements, the captured one
+    computes every reset inside the step kernel (no side-stream work under capture); same bits either way."""
+    cfg = NavConfig(num_agents=N, num_obstacles=3)
     runs = []
     for use_graph in (False, True):
         fm, env, actor, critic = _make(cfg, 128, seed=11)
