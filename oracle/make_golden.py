@@ -35,6 +35,9 @@ CONFIGS = {
     "n4_o2_collab": (NavConfig(num_agents=4, num_obstacles=2, collaborative=True), 16, 3),
     "n3_o3_global": (NavConfig(num_agents=3, num_obstacles=3, graph_feat_type="global"), 17, 4),
     "n7_o3_global": (NavConfig(num_agents=7, num_obstacles=3, graph_feat_type="global"), 18, 2),
+    # walls: oracle-only fixtures (the CUDA path does not take num_walls > 0 yet; tests skip them on the device)
+    "n3_o3_w2": (NavConfig(num_agents=3, num_obstacles=3, num_walls=2), 19, 10),
+    "n4_o2_w1": (NavConfig(num_agents=4, num_obstacles=2, num_walls=1, goal_rew=30.0, collision_rew=30.0), 20, 6),
 }
 
 
@@ -50,7 +53,7 @@ def _seek_actions(state: NavState, rng, p_random: float) -> np.ndarray:
 
 def _stack_states(states):
     return {"state_" + f.name: np.concatenate([getattr(s, f.name) for s in states], axis=0)
-            for f in fields(NavState)}
+            for f in fields(NavState) if getattr(states[0], f.name) is not None}
 
 
 def generate(name: str) -> str:
@@ -117,7 +120,8 @@ def load(name: str):
 
 
 def state_from(data, prefix: str, sl=slice(None)) -> NavState:
-    return NavState(**{f.name: data[prefix + f.name][sl] for f in fields(NavState)})
+    # optional fields (walls) are absent from fixtures of configs without them
+    return NavState(**{f.name: (data[prefix + f.name][sl] if prefix + f.name in data else None) for f in fields(NavState)})
 
 
 if __name__ == "__main__":

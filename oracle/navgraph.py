@@ -52,6 +52,13 @@ class NavConfig:
     fairness_reward: bool = True
     # 'relative': ego-relative 11-dim node features (:1079-1124);  'global': 7-dim absolute features (:1058-1077)
     graph_feat_type: str = "relative"
+    # walls (navigation_graph.py:181-196, :287-324; core.py:36-55, :407-462): 0, 1 or 2 axis-aligned segments of
+    # width 0.1 at +-axis, half-length wall_len, orientation redrawn every episode.  ORACLE ONLY so far: the CUDA
+    # path rejects num_walls > 0 (SimConfig.from_args); pinned by tests/golden/*_w2.npz for the kernels to come.
+    num_walls: int = 0
+    wall_width: float = 0.1
+    wall_contact_force: float = 2.2e2
+    wall_contact_margin: float = 2.4e-2
     dt: float = 0.1
     damping: float = 0.25
     contact_force: float = 3e2
@@ -62,7 +69,7 @@ class NavConfig:
 
     @property
     def num_entities(self) -> int:
-        return 2 * self.num_agents + self.num_obstacles
+        return 2 * self.num_agents + self.num_obstacles + self.num_walls
 
     @property
     def node_feat_dim(self) -> int:
@@ -94,9 +101,14 @@ class NavState:
     step: np.ndarray                     # [B] int  env.current_step == world.current_time_step
     min_time: np.ndarray                 # [B,N]   agent.goal_min_time
     episode: np.ndarray                  # [B] int  number of resets so far (RNG counter)
+    # walls (None when num_walls == 0)
+    wall_axis: Optional[np.ndarray] = None    # [B,W]  wall.axis_pos (navigation_graph.py:288-289, :308)
+    wall_orient: Optional[np.ndarray] = None  # [B,W] int  0 = 'H', 1 = 'V' (:298)
+    wall_len: Optional[np.ndarray] = None     # [B]    scenario.wall_length = half-length (:183-185, :307)
 
     def copy(self) -> "NavState":
-        return NavState(**{f.name: getattr(self, f.name).copy() for f in fields(self)})
+        return NavState(**{f.name: (None if getattr(self, f.name) is None else getattr(self, f.name).copy())
+                           for f in fields(self)})
 
 
 def _norm2(d):
@@ -132,6 +144,19 @@ class NavGraphOracle:
             dist_left_to_goal=-np.ones((B, N)), num_agent_collisions=z((B, N)),
             num_obstacle_collisions=z((B, N)), dist_traveled_mean=z(B), dist_traveled_stddev=z(B),
             step=z(B, dtype=np.int64), min_time=np.full((B, N), np.inf), episode=z(B, dtype=np.int64))
+        if cfg.num_walls:
+            if cfg.num_walls > 2:
+                raise ValueError("navigation_graph places at most 2 walls (wall_axis has two entries, :289)")
+            self.s.wall_axis = z((B, cfg.num_walls))
+            self.s.wall_orient = z((B, cfg.num_walls), dtype=np.int64)
+            # scenario.wall_length = U(0.2, 0.8) * world_size / 4, drawn once in make_world (:183-185): one Philox
+            # draw per env under the reserved episode key 0xFFFFFFFF
+            g = (np.arange(B) + self.env_offset).astype(np.uint64)
+            r0, _, _, _ = philox4x32_10(
+                np.zeros(B, np.uint32), np.full(B, 0xFFFFFFFF, np.uint32), (g & np.uint64(0xFFFFFFFF)).astype(np.uint32),
+                (g >> np.uint64(32)).astype(np.uint32), np.uint32(self.seed & 0xFFFFFFFF), np.uint32((self.seed >> 32) & 0xFFFFFFFF))
+            u = u01_24(r0)
+            self.s.wall_len = ((np.float32(0.2) + np.float32(0.6) * u) * np.float32(cfg.world_size / 4)).astype(np.float64)
         self.last_info: Optional[Dict[str, np.ndarray]] = None
 
     # ------------------------------------------------------------------ state access
@@ -142,8 +167,11 @@ class NavGraphOracle:
         """Inject a state (float64 copies; ints stay ints)."""
         d = {}
         for f in fields(NavState):
+            if getattr(state, f.name) is None:
+                d[f.name] = None
+                continue
             a = np.asarray(getattr(state, f.name))
-            if f.name in ("goal_match", "step", "episode"):
+            if f.name in ("goal_match", "step", "episode", "wall_orient"):
                 d[f.name] = a.astype(np.int64).copy()
             else:
                 d[f.name] = a.astype(np.float64).copy()
@@ -162,9 +190,18 @@ class NavGraphOracle:
         u *= self.cfg.sensitivity
         return u
 
+    def _wall_pos(self) -> np.ndarray:
+        """wall.state.p_pos (navigation_graph.py:309-324): the midpoint, (0, axis) for 'H', (axis, 0) for 'V'."""
+        s = self.s
+        horiz = s.wall_orient == 0
+        return np.stack([np.where(horiz, 0.0, s.wall_axis), np.where(horiz, s.wall_axis, 0.0)], axis=-1)   # [B,W,2]
+
     def _entity_pos(self) -> np.ndarray:
         s = self.s
-        return np.concatenate([s.pos, s.landmark_pos, s.obstacle_pos], axis=1)   # [B,E,2]
+        parts = [s.pos, s.landmark_pos, s.obstacle_pos]
+        if self.cfg.num_walls:
+            parts.append(self._wall_pos())               # core.py:186: walls come last in world.entities
+        return np.concatenate(parts, axis=1)             # [B,E,2]
 
     def _forces(self, u: np.ndarray) -> np.ndarray:
         """core.py:277-298 (apply_action_force) + :301-316 (apply_environment_force) +
@@ -174,7 +211,10 @@ class NavGraphOracle:
         ent = self._entity_pos()
         F = cfg.mass * u + 0.0                                   # core.py:291-293 (noise = 0.0)
         k = cfg.contact_margin
-        dist_min = cfg.entity_size + cfg.entity_size             # core.py:215
+        W, O = cfg.num_walls, cfg.num_obstacles
+        size = np.full(E, cfg.entity_size)
+        if W:
+            size[E - W:] = cfg.wall_width                        # Wall.size = width (core.py:48-49): a circle at its midpoint
         for a in range(E):
             a_agent = a < N
             a_collide = a_agent or a >= 2 * N                    # landmarks: collide=False (:169)
@@ -185,6 +225,7 @@ class NavGraphOracle:
                     continue                                     # core.py:373-374
                 if not (a_agent or b_agent):
                     continue                                     # core.py:375-376
+                dist_min = size[a] + size[b]                     # core.py:215
                 delta = ent[:, a] - ent[:, b]                    # cached_dist_vect[ia, ib], core.py:222
                 dist = _norm2(delta)                             # cached_dist_mag, core.py:226
                 pen = np.logaddexp(0, -(dist - dist_min) / k) * k            # core.py:391
@@ -197,7 +238,37 @@ class NavGraphOracle:
                     F[:, a] = force + F[:, a]                    # core.py:401
                 else:
                     F[:, b] = -force + F[:, b]                   # core.py:402 (unreachable: agents come first)
+            if a_agent and W:                                    # core.py:317-327: after the pair row of a movable entity
+                for w in range(W):
+                    F[:, a] = F[:, a] + self._wall_force(ent[:, a], w)
         return F
+
+    def _wall_force(self, pos: np.ndarray, w: int) -> np.ndarray:
+        """core.py:407-462 (get_wall_collision_force) of one agent position [B,2] against wall w; zeros where None."""
+        cfg, s = self.cfg, self.s
+        horiz = s.wall_orient[:, w] == 0
+        prll = np.where(horiz, pos[:, 0], pos[:, 1])             # coordinate along the wall
+        perp = np.where(horiz, pos[:, 1], pos[:, 0])
+        lo, hi = -s.wall_len, s.wall_len                         # wall.endpoints (:307)
+        r = cfg.entity_size
+        beyond = (prll < lo - r) | (prll > hi + r)               # :417-419 -> None
+        partial = ~beyond & ((prll < lo) | (prll > hi))          # :420-428
+        past = np.where(prll < lo, prll - lo, prll - hi)
+        with np.errstate(invalid="ignore"):
+            theta = np.where(partial, np.arcsin(np.where(partial, past, 0.0) / r), 0.0)
+        dist_min = np.where(partial, np.cos(theta) * r + 0.5 * cfg.wall_width, r + 0.5 * cfg.wall_width)
+        delta = perp - s.wall_axis[:, w]                         # :435
+        dist = np.abs(delta)
+        kk = cfg.wall_contact_margin
+        pen = np.logaddexp(0, -(dist - dist_min) / kk) * kk      # :439
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mag = cfg.wall_contact_force * delta / dist * pen    # :440
+        f_perp = np.cos(theta) * mag                             # :444
+        f_prll = np.sin(theta) * np.abs(mag)                     # :445
+        fx = np.where(horiz, f_prll, f_perp)
+        fy = np.where(horiz, f_perp, f_prll)
+        out = np.stack([fx, fy], axis=-1)
+        return np.where(beyond[:, None], 0.0, out)
 
     def _integrate(self, F: np.ndarray) -> None:
         """core.py:338-356 (integrate_state)."""
@@ -252,7 +323,26 @@ class NavGraphOracle:
         obst = np.zeros(self.B, dtype=bool)
         for kk in range(cfg.num_obstacles):
             obst |= _norm2(s.obstacle_pos[:, kk] - s.pos[:, i]) < dmin
+        if cfg.num_walls:
+            obst |= self._in_wall_box(s.pos[:, i], cfg.entity_size)
         return n_agent, obst
+
+    def _in_wall_box(self, pos: np.ndarray, entity_size: float, sel=None) -> np.ndarray:
+        """navigation_graph.py:670-683: inside the 1.05-scaled box of any wall (note the scaling of the bounds
+        themselves, not of the distances, and entity_size / 2)."""
+        s = self.s
+        axis = s.wall_axis if sel is None else s.wall_axis[sel]
+        orient = s.wall_orient if sel is None else s.wall_orient[sel]
+        wl = s.wall_len if sel is None else s.wall_len[sel]
+        hit = np.zeros(pos.shape[0], dtype=bool)
+        h = entity_size / 2
+        for w in range(self.cfg.num_walls):
+            horiz = orient[:, w] == 0
+            perp = np.where(horiz, pos[:, 1], pos[:, 0])
+            prll = np.where(horiz, pos[:, 0], pos[:, 1])
+            hit |= ((1.05 * (axis[:, w] - h) <= perp) & (perp <= 1.05 * (axis[:, w] + h)) &
+                    (1.05 * (-wl - h) <= prll) & (prll <= 1.05 * (wl + h)))
+        return hit
 
     def _observation(self, i: int, goal: np.ndarray) -> np.ndarray:
         """navigation_graph.py:826-857: [vel, pos, goal - pos, fairness_param]."""
@@ -296,9 +386,12 @@ class NavGraphOracle:
         :1058-1077 (global features [vel, pos, goal, type], the same rows for every agent) -> [B,N,E,7]."""
         cfg, s = self.cfg, self.s
         N, O, E = cfg.num_agents, cfg.num_obstacles, cfg.num_entities
+        W = cfg.num_walls
         ent_pos = self._entity_pos()
-        ent_vel = np.concatenate([s.vel, np.zeros((self.B, N + O, 2))], axis=1)
+        ent_vel = np.concatenate([s.vel, np.zeros((self.B, N + O + W, 2))], axis=1)
         if cfg.graph_feat_type == "global":
+            if W:
+                raise ValueError("wall entities are not supported by the global features (navigation_graph.py:1074-1075)")
             g = ent_pos.copy()
             g[:, :N] = goal
             typ = np.concatenate([np.zeros(N), np.ones(N), 2.0 * np.ones(O)])
@@ -317,7 +410,14 @@ class NavGraphOracle:
             out[:, a, :, 8:10] = rel_pos
             out[:, a, :N, 10] = 0.0          # entity_mapping (navigation_graph.py:22)
             out[:, a, N:2 * N, 10] = 1.0
-            out[:, a, 2 * N:, 10] = 2.0
+            out[:, a, 2 * N:2 * N + O, 10] = 2.0
+            for w in range(W):               # :1108-1118: corner offsets instead of the repeated rel_pos
+                e = 2 * N + O + w            # (endpoints[0], axis + width/2) and (endpoints[1], axis - width/2) as
+                o_c = np.stack([-s.wall_len, s.wall_axis[:, w] + cfg.wall_width / 2], axis=-1)   # (x, y), whatever the orientation
+                d_c = np.stack([s.wall_len, s.wall_axis[:, w] - cfg.wall_width / 2], axis=-1)
+                out[:, a, e, 6:8] = o_c - s.pos[:, a]
+                out[:, a, e, 8:10] = d_c - s.pos[:, a]
+                out[:, a, e, 10] = 3.0
         return out
 
     # ------------------------------------------------------------------ env step
@@ -430,6 +530,17 @@ class NavGraphOracle:
             ob = np.zeros((nb, O, 2), dtype=np.float32)
             for kk in range(O):
                 ob[:, kk] = np.float32(0.8) * uniform(all_sel)
+            W = cfg.num_walls
+            if W:                                                      # :287-324, after the obstacles
+                ux, _ = self._draw(envs, draw); draw += 1
+                wp = (np.float32(0.2) + np.float32(0.7) * ux) * np.float32(cfg.world_size / 2)    # U(0.2, 0.9) * ws / 2
+                axis = np.stack([wp, -wp], axis=-1)[:, :W]
+                orient = np.zeros((nb, W), dtype=np.int64)
+                for w in range(W):
+                    uo, _ = self._draw(envs, draw); draw += 1
+                    orient[:, w] = (uo >= np.float32(0.5)).astype(np.int64)     # np.random.choice(['H', 'V'])
+                s.wall_axis[envs] = axis.astype(np.float64)
+                s.wall_orient[envs] = orient
             ag = np.zeros((nb, N, 2), dtype=np.float32)
             lm = np.zeros((nb, N, 2), dtype=np.float32)
 
@@ -446,6 +557,8 @@ class NavGraphOracle:
                             bad |= _norm2(ob[pending, kk].astype(np.float64) - c64) < dmin
                         for j in range(i):
                             bad |= _norm2(dst[pending, j].astype(np.float64) - c64) < dmin
+                        if W:                                          # is_obstacle_collision's wall boxes (:670-683)
+                            bad |= self._in_wall_box(c64, cfg.entity_size, sel=envs[pending])
                         bad &= draw[pending] < self.MAX_DRAWS          # give up rejecting (device cap)
                         ok = ~bad
                         dst[pending[ok], i] = cand[ok]

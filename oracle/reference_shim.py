@@ -72,7 +72,7 @@ def args_from_config(cfg: NavConfig) -> Namespace:
         max_speed=cfg.max_speed, collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew,
         min_dist_thresh=cfg.min_dist_thresh, use_dones=False, episode_length=cfg.episode_length,
         max_edge_dist=cfg.max_edge_dist, graph_feat_type=cfg.graph_feat_type, fair_wt=1, fair_rew=cfg.fair_rew,
-        num_walls=0, zeroshift=cfg.zeroshift, scenario_name="navigation_graph",
+        num_walls=cfg.num_walls, zeroshift=cfg.zeroshift, scenario_name="navigation_graph",
         algorithm_name="rmappo")
 
 
@@ -123,7 +123,10 @@ def extract_state(env, scenario) -> NavState:
         dist_traveled_stddev=np.array([getattr(w, "dist_traveled_stddev", 0.0)], dtype=np.float64),
         step=np.array([env.current_step], dtype=np.int64),
         min_time=np.array([[a.goal_min_time for a in w.agents]], dtype=np.float64),
-        episode=np.zeros(1, dtype=np.int64))
+        episode=np.zeros(1, dtype=np.int64),
+        wall_axis=np.array([[wl.axis_pos for wl in w.walls]], dtype=np.float64) if len(w.walls) else None,
+        wall_orient=np.array([[0 if wl.orient == "H" else 1 for wl in w.walls]], dtype=np.int64) if len(w.walls) else None,
+        wall_len=np.array([scenario.wall_length], dtype=np.float64) if len(w.walls) else None)
 
 
 def inject_state(env, scenario, st: NavState, b: int = 0) -> None:
@@ -140,6 +143,14 @@ def inject_state(env, scenario, st: NavState, b: int = 0) -> None:
     for i, o in enumerate(w.obstacles):
         o.state.p_pos = np.array(st.obstacle_pos[b, i], dtype=np.float64)
         o.state.p_vel = np.zeros(2)
+    for i, wl in enumerate(w.walls):                  # what random_scenario sets per episode (navigation_graph.py:294-324)
+        scenario.wall_length = float(st.wall_len[b])
+        wl.orient = "H" if int(st.wall_orient[b, i]) == 0 else "V"
+        wl.width, wl.hard = 0.1, True
+        wl.endpoints = np.array([-scenario.wall_length, scenario.wall_length])
+        wl.axis_pos = float(st.wall_axis[b, i])
+        wl.state.p_pos = np.array([0.0, wl.axis_pos]) if wl.orient == "H" else np.array([wl.axis_pos, 0.0])
+        wl.state.p_vel = np.zeros(2)
     scenario.goal_match_index = np.array(st.goal_match[b], dtype=np.int64)
     w.dists_to_goal = np.array(st.dists_to_goal[b], dtype=np.float64)
     w.times_required = np.array(st.times_required[b], dtype=np.float64)

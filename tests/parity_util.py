@@ -3,7 +3,7 @@ from dataclasses import fields
 
 import numpy as np
 
-from oracle.navgraph import NavConfig, NavGraphOracle, NavState
+from oracle.navgraph import STATE_FIELDS, NavConfig, NavGraphOracle, NavState
 
 MAPPING = "auto"   # kernel mapping under test (set per test by conftest.kernel_mapping)
 RTOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative in fp32"
@@ -39,6 +39,8 @@ def assert_fairness_close(dev, ref, name="fairness_param"):
 
 def sim_config_from(cfg: NavConfig, **kw):
     from fair_marl_b200 import SimConfig
+    if cfg.num_walls:
+        raise NotImplementedError("the CUDA path does not take num_walls > 0 (oracle-only fixtures)")
     return SimConfig(num_agents=cfg.num_agents, num_obstacles=cfg.num_obstacles, world_size=cfg.world_size,
                      max_speed=cfg.max_speed, collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew,
                      min_dist_thresh=cfg.min_dist_thresh, episode_length=cfg.episode_length,
@@ -51,23 +53,25 @@ def sim_config_from(cfg: NavConfig, **kw):
 def state_to_fp32(st: NavState) -> NavState:
     """Round a float64 state to the device dtype (and back to float64 for the oracle)."""
     d = {}
-    for f in fields(NavState):
-        a = np.asarray(getattr(st, f.name))
-        if f.name in ("goal_match", "step", "episode"):
-            d[f.name] = a.astype(np.int64)
+    for name in STATE_FIELDS:                       # the wall fields are oracle-only (None on the device path)
+        a = np.asarray(getattr(st, name))
+        if name in ("goal_match", "step", "episode"):
+            d[name] = a.astype(np.int64)
         else:
             with np.errstate(over="ignore"):
-                d[f.name] = a.astype(np.float32).astype(np.float64)
+                d[name] = a.astype(np.float32).astype(np.float64)
     return NavState(**d)
 
 
 def state_to_device_dict(st: NavState):
-    return {f.name: np.asarray(getattr(st, f.name)) for f in fields(NavState)}
+    return {name: np.asarray(getattr(st, name)) for name in STATE_FIELDS}
 
 
 def device_state_to_nav(dev_state) -> NavState:
     d = {}
     for f in fields(NavState):
+        if f.name not in STATE_FIELDS:
+            continue
         a = dev_state[f.name].cpu().numpy()
         d[f.name] = a.astype(np.int64) if f.name in ("goal_match", "step", "episode") else a.astype(np.float64)
     return NavState(**d)

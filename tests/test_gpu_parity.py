@@ -11,6 +11,9 @@ import pytest
 from oracle.edges import process_adj as oracle_process_adj
 from oracle.lexifair import lexifair, lexifair_bruteforce_batched, lexifair_descent
 from oracle.make_golden import CONFIGS, load, state_from
+
+# fixtures with walls pin the ORACLE only (the CUDA path rejects num_walls > 0 for now)
+DEVICE_CONFIGS = sorted(n for n in CONFIGS if CONFIGS[n][0].num_walls == 0)
 from oracle.navgraph import INFO_KEYS, NavConfig, NavGraphOracle
 from parity_util import (assert_close, assert_fairness_close, compare_step_outputs, device_state_to_nav,
                          sim_config_from, state_to_device_dict, state_to_fp32)
@@ -33,7 +36,7 @@ def _actions(a):
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", sorted(CONFIGS))
+@pytest.mark.parametrize("name", DEVICE_CONFIGS)
 def test_step_matches_oracle_on_golden_states(name):
     """One step from every recorded reference state (rounded to fp32): device vs float64 oracle."""
     cfg, g = load(name)
