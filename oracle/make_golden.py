@@ -36,8 +36,8 @@ CONFIGS = {
     "n3_o3_global": (NavConfig(num_agents=3, num_obstacles=3, graph_feat_type="global"), 17, 4),
     "n7_o3_global": (NavConfig(num_agents=7, num_obstacles=3, graph_feat_type="global"), 18, 2),
     # walls: oracle-only fixtures (the CUDA path does not take num_walls > 0 yet; tests skip them on the device)
-    "n3_o3_w2": (NavConfig(num_agents=3, num_obstacles=3, num_walls=2), 19, 10),
-    "n4_o2_w1": (NavConfig(num_agents=4, num_obstacles=2, num_walls=1, goal_rew=30.0, collision_rew=30.0), 20, 6),
+    "n3_o3_w2": (NavConfig(num_agents=3, num_obstacles=3, num_walls=2), 19, 12),
+    "n4_o2_w1": (NavConfig(num_agents=4, num_obstacles=2, num_walls=1, goal_rew=30.0, collision_rew=30.0), 20, 9),
 }
 
 
@@ -49,6 +49,23 @@ def _seek_actions(state: NavState, rng, p_random: float) -> np.ndarray:
     a = np.where(np.abs(d[:, 0]) > np.abs(d[:, 1]), np.where(d[:, 0] > 0, 1, 2), np.where(d[:, 1] > 0, 3, 4))
     rnd = rng.random(a.shape[0]) < p_random
     return np.where(rnd, rng.integers(0, 5, a.shape[0]), a)
+
+
+def _seek_walls(state: NavState, rng, p_random: float) -> np.ndarray:
+    """Drive every agent at the nearest point of wall (agent index mod W), ends included, so that the fixtures hold
+    wall contact forces in both branches of core.py:417-432 and wall-box collisions (navigation_graph.py:670-683)."""
+    N, W = state.pos.shape[1], state.wall_axis.shape[1]
+    a = np.zeros(N, dtype=np.int64)
+    for i in range(N):
+        w = i % W
+        horiz = state.wall_orient[0, w] == 0
+        L = state.wall_len[0]
+        along = np.clip(state.pos[0, i, 0 if horiz else 1], -1.3 * L, 1.3 * L)   # aim slightly past the ends too
+        target = np.array([along, state.wall_axis[0, w]]) if horiz else np.array([state.wall_axis[0, w], along])
+        d = target - state.pos[0, i]
+        a[i] = (1 if d[0] > 0 else 2) if abs(d[0]) > abs(d[1]) else (3 if d[1] > 0 else 4)
+    rnd = rng.random(N) < p_random
+    return np.where(rnd, rng.integers(0, 5, N), a)
 
 
 def _stack_states(states):
@@ -76,7 +93,10 @@ def generate(name: str) -> str:
         r_adj.append(np.array(o[3])[0][None])
         for t in range(cfg.episode_length):
             st = extract_state(env, sc)
-            a = rng.integers(0, 5, N) if ep % 2 == 0 else _seek_actions(st, rng, 0.15)
+            if cfg.num_walls and ep % 3 == 2:
+                a = _seek_walls(st, rng, 0.2)
+            else:
+                a = rng.integers(0, 5, N) if ep % 2 == 0 else _seek_actions(st, rng, 0.15)
             oh = np.eye(5)[a]
             ob, ag_id, node, adj, rew, done, info = env.step([oh[i] for i in range(N)])
             pre.append(st)
