@@ -117,3 +117,17 @@ def test_shard_range_partitions():
         assert spans[0][0] == 0 and sum(c for _, c in spans) == total
         for (o1, c1), (o2, _) in zip(spans, spans[1:]):
             assert o1 + c1 == o2
+
+
+def test_integration_doc_stub_matches_binding():
+    """The raw ctypes stub shown to maintainers in INTEGRATION.md must declare FmConfig exactly like the binding
+    (a shorter struct would make fm_create read past it)."""
+    import re
+    from fair_marl_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class FmConfig(C.Structure):"):text.index("class FmOutputs(C.Structure):")]
+    doc_fields = re.findall(r'\("(\w+)", C\.(c_\w+)\)', block)
+    lib_fields = [(name, ctype.__name__) for name, ctype in _lib.FmConfig._fields_]
+    # ctypes aliases: c_int32 is c_int, c_int64 is c_long, ... compare through the types themselves
+    import ctypes as C
+    assert [(n, getattr(C, t)) for n, t in doc_fields] == list(_lib.FmConfig._fields_), (doc_fields, lib_fields)
