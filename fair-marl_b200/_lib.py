@@ -26,6 +26,7 @@ class FmConfig(C.Structure):
         ("zeroshift", C.c_double), ("max_edge_dist", C.c_double),
         ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32),
         ("info_every_step", C.c_int32), ("mapping", C.c_int32), ("graph_feat_global", C.c_int32),
+        ("num_walls", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -36,8 +37,9 @@ class FmOutputs(C.Structure):
 
 STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_match", "dists_to_goal",
                 "times_required", "dist_left_to_goal", "num_agent_collisions", "num_obstacle_collisions",
-                "dist_traveled_mean", "dist_traveled_stddev", "step", "min_time", "episode")
-STATE_INT_FIELDS = ("goal_match", "num_agent_collisions", "num_obstacle_collisions", "step", "episode")
+                "dist_traveled_mean", "dist_traveled_stddev", "step", "min_time", "episode",
+                "wall_axis", "wall_orient", "wall_len")
+STATE_INT_FIELDS = ("goal_match", "num_agent_collisions", "num_obstacle_collisions", "step", "episode", "wall_orient")
 
 
 class FmState(C.Structure):

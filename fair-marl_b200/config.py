@@ -10,6 +10,7 @@ from typing import Any, Optional
 class SimConfig:
     num_agents: int = 3
     num_obstacles: int = 3
+    num_walls: int = 0          # 0, 1 or 2 wall segments (group-per-env kernels; not with graph_feat_type='global')
     world_size: float = 2.0
     max_speed: Optional[float] = 2.0
     collision_rew: float = 5.0
@@ -32,7 +33,7 @@ class SimConfig:
 
     @property
     def num_entities(self) -> int:
-        return 2 * self.num_agents + self.num_obstacles
+        return 2 * self.num_agents + self.num_obstacles + self.num_walls
 
     @property
     def node_feat_dim(self) -> int:
@@ -48,8 +49,10 @@ class SimConfig:
         if hasattr(args, "num_landmarks") and args.num_landmarks != kw.get("num_agents", 3):
             raise ValueError("navigation_graph needs num_landmarks == num_agents "
                              f"(got {args.num_landmarks} vs {kw.get('num_agents')})")
-        if getattr(args, "num_walls", 0):
-            raise NotImplementedError("num_walls > 0 is not supported (SURVEY.md row N4)")
+        if not 0 <= int(getattr(args, "num_walls", 0) or 0) <= 2:
+            raise ValueError("navigation_graph places at most 2 walls (navigation_graph.py:289)")
+        if getattr(args, "num_walls", 0) and getattr(args, "graph_feat_type", "relative") == "global":
+            raise NotImplementedError("wall entities have no global features (navigation_graph.py:1074-1075)")
         if getattr(args, "graph_feat_type", "relative") not in ("relative", "global"):
             raise ValueError(f"graph_feat_type must be 'relative' or 'global' (got {args.graph_feat_type!r})")
         if getattr(args, "num_scripted_agents", 0):

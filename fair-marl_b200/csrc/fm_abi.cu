@@ -80,6 +80,12 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   if (cfg->num_envs <= 0) return fail(FM_ERR_INVALID_ARG, "fm_create: num_envs must be > 0 (got %d)", cfg->num_envs);
   if (cfg->num_agents < 1 || cfg->num_agents > FM_MAX_AGENTS)
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_agents must be in 1..%d (got %d)", FM_MAX_AGENTS, cfg->num_agents);
+  if (cfg->num_walls < 0 || cfg->num_walls > 2)
+    return fail(FM_ERR_INVALID_ARG, "fm_create: num_walls must be 0, 1 or 2 (got %d)", cfg->num_walls);
+  if (cfg->num_walls > 0 && cfg->graph_feat_global)
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: wall entities have no global features (navigation_graph.py:1074-1075)");
+  if (cfg->num_walls > 0 && cfg->mapping == 2)
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: the agent-warp kernels do not take walls");
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > 64)
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_obstacles must be in 0..64 (got %d)", cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_create: episode_length must be >= 1");
@@ -99,14 +105,14 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   h->cfg = *cfg;
   h->device = device;
   DevParams& p = h->p;
-  const int B = cfg->num_envs, N = cfg->num_agents, O = cfg->num_obstacles, E = 2 * N + O;
-  p.B = B; p.N = N; p.O = O; p.E = E;
+  const int B = cfg->num_envs, N = cfg->num_agents, O = cfg->num_obstacles, W = cfg->num_walls, E = 2 * N + O + W;
+  p.B = B; p.N = N; p.O = O; p.E = E; p.W = W;
   p.env_begin = 0; p.env_end = B;
   p.Bp = (B + 63) & ~63;
   const size_t Bp = (size_t)p.Bp;
-  const int SP = (N + O) * (N + O - 1) / 2;
+  const int SP = (N + O + W) * (N + O + W - 1) / 2;    // static entities: landmarks, obstacles, walls
   const int SPp = (SP + 3) & ~3;                   // per-env row of the group mapping's layout
-  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4 + SPp);
+  const size_t words = Bp * (size_t)(9 * N + 3 * N + 2 * N + 2 * O + 4 + SPp + 2 * W + 1);
   cudaError_t e = cudaMalloc(&h->state_block, words * 4);
   if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc(%zu B): %s", words * 4, cudaGetErrorString(e)); }
   cudaMemset(h->state_block, 0, words * 4);
@@ -119,6 +125,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.ox = take(Bp * O); p.oy = take(Bp * O);
   p.dmean = take(Bp); p.dstd = take(Bp); p.step = (int*)take(Bp); p.episode = (int*)take(Bp);
   p.sdist = take(Bp * SPp);
+  p.wax = take(Bp * W); p.wor = (int*)take(Bp * W); p.wlen = take(Bp);     // after sdist: the agent-warp kernels index rows up to sdist
 
   // config -> device constants.  Collision threshold exactly as the reference spells it:
   // 1.05*(size + size) (navigation_graph.py:655, :704); cached min_dist = size + size (core.py:215).
@@ -168,7 +175,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: agent-warp kernels are not compiled for N=%d O=%d", N, O);
   }
-  p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || fm::aw_supported(N, O)) ? 1 : 0);
+  p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || (W == 0 && fm::aw_supported(N, O))) ? 1 : 0);
   p.sd_env_stride = p.mapping == 0 ? SPp : 0;      // group mapping: [env][SPp];  agent-warp mapping: [pair][Bp]
   // pending block of the next-episode prefetch (group mapping with auto-reset; FM_PREFETCH=0 disables it)
   h->lockstep = 1; h->host_step = 0;
@@ -177,13 +184,14 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     h->pf_on = p.mapping == 0 && cfg->auto_reset && !(ev && atoi(ev) == 0);
   }
   if (h->pf_on) {
-    const size_t rows = (size_t)(5 * N + 2 * O);
+    const size_t rows = (size_t)(5 * N + 2 * O + 2 * W);
     e = cudaMalloc(&h->pend_block, (rows * Bp + Bp) * 4);
     if (e != cudaSuccess) { cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: cudaMalloc pending block: %s", cudaGetErrorString(e)); }
     float* g = (float*)h->pend_block;
     auto takeq = [&](size_t n) { float* r = g; g += n; return r; };
     p.q_px = takeq(Bp * N); p.q_py = takeq(Bp * N); p.q_lx = takeq(Bp * N); p.q_ly = takeq(Bp * N);
-    p.q_ox = takeq(Bp * O); p.q_oy = takeq(Bp * O); p.q_gm = (int*)takeq(Bp * N); p.q_tag = (int*)takeq(Bp);
+    p.q_ox = takeq(Bp * O); p.q_oy = takeq(Bp * O); p.q_gm = (int*)takeq(Bp * N);
+    p.q_wax = takeq(Bp * W); p.q_wor = (int*)takeq(Bp * W); p.q_tag = (int*)takeq(Bp);
     cudaMemset(p.q_tag, 0xff, Bp * 4);              // -1: no entry
   }
   const int G = fm::group_size(N), EPW = 32 / G;
@@ -543,7 +551,7 @@ int fm_set_state(FmHandle* h, const FmState* st, void* stream) {
   FM_CUDA(fm::launch_state_io(h->p, *st, 1, (cudaStream_t)stream));
   h->launches += 1;
   if (st->step || st->episode) h->lockstep = 0;      // the host no longer knows the episode phase of every env
-  if (st->landmark_pos || st->obstacle_pos) {                              // cached static distances follow the positions
+  if (st->landmark_pos || st->obstacle_pos || st->wall_axis || st->wall_orient) {   // cached static distances follow the positions
     FM_CUDA(fm::launch_static_dists(h->p, (cudaStream_t)stream));
     h->launches += 1;
   }

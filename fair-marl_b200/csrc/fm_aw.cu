@@ -649,15 +649,26 @@ aw_kernel(const __grid_constant__ DevParams p) {
 // =============================================================================================
 // Distances between static entities from the SoA state (after fm_set_state injected positions).
 __global__ void aw_static_kernel(const DevParams p, float* __restrict__ sdist) {
-  const int M = p.N + p.O, SP = M * (M - 1) / 2;
+  const int M = p.N + p.O + p.W, SP = M * (M - 1) / 2;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)p.Bp * SP) return;
   const int q = (int)(t / p.Bp), env = (int)(t % p.Bp);
   int a = 0, rem = q;
   while (rem >= M - 1 - a) { rem -= M - 1 - a; ++a; }
   const int b = a + 1 + rem;
-  auto X = [&](int s) { return s < p.N ? p.lx[(size_t)s * p.Bp + env] : p.ox[(size_t)(s - p.N) * p.Bp + env]; };
-  auto Y = [&](int s) { return s < p.N ? p.ly[(size_t)s * p.Bp + env] : p.oy[(size_t)(s - p.N) * p.Bp + env]; };
+  // static entity s: landmark, obstacle, or wall midpoint ((0, axis) for 'H', (axis, 0) for 'V')
+  auto X = [&](int s) {
+    if (s < p.N) return p.lx[(size_t)s * p.Bp + env];
+    if (s < p.N + p.O) return p.ox[(size_t)(s - p.N) * p.Bp + env];
+    const size_t wi = (size_t)(s - p.N - p.O) * p.Bp + env;
+    return p.wor[wi] == 0 ? 0.0f : p.wax[wi];
+  };
+  auto Y = [&](int s) {
+    if (s < p.N) return p.ly[(size_t)s * p.Bp + env];
+    if (s < p.N + p.O) return p.oy[(size_t)(s - p.N) * p.Bp + env];
+    const size_t wi = (size_t)(s - p.N - p.O) * p.Bp + env;
+    return p.wor[wi] == 0 ? p.wax[wi] : 0.0f;
+  };
   const size_t at = p.sd_env_stride ? (size_t)env * p.sd_env_stride + q : (size_t)q * p.Bp + env;
   sdist[at] = (float)dist64(X(a), Y(a), X(b), Y(b));
 }
@@ -718,7 +729,7 @@ cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset) {
 }
 
 cudaError_t launch_static_dists(const DevParams& p, cudaStream_t st) {
-  const int M = p.N + p.O, SP = M * (M - 1) / 2;
+  const int M = p.N + p.O + p.W, SP = M * (M - 1) / 2;
   if (SP == 0 || !p.sdist) return cudaSuccess;
   const long long total = (long long)p.Bp * SP;
   aw_static_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(p, p.sdist);

@@ -9,6 +9,8 @@
 //   pack/unpack       API-layout FmState <-> internal SoA state.
 //   edge_*            policy-side edge list (process_adj) by warp ballot + prefix compaction.
 //   stats_reduce      fixed-order reduction of the per-warp statistic partial sums.
+#include <algorithm>
+
 #include "fm_device.cuh"
 #include "fm_launch.h"
 
@@ -21,8 +23,8 @@ __host__ __device__ inline int assign_smem_floats(int n) { return (2 * n * n + (
 
 // =============================================================================================
 // The fused step.  Reference call stack: MultiAgentGraphEnv.step (environment.py:816-877).
-template <int G>
-__global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ? 4 : 3))) step_kernel(const __grid_constant__ DevParams p) {
+template <int G, bool WALLS>
+__global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 5 : (G == 16 ? 4 : 3))) step_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EPW = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
   const int el = lane / G, i = lane % G;
   const int env = env0 + el;
   const int N = p.N, O = p.O, E = p.E;
+  const int W = WALLS ? p.W : 0;                 // walls: entities 2N+O .. E-1 (their own instantiation)
   const bool venv = el < nenv;
   const bool act = venv && i < N;
   const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
       const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
       ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
     }
+    for (int k = i; k < W; k += G) load_wall(p, ent, env, k);
   }
   __syncwarp();
 
@@ -87,6 +91,16 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
     for (int k = 0; k < O; ++k) {
       const float* o = ent + (2 * N + k) * ENT_STRIDE;
       contact_force(p, px, py, o[0], o[1], cfx, cfy);
+    }
+    // walls: first as circle entities of the pair loop (they close world.entities), then the wall forces proper
+    // (core.py:317-327), both from the positions at step entry
+    for (int k = 0; k < W; ++k) {
+      const float* w = ent + (2 * N + O + k) * ENT_STRIDE;
+      contact_force_dmin(p, 0.15f, px, py, w[0], w[1], cfx, cfy);
+    }
+    for (int k = 0; k < W; ++k) {
+      const float* w = ent + (2 * N + O + k) * ENT_STRIDE;
+      wall_force(px, py, w[7] == 0.0f, w[5], w[4], cfx, cfy);
     }
   }
   const double Fx = __dadd_rn((double)ux, (double)cfx), Fy = __dadd_rn((double)uy, (double)cfy);   // mass(1.0) * u + contact
@@ -107,8 +121,14 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
 
   // ---- calculate_distances (core.py:204-228) at the new positions -----------------------------
   double dgoal; int ncoll; bool ocoll;
-  if (venv) distance_tile<G>(p, ent, adj, env, false, i, act, gm, dgoal, ncoll, ocoll);
+  if (venv) distance_tile<G, WALLS>(p, ent, adj, env, false, i, act, gm, dgoal, ncoll, ocoll);
   else { dgoal = 0.0; ncoll = 0; ocoll = false; }
+  if (act) {
+    for (int k = 0; k < W; ++k) {                // is_obstacle_collision also tests the wall boxes (:670-683)
+      const float* w = ent + (2 * N + O + k) * ENT_STRIDE;
+      ocoll = ocoll || in_wall_box(npx, npy, w[7] == 0.0f, w[5], w[4]);
+    }
+  }
 
   // ---- per-agent loop of MultiAgentGraphEnv.step (environment.py:832-864): agent i's observation
   // and reward read world.dist_traveled_mean/stddev as left by agent i-1's info_callback
@@ -248,6 +268,11 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
           ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
           p.ox[(size_t)k * p.Bp + env] = x; p.oy[(size_t)k * p.Bp + env] = y;
         }
+        for (int k = i; k < W; k += G) {
+          const size_t wi = (size_t)k * p.Bp + env;
+          p.wax[wi] = p.q_wax[wi]; p.wor[wi] = p.q_wor[wi];
+          store_wall(ent, N, O, k, p.q_wax[wi], p.q_wor[wi], p.wlen[env]);
+        }
       }
       __syncwarp();
       if (use_pend && i < N) {
@@ -260,14 +285,14 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
       __syncwarp();
     }
     if (__any_sync(FULL, do_reset && !use_pend))
-      reset_group<G>(p, s, el, i, env, do_reset && !use_pend, gmask, episode, rgm, rx, ry, rmint, p.lx, p.ly, p.ox, p.oy, true);
+      reset_group<G, WALLS>(p, s, el, i, env, do_reset && !use_pend, gmask, episode, rgm, rx, ry, rmint, p.lx, p.ly, p.ox, p.oy, p.wax, p.wor, true);
     if (do_reset) {
       gm = rgm; npx = rx; npy = ry; nvx = 0.f; nvy = 0.f; npd = 0.f;
       ndtg = -1.f; ntreq = -1.f; ndleft = -1.f; nac = 0; noc = 0; nstep_store = 0; nepisode = episode + 1;
       fobs = 0.f;                                // mean(p_dist = 0) / (std + 1e-4)
       if (act) p.mintime[idx] = rmint;
       double d2; int c2; bool o2;
-      distance_tile<G>(p, ent, adj, env, true, i, act, gm, d2, c2, o2);
+      distance_tile<G, WALLS>(p, ent, adj, env, true, i, act, gm, d2, c2, o2);
     }
   }
   if (act) {
@@ -284,12 +309,12 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? 6 : (G == 4 ? 5 : (G == 16 ?
     p.step[env] = nstep_store; p.episode[env] = (int)nepisode; p.dmean[env] = ndmean; p.dstd[env] = ndstd;
   }
   __syncwarp();
-  emit_tiles(p, s, env0, nenv, lane);
+  emit_tiles<WALLS>(p, s, env0, nenv, lane);
 }
 
 // =============================================================================================
 // reset() / observe: GraphSubprocVecEnv.reset -> MultiAgentGraphEnv.reset (environment.py:882-898).
-template <int G>
+template <int G, bool WALLS>
 __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EPW = 32 / G;
@@ -301,6 +326,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   const int el = lane / G, i = lane % G;
   const int env = env0 + el;
   const int N = p.N, O = p.O, E = p.E;
+  const int W = WALLS ? p.W : 0;                 // walls: entities 2N+O .. E-1 (their own instantiation)
   const bool venv = el < nenv;
   const bool act = venv && i < N;
   const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (el * G));
@@ -328,6 +354,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
       const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
       ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
     }
+    for (int k = i; k < W; k += G) load_wall(p, ent, env, k);
   }
   __syncwarp();
   if (act) {
@@ -336,7 +363,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   }
   __syncwarp();
   if (__any_sync(FULL, do_reset)) {
-    reset_group<G>(p, s, el, i, env, do_reset, gmask, episode, gm, px, py, mint, p.lx, p.ly, p.ox, p.oy, true);
+    reset_group<G, WALLS>(p, s, el, i, env, do_reset, gmask, episode, gm, px, py, mint, p.lx, p.ly, p.ox, p.oy, p.wax, p.wor, true);
     if (do_reset && act) {
       vx = 0.f; vy = 0.f; pd = 0.f; dtg = -1.f;
       p.px[idx] = px; p.py[idx] = py; p.vx[idx] = 0.f; p.vy[idx] = 0.f; p.pdist[idx] = 0.f;
@@ -356,14 +383,14 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   const float std_p = std_from_q(q_p, inv_n);
   const float fparam = (dtg == -1.0f) ? ratio_eps((float)mean_p, std_p) : ratio_eps(dmean, dstd);
   double dgoal; int ncoll; bool ocoll;
-  if (venv) distance_tile<G>(p, ent, adj, env, do_reset, i, act, gm, dgoal, ncoll, ocoll);
+  if (venv) distance_tile<G, WALLS>(p, ent, adj, env, do_reset, i, act, gm, dgoal, ncoll, ocoll);
   if (act) {
     const float gx = ent[i * ENT_STRIDE + 4], gy = ent[i * ENT_STRIDE + 5];
     obs[i * OBS_F + 0] = vx; obs[i * OBS_F + 1] = vy; obs[i * OBS_F + 2] = px; obs[i * OBS_F + 3] = py;
     obs[i * OBS_F + 4] = gx - px; obs[i * OBS_F + 5] = gy - py; obs[i * OBS_F + 6] = (float)fparam;
   }
   __syncwarp();
-  emit_tiles(p, s, env0, nenv, lane);
+  emit_tiles<WALLS>(p, s, env0, nenv, lane);
 }
 
 // =============================================================================================
@@ -371,7 +398,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
 // depend only on (seed, global env, episode key)).  Launched on a side stream right after the kernel that advanced
 // the episode counters; it overlaps the memory-bound regular steps of the episode, and the terminal step copies the
 // entry (step_kernel, `use_pend`).  Envs whose entry already carries the current key are skipped.
-template <int G>
+template <int G, bool WALLS>
 __global__ void __launch_bounds__(THREADS) prefetch_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int EPW = 32 / G;
@@ -390,7 +417,7 @@ __global__ void __launch_bounds__(THREADS) prefetch_kernel(const __grid_constant
   if (!__any_sync(FULL, need)) return;
   int gm = 0;
   float x = 0.f, y = 0.f, mint = 0.f;
-  reset_group<G>(p, s, el, i, env, need, gmask, episode, gm, x, y, mint, p.q_lx, p.q_ly, p.q_ox, p.q_oy, false);
+  reset_group<G, WALLS>(p, s, el, i, env, need, gmask, episode, gm, x, y, mint, p.q_lx, p.q_ly, p.q_ox, p.q_oy, p.q_wax, p.q_wor, false);
   if (need && i < p.N) {
     const size_t idx = (size_t)i * p.Bp + env;
     p.q_px[idx] = x; p.q_py[idx] = y; p.q_gm[idx] = gm;
@@ -436,7 +463,7 @@ __global__ void __launch_bounds__(THREADS) assign_kernel(const double* __restric
 // =============================================================================================
 // FmState (API layout) <-> internal SoA.  One thread per (env, slot), slot < max(N, O).
 __global__ void state_io_kernel(const DevParams p, const HostState st, int to_internal) {
-  const int S = max(p.N, max(p.O, 1));
+  const int S = max(p.N, max(max(p.O, p.W), 1));
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)p.B * S) return;
   const int env = (int)(t / S), k = (int)(t % S);
@@ -458,6 +485,12 @@ __global__ void state_io_kernel(const DevParams p, const HostState st, int to_in
     if (to_internal) { p.ox[si] = st.obstacle_pos[oi]; p.oy[si] = st.obstacle_pos[oi + 1]; }
     else { st.obstacle_pos[oi] = p.ox[si]; st.obstacle_pos[oi + 1] = p.oy[si]; }
   }
+  if (k < p.W) {
+    const size_t wi = (size_t)env * p.W + k;
+    if (st.wall_axis) { if (to_internal) p.wax[si] = st.wall_axis[wi]; else st.wall_axis[wi] = p.wax[si]; }
+    if (st.wall_orient) { if (to_internal) p.wor[si] = st.wall_orient[wi]; else st.wall_orient[wi] = p.wor[si]; }
+  }
+  if (k == 0 && st.wall_len && p.W > 0) { if (to_internal) p.wlen[env] = st.wall_len[env]; else st.wall_len[env] = p.wlen[env]; }
   if (k == 0) {
 #define FM_IO_E(ptr, arr) \
   if (st.ptr) { if (to_internal) p.arr[env] = st.ptr[env]; else st.ptr[env] = p.arr[env]; }
@@ -473,6 +506,12 @@ __global__ void state_init_kernel(const DevParams p) {
   const int k = (int)(t / p.Bp);
   p.gm[t] = k; p.dtg[t] = -1.f; p.treq[t] = -1.f; p.dleft[t] = -1.f;
   p.mintime[t] = __int_as_float(0x7f800000);   // agent.goal_min_time = np.inf (core.py:127)
+  if (k == 0 && p.W > 0) {                       // scenario.wall_length = U(0.2, 0.8) * world_size / 4, once per env (:183-185)
+    const int env = (int)(t % p.Bp);
+    float u0, u1;
+    draw_u01(p, p.env_offset + env, 0xffffffffu, 0u, u0, u1);
+    p.wlen[env] = __fmul_rn(__fadd_rn(0.2f, __fmul_rn(0.6f, u0)), p.world_size * 0.25f);
+  }
 }
 
 // =============================================================================================
@@ -618,47 +657,50 @@ __global__ void stats_reduce_kernel(double* __restrict__ partial, int rows, int 
 
 // =============================================================================================
 // Launchers (host side of this translation unit).
-template <int G>
+template <int G, bool WALLS>
 static cudaError_t launch_step_g(const DevParams& p, cudaStream_t st, bool is_reset) {
   constexpr int EPW = 32 / G;
   const int warps = (p.env_end - p.env_begin + EPW - 1) / EPW;
   const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)p.sm_per_warp * (THREADS / 32) * sizeof(float);
-  if (is_reset) reset_kernel<G><<<blocks, THREADS, smem, st>>>(p);
-  else step_kernel<G><<<blocks, THREADS, smem, st>>>(p);
+  if (is_reset) reset_kernel<G, WALLS><<<blocks, THREADS, smem, st>>>(p);
+  else step_kernel<G, WALLS><<<blocks, THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
-template <int G>
+template <int G, bool WALLS>
 static cudaError_t launch_prefetch_g(const DevParams& p, cudaStream_t st) {
   constexpr int EPW = 32 / G;
   const int warps = (p.env_end - p.env_begin + EPW - 1) / EPW;
   const int blocks = (warps + THREADS / 32 - 1) / (THREADS / 32);
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)p.sm_pf_per_warp * (THREADS / 32) * sizeof(float);
-  prefetch_kernel<G><<<blocks, THREADS, smem, st>>>(p);
+  prefetch_kernel<G, WALLS><<<blocks, THREADS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_prefetch(const DevParams& p, cudaStream_t st) {
-  switch (group_size(p.N)) {
-    case 4: return launch_prefetch_g<4>(p, st);
-    case 8: return launch_prefetch_g<8>(p, st);
-    case 16: return launch_prefetch_g<16>(p, st);
-    default: return launch_prefetch_g<32>(p, st);
+// group size x walls -> instantiation (the wall terms live in their own kernels: the wall-free ones keep their
+// register budgets, e.g. 80 at G = 8)
+#define FM_DISPATCH_G(fn, ...)                                                              \
+  switch (group_size(p.N)) {                                                                \
+    case 4: return p.W > 0 ? fn<4, true>(__VA_ARGS__) : fn<4, false>(__VA_ARGS__);          \
+    case 8: return p.W > 0 ? fn<8, true>(__VA_ARGS__) : fn<8, false>(__VA_ARGS__);          \
+    case 16: return p.W > 0 ? fn<16, true>(__VA_ARGS__) : fn<16, false>(__VA_ARGS__);       \
+    default: return p.W > 0 ? fn<32, true>(__VA_ARGS__) : fn<32, false>(__VA_ARGS__);       \
   }
-}
 
-template <int G>
+cudaError_t launch_prefetch(const DevParams& p, cudaStream_t st) { FM_DISPATCH_G(launch_prefetch_g, p, st) }
+
+template <int G, bool WALLS>
 static cudaError_t prepare_g(const DevParams& p) {
   const int smem = p.sm_per_warp * (THREADS / 32) * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(reset_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(reset_kernel<G, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(prefetch_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(prefetch_kernel<G, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            p.sm_pf_per_warp * (THREADS / 32) * (int)sizeof(float));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return cudaFuncSetAttribute(step_kernel<G, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); }
@@ -667,22 +709,12 @@ int num_warps(int B, int N) { const int epw = 32 / group_size(N); return (B + ep
 
 cudaError_t prepare_kernels(const DevParams& p) {
   if (p.mapping == 1) return aw_prepare(p);
-  switch (group_size(p.N)) {
-    case 4: return prepare_g<4>(p);
-    case 8: return prepare_g<8>(p);
-    case 16: return prepare_g<16>(p);
-    default: return prepare_g<32>(p);
-  }
+  FM_DISPATCH_G(prepare_g, p)
 }
 
 cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset) {
   if (p.mapping == 1) return aw_launch(p, st, is_reset);
-  switch (group_size(p.N)) {
-    case 4: return launch_step_g<4>(p, st, is_reset);
-    case 8: return launch_step_g<8>(p, st, is_reset);
-    case 16: return launch_step_g<16>(p, st, is_reset);
-    default: return launch_step_g<32>(p, st, is_reset);
-  }
+  FM_DISPATCH_G(launch_step_g, p, st, is_reset)
 }
 
 template <int G>
@@ -711,7 +743,7 @@ cudaError_t launch_assign(const double* costs, const float* apos, const float* g
 }
 
 cudaError_t launch_state_io(const DevParams& p, const HostState& hs, int to_internal, cudaStream_t st) {
-  const int S = p.N > p.O ? p.N : (p.O > 1 ? p.O : 1);
+  const int S = std::max(p.N, std::max(std::max(p.O, p.W), 1));
   const long long total = (long long)p.B * S;
   const int blocks = (int)((total + 255) / 256);
   state_io_kernel<<<blocks, 256, 0, st>>>(p, hs, to_internal);

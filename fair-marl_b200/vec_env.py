@@ -104,7 +104,7 @@ class B200GraphVecEnv:
             fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative),
             auto_reset=int(cfg.auto_reset), info_every_step=int(cfg.info_every_step),
             mapping={"auto": 0, "group": 1, "aw": 2}[cfg.mapping],
-            graph_feat_global=int(cfg.graph_feat_type == "global"))
+            graph_feat_global=int(cfg.graph_feat_type == "global"), num_walls=int(cfg.num_walls))
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_create")
 
@@ -406,8 +406,9 @@ class B200GraphVecEnv:
         return st
 
     def _state_shapes(self):
-        B, N, O = self.num_envs, self.num_agents, self.cfg.num_obstacles
-        return {"pos": (B, N, 2), "vel": (B, N, 2), "p_dist": (B, N), "landmark_pos": (B, N, 2),
+        B, N, O, W = self.num_envs, self.num_agents, self.cfg.num_obstacles, self.cfg.num_walls
+        walls = {"wall_axis": (B, W), "wall_orient": (B, W), "wall_len": (B,)} if W else {}
+        return {**walls, "pos": (B, N, 2), "vel": (B, N, 2), "p_dist": (B, N), "landmark_pos": (B, N, 2),
                 "obstacle_pos": (B, O, 2), "goal_match": (B, N), "dists_to_goal": (B, N),
                 "times_required": (B, N), "dist_left_to_goal": (B, N), "num_agent_collisions": (B, N),
                 "num_obstacle_collisions": (B, N), "dist_traveled_mean": (B,), "dist_traveled_stddev": (B,),

@@ -17,7 +17,7 @@
  *   - Return value: 0 on success, a negative FmStatus otherwise; fm_last_error() gives the text.
  *     Nothing here throws, aborts or falls back to a CPU path.
  *   - Entity order (reference World.entities, multiagent/core.py:186):
- *     agents 0..N-1, landmarks N..2N-1, obstacles 2N..2N+O-1;  E = 2N + O.
+ *     agents 0..N-1, landmarks N..2N-1, obstacles 2N..2N+O-1, walls 2N+O..2N+O+W-1;  E = 2N + O + W.
  */
 #ifndef FAIRMARL_H_
 #define FAIRMARL_H_
@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FM_ABI_VERSION 3
+#define FM_ABI_VERSION 4
 #define FM_OBS_DIM 7         /* navigation_graph.py:826-857 */
 #define FM_NODE_FEAT_DIM 11  /* navigation_graph.py:1079-1124 (relative features) */
 #define FM_INFO_DIM 14       /* navigation_graph.py:625-647 + environment.py:857 */
@@ -68,6 +68,9 @@ typedef struct FmConfig {
                               1 group-per-env, 2 agent-warp.  Results are identical. */
   int32_t graph_feat_global; /* 0: graph_feat_type 'relative' (node_obs [B,N,E,11], navigation_graph.py:1079-1124);
                                 1: 'global' (node_obs [B,N,E,7] = [vel, pos, goal, type], :1058-1077) */
+  int32_t num_walls;       /* W = 0, 1 or 2 axis-aligned wall segments (navigation_graph.py:181-196, :287-324; core.py:36-55,
+                              :407-462); group-per-env kernels only; not with graph_feat_global */
+  int32_t reserved_;
 } FmConfig;
 
 /* Per-step outputs, API layout (what GraphSubprocVecEnv.step_wait stacks, env_wrappers.py:988-996). */
@@ -106,6 +109,9 @@ typedef struct FmState {
   int32_t* step;                   /* [B] */
   float* min_time;                 /* [B, N] */
   int32_t* episode;                /* [B]  resets so far (RNG counter) */
+  float* wall_axis;                /* [B, W]  wall.axis_pos */
+  int32_t* wall_orient;            /* [B, W]  0 = 'H', 1 = 'V' */
+  float* wall_len;                 /* [B]     half-length (scenario.wall_length), fixed per env */
 } FmState;
 
 typedef struct FmHandle FmHandle;

@@ -39,23 +39,21 @@ def assert_fairness_close(dev, ref, name="fairness_param"):
 
 def sim_config_from(cfg: NavConfig, **kw):
     from fair_marl_b200 import SimConfig
-    if cfg.num_walls:
-        raise NotImplementedError("the CUDA path does not take num_walls > 0 (oracle-only fixtures)")
     return SimConfig(num_agents=cfg.num_agents, num_obstacles=cfg.num_obstacles, world_size=cfg.world_size,
                      max_speed=cfg.max_speed, collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew,
                      min_dist_thresh=cfg.min_dist_thresh, episode_length=cfg.episode_length,
                      fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift, max_edge_dist=cfg.max_edge_dist,
                      collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward,
-                     graph_feat_type=cfg.graph_feat_type,
+                     graph_feat_type=cfg.graph_feat_type, num_walls=cfg.num_walls,
                      **{"mapping": MAPPING, **kw})
 
 
 def state_to_fp32(st: NavState) -> NavState:
     """Round a float64 state to the device dtype (and back to float64 for the oracle)."""
     d = {}
-    for name in STATE_FIELDS:                       # the wall fields are oracle-only (None on the device path)
+    for name in _present(st):                       # the wall fields are None without walls
         a = np.asarray(getattr(st, name))
-        if name in ("goal_match", "step", "episode"):
+        if name in ("goal_match", "step", "episode", "wall_orient"):
             d[name] = a.astype(np.int64)
         else:
             with np.errstate(over="ignore"):
@@ -63,17 +61,21 @@ def state_to_fp32(st: NavState) -> NavState:
     return NavState(**d)
 
 
+def _present(st: NavState):
+    return [f.name for f in fields(NavState) if getattr(st, f.name) is not None]
+
+
 def state_to_device_dict(st: NavState):
-    return {name: np.asarray(getattr(st, name)) for name in STATE_FIELDS}
+    return {name: np.asarray(getattr(st, name)) for name in _present(st)}
 
 
 def device_state_to_nav(dev_state) -> NavState:
     d = {}
     for f in fields(NavState):
-        if f.name not in STATE_FIELDS:
+        if f.name not in dev_state:                 # wall fields exist only with num_walls > 0
             continue
         a = dev_state[f.name].cpu().numpy()
-        d[f.name] = a.astype(np.int64) if f.name in ("goal_match", "step", "episode") else a.astype(np.float64)
+        d[f.name] = a.astype(np.int64) if f.name in ("goal_match", "step", "episode", "wall_orient") else a.astype(np.float64)
     return NavState(**d)
 
 

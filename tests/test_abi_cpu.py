@@ -33,7 +33,7 @@ def test_binding_covers_header(lib_path):
     from fair_marl_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.load()
-    assert lib.fm_abi_version() == 3
+    assert lib.fm_abi_version() == 4
     assert lib.fm_stats_len(3) == 47
 
 
@@ -57,7 +57,7 @@ def test_struct_layouts_match_header(tmp_path):
         assert int(got[name]) == ctypes.sizeof(cls), name
         for field, _ in cls._fields_:
             assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
-    assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8 and ctypes.sizeof(_lib.FmState) == 16 * 8
+    assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8 and ctypes.sizeof(_lib.FmState) == 19 * 8
 
 
 def test_library_is_sm100a_only(lib_path):
@@ -106,6 +106,14 @@ def test_config_from_reference_namespace():
     a.scenario_name = "nav_graph_goalassign_noFair"
     assert not SimConfig.from_args(a).fairness_reward
     a.num_walls = 1
+    assert SimConfig.from_args(a).num_entities == 10            # walls close the entity list
+    a.graph_feat_type = "global"
+    with pytest.raises(NotImplementedError):                     # no global features for wall entities
+        SimConfig.from_args(a)
+    a.graph_feat_type, a.num_walls = "relative", 3
+    with pytest.raises(ValueError):
+        SimConfig.from_args(a)
+    a.num_walls, a.num_scripted_agents = 0, 1
     with pytest.raises(NotImplementedError):
         SimConfig.from_args(a)
 

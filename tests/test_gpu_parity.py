@@ -12,8 +12,7 @@ from oracle.edges import process_adj as oracle_process_adj
 from oracle.lexifair import lexifair, lexifair_bruteforce_batched, lexifair_descent
 from oracle.make_golden import CONFIGS, load, state_from
 
-# fixtures with walls pin the ORACLE only (the CUDA path rejects num_walls > 0 for now)
-DEVICE_CONFIGS = sorted(n for n in CONFIGS if CONFIGS[n][0].num_walls == 0)
+DEVICE_CONFIGS = sorted(CONFIGS)
 from oracle.navgraph import INFO_KEYS, NavConfig, NavGraphOracle
 from parity_util import (assert_close, assert_fairness_close, compare_step_outputs, device_state_to_nav,
                          sim_config_from, state_to_device_dict, state_to_fp32)
@@ -68,7 +67,7 @@ def test_step_matches_oracle_on_golden_states(name):
     env.close()
 
 
-@pytest.mark.parametrize("name", ["n3_o3_fafr", "n7_o3_fafr", "n16_o3_fafr"])
+@pytest.mark.parametrize("name", ["n3_o3_fafr", "n7_o3_fafr", "n16_o3_fafr", "n3_o3_w2", "n4_o2_w1"])
 def test_step_matches_reference_golden_directly(name):
     """Device outputs against the reference's own float64 outputs (inputs rounded to fp32 on the way
     in, so smooth quantities only: obs[0:6], node_obs, adj)."""
@@ -469,3 +468,40 @@ def test_outputs_at_any_alignment_and_partial_outputs(N, O, B):
         for a, b in zip(ref, got):
             for k in keep:
                 assert torch.equal(a[k], b[k]), (keep, k)
+
+
+@pytest.mark.parametrize("N,O,W,B,prefetch", [(3, 3, 2, 192, "1"), (4, 2, 1, 100, "0"), (7, 3, 2, 64, "1")])
+def test_walls_reset_and_rollout_match_oracle(N, O, W, B, prefetch, monkeypatch):
+    """num_walls > 0 (group-per-env kernels): the reset draws wall axis / orientation from the same Philox stream and
+    rejects placements inside the wall boxes exactly like the oracle (bit-exact state), and a random-action rollout
+    across auto-resets stays within tolerance step by step -- with the next-episode prefetch on and off."""
+    monkeypatch.setenv("FM_PREFETCH", prefetch)
+    cfg = NavConfig(num_agents=N, num_obstacles=O, num_walls=W, goal_rew=30.0, collision_rew=30.0, episode_length=9)
+    env = _env(cfg, B, seed=11, env_offset=5)
+    assert env.mapping == "group" and env.num_entities == 2 * N + O + W
+    orc = NavGraphOracle(cfg, B, seed=11, env_offset=5)
+    out = _np(env.reset_tensor())
+    ref = orc.reset()
+    st, rs = device_state_to_nav(env.get_state()), orc.get_state()
+    assert (st.wall_len == rs.wall_len.astype(np.float32)).all() and (st.wall_axis == rs.wall_axis).all()
+    assert (st.wall_orient == rs.wall_orient).all() and set(np.unique(st.wall_orient)) == {0, 1}
+    assert (st.pos == rs.pos).all() and (st.landmark_pos == rs.landmark_pos).all() and (st.goal_match == rs.goal_match).all()
+    assert not orc._in_wall_box(st.pos.reshape(-1, 2), 0.05, sel=np.repeat(np.arange(B), N)).any()
+    assert_close(out["node_obs"], ref["node_obs"], "reset node_obs")
+    assert (out["adj_env"] == ref["adj"].astype(np.float32)).all()
+    rng = np.random.default_rng(1)
+    for t in range(21):
+        orc.set_state(device_state_to_nav(env.get_state()))
+        a = rng.integers(0, 5, (B, N))
+        out = _np(env.step_tensor(_actions(a)))
+        ref = orc.step(actions=a, autoreset=True)
+        out["adj"] = out["adj_env"]
+        compare_step_outputs(out, ref, cfg)
+        post, rpost = device_state_to_nav(env.get_state()), orc.get_state()
+        if ref["reset"].any():
+            assert (post.pos == rpost.pos).all() and (post.goal_match == rpost.goal_match).all()
+            assert (post.wall_axis == rpost.wall_axis).all() and (post.wall_orient == rpost.wall_orient).all()
+        else:
+            assert_close(post.pos, rpost.pos, "pos")
+            assert (post.num_obstacle_collisions == rpost.num_obstacle_collisions).all()
+    env.close()
