@@ -35,7 +35,7 @@ CONFIGS = {
     "n4_o2_collab": (NavConfig(num_agents=4, num_obstacles=2, collaborative=True), 16, 3),
     "n3_o3_global": (NavConfig(num_agents=3, num_obstacles=3, graph_feat_type="global"), 17, 4),
     "n7_o3_global": (NavConfig(num_agents=7, num_obstacles=3, graph_feat_type="global"), 18, 2),
-    # walls: oracle-only fixtures (the CUDA path does not take num_walls > 0 yet; tests skip them on the device)
+    # walls (oracle and the wall instantiations of the group-per-env kernels)
     "n3_o3_w2": (NavConfig(num_agents=3, num_obstacles=3, num_walls=2), 19, 12),
     "n4_o2_w1": (NavConfig(num_agents=4, num_obstacles=2, num_walls=1, goal_rew=30.0, collision_rew=30.0), 20, 9),
 }

@@ -8,10 +8,9 @@ so that this file agrees with the imported reference to ~1e-13
 produced by running the UNMODIFIED reference: oracle/make_golden.py).
 
 Entity order is the reference's ``World.entities`` (core.py:186):
-agents 0..N-1, landmarks N..2N-1, obstacles 2N..2N+O-1.
+agents 0..N-1, landmarks N..2N-1, obstacles 2N..2N+O-1, walls 2N+O..2N+O+W-1.
 
-Not restated (out of scope, num_walls = 0 in every BASELINE config): walls
-(core.py:407-462), ``graph_feat_type='global'``.
+Also restated: walls (``num_walls`` 1 or 2; core.py:36-55, :407-462) and ``graph_feat_type='global'``.
 """
 from __future__ import annotations
 
@@ -53,8 +52,8 @@ class NavConfig:
     # 'relative': ego-relative 11-dim node features (:1079-1124);  'global': 7-dim absolute features (:1058-1077)
     graph_feat_type: str = "relative"
     # walls (navigation_graph.py:181-196, :287-324; core.py:36-55, :407-462): 0, 1 or 2 axis-aligned segments of
-    # width 0.1 at +-axis, half-length wall_len, orientation redrawn every episode.  ORACLE ONLY so far: the CUDA
-    # path rejects num_walls > 0 (SimConfig.from_args); pinned by tests/golden/*_w2.npz for the kernels to come.
+    # width 0.1 at +-axis, half-length wall_len, orientation redrawn every episode; pinned by tests/golden/n3_o3_w2.npz
+    # and n4_o2_w1.npz (the wall instantiations of the group-per-env kernels are held to the same fixtures).
     num_walls: int = 0
     wall_width: float = 0.1
     wall_contact_force: float = 2.2e2
