@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_AGENTS, N_OBST, EPISODE = 3, 3, 25
+N_WALLS = 0            # --walls W: diagnostic run of the wall instantiations; 0 in every BASELINE config
 ENVS_PER_GPU = 65536
 METRIC = "agent-steps/sec, navigation_graph step+obs+reward"
 WORKLOAD = ("navigation_graph 3 agents / 3 goals / 3 obstacles, FA+FR reward, goal_rew=collision_rew=30, "
@@ -66,8 +67,11 @@ def select_config(name: str, envs: int | None):
 
 
 def sim_kwargs():
-    return dict(num_agents=N_AGENTS, num_obstacles=N_OBST, goal_rew=GOAL_REW, collision_rew=COLL_REW,
-                episode_length=EPISODE, fairness_reward=FAIRNESS)
+    kw = dict(num_agents=N_AGENTS, num_obstacles=N_OBST, goal_rew=GOAL_REW, collision_rew=COLL_REW,
+              episode_length=EPISODE, fairness_reward=FAIRNESS)
+    if N_WALLS:
+        kw["num_walls"] = N_WALLS
+    return kw
 
 
 # ----------------------------------------------------------------------------------------------
@@ -362,7 +366,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env.algorithmic_bytes_per_step
     kernel_name = {"aw": f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)",
-                   "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}> (group-per-env)"}[env.mapping]
+                   "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}{', true' if N_WALLS else ''}> (group-per-env)"}[env.mapping]
     # One step = the step kernel over the whole batch (fm_step_many issues it as `launches / K` concurrent
     # env-range launches on side streams); the kernel is > 99 % of the timed region (profiles/: launch list),
     # so bytes per step / time per step is the kernel's achieved algorithmic bandwidth.
@@ -488,6 +492,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
 
 def main():
+    global N_WALLS, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5000)
@@ -500,6 +505,7 @@ def main():
     ap.add_argument("--mapping", default="auto", choices=["auto", "group", "aw"], help="kernel mapping (diagnostic)")
     ap.add_argument("--max-graphs", type=int, default=1 << 17, help="c5: graphs per policy forward chunk")
     ap.add_argument("--edge-list", action="store_true", help="also time step + policy-side edge list (default on for c3)")
+    ap.add_argument("--walls", type=int, default=0, choices=[0, 1, 2], help="diagnostic: num_walls (wall kernels, SURVEY N4)")
     ap.add_argument("--no-graph", action="store_true", help="c5: time the eager loop instead of the captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -507,6 +513,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     select_config(args.config, args.envs)
     args.envs = ENVS_PER_GPU
+    if args.walls:
+        N_WALLS = args.walls
+        WORKLOAD += f" + {args.walls} wall(s) [diagnostic, not a BASELINE config]"
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -635,9 +635,10 @@ int fm_mapping(const FmHandle* h) { return h ? h->p.mapping + 1 : 0; }
 
 int64_t fm_algorithmic_bytes_per_step(const FmHandle* h) {
   if (!h) return 0;
-  const int64_t N = h->p.N, O = h->p.O, E = h->p.E;
+  const int64_t N = h->p.N, O = h->p.O, E = h->p.E, W = h->p.W;
   const int64_t nf = h->p.feat_global ? fm::NODE_F_GLOBAL : fm::NODE_F;
-  return (30 * N + 2 * O + 5 + nf * N * E + E * E) * 4 * (int64_t)h->p.B;
+  const int64_t walls = W > 0 ? 2 * W + 1 : 0;                               // reads of wall axis / orientation / half-length
+  return (30 * N + 2 * O + 5 + walls + nf * N * E + E * E) * 4 * (int64_t)h->p.B;   // SURVEY.md section 8(d), E = 2N + O + W
 }
 
 int fm_kernel_launches(const FmHandle* h, int64_t* out) {
