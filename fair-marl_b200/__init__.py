@@ -9,6 +9,8 @@ missing.  Public surface mirrors the reference interfaces this package replaces:
 * ``process_adj`` -- ``onpolicy/algorithms/utils/gnn_new.py:381-413``
 * ``DeviceRolloutBuffer`` / ``RolloutCollector`` -- ``onpolicy/utils/graph_buffer.py`` ``GraphReplayBuffer`` and the
   collect / insert loop of ``onpolicy/runner/shared/graph_mpe_runner.py`` (device-resident, written by the step kernel)
+* ``B200FormationVecEnv`` -- the formation-family scenarios (``nav_fairassign_{fairrew,nofairrew}_formation_graph``), a first
+  tensor-native device path (N <= 4)
 * ``DenseGraphActor`` / ``DenseGraphCritic`` -- the forward pass of ``GR_Actor`` / ``GR_Critic`` without torch_geometric
 """
 from fair_marl_b200.build import build_library, library_path            # noqa: F401
@@ -20,8 +22,9 @@ from fair_marl_b200.edges import process_adj                            # noqa: 
 from fair_marl_b200.sharding import shard_range, EpisodeStats           # noqa: F401
 from fair_marl_b200.policy import DenseGraphActor, DenseGraphCritic, PolicyConfig, load_reference_state_dict  # noqa: F401
 from fair_marl_b200.rollout import DeviceRolloutBuffer, RolloutCollector  # noqa: F401
+from fair_marl_b200.formation import B200FormationVecEnv, FormationSimConfig  # noqa: F401
 
 __all__ = ["B200GraphVecEnv", "make_train_env", "SimConfig", "Box", "Discrete", "solve_fair_assignment",
            "lexifair_batched", "pair_dist", "process_adj", "shard_range", "EpisodeStats", "build_library", "library_path",
            "DenseGraphActor", "DenseGraphCritic", "PolicyConfig", "load_reference_state_dict", "DeviceRolloutBuffer",
-           "RolloutCollector"]
+           "RolloutCollector", "B200FormationVecEnv", "FormationSimConfig"]

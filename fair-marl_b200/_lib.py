@@ -46,6 +46,31 @@ class FmState(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in STATE_FIELDS]
 
 
+# formation family (include/fairmarl.h: FmFormationConfig / FmFormationState)
+FORMATION_OBS_DIM, FORMATION_NODE_FEAT_DIM, FORMATION_MAX_OBSTACLES = 11, 13, 8
+
+
+class FmFormationConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_agents", C.c_int32), ("num_obstacles", C.c_int32), ("episode_length", C.c_int32),
+        ("env_offset", C.c_int64), ("seed", C.c_uint64),
+        ("world_size", C.c_double), ("max_speed", C.c_double), ("collision_rew", C.c_double), ("goal_rew", C.c_double),
+        ("min_dist_thresh", C.c_double), ("min_obs_dist", C.c_double), ("fair_rew", C.c_double), ("zeroshift", C.c_double),
+        ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32), ("reserved_", C.c_int32),
+    ]
+
+
+FORMATION_STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_match", "dists_to_goal",
+                          "times_required", "dist_left_to_goal", "num_agent_collisions", "num_obstacle_collisions",
+                          "dist_traveled_mean", "dist_traveled_stddev", "step", "min_time", "episode", "status",
+                          "goal_reached", "occupied", "goal_history")
+FORMATION_STATE_INT_FIELDS = ("goal_match", "step", "episode")
+
+
+class FmFormationState(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in FORMATION_STATE_FIELDS]
+
+
 class FairMarlError(RuntimeError):
     pass
 
@@ -89,6 +114,12 @@ def load():
         "fm_mapping": ([vp], C.c_int),
         "fm_algorithmic_bytes_per_step": ([vp], i64),
         "fm_kernel_launches": ([vp, C.POINTER(i64)], C.c_int),
+        "fm_formation_create": ([C.POINTER(FmFormationConfig), C.c_int, C.POINTER(vp)], C.c_int),
+        "fm_formation_destroy": ([vp], C.c_int),
+        "fm_formation_reset": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_formation_step": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_formation_set_state": ([vp, C.POINTER(FmFormationState), vp], C.c_int),
+        "fm_formation_get_state": ([vp, C.POINTER(FmFormationState), vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the ABI
@@ -102,6 +133,8 @@ EXPORTED_SYMBOLS = (
     "fm_step_onehot", "fm_step_many", "fm_step_host", "fm_reset_host", "fm_read_info_host", "fm_set_state", "fm_get_state",
     "fm_assign_costs", "fm_assign_positions", "fm_pair_dist", "fm_edge_list", "fm_stats_read", "fm_num_entities", "fm_mapping",
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",
+    "fm_formation_create", "fm_formation_destroy", "fm_formation_reset", "fm_formation_step", "fm_formation_set_state",
+    "fm_formation_get_state",
 )
 
 

@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["fm_kernels.cu", "fm_aw.cu", "fm_abi.cu"]
+SOURCES = ["fm_kernels.cu", "fm_aw.cu", "fm_formation.cu", "fm_abi.cu"]
 HEADERS = ["fm_device.cuh", "fm_launch.h", "fm_small.cuh", os.path.join("..", "..", "include", "fairmarl.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

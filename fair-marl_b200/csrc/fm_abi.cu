@@ -24,6 +24,16 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+namespace fm {
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace fm
+
 #define FM_CUDA(expr)                                                                            \
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \
@@ -645,6 +655,109 @@ int fm_kernel_launches(const FmHandle* h, int64_t* out) {
   if (!h || !out) return fail(FM_ERR_INVALID_ARG, "fm_kernel_launches: null argument");
   *out = h->launches;
   return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Formation family (include/fairmarl.h, fm_formation.cu).
+struct FmFormation {
+  FmFormationConfig cfg;
+  int device;
+  fm::FormParams p;
+  void* block;
+  size_t field_bytes[20];
+};
+
+// the 20 members of FmFormationState, in declaration order: (words per env, element size)
+static void formation_fields(int N, int O, size_t B, size_t (&bytes)[20]) {
+  const size_t n = (size_t)N, o = (size_t)O;
+  const size_t words[20] = {2 * n, 2 * n, n, 2 * n, 2 * o, n, n, n, n, n, n, 1, 1, 1, n, 1, n, n, n, n};
+  for (int k = 0; k < 20; ++k) bytes[k] = words[k] * B * (k == 16 ? 1 : 4);      // status is uint8
+}
+
+int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** out) {
+  if (!cfg || !out) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: null argument");
+  *out = nullptr;
+  if (cfg->num_envs <= 0) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_envs must be > 0 (got %d)", cfg->num_envs);
+  if (cfg->num_agents < 2 || cfg->num_agents > 4)
+    return fail(FM_ERR_UNSUPPORTED, "fm_formation_create: num_agents must be 2..4 (got %d): the observation needs a second goal, "
+                "and the per-thread lexifair enumerates permutations", cfg->num_agents);
+  if (cfg->num_obstacles < 0 || cfg->num_obstacles > FM_FORMATION_MAX_OBSTACLES)
+    return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_obstacles must be in 0..%d (got %d)", FM_FORMATION_MAX_OBSTACLES, cfg->num_obstacles);
+  if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: episode_length must be >= 1");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(FM_ERR_NO_DEVICE, "fm_formation_create: no CUDA device (there is no CPU path)");
+  if (device < 0 || device >= count) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: device %d out of range (%d devices)", device, count);
+  if (int rc = use_device(device)) return rc;
+  FmFormation* h = new (std::nothrow) FmFormation();
+  if (!h) return fail(FM_ERR_CUDA, "fm_formation_create: out of host memory");
+  h->cfg = *cfg; h->device = device;
+  fm::FormParams& p = h->p;
+  memset(&p, 0, sizeof(p));
+  p.B = cfg->num_envs; p.N = cfg->num_agents; p.O = cfg->num_obstacles; p.episode_length = cfg->episode_length;
+  p.fairness_reward = cfg->fairness_reward; p.collaborative = cfg->collaborative; p.auto_reset = cfg->auto_reset;
+  p.has_max_speed = cfg->max_speed > 0.0; p.env_offset = cfg->env_offset;
+  p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
+  p.world_size = cfg->world_size; p.max_speed = cfg->max_speed; p.collision_rew = cfg->collision_rew; p.goal_rew = cfg->goal_rew;
+  p.min_dist_thresh = cfg->min_dist_thresh; p.min_obs_dist = cfg->min_obs_dist; p.fair_rew = cfg->fair_rew; p.zeroshift = cfg->zeroshift;
+  formation_fields(p.N, p.O, (size_t)p.B, h->field_bytes);
+  size_t total = 0;
+  for (int k = 0; k < 20; ++k) total += (h->field_bytes[k] + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(&h->block, total);
+  if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_formation_create: cudaMalloc(%zu B): %s", total, cudaGetErrorString(e)); }
+  cudaMemset(h->block, 0, total);
+  char* q = (char*)h->block;
+  void** member = reinterpret_cast<void**>(&p.st);                                 // 20 pointers, declaration order
+  for (int k = 0; k < 20; ++k) { member[k] = q; q += (h->field_bytes[k] + 255) & ~(size_t)255; }
+  *out = h;
+  return FM_OK;
+}
+
+int fm_formation_destroy(FmFormation* h) {
+  if (!h) return FM_OK;
+  if (int rc = use_device(h->device)) return rc;
+  cudaDeviceSynchronize();
+  cudaFree(h->block);
+  delete h;
+  return FM_OK;
+}
+
+int fm_formation_reset(FmFormation* h, const uint8_t* mask, const FmOutputs* out, void* stream) {
+  if (!h || !out) return fail(FM_ERR_INVALID_ARG, "fm_formation_reset: null argument");
+  if (int rc = use_device(h->device)) return rc;
+  fm::FormParams p = h->p;
+  p.out = *out; p.mask = mask; p.actions = nullptr;
+  FM_CUDA(fm::launch_formation(p, true, (cudaStream_t)stream));
+  return FM_OK;
+}
+
+int fm_formation_step(FmFormation* h, const int32_t* actions, const FmOutputs* out, void* stream) {
+  if (!h || !actions || !out) return fail(FM_ERR_INVALID_ARG, "fm_formation_step: null argument");
+  if (int rc = use_device(h->device)) return rc;
+  fm::FormParams p = h->p;
+  p.out = *out; p.actions = actions; p.mask = nullptr;
+  FM_CUDA(fm::launch_formation(p, false, (cudaStream_t)stream));
+  return FM_OK;
+}
+
+static int formation_state_copy(FmFormation* h, const FmFormationState* st, bool to_handle, void* stream, const char* who) {
+  if (!h || !st) return fail(FM_ERR_INVALID_ARG, "%s: null argument", who);
+  if (int rc = use_device(h->device)) return rc;
+  void* const* mine = reinterpret_cast<void* const*>(&h->p.st);
+  void* const* theirs = reinterpret_cast<void* const*>(st);
+  for (int k = 0; k < 20; ++k) {
+    if (!theirs[k] || h->field_bytes[k] == 0) continue;
+    FM_CUDA(cudaMemcpyAsync(to_handle ? mine[k] : theirs[k], to_handle ? theirs[k] : mine[k], h->field_bytes[k],
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return FM_OK;
+}
+
+int fm_formation_set_state(FmFormation* h, const FmFormationState* st, void* stream) {
+  return formation_state_copy(h, st, true, stream, "fm_formation_set_state");
+}
+
+int fm_formation_get_state(FmFormation* h, const FmFormationState* st, void* stream) {
+  return formation_state_copy(h, st, false, stream, "fm_formation_get_state");
 }
 
 }  // extern "C"

@@ -32,4 +32,18 @@ cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr,
                              long long* edge_index, float* edge_attr, long long* nnz_out, cudaStream_t st);
 cudaError_t launch_pair_dist(const float* a, const float* b, long long num, double* out, cudaStream_t st);
 cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st);
+
+// formation family (fm_formation.cu): one thread per env, state in API layout
+struct FormParams {
+  int B, N, O, episode_length, fairness_reward, collaborative, auto_reset, has_max_speed;
+  long long env_offset;
+  uint32_t seed_lo, seed_hi;
+  double world_size, max_speed, collision_rew, goal_rew, min_dist_thresh, min_obs_dist, fair_rew, zeroshift;
+  FmFormationState st;       // device pointers owned by the handle
+  FmOutputs out;             // this launch
+  const int32_t* actions;    // step
+  const uint8_t* mask;       // reset
+};
+cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st);
+int set_error(int code, const char* fmt, ...);   // fm_last_error text (fm_abi.cu)
 }  // namespace fm

@@ -202,6 +202,65 @@ int fm_kernel_launches(const FmHandle* h, int64_t* out);   /* kernels launched b
 int fm_abi_version(void);
 const char* fm_last_error(void);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Formation-family scenarios: nav_fairassign_fairrew_formation_graph.py (fairness_reward 1)
+ * and nav_fairassign_nofairrew_formation_graph.py (0) under MultiAgentGraphEnv.step (environment.py:816-877).  A first,
+ * correctness-first device path with its own handle: one thread per env, num_agents 2..4, no walls, relative node
+ * features.  Outputs use FmOutputs with obs [B, N, 11] (:840-1015), node_obs [B, N, E, 13] (:1222-1340), adj [B, E, E],
+ * reward / done [B, N], info [B, N, 14] (terminal values survive the auto-reset). */
+#define FM_FORMATION_OBS_DIM 11
+#define FM_FORMATION_NODE_FEAT_DIM 13
+#define FM_FORMATION_MAX_OBSTACLES 8
+
+typedef struct FmFormationConfig {
+  int32_t num_envs, num_agents, num_obstacles, episode_length;
+  int64_t env_offset;      /* global index of env 0 (Philox stream key; sharding does not change results) */
+  uint64_t seed;
+  double world_size, max_speed /* <= 0: None */, collision_rew, goal_rew, min_dist_thresh;
+  double min_obs_dist;     /* onpolicy/config.py:188 */
+  double fair_rew, zeroshift;
+  int32_t fairness_reward; /* 1: ..._fairrew_... (tanh fairness term, :770-786); 0: ..._nofairrew_... */
+  int32_t collaborative;   /* environment.py:867-870 */
+  int32_t auto_reset;      /* graphworker, env_wrappers.py:859-865: reset once ALL agents of an env are done */
+  int32_t reserved_;
+} FmFormationConfig;
+
+/* State in API layout; the handle keeps it in exactly this layout (device), get / set are copies.  NULL: skipped. */
+typedef struct FmFormationState {
+  float* pos;                      /* [B, N, 2] */
+  float* vel;                      /* [B, N, 2] */
+  float* p_dist;                   /* [B, N] */
+  float* landmark_pos;             /* [B, N, 2]  scenario.landmark_poses */
+  float* obstacle_pos;             /* [B, O, 2] */
+  int32_t* goal_match;             /* [B, N]  re-solved every step (:704-721) */
+  float* dists_to_goal;            /* [B, N] */
+  float* times_required;           /* [B, N] */
+  float* dist_left_to_goal;        /* [B, N] */
+  float* num_agent_collisions;     /* [B, N] */
+  float* num_obstacle_collisions;  /* [B, N] */
+  float* dist_traveled_mean;       /* [B] */
+  float* dist_traveled_stddev;     /* [B] */
+  int32_t* step;                   /* [B] */
+  float* min_time;                 /* [B, N] */
+  int32_t* episode;                /* [B] */
+  uint8_t* status;                 /* [B, N]  agent.status (:408, :728; core.py:397-398; environment.py:240-242) */
+  float* goal_reached;             /* [B, N]  scenario.goal_reached, -1 = none */
+  float* occupied;                 /* [B, N]  scenario.landmark_poses_occupied */
+  float* goal_history;             /* [B, N]  scenario.goal_history, -1 = none */
+} FmFormationState;
+
+typedef struct FmFormation FmFormation;
+
+int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** out);
+int fm_formation_destroy(FmFormation* h);
+/* env.reset() (environment.py:882-898 over reset_world / random_scenario, :217-487): mask uint8 [B] or NULL (= all);
+ * every env is (re-)observed into `out` -- which, as in the reference, updates the goal-occupancy table. */
+int fm_formation_reset(FmFormation* h, const uint8_t* mask, const FmOutputs* out, void* stream);
+/* actions: int32 [B, N] in {0..4} (0 no-op, 1 +x, 2 -x, 3 +y, 4 -y). */
+int fm_formation_step(FmFormation* h, const int32_t* actions, const FmOutputs* out, void* stream);
+int fm_formation_set_state(FmFormation* h, const FmFormationState* st, void* stream);
+int fm_formation_get_state(FmFormation* h, const FmFormationState* st, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

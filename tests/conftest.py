@@ -17,6 +17,8 @@ def pytest_configure(config):
 def pytest_generate_tests(metafunc):
     """Every GPU test runs under both kernel mappings: 'auto' (agent-warp where compiled, i.e. the
     product default) and 'group' (group-per-env kernels forced)."""
+    if metafunc.module.__name__.endswith("test_gpu_formation"):
+        return                                  # the formation kernels have one mapping (thread per env)
     if metafunc.definition.get_closest_marker("gpu") and "kernel_mapping" in metafunc.fixturenames:
         metafunc.parametrize("kernel_mapping", ["auto", "group"], indirect=True)
 

@@ -41,7 +41,8 @@ def test_struct_layouts_match_header(tmp_path):
     """sizeof / offsetof of every struct as gcc lays out include/fairmarl.h == the ctypes mirror."""
     import subprocess
     from fair_marl_b200 import _lib
-    structs = {"FmConfig": _lib.FmConfig, "FmOutputs": _lib.FmOutputs, "FmState": _lib.FmState}
+    structs = {"FmConfig": _lib.FmConfig, "FmOutputs": _lib.FmOutputs, "FmState": _lib.FmState,
+               "FmFormationConfig": _lib.FmFormationConfig, "FmFormationState": _lib.FmFormationState}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fairmarl.h"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
@@ -58,6 +59,7 @@ def test_struct_layouts_match_header(tmp_path):
         for field, _ in cls._fields_:
             assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
     assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8 and ctypes.sizeof(_lib.FmState) == 19 * 8
+    assert ctypes.sizeof(_lib.FmFormationState) == 20 * 8       # fm_abi.cu walks it as 20 pointers
 
 
 def test_library_is_sm100a_only(lib_path):
@@ -92,6 +94,40 @@ def test_invalid_config_is_rejected(lib_path):
     cfg = _lib.FmConfig(num_envs=4, num_agents=33, num_obstacles=3, episode_length=25)
     assert lib.fm_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
     assert b"num_agents" in lib.fm_last_error()
+
+
+def test_formation_entry_points_reject_bad_configs_and_have_no_cpu_path(lib_path):
+    import torch
+    from fair_marl_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _lib.FmFormationConfig(num_envs=4, num_agents=5, num_obstacles=3, episode_length=25)
+    assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -3 and b"num_agents" in lib.fm_last_error()
+    cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=9, episode_length=25)
+    assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+    if not torch.cuda.is_available():
+        cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=3, episode_length=25)
+        assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -4
+        import fair_marl_b200
+        with pytest.raises(_lib.FairMarlError):
+            fair_marl_b200.B200FormationVecEnv(fair_marl_b200.FormationSimConfig(), num_envs=4)
+
+
+def test_formation_config_from_reference_namespace():
+    from argparse import Namespace
+    from fair_marl_b200 import FormationSimConfig
+    a = Namespace(num_agents=3, num_landmarks=3, num_obstacles=3, world_size=2, max_speed=2, collision_rew=30, goal_rew=30,
+                  min_dist_thresh=0.05, min_obs_dist=0.5, episode_length=25, fair_rew=1.0, zeroshift=5.0, collaborative=False,
+                  num_walls=0, num_scripted_agents=0, graph_feat_type="relative",
+                  scenario_name="nav_fairassign_nofairrew_formation_graph")
+    c = FormationSimConfig.from_args(a)
+    assert not c.fairness_reward and c.num_entities == 9 and c.goal_rew == 30
+    a.scenario_name = "navigation_graph"
+    with pytest.raises(NotImplementedError):
+        FormationSimConfig.from_args(a)
+    a.scenario_name, a.num_walls = "nav_fairassign_fairrew_formation_graph", 1
+    with pytest.raises(NotImplementedError):
+        FormationSimConfig.from_args(a)
 
 
 def test_config_from_reference_namespace():

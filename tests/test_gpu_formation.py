@@ -1,0 +1,164 @@
+"""Formation-family kernels (csrc/fm_formation.cu through fm_formation_*) against the float64 oracle
+(oracle/formation.py, itself pinned to the unmodified reference by tests/test_oracle_formation.py)."""
+from dataclasses import fields
+
+import numpy as np
+import pytest
+
+from oracle.formation import FormationConfig, FormationOracle, FormationState
+from oracle.make_formation_golden import load, state_from
+from oracle.navgraph import INFO_KEYS
+from parity_util import assert_close, assert_fairness_close
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ("goal_match", "step", "episode")
+RATIO_KEYS = ("Mean_by_variance", "Time_mean_by_stddev")
+
+
+def _sim(cfg: FormationConfig, **kw):
+    from fair_marl_b200 import FormationSimConfig
+    return FormationSimConfig(
+        num_agents=cfg.num_agents, num_obstacles=cfg.num_obstacles, world_size=cfg.world_size, max_speed=cfg.max_speed,
+        collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
+        min_obs_dist=cfg.min_obs_dist, episode_length=cfg.episode_length, fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift,
+        collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, **kw)
+
+
+def _fp32(st: FormationState) -> FormationState:
+    d = {}
+    for f in fields(FormationState):
+        a = np.asarray(getattr(st, f.name))
+        if f.name in INT_FIELDS:
+            d[f.name] = a.astype(np.int64)
+        elif f.name == "status":
+            d[f.name] = a.astype(bool)
+        else:
+            with np.errstate(over="ignore"):
+                d[f.name] = a.astype(np.float32).astype(np.float64)
+    return FormationState(**d)
+
+
+def _to_device(st: FormationState):
+    return {f.name: (np.asarray(getattr(st, f.name)).astype(np.uint8) if f.name == "status" else np.asarray(getattr(st, f.name)))
+            for f in fields(FormationState)}
+
+
+def _from_device(dev) -> FormationState:
+    d = {}
+    for f in fields(FormationState):
+        a = dev[f.name].cpu().numpy()
+        d[f.name] = a.astype(np.int64) if f.name in INT_FIELDS else (a.astype(bool) if f.name == "status" else a.astype(np.float64))
+    return FormationState(**d)
+
+
+def _np(out):
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _actions(a):
+    import torch
+    return torch.as_tensor(np.asarray(a), dtype=torch.int32, device="cuda")
+
+
+def _compare_step(out, ref, post: FormationState, rpost: FormationState):
+    assert_close(out["obs"], ref["obs"], "obs")
+    assert_close(out["node_obs"], ref["node_obs"], "node_obs")
+    assert_close(out["adj_env"], ref["adj"], "adj")
+    assert_close(out["reward"], ref["reward"], "reward")
+    assert (out["done"].astype(bool) == ref["done"]).all(), "done"
+    for k, key in enumerate(INFO_KEYS):
+        (assert_fairness_close if key in RATIO_KEYS else assert_close)(out["info"][..., k], ref["info"][key], key)
+    for f in ("goal_match", "step", "status"):
+        assert (getattr(post, f) == getattr(rpost, f)).all(), f
+
+
+@pytest.mark.parametrize("name", ["formation_n3_o3_fafr", "formation_n4_o2_fa"])
+def test_step_matches_oracle_on_reference_states(name):
+    """One step from every recorded reference state (rounded to fp32): device vs float64 oracle, outputs, info and the
+    whole post-step state -- status latches, occupancy table, goal history and nearest-landmark latches included."""
+    import fair_marl_b200 as fm
+    cfg, g = load(name)
+    pre = _fp32(state_from(g, "pre_"))
+    T = pre.pos.shape[0]
+    env = fm.B200FormationVecEnv(_sim(cfg, auto_reset=False), num_envs=T)
+    env.set_state(_to_device(pre))
+    out = _np(env.step_tensor(_actions(g["actions"])))
+    orc = FormationOracle(cfg, T)
+    orc.set_state(pre)
+    ref = orc.step(g["actions"], autoreset=False)
+    post, rpost = _from_device(env.get_state()), orc.get_state()
+    _compare_step(out, ref, post, rpost)
+    for f in ("pos", "vel", "p_dist", "dists_to_goal", "times_required", "dist_left_to_goal", "num_agent_collisions",
+              "num_obstacle_collisions", "dist_traveled_mean", "dist_traveled_stddev", "goal_reached", "occupied", "goal_history"):
+        assert_close(getattr(post, f), getattr(rpost, f), f)
+    # smooth quantities straight against the reference's own float64 outputs (inputs were rounded to fp32 on the way in)
+    assert_close(out["adj_env"], g["out_adj"], "adj vs reference")
+    assert_close(out["obs"][..., :4], g["out_obs"][..., :4], "vel / pos vs reference")
+    assert orc.branch_hits.get("status_latched", 0) > 0 and orc.branch_hits.get("subset_index_quirk", 0) > 0
+    env.close()
+
+
+@pytest.mark.parametrize("N,O,B,collab,fair", [(3, 3, 48, False, True), (4, 2, 32, True, False), (2, 1, 32, False, True)])
+def test_reset_and_rollout_match_oracle(N, O, B, collab, fair):
+    """Device reset == oracle reset bit for bit (same Philox draws, same acceptance rules, same lexifair), then a rollout
+    that steers at the goals (so agents latch and envs finish early) across auto-resets, compared step by step."""
+    import fair_marl_b200 as fm
+    cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=15,
+                          collaborative=collab, fairness_reward=fair)
+    env = fm.B200FormationVecEnv(_sim(cfg), num_envs=B, seed=7, env_offset=3)
+    orc = FormationOracle(cfg, B, seed=7, env_offset=3)
+    out, ref = _np(env.reset_tensor()), orc.reset()
+    st, rs = _from_device(env.get_state()), orc.get_state()
+    for f in ("pos", "landmark_pos", "obstacle_pos"):
+        assert (getattr(st, f) == getattr(rs, f)).all(), f
+    assert (st.goal_match == rs.goal_match).all() and (st.episode == 1).all() and not st.status.any()
+    assert_close(st.min_time, rs.min_time, "min_time")
+    assert_close(st.occupied, rs.occupied, "occupancy after the reset observation")
+    assert_close(out["obs"], ref["obs"], "reset obs")
+    assert_close(out["node_obs"], ref["node_obs"], "reset node_obs")
+    assert_close(out["adj_env"], ref["adj"], "reset adj")
+    rng = np.random.default_rng(5)
+    resets = early = 0
+    for t in range(32):
+        cur = _from_device(env.get_state())
+        orc.set_state(cur)
+        d = np.take_along_axis(cur.landmark_pos, cur.goal_match[..., None], axis=1) - cur.pos
+        seek = np.where(np.abs(d[..., 0]) > np.abs(d[..., 1]), np.where(d[..., 0] > 0, 1, 2), np.where(d[..., 1] > 0, 3, 4))
+        a = np.where(rng.random((B, N)) < 0.25, rng.integers(0, 5, (B, N)), seek)
+        out = _np(env.step_tensor(_actions(a)))
+        ref = orc.step(a, autoreset=True)
+        post, rpost = _from_device(env.get_state()), orc.get_state()
+        _compare_step(out, ref, post, rpost)
+        hit = ref["reset"]
+        resets += int(hit.sum())
+        early += int((hit & (cur.step + 1 < cfg.episode_length)).sum())
+        assert (post.episode == rpost.episode).all()
+        if hit.any():
+            assert (post.pos[hit] == rpost.pos[hit]).all() and (post.landmark_pos[hit] == rpost.landmark_pos[hit]).all()
+            assert (post.obstacle_pos[hit] == rpost.obstacle_pos[hit]).all()
+        assert_close(post.pos, rpost.pos, "pos")
+        assert_close(post.occupied, rpost.occupied, "occupied")
+        assert_close(post.goal_history, rpost.goal_history, "goal_history")
+    assert resets >= B and early > 0              # time-outs and all-agents-latched early resets both happened
+    env.close()
+
+
+def test_masked_reset_and_errors():
+    import torch
+    import fair_marl_b200 as fm
+    cfg = FormationConfig(num_agents=3, num_obstacles=2)
+    env = fm.B200FormationVecEnv(_sim(cfg), num_envs=40, seed=1)
+    env.reset_tensor()
+    before = _from_device(env.get_state())
+    mask = np.zeros(40, np.uint8); mask[::3] = 1
+    env.reset_tensor(mask)
+    after = _from_device(env.get_state())
+    keep = mask == 0
+    assert (after.pos[keep] == before.pos[keep]).all() and (after.episode[keep] == 1).all()
+    assert (after.episode[~keep] == 2).all() and (after.pos[~keep] != before.pos[~keep]).any()
+    with pytest.raises(ValueError):
+        env.step_tensor(torch.zeros((40, 3), dtype=torch.int64, device="cuda"))
+    with pytest.raises(fm._lib.FairMarlError):
+        fm.B200FormationVecEnv(fm.FormationSimConfig(num_agents=5), num_envs=8)
+    env.close()
