@@ -66,6 +66,14 @@ def select_config(name: str, envs: int | None):
     ENVS_PER_GPU = envs if envs else c["envs"]
 
 
+def lookup_traffic(table: dict, kernel_name: str, envs_per_gpu: int, walls: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu capture that matches this run, else None."""
+    for key, ent in table.get("by_kernel", {}).items():
+        if kernel_name.startswith(key + " ") and ent.get("envs_per_gpu") == envs_per_gpu and ent.get("walls", 0) == walls:
+            return ent.get("dram_bytes_per_launch")
+    return None
+
+
 def sim_kwargs():
     kw = dict(num_agents=N_AGENTS, num_obstacles=N_OBST, goal_rew=GOAL_REW, collision_rew=COLL_REW,
               episode_length=EPISODE, fairness_reward=FAIRNESS)
@@ -374,11 +382,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    if os.path.isfile(tpath):                    # ncu --set full captures, per launch; only the entry of THIS kernel / size
+        traffic = lookup_traffic(json.load(open(tpath)), kernel_name, B, N_WALLS)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_step": alg_bytes,
                 "launches_per_step": launches / K, "peak_source": peak_src,

@@ -175,3 +175,20 @@ def test_integration_doc_stub_matches_binding():
     # ctypes aliases: c_int32 is c_int, c_int64 is c_long, ... compare through the types themselves
     import ctypes as C
     assert [(n, getattr(C, t)) for n, t in doc_fields] == list(_lib.FmConfig._fields_), (doc_fields, lib_fields)
+
+
+def test_bench_reports_ncu_traffic_only_for_the_matching_kernel():
+    """roofline.traffic comes from the ncu capture of the SAME kernel at the SAME size (profiles/step_kernel_traffic.json)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    table = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
+    assert bench.lookup_traffic(table, "fm::aw_kernel<3,3,0> (agent-warp)", 65536, 0) == 13900800
+    c3 = bench.lookup_traffic(table, "fm::step_kernel<8> (group-per-env)", 262144, 0)
+    alg = table["by_kernel"]["fm::step_kernel<8>"]["algorithmic_bytes_per_launch"]
+    assert c3 is not None and 0.9 < c3 / alg < 1.1                       # no wasted re-reads
+    assert bench.lookup_traffic(table, "fm::step_kernel<8> (group-per-env)", 4096, 0) is None
+    assert bench.lookup_traffic(table, "fm::step_kernel<8> (group-per-env)", 262144, 2) is None
+    assert bench.lookup_traffic(table, "fm::step_kernel<8, true> (group-per-env)", 262144, 2) is not None
