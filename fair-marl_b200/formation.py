@@ -4,8 +4,9 @@ tensor-native env over ``fm_formation_*`` (include/fairmarl.h; kernels in csrc/f
 A first, correctness-first path: device tensors in, device tensors out, the same dict keys
 as ``B200GraphVecEnv.step_tensor`` with this family's shapes -- ``obs [B,N,11]`` (scenario ``observation``, :840-1015),
 ``node_obs [B,N,E,13]`` (``_get_entity_feat_relative``, :1222-1340), ``adj_env [B,E,E]``, ``reward [B,N]``,
-``done [B,N]`` (per-agent early done, environment.py:240-242), ``info [B,N,14]``.  The numpy ``ShareVecEnv`` tuple
-interface is not wrapped around it yet.  No CPU path: raises without the library or a CUDA device.
+``done [B,N]`` (per-agent early done, environment.py:240-242), ``info [B,N,14]``.  ``reset()`` / ``step()`` wrap the same
+calls in the numpy tuples of ``GraphSubprocVecEnv`` (env_wrappers.py:983-1002) with the spaces the runner reads.
+No CPU path: raises without the library or a CUDA device.
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ from typing import Any, Dict, Optional
 import numpy as np
 
 from fair_marl_b200 import _lib
+from fair_marl_b200.spaces import Box, Discrete
 
 
 @dataclass
@@ -58,6 +60,46 @@ class FormationSimConfig:
         return cls(**kw)
 
 
+def decode_onehot_actions(actions_env, num_envs: int, num_agents: int) -> np.ndarray:
+    """``[B,N,5]`` one-hot (graph_mpe_runner.py:429-431) or ``[B,N]`` indices -> int32 ``[B,N]``.  The reference decodes
+    ``u = [a1 - a2, a3 - a4]`` (environment.py:301-311); for a one-hot row that is the move of its hot index, so anything
+    that is not exactly one-hot is refused instead of being reinterpreted."""
+    a = np.asarray(actions_env)
+    if a.shape == (num_envs, num_agents):
+        idx = a.astype(np.int64)
+    elif a.shape == (num_envs, num_agents, 5):
+        idx = a.argmax(axis=-1)
+        if not (np.isin(a, (0, 1)).all() and (a.sum(axis=-1) == 1).all()):
+            raise ValueError("actions must be exact one-hot rows over the 5 discrete moves")
+    else:
+        raise ValueError(f"actions must be [B,N,5] one-hot (or [B,N] indices), got {a.shape}")
+    if idx.min(initial=0) < 0 or idx.max(initial=0) > 4:
+        raise ValueError("action indices must be in 0..4")
+    return idx.astype(np.int32)
+
+
+def infos_from_rows(rows: np.ndarray, with_min_time: bool = True):
+    """``[B,N,14]`` info rows -> the reference's ``infos``: B lists of N dicts (formation ``info_callback`` :538-575 +
+    ``individual_reward``, environment.py:857)."""
+    keys = _lib.INFO_KEYS if with_min_time else _lib.INFO_KEYS[:-1]
+    return [[{k: float(rows[b, i, j]) for j, k in enumerate(keys)} for i in range(rows.shape[1])] for b in range(rows.shape[0])]
+
+
+def share_vec_env_tuple(out: Dict[str, np.ndarray], with_min_time: bool = True):
+    """numpy outputs of one step -> ``(obs, agent_id, node_obs, adj, rewards, dones, infos)`` as
+    ``GraphSubprocVecEnv.step_wait`` stacks them (env_wrappers.py:988-996): ``adj`` per agent ``[B,N,E,E]`` (a broadcast
+    view: the reference stores the same matrix N times), ``agent_id [B,N,1]`` = the agents' global ids 0..N-1 (:1017)."""
+    obs = out["obs"]
+    B, N = obs.shape[:2]
+    E = out["adj_env"].shape[-1]
+    agent_id = np.broadcast_to(np.arange(N, dtype=np.float32).reshape(1, N, 1), (B, N, 1))
+    adj = np.broadcast_to(out["adj_env"][:, None], (B, N, E, E))
+    head = (obs, agent_id, out["node_obs"], adj)
+    if "reward" not in out:
+        return head                                                    # reset(): the 4-tuple (env_wrappers.py:997-1002)
+    return head + (out["reward"], out["done"].astype(bool), infos_from_rows(out["info"], with_min_time))
+
+
 class B200FormationVecEnv:
     """B formation envs on one GPU.  ``reset_tensor()`` / ``step_tensor(actions int32 [B,N])`` return dicts of CUDA
     tensors (views of buffers owned by this object, overwritten by the next call)."""
@@ -86,6 +128,15 @@ class B200FormationVecEnv:
             "adj_env": torch.zeros((B, E, E), **f32), "reward": torch.zeros((B, N), **f32),
             "done": torch.zeros((B, N), dtype=torch.uint8, device=self.device),
             "info": torch.zeros((B, N, _lib.INFO_DIM), **f32)}
+        inf, No, Nn = float("inf"), _lib.FORMATION_OBS_DIM, _lib.FORMATION_NODE_FEAT_DIM
+        self.observation_space = [Box(-inf, inf, (No,)) for _ in range(N)]          # environment.py:117-120, :781-813
+        self.share_observation_space = [Box(-inf, inf, (No * N,)) for _ in range(N)]
+        self.action_space = [Discrete(5) for _ in range(N)]
+        self.node_observation_space = [Box(-inf, inf, (E, Nn)) for _ in range(N)]
+        self.adj_observation_space = [Box(-inf, inf, (E, E)) for _ in range(N)]
+        self.edge_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
+        self.agent_id_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
+        self.share_agent_id_observation_space = [Box(-inf, inf, (N,)) for _ in range(N)]
         b = self._buf
         self._out = _lib.FmOutputs(b["obs"].data_ptr(), b["node_obs"].data_ptr(), b["adj_env"].data_ptr(),
                                    b["reward"].data_ptr(), b["done"].data_ptr(), b["info"].data_ptr())
@@ -116,6 +167,30 @@ class B200FormationVecEnv:
         out = dict(self._buf)
         out["done"] = self._buf["done"].view(t.bool)
         return out
+
+    # ------------------------------------------------------------------ ShareVecEnv interface (numpy)
+    def reset(self):
+        """``(obs, agent_id, node_obs, adj)`` (env_wrappers.py:997-1002)."""
+        out = self.reset_tensor()
+        return share_vec_env_tuple({k: v.cpu().numpy() for k, v in out.items()})
+
+    def step(self, actions_env):
+        """``(obs, agent_id, node_obs, adj, rewards [B,N], dones [B,N] bool, infos)`` (env_wrappers.py:983-996), auto-reset
+        included when every agent of an env is done (:859-865)."""
+        t = self.torch
+        idx = decode_onehot_actions(actions_env, self.num_envs, self.num_agents)
+        out = self.step_tensor(t.as_tensor(idx, dtype=t.int32).to(self.device))
+        return share_vec_env_tuple({k: v.cpu().numpy() for k, v in out.items()}, self.cfg.max_speed is not None)
+
+    def step_async(self, actions_env):
+        self._pending = self.step(actions_env)
+
+    def step_wait(self):
+        r, self._pending = self._pending, None
+        return r
+
+    def render(self, mode: str = "human"):
+        raise NotImplementedError("rendering is out of scope (SURVEY.md section 2, row 15)")
 
     # ------------------------------------------------------------------ state
     def _shapes(self):

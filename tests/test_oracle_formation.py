@@ -98,3 +98,33 @@ def test_own_reset_obeys_the_rules_and_rollout_runs():
         resets += int(out["reset"].sum())
         assert np.isfinite(out["obs"]).all() and np.isfinite(out["node_obs"]).all()
     assert resets == 32 and (orc.get_state().episode == 3).all()
+
+
+def test_share_vec_env_tuple_matches_the_reference_tuples():
+    """Host glue of B200FormationVecEnv (pure numpy, no device): oracle outputs packed by share_vec_env_tuple equal the
+    tuples the reference env returned when the fixture was recorded; one-hot decode follows environment.py:301-311."""
+    from fair_marl_b200.formation import decode_onehot_actions, share_vec_env_tuple
+    cfg, g = load("formation_n3_o3_fafr")
+    pre = state_from(g, "pre_")
+    T, N, E = pre.pos.shape[0], cfg.num_agents, cfg.num_entities
+    orc = FormationOracle(cfg, T)
+    orc.set_state(pre)
+    idx = decode_onehot_actions(np.eye(5)[g["actions"]], T, N)
+    assert idx.dtype == np.int32 and (idx == g["actions"]).all() and (decode_onehot_actions(g["actions"], T, N) == idx).all()
+    out = orc.step(idx, autoreset=False)
+    rows = np.stack([out["info"][k] for k in INFO_KEYS], axis=-1)
+    tup = share_vec_env_tuple(dict(obs=out["obs"], node_obs=out["node_obs"], adj_env=out["adj"], reward=out["reward"],
+                                   done=out["done"].astype(np.uint8), info=rows))
+    obs, agent_id, node, adj, rew, done, infos = tup
+    assert obs.shape == (T, N, OBS_DIM) and node.shape == (T, N, E, NODE_FEAT_DIM) and adj.shape == (T, N, E, E)
+    assert agent_id.shape == (T, N, 1) and (agent_id[5, :, 0] == np.arange(N)).all()          # get_id: global ids (:1017)
+    _close(adj[:, 2], g["out_adj"], "adj of agent 2 == the env's matrix")
+    _close(rew, g["out_reward"], "rewards")
+    assert done.dtype == bool and (done == g["out_done"]).all()
+    assert len(infos) == T and len(infos[0]) == N and list(infos[7][1]) == list(INFO_KEYS)
+    assert abs(infos[7][1]["Dist_to_goal"] - g["info_Dist_to_goal"][7, 1]) < 1e-12
+    assert len(share_vec_env_tuple(dict(obs=out["obs"], node_obs=out["node_obs"], adj_env=out["adj"]))) == 4   # reset()
+    with pytest.raises(ValueError):
+        decode_onehot_actions(np.full((T, N, 5), 0.2), T, N)
+    with pytest.raises(ValueError):
+        decode_onehot_actions(np.zeros((T, N + 1)), T, N)
