@@ -3,7 +3,8 @@
     python -m oracle.make_formation_golden            # writes tests/golden/formation_*.npz
 
 Each fixture holds, per recorded step of the live reference env (``MultiAgentGraphEnv`` over
-``nav_fairassign_fairrew_formation_graph.Scenario`` / its ``nofairrew`` twin): the full pre-step state, the actions,
+``nav_fairassign_fairrew_formation_graph.Scenario`` / its ``nofairrew`` twin / the base scenarios
+``nav_base_formation_graph_mask`` and ``..._randomgoal``): the full pre-step state, the actions,
 the 7-tuple outputs and info dicts, and the post-step state; plus the post-reset states and reset outputs.  Half of
 the episodes steer the agents at their assigned goals (with noise) so that ``agent.status`` latches, goals get
 occupied / vacated and the early ``done`` path is taken; the rest are random walks.
@@ -27,14 +28,22 @@ CONFIGS = {
     "formation_n4_o2_fa": (FormationConfig(num_agents=4, num_obstacles=2, fairness_reward=False, min_obs_dist=0.8,
                                            episode_length=20), 32, 12),
     "formation_n7_o3_fafr": (FormationConfig(num_agents=7, num_obstacles=3, collaborative=True, episode_length=30), 33, 8),
+    # the base formation scenarios of model_weights/OA and RA (config.yaml: 3 agents, 3 obstacles, rewards 30)
+    "formation_n3_o3_oa": (FormationConfig(num_agents=3, num_obstacles=3, goal_rew=30.0, collision_rew=30.0,
+                                           fairness_reward=False, assignment="optimal"), 34, 10),
+    "formation_n3_o3_ra": (FormationConfig(num_agents=3, num_obstacles=3, goal_rew=30.0, collision_rew=30.0,
+                                           fairness_reward=False, assignment="random"), 35, 10),
 }
+
+SCENARIO_FILES = {("fair", True): "nav_fairassign_fairrew_formation_graph.py",
+                  ("fair", False): "nav_fairassign_nofairrew_formation_graph.py",
+                  ("optimal", False): "nav_base_formation_graph_mask.py",
+                  ("random", False): "nav_base_formation_graph_randomgoal.py"}
 
 
 def make_reference_env(cfg: FormationConfig, seed: int):
     install_stubs()
-    fname = ("nav_fairassign_fairrew_formation_graph.py" if cfg.fairness_reward
-             else "nav_fairassign_nofairrew_formation_graph.py")
-    mod = _load_scenario(fname)
+    mod = _load_scenario(SCENARIO_FILES[(cfg.assignment, bool(cfg.fairness_reward))])
     from multiagent.environment import MultiAgentGraphEnv
     np.random.seed(seed)
     sc = mod.Scenario()
@@ -56,7 +65,9 @@ def extract_state(env, sc) -> FormationState:
         pos=f64([a.state.p_pos for a in w.agents]), vel=f64([a.state.p_vel for a in w.agents]),
         p_dist=f64([a.state.p_dist for a in w.agents]), landmark_pos=f64(sc.landmark_poses),
         obstacle_pos=f64([o.state.p_pos for o in w.obstacles]).reshape(1, len(w.obstacles), 2),
-        goal_match=np.array([sc.goal_match_index], dtype=np.int64), dists_to_goal=f64(w.dists_to_goal),
+        # the mask scenario calls it optimal_match_index (set at reset only)
+        goal_match=np.array([sc.goal_match_index if hasattr(sc, "goal_match_index") else sc.optimal_match_index],
+                            dtype=np.int64), dists_to_goal=f64(w.dists_to_goal),
         times_required=f64(w.times_required), dist_left_to_goal=f64(w.dist_left_to_goal),
         num_agent_collisions=f64(w.num_agent_collisions), num_obstacle_collisions=f64(w.num_obstacle_collisions),
         dist_traveled_mean=f64(getattr(w, "dist_traveled_mean", 0.0)),
