@@ -56,11 +56,10 @@ class FmFormationConfig(C.Structure):
         ("env_offset", C.c_int64), ("seed", C.c_uint64),
         ("world_size", C.c_double), ("max_speed", C.c_double), ("collision_rew", C.c_double), ("goal_rew", C.c_double),
         ("min_dist_thresh", C.c_double), ("min_obs_dist", C.c_double), ("fair_rew", C.c_double), ("zeroshift", C.c_double),
-        ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32), ("assignment", C.c_int32),
+        ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
-FORMATION_ASSIGNMENTS = {"fair": 0, "optimal": 1, "random": 2}
 FORMATION_STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_match", "dists_to_goal",
                           "times_required", "dist_left_to_goal", "num_agent_collisions", "num_obstacle_collisions",
                           "dist_traveled_mean", "dist_traveled_stddev", "step", "min_time", "episode", "status",

@@ -684,10 +684,6 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > FM_FORMATION_MAX_OBSTACLES)
     return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_obstacles must be in 0..%d (got %d)", FM_FORMATION_MAX_OBSTACLES, cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: episode_length must be >= 1");
-  if (cfg->assignment < 0 || cfg->assignment > 2)
-    return fail(FM_ERR_INVALID_ARG, "fm_formation_create: assignment must be 0 (lexifair), 1 (min-sum) or 2 (random) (got %d)", cfg->assignment);
-  if (cfg->assignment != 0 && cfg->fairness_reward)
-    return fail(FM_ERR_INVALID_ARG, "fm_formation_create: the base formation scenarios (assignment 1, 2) have no fairness term");
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(FM_ERR_NO_DEVICE, "fm_formation_create: no CUDA device (there is no CPU path)");
   if (device < 0 || device >= count) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: device %d out of range (%d devices)", device, count);
@@ -699,7 +695,7 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   memset(&p, 0, sizeof(p));
   p.B = cfg->num_envs; p.N = cfg->num_agents; p.O = cfg->num_obstacles; p.episode_length = cfg->episode_length;
   p.fairness_reward = cfg->fairness_reward; p.collaborative = cfg->collaborative; p.auto_reset = cfg->auto_reset;
-  p.has_max_speed = cfg->max_speed > 0.0; p.env_offset = cfg->env_offset; p.assignment = cfg->assignment;
+  p.has_max_speed = cfg->max_speed > 0.0; p.env_offset = cfg->env_offset;
   p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
   p.world_size = cfg->world_size; p.max_speed = cfg->max_speed; p.collision_rew = cfg->collision_rew; p.goal_rew = cfg->goal_rew;
   p.min_dist_thresh = cfg->min_dist_thresh; p.min_obs_dist = cfg->min_obs_dist; p.fair_rew = cfg->fair_rew; p.zeroshift = cfg->zeroshift;

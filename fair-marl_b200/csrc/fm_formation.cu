@@ -198,24 +198,6 @@ __device__ void f_assign(FEnv<N>& e) {                                     // cd
   lexifair_small<N>(c, e.gm);
 }
 
-// Min-sum matching of the current agent -> goal distances by enumeration (scipy linear_sum_assignment in
-// nav_base_formation_graph_mask.py:255-260 and _bipartite_min_dists :686-689): match[i] = goal of agent i, delta[i] its distance.
-template <int N>
-__device__ void f_min_sum(const FEnv<N>& e, int (&match)[N], double (&delta)[N]) {
-  double c[N * N];
-  for (int a = 0; a < N; ++a)
-    for (int g = 0; g < N; ++g) c[a * N + g] = dn(e.px[a] - e.lx[g], e.py[a] - e.ly[g]);
-  double best = 0.0;
-  for (int k = 0; k < factorial(N); ++k) {
-    double sum = 0.0;
-    for (int i = 0; i < N; ++i) sum += c[i * N + perm_elem(N, k, i)];
-    if (k == 0 || sum < best) {
-      best = sum;
-      for (int i = 0; i < N; ++i) { match[i] = perm_elem(N, k, i); delta[i] = c[i * N + match[i]]; }
-    }
-  }
-}
-
 // env.reset()'s observation pass (environment.py:882-898): obs_i, then node rows_i, per agent.
 template <int N>
 __device__ void f_observe(const FormParams& p, int b, FEnv<N>& e) {
@@ -246,7 +228,7 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
   const double r2 = 0.05 + 0.05;
   for (int pass = 0; pass < 2; ++pass) {
     double* X = pass ? e.lx : e.px; double* Y = pass ? e.ly : e.py;
-    const double dsame = pass ? (p.assignment == 0 ? 1.2 : 1.5) * r2 : 1.05 * r2;   // goals: 1.2x (:638-648), 1.5x in the base files
+    const double dsame = pass ? 1.2 * r2 : 1.05 * r2;
     for (int a = 0; a < N; ++a) {
       while (true) {
         float fx, fy; draw(fx, fy);
@@ -264,21 +246,7 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
     if (p.has_max_speed) e.mint[i] = dn(e.px[i] - e.lx[i], e.py[i] - e.ly[i]) / p.max_speed;   // goal_match = arange here (:229, :474-476)
   }
   e.step = 0;
-  if (p.assignment == 0) {
-    f_assign<N>(e);
-  } else if (p.assignment == 1) {
-    double delta[N];
-    f_min_sum<N>(e, e.gm, delta);
-  } else {                                                                 // np.random.shuffle(arange): Fisher-Yates on the draw stream
-    for (int i = 0; i < N; ++i) e.gm[i] = i;
-    for (int k = N - 1; k > 0; --k) {
-      float x, y; draw(x, y);
-      const float u = __fdiv_rn(__fadd_rn(x, half), ws);
-      int j = (int)__fmul_rn(u, (float)(k + 1));
-      j = j < k ? j : k;
-      const int t = e.gm[k]; e.gm[k] = e.gm[j]; e.gm[j] = t;
-    }
-  }
+  f_assign<N>(e);
   e.episode += 1;
 }
 
@@ -343,9 +311,8 @@ __global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p)
   f_adj<N>(p, e, p.out.adj ? p.out.adj + (size_t)b * E * E : nullptr);
 
   // ---- per-agent loop (environment.py:832-864): observation, reward, node rows, done, info -- in this order
-  double rew[N], delta[N];
+  double rew[N];
   bool done[N], all_done = true;
-  for (int i = 0; i < N; ++i) delta[i] = 0.0;
   const double th = p.min_dist_thresh, dcoll = 1.05 * (0.05 + 0.05);
   for (int i = 0; i < N; ++i) {
     f_observation<N>(p, e, i, p.out.obs ? p.out.obs + ((size_t)b * N + i) * F_OBS : nullptr);
@@ -353,10 +320,9 @@ __global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p)
     double fairness;
     if (e.dtg[i] == -1.0) { double m, s; f_mean_std<N>(e.pd, m, s); fairness = m / (s + 0.0001); }
     else fairness = e.dmean / (e.dstd + 0.0001);
-    if (i == 0 && p.assignment == 0) f_assign<N>(e);                       // :704-721: re-assignment every step
-    if (i == 0 && p.assignment == 1) { int m[N]; f_min_sum<N>(e, m, delta); }   // mask.py:666-706 (optimal_match_index stays)
+    if (i == 0) f_assign<N>(e);                                            // :704-721: re-assignment every step
     const double x = e.px[i], y = e.py[i];
-    const double dg = p.assignment == 1 ? delta[i] : dn(x - e.lx[e.gm[i]], y - e.ly[e.gm[i]]);
+    const double dg = dn(x - e.lx[e.gm[i]], y - e.ly[e.gm[i]]);
     double r = 0.0;
     if (dg < th) {                                                         // :725-733
       if (!e.status[i]) { e.status[i] = true; e.vx[i] = 0.0; e.vy[i] = 0.0; r += p.goal_rew; }

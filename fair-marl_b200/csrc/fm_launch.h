@@ -36,7 +36,6 @@ cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, i
 // formation family (fm_formation.cu): one thread per env, state in API layout
 struct FormParams {
   int B, N, O, episode_length, fairness_reward, collaborative, auto_reset, has_max_speed;
-  int assignment;            // 0 lexifair per step, 1 min-sum matching per step, 2 random permutation at reset
   long long env_offset;
   uint32_t seed_lo, seed_hi;
   double world_size, max_speed, collision_rew, goal_rew, min_dist_thresh, min_obs_dist, fair_rew, zeroshift;

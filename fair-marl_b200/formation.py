@@ -37,9 +37,6 @@ class FormationSimConfig:
     collaborative: bool = False
     fairness_reward: bool = True       # True: ..._fairrew_... scenario; False: ..._nofairrew_...
     auto_reset: bool = True
-    # 'fair': lexifair re-solved every step (nav_fairassign_*_formation_graph); 'optimal': min-sum matching re-solved every
-    # step (nav_base_formation_graph_mask); 'random': a permutation drawn at reset (nav_base_formation_graph_randomgoal)
-    assignment: str = "fair"
 
     @property
     def num_entities(self) -> int:
@@ -49,13 +46,9 @@ class FormationSimConfig:
     def from_args(cls, args: Any, **overrides) -> "FormationSimConfig":
         kw = {f: getattr(args, f) for f in cls.__dataclass_fields__ if hasattr(args, f)}
         name = getattr(args, "scenario_name", "nav_fairassign_fairrew_formation_graph")
-        scenarios = {"nav_fairassign_fairrew_formation_graph": ("fair", True),          # model_weights/FA+FR
-                     "nav_fairassign_nofairrew_formation_graph": ("fair", False),       # model_weights/FA
-                     "nav_base_formation_graph_mask": ("optimal", False),               # model_weights/OA
-                     "nav_base_formation_graph_randomgoal": ("random", False)}          # model_weights/RA
-        if name not in scenarios:
-            raise NotImplementedError(f"scenario {name!r} is not one of the formation scenarios this path covers: {sorted(scenarios)}")
-        kw["assignment"], kw["fairness_reward"] = scenarios[name]
+        if name not in ("nav_fairassign_fairrew_formation_graph", "nav_fairassign_nofairrew_formation_graph"):
+            raise NotImplementedError(f"scenario {name!r} is not one of the two formation scenarios this path covers")
+        kw["fairness_reward"] = name == "nav_fairassign_fairrew_formation_graph"
         for unsupported in ("num_walls", "num_scripted_agents"):
             if getattr(args, unsupported, 0):
                 raise NotImplementedError(f"{unsupported} > 0 is not supported by the formation kernels")
@@ -124,8 +117,7 @@ class B200FormationVecEnv:
             world_size=cfg.world_size, max_speed=cfg.max_speed if cfg.max_speed is not None else -1.0,
             collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
             min_obs_dist=cfg.min_obs_dist, fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift,
-            fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative), auto_reset=int(cfg.auto_reset),
-            assignment=_lib.FORMATION_ASSIGNMENTS[cfg.assignment])
+            fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative), auto_reset=int(cfg.auto_reset))
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_formation_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_formation_create")
         B, N, E = self.num_envs, self.num_agents, self.num_entities

@@ -203,9 +203,8 @@ int fm_abi_version(void);
 const char* fm_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Formation-family scenarios: nav_fairassign_fairrew_formation_graph.py (fairness_reward 1),
- * nav_fairassign_nofairrew_formation_graph.py (0) and the base scenarios nav_base_formation_graph_mask.py /
- * nav_base_formation_graph_randomgoal.py (FmFormationConfig.assignment) under MultiAgentGraphEnv.step (environment.py:816-877).  A first,
+ * Formation-family scenarios: nav_fairassign_fairrew_formation_graph.py (fairness_reward 1)
+ * and nav_fairassign_nofairrew_formation_graph.py (0) under MultiAgentGraphEnv.step (environment.py:816-877).  A first,
  * correctness-first device path with its own handle: one thread per env, num_agents 2..4, no walls, relative node
  * features.  Outputs use FmOutputs with obs [B, N, 11] (:840-1015), node_obs [B, N, E, 13] (:1222-1340), adj [B, E, E],
  * reward / done [B, N], info [B, N, 14] (terminal values survive the auto-reset). */
@@ -223,10 +222,7 @@ typedef struct FmFormationConfig {
   int32_t fairness_reward; /* 1: ..._fairrew_... (tanh fairness term, :770-786); 0: ..._nofairrew_... */
   int32_t collaborative;   /* environment.py:867-870 */
   int32_t auto_reset;      /* graphworker, env_wrappers.py:859-865: reset once ALL agents of an env are done */
-  int32_t assignment;      /* the goal an agent is rewarded for: 0 lexifair re-solved every step (nav_fairassign_*_formation_graph.py
-                              :704-721); 1 min-sum matching re-solved every step (nav_base_formation_graph_mask.py:666-706);
-                              2 random permutation drawn at reset (nav_base_formation_graph_randomgoal.py:258-259).
-                              1 and 2: goal clearance 1.5x instead of 1.2x, fairness_reward must be 0 */
+  int32_t reserved_;
 } FmFormationConfig;
 
 /* State in API layout; the handle keeps it in exactly this layout (device), get / set are copies.  NULL: skipped. */

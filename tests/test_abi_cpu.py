@@ -105,10 +105,6 @@ def test_formation_entry_points_reject_bad_configs_and_have_no_cpu_path(lib_path
     assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -3 and b"num_agents" in lib.fm_last_error()
     cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=9, episode_length=25)
     assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
-    cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=3, episode_length=25, assignment=1, fairness_reward=1)
-    assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1 and b"fairness" in lib.fm_last_error()
-    cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=3, episode_length=25, assignment=3)
-    assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
     if not torch.cuda.is_available():
         cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=3, episode_length=25)
         assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -4
@@ -126,11 +122,6 @@ def test_formation_config_from_reference_namespace():
                   scenario_name="nav_fairassign_nofairrew_formation_graph")
     c = FormationSimConfig.from_args(a)
     assert not c.fairness_reward and c.num_entities == 9 and c.goal_rew == 30
-    a.scenario_name = "nav_base_formation_graph_mask"
-    c = FormationSimConfig.from_args(a)
-    assert c.assignment == "optimal" and not c.fairness_reward
-    a.scenario_name = "nav_base_formation_graph_randomgoal"
-    assert FormationSimConfig.from_args(a).assignment == "random"
     a.scenario_name = "navigation_graph"
     with pytest.raises(NotImplementedError):
         FormationSimConfig.from_args(a)

@@ -22,7 +22,7 @@ def _sim(cfg: FormationConfig, **kw):
         num_agents=cfg.num_agents, num_obstacles=cfg.num_obstacles, world_size=cfg.world_size, max_speed=cfg.max_speed,
         collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
         min_obs_dist=cfg.min_obs_dist, episode_length=cfg.episode_length, fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift,
-        collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, assignment=cfg.assignment, **kw)
+        collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, **kw)
 
 
 def _fp32(st: FormationState) -> FormationState:
@@ -73,7 +73,7 @@ def _compare_step(out, ref, post: FormationState, rpost: FormationState):
         assert (getattr(post, f) == getattr(rpost, f)).all(), f
 
 
-@pytest.mark.parametrize("name", ["formation_n3_o3_fafr", "formation_n4_o2_fa", "formation_n3_o3_oa", "formation_n3_o3_ra"])
+@pytest.mark.parametrize("name", ["formation_n3_o3_fafr", "formation_n4_o2_fa"])
 def test_step_matches_oracle_on_reference_states(name):
     """One step from every recorded reference state (rounded to fp32): device vs float64 oracle, outputs, info and the
     whole post-step state -- status latches, occupancy table, goal history and nearest-landmark latches included."""
@@ -95,20 +95,17 @@ def test_step_matches_oracle_on_reference_states(name):
     # smooth quantities straight against the reference's own float64 outputs (inputs were rounded to fp32 on the way in)
     assert_close(out["adj_env"], g["out_adj"], "adj vs reference")
     assert_close(out["obs"][..., :4], g["out_obs"][..., :4], "vel / pos vs reference")
-    assert orc.branch_hits.get("status_latched", 0) > 0
-    assert orc.branch_hits.get("subset_index_quirk", 0) > 0 or cfg.assignment != "fair"
+    assert orc.branch_hits.get("status_latched", 0) > 0 and orc.branch_hits.get("subset_index_quirk", 0) > 0
     env.close()
 
 
-@pytest.mark.parametrize("N,O,B,collab,fair,mode", [(3, 3, 48, False, True, "fair"), (4, 2, 32, True, False, "fair"),
-                                                    (2, 1, 32, False, True, "fair"), (3, 3, 32, False, False, "optimal"),
-                                                    (3, 2, 32, False, False, "random")])
-def test_reset_and_rollout_match_oracle(N, O, B, collab, fair, mode):
+@pytest.mark.parametrize("N,O,B,collab,fair", [(3, 3, 48, False, True), (4, 2, 32, True, False), (2, 1, 32, False, True)])
+def test_reset_and_rollout_match_oracle(N, O, B, collab, fair):
     """Device reset == oracle reset bit for bit (same Philox draws, same acceptance rules, same lexifair), then a rollout
     that steers at the goals (so agents latch and envs finish early) across auto-resets, compared step by step."""
     import fair_marl_b200 as fm
     cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=15,
-                          collaborative=collab, fairness_reward=fair, assignment=mode)
+                          collaborative=collab, fairness_reward=fair)
     env = fm.B200FormationVecEnv(_sim(cfg), num_envs=B, seed=7, env_offset=3)
     orc = FormationOracle(cfg, B, seed=7, env_offset=3)
     out, ref = _np(env.reset_tensor()), orc.reset()
@@ -116,8 +113,6 @@ def test_reset_and_rollout_match_oracle(N, O, B, collab, fair, mode):
     for f in ("pos", "landmark_pos", "obstacle_pos"):
         assert (getattr(st, f) == getattr(rs, f)).all(), f
     assert (st.goal_match == rs.goal_match).all() and (st.episode == 1).all() and not st.status.any()
-    if mode == "random":
-        assert len({tuple(m) for m in st.goal_match}) > 3                 # the shuffles differ across envs
     assert_close(st.min_time, rs.min_time, "min_time")
     assert_close(st.occupied, rs.occupied, "occupancy after the reset observation")
     assert_close(out["obs"], ref["obs"], "reset obs")
