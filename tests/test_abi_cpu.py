@@ -177,6 +177,16 @@ def test_integration_doc_stub_matches_binding():
     assert [(n, getattr(C, t)) for n, t in doc_fields] == list(_lib.FmConfig._fields_), (doc_fields, lib_fields)
 
 
+def test_integration_doc_formation_stub_matches_binding():
+    import ctypes as C
+    import re
+    from fair_marl_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class FmFormationConfig(C.Structure):"):text.index("fcfg = FmFormationConfig(")]
+    doc_fields = re.findall(r'\("(\w+)", C\.(c_\w+)\)', block)
+    assert [(n, getattr(C, t)) for n, t in doc_fields] == list(_lib.FmFormationConfig._fields_)
+
+
 def test_bench_reports_ncu_traffic_only_for_the_matching_kernel():
     """roofline.traffic comes from the ncu capture of the SAME kernel at the SAME size (profiles/step_kernel_traffic.json)."""
     import importlib.util
