@@ -66,12 +66,18 @@ def select_config(name: str, envs: int | None):
     ENVS_PER_GPU = envs if envs else c["envs"]
 
 
-def lookup_traffic(table: dict, kernel_name: str, envs_per_gpu: int, walls: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu capture that matches this run, else None."""
+def lookup_traffic_entry(table: dict, kernel_name: str, envs_per_gpu: int, walls: int):
+    """Entry of profiles/step_kernel_traffic.json (one ncu --set full capture) that matches this run, else None."""
     for key, ent in table.get("by_kernel", {}).items():
         if kernel_name.startswith(key + " ") and ent.get("envs_per_gpu") == envs_per_gpu and ent.get("walls", 0) == walls:
-            return ent.get("dram_bytes_per_launch")
+            return ent
     return None
+
+
+def lookup_traffic(table: dict, kernel_name: str, envs_per_gpu: int, walls: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu capture that matches this run, else None."""
+    ent = lookup_traffic_entry(table, kernel_name, envs_per_gpu, walls)
+    return ent.get("dram_bytes_per_launch") if ent else None
 
 
 def sim_kwargs():
@@ -380,12 +386,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # so bytes per step / time per step is the kernel's achieved algorithmic bandwidth.
     step_kernel_ms = elapsed_ms / K              # rank-max
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_alg = None
     tpath = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.isfile(tpath):                    # ncu --set full captures, per launch; only the entry of THIS kernel / size
-        traffic = lookup_traffic(json.load(open(tpath)), kernel_name, B, N_WALLS)
+        ent = lookup_traffic_entry(json.load(open(tpath)), kernel_name, B, N_WALLS)
+        if ent:                                  # one captured launch = one env-range lane of fm_step_many (half a step)
+            traffic, traffic_alg = ent.get("dram_bytes_per_launch"), ent.get("algorithmic_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_step": alg_bytes,
+                "traffic": traffic, "traffic_launch_algorithmic_bytes": traffic_alg, "kernel": kernel_name,
+                "algorithmic_bytes_per_step": alg_bytes,
                 "launches_per_step": launches / K, "peak_source": peak_src,
                 "note": "the SoA state (14 % of the algorithmic bytes) is L2-resident between steps; the outputs "
                         "(86 %) stream to HBM through a slab ring larger than L2"}
