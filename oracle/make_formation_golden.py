@@ -150,3 +150,36 @@ if __name__ == "__main__":
         print(n, "->", p, os.path.getsize(p) // 1024, "KiB;", z["actions"].shape[0], "steps,",
               int(z["post_status"].any(axis=1).sum()), "with a latched agent,", int((z["pre_occupied"] == 1).any(axis=1).sum()),
               "with an occupied goal")
+
+
+def inject_state(env, sc, st: FormationState, b: int = 0) -> None:
+    """Write env ``b`` of ``st`` into the live reference objects (what reset_world / random_scenario / the callbacks set)."""
+    w = env.world
+    for i, a in enumerate(w.agents):
+        a.state.p_pos = np.array(st.pos[b, i], dtype=np.float64)
+        a.state.p_vel = np.array(st.vel[b, i], dtype=np.float64)
+        a.state.p_dist = float(st.p_dist[b, i])
+        a.goal_min_time = float(st.min_time[b, i])
+        a.status = bool(st.status[b, i])
+    for i, l in enumerate(w.landmarks):
+        l.state.p_pos = np.array(st.landmark_pos[b, i], dtype=np.float64)
+    for i, o in enumerate(w.obstacles):
+        o.state.p_pos = np.array(st.obstacle_pos[b, i], dtype=np.float64)
+    sc.landmark_poses = np.array(st.landmark_pos[b], dtype=np.float64)
+    if hasattr(sc, "goal_match_index"):
+        sc.goal_match_index = np.array(st.goal_match[b], dtype=np.int64)
+    else:
+        sc.optimal_match_index = np.array(st.goal_match[b], dtype=np.int64)
+    sc.goal_reached = np.array(st.goal_reached[b], dtype=np.float64)
+    sc.landmark_poses_occupied = np.array(st.occupied[b], dtype=np.float64)
+    sc.goal_history = np.array(st.goal_history[b], dtype=np.float64)
+    w.dists_to_goal = np.array(st.dists_to_goal[b], dtype=np.float64)
+    w.times_required = np.array(st.times_required[b], dtype=np.float64)
+    w.dist_left_to_goal = np.array(st.dist_left_to_goal[b], dtype=np.float64)
+    w.num_agent_collisions = np.array(st.num_agent_collisions[b], dtype=np.float64)
+    w.num_obstacle_collisions = np.array(st.num_obstacle_collisions[b], dtype=np.float64)
+    w.dist_traveled_mean = float(st.dist_traveled_mean[b])
+    w.dist_traveled_stddev = float(st.dist_traveled_stddev[b])
+    env.current_step = int(st.step[b])
+    w.current_time_step = int(st.step[b])
+    w.calculate_distances()

@@ -166,3 +166,27 @@ def test_reset_and_rollout_source_is_sanitizer_clean_and_matches_oracle(host_exe
         _compare(out, ref, st, orc.get_state())
         resets += int(ref["reset"].sum())
     assert resets >= B
+
+
+@pytest.mark.parametrize("N,O", [(3, 3), (4, 0), (2, 2)])
+def test_rare_branches_directed(host_exe, tmp_path, N, O):
+    """States built to reach what the recorded fixtures do not: every goal marked occupied with all agents far away (the
+    table is cleared and the agent 'goes to itself', :951 / :1266), no obstacles at all, the smallest team."""
+    B = 16
+    cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, min_obs_dist=0.3, episode_length=25)
+    orc = FormationOracle(cfg, B, seed=11)
+    orc.reset()
+    st = orc.get_state()
+    rng = np.random.default_rng(N * 10 + O)
+    st.occupied[: B // 2] = 1.0                                   # half of the envs: every goal taken
+    st.goal_history[: B // 2] = rng.integers(0, N, (B // 2, N)).astype(np.float64)
+    st.landmark_pos[: B // 4] += 3.0                              # a quarter: all goals far from every agent
+    st.occupied[B // 2:] = rng.random((B - B // 2, N))            # the rest: partial occupancies, one exact 1.0 each
+    st.occupied[B // 2:, 0] = 1.0
+    st = _fp32(st)
+    orc.set_state(st)
+    a = rng.integers(0, 5, (B, N))
+    out, post = _run(host_exe, str(tmp_path), cfg, st, actions=a)
+    ref = orc.step(a, autoreset=False)
+    _compare(out, ref, post, orc.get_state())
+    assert orc.branch_hits.get("all_occupied_cleared", 0) > 0

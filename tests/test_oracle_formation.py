@@ -160,3 +160,47 @@ def test_share_vec_env_tuple_matches_the_reference_tuples():
         decode_onehot_actions(np.full((T, N, 5), 0.2), T, N)
     with pytest.raises(ValueError):
         decode_onehot_actions(np.zeros((T, N + 1)), T, N)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("mode,fair", [("fair", True), ("optimal", False), ("random", False)])
+def test_rare_branches_against_the_live_reference(mode, fair):
+    """Build container only: directed states the recorded fixtures do not reach -- every goal marked occupied with all
+    agents far away (the table is cleared and the agent 'goes to itself', :951 / :1266), partial occupancies with an exact
+    1.0 -- injected into the LIVE unmodified reference and stepped once; oracle == reference at 1e-12."""
+    from oracle.formation import FormationConfig
+    from oracle.make_formation_golden import extract_state, inject_state, make_reference_env
+    N, O, B = 3, 3, 12
+    cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, min_obs_dist=0.3,
+                          fairness_reward=fair, assignment=mode)
+    orc = FormationOracle(cfg, B, seed=11)
+    orc.reset()
+    st = orc.get_state()
+    rng = np.random.default_rng(3)
+    st.occupied[: B // 2] = 1.0
+    st.goal_history[: B // 2] = rng.integers(0, N, (B // 2, N)).astype(np.float64)
+    st.landmark_pos[: B // 4] += 3.0
+    st.occupied[B // 2:] = rng.random((B - B // 2, N))
+    st.occupied[B // 2:, 0] = 1.0
+    orc.set_state(st)
+    a = rng.integers(0, 5, (B, N))
+    out = orc.step(a, autoreset=False)
+    post = orc.get_state()
+    assert orc.branch_hits.get("all_occupied_cleared", 0) > 0
+    env, sc = make_reference_env(cfg, seed=1)
+    for b in range(B):
+        env.reset()
+        inject_state(env, sc, st, b)
+        oh = np.eye(5)[a[b]]
+        ob, ag_id, node, adj, rew, done, info = env.step([oh[i] for i in range(N)])
+        _close(out["obs"][b], np.array(ob), f"obs[{b}]")
+        _close(out["node_obs"][b], np.array(node), f"node_obs[{b}]")
+        _close(out["adj"][b], np.array(adj)[0], f"adj[{b}]")
+        _close(out["reward"][b], np.array(rew, dtype=np.float64).reshape(N), f"reward[{b}]")
+        assert (out["done"][b] == np.array(done)).all()
+        for k in INFO_KEYS:
+            _close(out["info"][k][b], np.array([info[i][k] for i in range(N)]), f"{k}[{b}]")
+        ref_post = extract_state(env, sc)
+        for f in ("pos", "vel", "p_dist", "occupied", "goal_history", "goal_reached", "dists_to_goal", "times_required"):
+            _close(getattr(post, f)[b], getattr(ref_post, f)[0], f"{f}[{b}]")
+        assert (post.status[b] == ref_post.status[0]).all()
