@@ -4,7 +4,6 @@ here, not as layout-dependent wrong answers on the GPU) plus a CPU-side parity c
 oracle.  The translation unit is assembled from the real csrc files (tests/host_emul/prelude.h stands in for the CUDA
 built-ins).  This is test infrastructure: not a CPU path of the product."""
 import os
-import re
 import subprocess
 import sys
 from dataclasses import fields
