@@ -49,7 +49,7 @@ def host_exe(tmp_path_factory):
     cpp, exe = d / "formation_host.cpp", d / "formation_host"
     cpp.write_text(src)
     # -ftrivial-auto-var-init=pattern: a read of an uninitialised local gives a wrong answer here instead of a lucky one
-    cmd = ["g++", "-std=c++17", "-O1", "-g", *os.environ.get("FM_HOST_EMUL_FP", "-ffp-contract=off").split(), "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+    cmd = ["g++", "-std=c++17", os.environ.get("FM_HOST_EMUL_OPT", "-O1"), "-g", *os.environ.get("FM_HOST_EMUL_FP", "-ffp-contract=off").split(), "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
            "-ftrivial-auto-var-init=pattern",
            "-I", EMUL, "-I", os.path.join(ROOT, "include"), str(cpp), "-o", str(exe)]
     res = subprocess.run(cmd, capture_output=True, text=True)
