@@ -36,7 +36,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources if the library is missing or older than them.  Returns its path."""
     if not force and not _stale():
         return library_path()
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(_CSRC, s) for s in SOURCES] + ["-o", library_path()]
+    extra = os.environ.get("FM_NVCC_EXTRA", "").split()      # diagnostics only, e.g. FM_NVCC_EXTRA="-G" for compute-sanitizer runs
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(_CSRC, s) for s in SOURCES] + ["-o", library_path()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
