@@ -33,6 +33,10 @@ CONFIGS = {
                                            fairness_reward=False, assignment="optimal"), 34, 10),
     "formation_n3_o3_ra": (FormationConfig(num_agents=3, num_obstacles=3, goal_rew=30.0, collision_rew=30.0,
                                            fairness_reward=False, assignment="random"), 35, 10),
+    # walls in this family (box test 1.5 * size, wall.id in the node rows, wall length redrawn per reset)
+    "formation_n3_o2_w2": (FormationConfig(num_agents=3, num_obstacles=2, num_walls=2, goal_rew=30.0, collision_rew=30.0), 36, 12),
+    "formation_n3_o3_w1_oa": (FormationConfig(num_agents=3, num_obstacles=3, num_walls=1, goal_rew=30.0, collision_rew=30.0,
+                                              fairness_reward=False, assignment="optimal"), 37, 9),
 }
 
 SCENARIO_FILES = {("fair", True): "nav_fairassign_fairrew_formation_graph.py",
@@ -77,6 +81,29 @@ def extract_state(env, sc) -> FormationState:
         goal_reached=f64(sc.goal_reached), occupied=f64(sc.landmark_poses_occupied), goal_history=f64(sc.goal_history))
 
 
+def extract_walls(env, sc):
+    """(wall_axis [1,W], wall_orient [1,W] (0 = 'H', 1 = 'V'), wall_len [1]) of the live reference."""
+    w = env.world.walls
+    return (np.array([[x.axis_pos for x in w]], dtype=np.float64).reshape(1, len(w)),
+            np.array([[0 if x.orient == "H" else 1 for x in w]], dtype=np.int64).reshape(1, len(w)),
+            np.array([sc.wall_length], dtype=np.float64))
+
+
+def _seek_walls(st: FormationState, walls, rng, p_random: float) -> np.ndarray:
+    """Drive every agent at the nearest point of wall (agent index mod W), slightly past its ends too."""
+    axis, orient, length = walls
+    N, W = st.pos.shape[1], axis.shape[1]
+    a = np.zeros(N, dtype=np.int64)
+    for i in range(N):
+        w = i % W
+        horiz = orient[0, w] == 0
+        along = np.clip(st.pos[0, i, 0 if horiz else 1], -1.3 * length[0], 1.3 * length[0])
+        target = np.array([along, axis[0, w]]) if horiz else np.array([axis[0, w], along])
+        d = target - st.pos[0, i]
+        a[i] = (1 if d[0] > 0 else 2) if abs(d[0]) > abs(d[1]) else (3 if d[1] > 0 else 4)
+    return np.where(rng.random(N) < p_random, rng.integers(0, 5, N), a)
+
+
 def _seek(st: FormationState, rng, p_random: float) -> np.ndarray:
     """Greedy axis move towards the assigned goal, random with probability p_random."""
     N = st.pos.shape[1]
@@ -100,13 +127,19 @@ def generate(name: str) -> str:
     outs = {k: [] for k in ("obs", "node_obs", "adj", "reward", "done")}
     infos = {k: [] for k in INFO_KEYS}
     r_obs, r_node, r_adj = [], [], []
+    walls_pre, walls_reset = [], []
     for ep in range(episodes):
         o = env.reset()
         resets.append(extract_state(env, sc))
+        walls_reset.append(extract_walls(env, sc))
         r_obs.append(np.array(o[0])[None]); r_node.append(np.array(o[2])[None]); r_adj.append(np.array(o[3])[0][None])
         for t in range(cfg.episode_length):
             st = extract_state(env, sc)
-            a = rng.integers(0, 5, N) if ep % 2 else _seek(st, rng, 0.1 if ep % 4 == 0 else 0.3)
+            if cfg.num_walls and ep % 3 == 2:
+                a = _seek_walls(st, extract_walls(env, sc), rng, 0.2)
+            else:
+                a = rng.integers(0, 5, N) if ep % 2 else _seek(st, rng, 0.1 if ep % 4 == 0 else 0.3)
+            walls_pre.append(extract_walls(env, sc))
             oh = np.eye(5)[a]
             ob, ag_id, node, adj, rew, done, info = env.step([oh[i] for i in range(N)])
             pre.append(st); acts.append(a[None]); post.append(extract_state(env, sc))
@@ -121,6 +154,10 @@ def generate(name: str) -> str:
     data = {"config_" + k: np.array(v) for k, v in asdict(cfg).items()}
     data.update(_stack(pre, "pre_")); data.update(_stack(post, "post_")); data.update(_stack(resets, "reset_"))
     data["reset_obs"], data["reset_node_obs"], data["reset_adj"] = map(np.concatenate, (r_obs, r_node, r_adj))
+    if cfg.num_walls:
+        for prefix, rec in (("pre_", walls_pre), ("reset_", walls_reset)):
+            for k, field in enumerate(("wall_axis", "wall_orient", "wall_len")):
+                data[prefix + field] = np.concatenate([r[k] for r in rec], axis=0)
     data["actions"] = np.concatenate(acts)
     for k, v in outs.items():
         data["out_" + k] = np.concatenate(v)
@@ -136,6 +173,14 @@ def load(name: str):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     kw = {f.name: z["config_" + f.name].item() for f in fields(FormationConfig) if "config_" + f.name in z.files}
     return FormationConfig(**kw), {k: z[k] for k in z.files if not k.startswith("config_")}
+
+
+def set_walls(orc, data, prefix: str) -> None:
+    """Load the recorded wall geometry (kept beside FormationState) into a FormationOracle."""
+    if prefix + "wall_axis" in data:
+        orc.wall_axis = data[prefix + "wall_axis"].astype(np.float64).copy()
+        orc.wall_orient = data[prefix + "wall_orient"].astype(np.int64).copy()
+        orc.wall_len = data[prefix + "wall_len"].astype(np.float64).copy()
 
 
 def state_from(data, prefix: str) -> FormationState:

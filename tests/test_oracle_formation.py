@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.formation import NODE_FEAT_DIM, OBS_DIM, FormationOracle, FormationState
-from oracle.make_formation_golden import CONFIGS, load, state_from
+from oracle.make_formation_golden import CONFIGS, load, set_walls, state_from
 from oracle.navgraph import INFO_KEYS
 
 TOL = 1e-12
@@ -28,6 +28,7 @@ def test_step_matches_reference(name):
     T = pre.pos.shape[0]
     orc = FormationOracle(cfg, T)
     orc.set_state(pre)
+    set_walls(orc, g, "pre_")
     out = orc.step(g["actions"], autoreset=False)
     assert out["obs"].shape[-1] == OBS_DIM and out["node_obs"].shape[-1] == NODE_FEAT_DIM
     for k in ("obs", "node_obs", "adj", "reward"):
@@ -51,6 +52,8 @@ def test_step_matches_reference(name):
     else:
         assert (g["pre_goal_match"] == g["post_goal_match"]).all()        # fixed for the episode (set at reset)
     rare = ("status_latched", "contact_force_suppressed", "vacated_goal", "info_unlatched")
+    if cfg.num_walls:
+        rare += ("wall_end_cap", "wall_force_above_1", "wall_box_hit")
     for branch in rare + (("subset_index_quirk",) if cfg.assignment == "fair" else ()):
         assert orc.branch_hits.get(branch, 0) > 0, branch                 # rare paths of the state machine are in the fixture
 
@@ -67,6 +70,7 @@ def test_reset_outputs_match_reference(name):
     pre.occupied[:] = 0.0
     pre.goal_history[:] = -1.0
     orc.set_state(pre)
+    set_walls(orc, g, "reset_")
     r = orc.reset(mask=np.zeros(st.pos.shape[0], bool))                   # observe only
     _close(orc.get_state().occupied, st.occupied, "occupancy after the reset observation")
     _close(orc.get_state().goal_history, st.goal_history, "goal_history after the reset observation")
@@ -204,3 +208,27 @@ def test_rare_branches_against_the_live_reference(mode, fair):
         for f in ("pos", "vel", "p_dist", "occupied", "goal_history", "goal_reached", "dists_to_goal", "times_required"):
             _close(getattr(post, f)[b], getattr(ref_post, f)[0], f"{f}[{b}]")
         assert (post.status[b] == ref_post.status[0]).all()
+
+
+def test_own_reset_with_walls():
+    from oracle.formation import FormationConfig
+    cfg = FormationConfig(num_agents=3, num_obstacles=2, num_walls=2, episode_length=4)
+    orc = FormationOracle(cfg, 32, seed=5)
+    out = orc.reset()
+    assert out["node_obs"].shape == (32, 3, 10, NODE_FEAT_DIM) and (out["node_obs"][:, :, 8:, 12] == 3.0).all()
+    s = orc.get_state()
+    assert set(np.unique(orc.wall_orient)) == {0, 1} and (orc.wall_axis[:, 0] == -orc.wall_axis[:, 1]).all()
+    assert ((orc.wall_len >= 0.1 - 1e-6) & (orc.wall_len <= 0.4 + 1e-6)).all()          # U(0.2, 0.8) * ws / 4
+    assert ((np.abs(orc.wall_axis) >= 0.2 - 1e-6) & (np.abs(orc.wall_axis) <= 0.9 + 1e-6)).all()
+    hits0 = orc.branch_hits.get("wall_box_hit", 0)
+    for b in range(32):
+        for i in range(3):
+            assert not orc._obstacle_collision(b, s.pos[b, i]) and not orc._obstacle_collision(b, s.landmark_pos[b, i])
+    assert orc.branch_hits.get("wall_box_hit", 0) == hits0
+    lens = orc.wall_len.copy()
+    for t in range(5):
+        out = orc.step(np.random.default_rng(t).integers(0, 5, (32, 3)))
+    assert out["reset"].all() or (orc.get_state().episode >= 2).all()
+    assert (orc.wall_len != lens).any()                                                  # redrawn per reset in this family
+    with pytest.raises(ValueError):
+        FormationOracle(FormationConfig(num_walls=3), 2)
