@@ -11,7 +11,7 @@ What is here
   observation / graph-observation / info / reset path, batched over envs.
   Every function cites the reference file:line it follows.
 * ``formation.py``  the formation-family scenarios restated one env at a time; pinned by
-  ``tests/golden/formation_*.npz`` (``make_formation_golden.py``); covers the FA+FR / FA / OA / RA scenario files.
+  ``tests/golden/formation_*.npz`` (``make_formation_golden.py``); covers the FA+FR / FA / OA / RA scenario files, walls included.
 * ``lexifair.py``   exact solvers for the lexicographic bottleneck ("lexifair")
   assignment of ``marl_fair_assign.py`` (brute force, threshold descent, and a
   HiGHS MILP restatement of the reference's iterative MILP).
