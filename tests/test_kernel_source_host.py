@@ -189,3 +189,49 @@ def test_rare_branches_directed(host_exe, tmp_path, N, O):
     ref = orc.step(a, autoreset=False)
     _compare(out, ref, post, orc.get_state())
     assert orc.branch_hits.get("all_occupied_cleared", 0) > 0
+
+
+@pytest.mark.parametrize("N,O,fair,collab", [(4, 8, True, False), (3, 0, False, True), (2, 8, True, True), (4, 3, False, False)])
+def test_fuzzed_states(host_exe, tmp_path, N, O, fair, collab):
+    """Random (not reachable-by-rollout) states: clustered agents and goals so that thresholds, occupancies equal to 1.0,
+    latched agents and collisions all occur; the maximum obstacle count (FM_FORMATION_MAX_OBSTACLES) included."""
+    B = 192
+    rng = np.random.default_rng(100 * N + O)
+    cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, min_obs_dist=0.4,
+                          episode_length=25, fairness_reward=fair, collaborative=collab)
+    st = FormationOracle(cfg, B).get_state()
+    st.landmark_pos[:] = rng.uniform(-0.8, 0.8, (B, N, 2))
+    near = rng.random((B, N)) < 0.5                               # half of the agents sit next to some goal
+    which = rng.integers(0, N, (B, N))
+    at_goal = np.take_along_axis(st.landmark_pos, which[..., None], axis=1) + rng.normal(0, 0.04, (B, N, 2))
+    st.pos[:] = np.where(near[..., None], at_goal, rng.uniform(-1, 1, (B, N, 2)))
+    st.vel[:] = rng.normal(0, 0.5, (B, N, 2))
+    st.p_dist[:] = rng.uniform(0, 2, (B, N))
+    st.obstacle_pos[:] = rng.uniform(-0.8, 0.8, (B, O, 2))
+    st.goal_match[:] = np.argsort(rng.random((B, N)), axis=1)
+    st.status[:] = rng.random((B, N)) < 0.3
+    st.occupied[:] = np.where(rng.random((B, N)) < 0.4, 1.0, rng.random((B, N)))
+    st.goal_history[:] = rng.integers(-1, N, (B, N))
+    st.goal_reached[:] = rng.integers(-1, N, (B, N))
+    latched = rng.random((B, N)) < 0.4
+    st.times_required[:] = np.where(latched, rng.integers(1, 10, (B, N)) * 0.1, -1.0)
+    st.dists_to_goal[:] = np.where(rng.random((B, N)) < 0.2, -1.0, rng.uniform(0, 2, (B, N)))
+    st.dist_left_to_goal[:] = rng.uniform(0, 1, (B, N))
+    st.num_agent_collisions[:] = rng.integers(0, 5, (B, N))
+    st.num_obstacle_collisions[:] = rng.integers(0, 5, (B, N))
+    st.dist_traveled_mean[:] = rng.uniform(0, 2, B)
+    st.dist_traveled_stddev[:] = rng.uniform(0, 0.5, B)
+    st.step[:] = rng.integers(0, 24, B)
+    st.min_time[:] = rng.uniform(0, 1, (B, N))
+    # the reference raises (argmin of an empty list, :921) when the nearest goal is taken, someone stands on it and no goal
+    # is free; keep one goal free per env so that both sides stay defined
+    st.occupied[np.arange(B), rng.integers(0, N, B)] = 0.5
+    st = _fp32(st)
+    orc = FormationOracle(cfg, B)
+    orc.set_state(st)
+    a = rng.integers(0, 5, (B, N))
+    out, post = _run(host_exe, str(tmp_path), cfg, st, actions=a)
+    ref = orc.step(a, autoreset=False)
+    _compare(out, ref, post, orc.get_state())
+    for branch in ("status_latched", "contact_force_suppressed", "vacated_goal", "info_unlatched", "subset_index_quirk"):
+        assert orc.branch_hits.get(branch, 0) > 0, branch
