@@ -191,14 +191,15 @@ def test_rare_branches_directed(host_exe, tmp_path, N, O):
     assert orc.branch_hits.get("all_occupied_cleared", 0) > 0
 
 
-@pytest.mark.parametrize("N,O,fair,collab", [(4, 8, True, False), (3, 0, False, True), (2, 8, True, True), (4, 3, False, False)])
-def test_fuzzed_states(host_exe, tmp_path, N, O, fair, collab):
+@pytest.mark.parametrize("N,O,fair,collab,max_speed", [(4, 8, True, False, 2.0), (3, 0, False, True, 2.0), (2, 8, True, True, 2.0),
+                                                      (4, 3, False, False, 2.0), (3, 2, True, False, None), (4, 1, True, False, 0.7)])
+def test_fuzzed_states(host_exe, tmp_path, N, O, fair, collab, max_speed):
     """Random (not reachable-by-rollout) states: clustered agents and goals so that thresholds, occupancies equal to 1.0,
     latched agents and collisions all occur; the maximum obstacle count (FM_FORMATION_MAX_OBSTACLES) included."""
     B = 192
     rng = np.random.default_rng(100 * N + O)
     cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, min_obs_dist=0.4,
-                          episode_length=25, fairness_reward=fair, collaborative=collab)
+                          episode_length=25, fairness_reward=fair, collaborative=collab, max_speed=max_speed)
     st = FormationOracle(cfg, B).get_state()
     st.landmark_pos[:] = rng.uniform(-0.8, 0.8, (B, N, 2))
     near = rng.random((B, N)) < 0.5                               # half of the agents sit next to some goal
