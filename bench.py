@@ -117,6 +117,18 @@ class ClockSampler:
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
+    def sample_now(self):
+        """One sample taken by the calling thread (NVML only)."""
+        try:
+            if self._nvml is not None:
+                n = self._nvml
+                mhz = int(n.nvmlDeviceGetClockInfo(self._dev, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._dev)) if hasattr(
+                    n, "nvmlDeviceGetCurrentClocksEventReasons") else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev))
+                self.samples.append((time.perf_counter(), mhz, mask))
+        except Exception:
+            pass
+
     def _run(self):
         import subprocess
         while not self._stop.is_set():
@@ -332,23 +344,43 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # synthetic random actions for one episode, resident in HBM before the timed region
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = torch.randint(0, 5, (EPISODE, B, N_AGENTS), generator=g, device=dev, dtype=torch.int32)
-    env.reset_tensor()
-    launches0 = None
+    stats_vec = torch.empty(env.lib.fm_stats_len(N_AGENTS), dtype=torch.float64, device=dev)
+    Wn = max(W, 3)
+    # Episode phase at which the warm-up starts, chosen so that a terminal step (auto-reset + lexifair + statistics
+    # reduction + all-reduce) lies in the MIDDLE of the timed region, as in a long rollout: its all-reduce then overlaps
+    # the following steps instead of being the last thing the timer waits for.
+    phase0 = (-(Wn + (K + 1) // 2)) % EPISODE
 
-    def run_steps(n):
-        done_steps = 0
-        while done_steps < n:
-            t = min(EPISODE, n - done_steps)
-            env.rollout_tensor(actions[:t])
-            done_steps += t
-            if t == EPISODE:              # statistics change on terminal steps: reduce + all-reduce per episode
-                stats.all_reduce_async(env.read_stats())
+    def run_steps(n, phase):
+        """n env steps from episode phase `phase`, in chunks that end at episode boundaries; every terminal step is
+        followed by the statistics reduction and its all-reduce (side stream).  Returns the new phase."""
+        while n > 0:
+            t = min(n, EPISODE - phase)
+            env.rollout_tensor(actions[phase:phase + t])
+            n -= t
+            phase = (phase + t) % EPISODE
+            if phase == 0:
+                stats.all_reduce_async(env.read_stats(out=stats_vec))
+        return phase
 
-    run_steps(max(W, 3))
+    def prepare():
+        env.reset_tensor()
+        return run_steps(phase0, 0)
+
+    # dry run of the exact call sequence (plans, lazily created streams / buffers, NCCL channels), then the real one
+    ph = prepare()
+    ph = run_steps(Wn, ph)
+    run_steps(K, ph)
+    stats.join()
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local_rank)
+    env.read_stats(clear=True, out=stats_vec)
+    ph = prepare()
+    ph = run_steps(Wn, ph)
+    stats.join()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank, period=0.0005)
     sampler.start()
-    time.sleep(0.05)
+    time.sleep(0.02)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -356,12 +388,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    run_steps(K)
+    run_steps(K, ph)
+    stats.join()                                  # the all-reduce of the region's terminal steps is inside the measurement
     ev1.record()
+    sampler.sample_now()                          # one NVML read by this thread while the GPU is still working on the region
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     t1 = time.perf_counter()
+    sampler.period = 0.02
     launches = env.kernel_launches - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary(t0, t1)
@@ -379,11 +414,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env.algorithmic_bytes_per_step
-    kernel_name = {"aw": f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)",
+    kernel_name = {"aw": f"fm::aw_roll_kernel<{N_AGENTS},{N_OBST},11> (agent-warp, persistent rollout)",
                    "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}{', true' if N_WALLS else ''}> (group-per-env)"}[env.mapping]
-    # One step = the step kernel over the whole batch (fm_step_many issues it as `launches / K` concurrent
-    # env-range launches on side streams); the kernel is > 99 % of the timed region (profiles/: launch list),
-    # so bytes per step / time per step is the kernel's achieved algorithmic bandwidth.
+    # One step = the step kernel's work over the whole batch (agent-warp mapping: (step, tile) items of one persistent
+    # launch per chunk of steps; group mapping: concurrent env-range launches on side streams); that kernel is > 99 %
+    # of the timed region (profiles/: launch list), so bytes per step / time per step is its achieved algorithmic bandwidth.
     step_kernel_ms = elapsed_ms / K              # rank-max
     achieved = alg_bytes / (step_kernel_ms * 1e-3) / 1e9
     traffic = traffic_alg = None
@@ -400,7 +435,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                         "(86 %) stream to HBM through a slab ring larger than L2"}
 
     # closed loop: one fm_step per call (what a policy-in-the-loop rollout does), no host sync in between
-    cl_steps = min(K, 1000)
+    cl_steps = max(200, min(K, 1000))
     for k in range(3):
         env.step_tensor(actions[k])
     torch.cuda.synchronize(dev)
@@ -494,7 +529,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "entities": E, "sharding": f"env-index x{world}" if world > 1 else "single GPU",
                        "l2": f"outputs cycle through a {slots}-slot slab ring ({slab_gb:.1f} GB per GPU > 126 MB L2); the SoA "
                              "state is read+written every step",
-                       "stats_allreduce": "per episode (25 steps), side stream" if world > 1 else "local reduce per episode"},
+                       "stats_allreduce": ("after every terminal step, side stream, joined before the timer stops" if world > 1
+                                           else "local reduce after every terminal step"),
+                       "episode_phase_at_start": (phase0 + Wn) % EPISODE,
+                       "launch": "fm_step_many: one persistent kernel per chunk of steps (chunks end at episode boundaries)"
+                                 if env.mapping == "aw" else "fm_step_many: env-range lanes on side streams"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "closed_loop": closed_loop, "edge_list": edge_list,
             "gpu_launches": launches, "clocks": clocks,
             "episode_stats": {"episodes": total_stats["episodes"], "env_steps": total_stats["env_steps"]},

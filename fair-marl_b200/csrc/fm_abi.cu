@@ -62,6 +62,10 @@ struct FmHandle {
   cudaStream_t pf_stream[FM_MAX_LANES];
   cudaEvent_t pf_go[FM_MAX_LANES], pf_ready[FM_MAX_LANES];
   int lockstep, host_step;
+  // agent-warp mapping: persistent rollout kernel (fm_roll.cu).  Control block (zero between launches), one wave of CTAs.
+  void* roll_ctl;
+  int roll_on, roll_max_ctas;
+  int lanes_override;        // FM_LANES (diagnostic), read once at fm_create; 0 = automatic
   // device staging for the *_host entry points (allocated on first use)
   float* st_onehot;
   uint8_t* st_mask;
@@ -240,6 +244,25 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   p.stats = h->stats;
   e = fm::prepare_kernels(p);
   if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->pend_block); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: kernel attributes: %s", cudaGetErrorString(e)); }
+  if (const char* ev = getenv("FM_LANES")) {          // diagnostic override of the env-range lanes of fm_step_many
+    const int v = atoi(ev);
+    if (v >= 1 && v <= FM_MAX_LANES) h->lanes_override = v;
+  }
+  if (p.mapping == 1) {                               // persistent rollout kernel (FM_ROLL=0: one-shot launches, diagnostic)
+    const char* ev = getenv("FM_ROLL");
+    h->roll_on = !(ev && atoi(ev) == 0);
+    int per_sm = 0, sms = 0;
+    e = fm::roll_prepare(p, &per_sm);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->roll_ctl, fm::roll_ctl_bytes(B));
+    if (e == cudaSuccess) e = cudaMemset(h->roll_ctl, 0, fm::roll_ctl_bytes(B));
+    if (e != cudaSuccess || per_sm < 1) {
+      cudaFree(h->roll_ctl); cudaFree(h->stats); cudaFree(h->pend_block); cudaFree(h->state_block); delete h;
+      return fail(FM_ERR_CUDA, "fm_create: rollout kernel: %s", cudaGetErrorString(e));
+    }
+    h->roll_max_ctas = per_sm * sms;
+    if (const char* ev2 = getenv("FM_ROLL_CTAS")) { const int v = atoi(ev2); if (v >= 1) h->roll_max_ctas = v; }   // diagnostic
+  }
   e = fm::launch_state_init(p, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   if (e != cudaSuccess) { cudaFree(h->stats); cudaFree(h->pend_block); cudaFree(h->state_block); delete h; return fail(FM_ERR_CUDA, "fm_create: init: %s", cudaGetErrorString(e)); }
@@ -268,6 +291,7 @@ int fm_destroy(FmHandle* h) {
     for (int k = 1; k < FM_MAX_LANES; ++k) { cudaStreamDestroy(h->lane_stream[k]); cudaEventDestroy(h->lane_join[k]); }
     cudaEventDestroy(h->lane_fork);
   }
+  cudaFree(h->roll_ctl);
   cudaFree(h->stats);
   cudaFree(h->state_block);
   delete h;
@@ -382,7 +406,13 @@ static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, con
   const bool terminal = step_is_terminal(h);
   rc = prefetch_before_step(h, p, (cudaStream_t)stream, terminal);
   if (rc) return rc;
-  FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, false));
+  if (h->roll_on) {                                  // agent-warp mapping: one-step launch of the persistent kernel
+    FmOutputs o{p.o_obs, p.o_node, p.o_adj, p.o_rew, p.o_done, p.o_info};
+    fm::RollLaunch r{1, 1, h->roll_max_ctas, h->roll_ctl, idx, onehot, 0, &o};
+    FM_CUDA(fm::roll_launch(p, r, (cudaStream_t)stream));
+  } else {
+    FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, false));
+  }
   h->launches += 1;
   advance_phase(h, terminal);
   if (terminal && h->p.auto_reset) return prefetch_after_reset(h, (cudaStream_t)stream, 0, 0, h->p.B);
@@ -403,6 +433,29 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
   int rc = use_device(h->device);
   if (rc) return rc;
   const size_t stride = (size_t)h->p.B * h->p.N;
+  if (h->roll_on) {
+    // Agent-warp mapping: the whole rollout is (step, tile) items of ONE persistent kernel per chunk of <=
+    // FM_ROLL_MAX_STEPS steps (fm_roll.cu).  A tile's next step may start as soon as its state is written back when
+    // every step of the chunk has its own output arrays; otherwise only after its outputs have been written.
+    for (int t0 = 0; t0 < num_steps; t0 += FM_ROLL_MAX_STEPS) {
+      const int n = std::min(FM_ROLL_MAX_STEPS, num_steps - t0);
+      int early = 1;
+      for (int a = 0; a < n && early; ++a)
+        for (int b = a + 1; b < n && early; ++b) {
+          const FmOutputs &x = outs[t0 + a], &y = outs[t0 + b];
+          if ((x.obs && x.obs == y.obs) || (x.node_obs && x.node_obs == y.node_obs) || (x.adj && x.adj == y.adj) ||
+              (x.reward && x.reward == y.reward) || (x.done && x.done == y.done)) early = 0;
+        }
+      DevParams p = h->p;
+      set_outputs(p, nullptr);
+      p.act_idx = nullptr; p.act_onehot = nullptr; p.reset_mask = nullptr;
+      fm::RollLaunch r{n, early, h->roll_max_ctas, h->roll_ctl, actions + (size_t)t0 * stride, nullptr, (long long)stride, outs + t0};
+      FM_CUDA(fm::roll_launch(p, r, (cudaStream_t)stream));
+      h->launches += 1;
+      for (int t = 0; t < n; ++t) advance_phase(h, step_is_terminal(h));
+    }
+    return FM_OK;
+  }
   // Envs are independent, so a rollout of T steps is T x L independent kernel chains, one per env-range
   // lane.  Lane 0 runs on the caller's stream, the others on side streams forked from / joined to it; the
   // GPU then always has runnable CTAs of another lane while one lane's last wave drains or its next
@@ -410,10 +463,7 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
   const int B = h->p.B;
   int lanes = 1;
   if (num_steps > 1 && B >= 32768) lanes = 2;           // 2, 3, 4 lanes measure the same at C2; 8 is launch bound
-  if (const char* ev = getenv("FM_LANES")) {                          // diagnostic override
-    const int v = atoi(ev);
-    if (v >= 1 && v <= FM_MAX_LANES) lanes = v;
-  }
+  if (h->lanes_override) lanes = h->lanes_override;                   // FM_LANES, diagnostic
   if (lanes > 1) { rc = ensure_lanes(h); if (rc) return rc; }
   cudaStream_t user = (cudaStream_t)stream;
   if (lanes > 1) {

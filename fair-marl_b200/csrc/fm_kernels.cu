@@ -158,11 +158,11 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 
     const double dp = __dsub_rn(pj, mean_p), da = __dsub_rn(aj, mean_a), dv = __dsub_rn((j < i) ? aj : bj, mean_v);
     q_p = sq_acc(q_p, dp); q_a = sq_acc(q_a, da); q_v = sq_acc(q_v, dv);
   }
-  const float std_p = std_from_q(q_p, inv_n), std_v = std_from_q(q_v, inv_n), std_a = std_from_q(q_a, inv_n);
+  const double std_p = std_from_q(q_p, inv_n), std_v = std_from_q(q_v, inv_n), std_a = std_from_q(q_a, inv_n);
   float fparam;                                  // navigation_graph.py:764-769 / :849-853
-  if (dtg == -1.0f) fparam = ratio_eps((float)mean_p, std_p);
-  else if (i == 0) fparam = ratio_eps(dmean, dstd);
-  else fparam = ratio_eps((float)mean_v, std_v);
+  if (dtg == -1.0f) fparam = ratio_eps(mean_p, std_p);
+  else if (i == 0) fparam = ratio_eps((double)dmean, (double)dstd);
+  else fparam = ratio_eps(mean_v, std_v);
 
   // reward (navigation_graph.py:760-824)
   float rew = reached ? p.goal_rew : -(float)dgoal;
@@ -204,12 +204,12 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 
       const double dd = __dsub_rn((j <= i) ? aj : bj, md), dtt = __dsub_rn((j <= i) ? tj : uj, mt);
       qd = sq_acc(qd, dd); qt = sq_acc(qt, dtt);
     }
-    const float sdv = std_from_q(qd, inv_n), stv = std_from_q(qt, inv_n);
+    const double sdv = std_from_q(qd, inv_n), stv = std_from_q(qt, inv_n);
     double tacc = 0.0;                           // entity.state.time += dt per step (core.py:355)
     for (int k = 0; k < nstep; ++k) tacc += p.dt;
     info[0] = own_rew; info[1] = dleft_new; info[2] = (float)treq_new; info[3] = (float)nac; info[4] = (float)noc;
-    info[5] = (float)md; info[6] = sdv; info[7] = ratio_eps((float)md, sdv); info[8] = (float)dtg_new;
-    info[9] = (float)tacc; info[10] = (float)mt; info[11] = stv; info[12] = ratio_eps((float)mt, stv);
+    info[5] = (float)md; info[6] = (float)sdv; info[7] = ratio_eps(md, sdv); info[8] = (float)dtg_new;
+    info[9] = (float)tacc; info[10] = (float)mt; info[11] = (float)stv; info[12] = ratio_eps(mt, stv);
     info[13] = mint = act ? p.mintime[idx] : 0.f;
     if (act && want_info && p.o_info) {
       float* o = p.o_info + ((size_t)env * N + i) * INFO_F;
@@ -380,8 +380,8 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   const double mean_p = __dmul_rn(sum_p, inv_n);
   double q_p = 0.0;
   for (int j = 0; j < N; ++j) { const double d = __dsub_rn(__shfl_sync(FULL, pd64, gl + j), mean_p); q_p = sq_acc(q_p, d); }
-  const float std_p = std_from_q(q_p, inv_n);
-  const float fparam = (dtg == -1.0f) ? ratio_eps((float)mean_p, std_p) : ratio_eps(dmean, dstd);
+  const double std_p = std_from_q(q_p, inv_n);
+  const float fparam = (dtg == -1.0f) ? ratio_eps(mean_p, std_p) : ratio_eps((double)dmean, (double)dstd);
   double dgoal; int ncoll; bool ocoll;
   if (venv) distance_tile<G, WALLS>(p, ent, adj, env, do_reset, i, act, gm, dgoal, ncoll, ocoll);
   if (act) {

@@ -18,6 +18,21 @@ bool aw_supported(int N, int O);
 int aw_stats_rows(int B);
 cudaError_t aw_prepare(const DevParams& p);
 cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset);
+// persistent rollout kernel of the agent-warp mapping (fm_roll.cu): num_steps <= FM_ROLL_MAX_STEPS env steps in one launch
+#define FM_ROLL_MAX_STEPS 32
+struct RollLaunch {
+  int num_steps;
+  int early;                 // every step writes its own output arrays: a tile is released right after its state write-back
+  int max_ctas;              // one wave: SMs x resident CTAs per SM
+  void* ctl;                 // device control block (roll_ctl_bytes), zero between launches
+  const int* act_idx;        // step t reads act_idx + t * act_stride, or act_onehot + t * act_stride
+  const float* act_onehot;
+  long long act_stride;      // elements between consecutive steps' actions
+  const FmOutputs* outs;     // [num_steps] (host memory; copied into the kernel parameters)
+};
+size_t roll_ctl_bytes(int B);
+cudaError_t roll_prepare(const DevParams& p, int* ctas_per_sm);
+cudaError_t roll_launch(const DevParams& p, const RollLaunch& r, cudaStream_t st);
 cudaError_t launch_static_dists(const DevParams& p, cudaStream_t st);   // recompute p.sdist from the static positions
 cudaError_t prepare_kernels(const DevParams& p);   // opt in to > 48 KB dynamic shared memory, once per handle
 cudaError_t launch_step(const DevParams& p, cudaStream_t st, bool is_reset);

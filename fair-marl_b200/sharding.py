@@ -50,6 +50,7 @@ class EpisodeStats:
         import torch.distributed as dist
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream(self.device))
+            local_vec.record_stream(self.side)          # the caller may drop `local_vec` as soon as this returns
             with torch.cuda.stream(self.side):
                 self.buf.copy_(local_vec, non_blocking=True)
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -58,6 +59,11 @@ class EpisodeStats:
             self.buf.copy_(local_vec)
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
                 dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+
+    def join(self) -> None:
+        """Make the current stream wait for the all-reduce in flight (no host synchronisation)."""
+        if self.side is not None:
+            self.torch.cuda.current_stream(self.device).wait_stream(self.side)
 
     def result(self):
         if self.side is not None:

@@ -243,12 +243,17 @@ class B200GraphVecEnv:
         s = self._ensure_slabs()
         if out is not None:
             views = self._check_out(out, with_step=True)
-            slot = None
+            views["info"] = s["info"]
+            o = self._outputs_struct(views, with_step=True)
+            result = None
         else:
             self._slot = slot = (self._slot + 1) % self.num_slots
-            views = {k: s[k][slot] for k in ("obs", "node_obs", "adj", "reward", "done")}
-        views["info"] = s["info"]
-        o = self._outputs_struct(views, with_step=True)
+            cached = self._plans.get(("slot", slot))
+            if cached is None:                      # FmOutputs struct and result views of a ring slot are built once
+                views = {k: s[k][slot] for k in ("obs", "node_obs", "adj", "reward", "done")}
+                views["info"] = s["info"]
+                cached = self._plans[("slot", slot)] = (self._outputs_struct(views, with_step=True), self._package(slot, with_step=True))
+            o, result = cached
         B, N = self.num_envs, self.num_agents
         if actions.dim() == 2:
             if actions.dtype != t.int32 or not actions.is_contiguous() or actions.shape != (B, N):
@@ -261,7 +266,7 @@ class B200GraphVecEnv:
         _lib.check(rc, "fm_step")
         self._step_version += 1
         self._last_step_api = "tensor"
-        return self._package_out(views, with_step=True) if out is not None else self._package(slot, with_step=True)
+        return self._package_out(views, with_step=True) if result is None else dict(result)
 
     def edge_list_tensor(self, adj_env, repeat: int = 1, inclusive: bool = False) -> Dict[str, Any]:
         """Policy-side edge list of ``adj_env [B,E,E]`` (``process_adj``, gnn_new.py:381-413) WITHOUT a host sync:
@@ -299,20 +304,27 @@ class B200GraphVecEnv:
         if actions.dtype != t.int32 or not actions.is_contiguous() or actions.dim() != 3 or actions.shape[1:] != (B, N):
             raise ValueError("actions must be a contiguous int32 CUDA tensor [T, B, N]")
         T = int(actions.shape[0])
-        key = (T, self._slot)
-        plan = self._plans.get(key)
-        if plan is None:
-            arr = (_lib.FmOutputs * T)()
-            slots = []
-            for k in range(T):
-                slot = (self._slot + 1 + k) % self.num_slots
-                views = {name: s[name][slot] for name in ("obs", "node_obs", "adj", "reward", "done")}
+        if T == 0:
+            return []
+        S = self.num_slots
+        start = (self._slot + 1) % S
+        # One FmOutputs table for the slab ring, repeated often enough that any (start slot, T) is a contiguous run of
+        # it: a rollout call does no per-step Python work (no tensor slicing, no data_ptr(), no struct filling).
+        reps = (S - 1 + T + S - 1) // S
+        ring = self._plans.get("ring")
+        if ring is None or ring[1] < reps:
+            arr = (_lib.FmOutputs * (S * reps))()
+            for k in range(S):
+                views = {name: s[name][k] for name in ("obs", "node_obs", "adj", "reward", "done")}
                 views["info"] = s["info"]
-                arr[k] = self._outputs_struct(views, with_step=True)
-                slots.append(slot)
-            plan = self._plans[key] = (arr, slots)
-        arr, slots = plan
-        _lib.check(self.lib.fm_step_many(self._h, actions.data_ptr(), T, arr, self._stream()), "fm_step_many")
+                o = self._outputs_struct(views, with_step=True)
+                for r in range(reps):
+                    arr[r * S + k] = o
+            ring = self._plans["ring"] = (arr, reps)
+        arr = ring[0]
+        first = C.cast(C.addressof(arr) + start * C.sizeof(_lib.FmOutputs), C.POINTER(_lib.FmOutputs))
+        slots = [(start + k) % S for k in range(T)]
+        _lib.check(self.lib.fm_step_many(self._h, actions.data_ptr(), T, first, self._stream()), "fm_step_many")
         self._slot = slots[-1] if slots else self._slot
         self._step_version += T
         self._last_step_api = "tensor"
@@ -442,10 +454,11 @@ class B200GraphVecEnv:
         _lib.check(self.lib.fm_set_state(self._h, C.byref(st), self._stream()), "fm_set_state")
         self.torch.cuda.current_stream(self.device).synchronize()      # keep `tensors` alive until consumed
 
-    def read_stats(self, clear: bool = False):
-        """Local episode-statistics vector (float64 CUDA tensor [15N+2]); see fm_stats_read."""
+    def read_stats(self, clear: bool = False, out=None):
+        """Local episode-statistics vector (float64 CUDA tensor [15N+2]); see fm_stats_read.  ``out``: reuse a tensor."""
         t = self.torch
-        out = t.empty(self.lib.fm_stats_len(self.num_agents), dtype=t.float64, device=self.device)
+        if out is None:
+            out = t.empty(self.lib.fm_stats_len(self.num_agents), dtype=t.float64, device=self.device)
         _lib.check(self.lib.fm_stats_read(self._h, out.data_ptr(), int(clear), self._stream()), "fm_stats_read")
         return out
 

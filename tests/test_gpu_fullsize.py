@@ -95,3 +95,81 @@ def test_rollout_lanes_equal_single_steps(N, O, B):
         assert torch.equal(s_r[k], s_s[k]), k
     assert torch.equal(e_r.read_stats(), e_s.read_stats())
     e_r.close(); e_s.close()
+
+
+@pytest.mark.parametrize("B,T,slots,episode_length", [
+    (128, 70, 70, 5),        # 4 tiles << resident CTAs: every item waits on its predecessor's flag; 3 launches (32 + 32 + 6)
+    (100, 40, 2, 7),         # ragged last tile (vectorised-store path) + only 2 output slabs -> late release of the tiles
+    (65536 + 40, 12, 12, 5), # more tiles than one wave of CTAs: dynamic (step, tile) scheduling, early release
+    (4096, 33, 3, 4),        # late release across a chunk boundary
+])
+def test_persistent_rollout_kernel_equals_single_steps(B, T, slots, episode_length):
+    """fm_step_many on the agent-warp mapping is ONE persistent kernel per <= 32 steps (fm_roll.cu: (step, tile) work
+    items, per-tile dependency flags).  Every output of every step still visible in the slab ring, the final state and
+    the episode statistics are bit-identical to stepping one fm_step at a time -- and to the one-shot kernels
+    (FM_ROLL=0), which share the tile body but none of the scheduling."""
+    import os
+    import fair_marl_b200 as fm
+    import torch
+    cfg = NavConfig(num_agents=3, num_obstacles=3, goal_rew=30.0, collision_rew=30.0, episode_length=episode_length)
+    sim = sim_config_from(cfg, mapping="aw")
+    e_r = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)
+    e_s = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)
+    os.environ["FM_ROLL"] = "0"
+    try:
+        e_o = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)        # one-shot launches
+    finally:
+        del os.environ["FM_ROLL"]
+    for e in (e_r, e_s, e_o):
+        e.reset_tensor()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = torch.randint(0, 5, (T, B, 3), generator=g, device="cuda", dtype=torch.int32)
+    slot_of = e_r.rollout_tensor(acts)
+    for t in range(T):
+        o_s, o_o = e_s.step_tensor(acts[t]), e_o.step_tensor(acts[t])
+        for k in ("obs", "node_obs", "adj_env", "reward", "done"):
+            assert torch.equal(o_s[k], o_o[k]), (t, k)
+            if slot_of[t] not in slot_of[t + 1:]:                       # not overwritten by a later step of the rollout
+                assert torch.equal(e_r.slot_outputs(slot_of[t])[k], o_s[k]), (t, k)
+    s_r, s_s, s_o = e_r.get_state(), e_s.get_state(), e_o.get_state()
+    for k in s_r:
+        assert torch.equal(s_r[k], s_s[k]) and torch.equal(s_o[k], s_s[k]), k
+    assert torch.equal(e_r.read_stats(), e_s.read_stats()) and torch.equal(e_o.read_stats(), e_s.read_stats())
+    # the control block was reset by the last CTA: a second rollout works and continues the same trajectory
+    slot_of = e_r.rollout_tensor(acts[:5])
+    for t in range(5):
+        o_s = e_s.step_tensor(acts[t])
+        if slot_of[t] not in slot_of[t + 1:]:
+            assert torch.equal(e_r.slot_outputs(slot_of[t])["node_obs"], o_s["node_obs"]), t
+    for e in (e_r, e_s, e_o):
+        e.close()
+
+
+def test_persistent_rollout_kernel_in_a_cuda_graph():
+    """A captured fm_step_many launch can be replayed: the kernel leaves its control block zeroed."""
+    import fair_marl_b200 as fm
+    import torch
+    cfg = NavConfig(num_agents=3, num_obstacles=3, episode_length=6)
+    B, T = 2048, 6
+    e_g = fm.B200GraphVecEnv(sim_config_from(cfg, mapping="aw"), num_envs=B, seed=9, num_slots=T)
+    e_s = fm.B200GraphVecEnv(sim_config_from(cfg, mapping="aw"), num_envs=B, seed=9, num_slots=T)
+    e_g.reset_tensor(); e_s.reset_tensor()
+    acts = torch.randint(0, 5, (T, B, 3), device="cuda", dtype=torch.int32)
+    e_g.rollout_tensor(acts)                                          # warm-up (plan), also moves the slot cursor full circle
+    for t in range(T):
+        e_s.step_tensor(acts[t])
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        slot_of = e_g.rollout_tensor(acts)
+    for rep in range(3):
+        graph.replay()
+        for t in range(T):
+            o_s = e_s.step_tensor(acts[t])
+            if rep == 2:
+                for k in ("obs", "node_obs", "adj_env", "reward", "done"):
+                    assert torch.equal(e_g.slot_outputs(slot_of[t])[k], o_s[k]), (t, k)
+    s_g, s_s = e_g.get_state(), e_s.get_state()
+    for k in s_g:
+        assert torch.equal(s_g[k], s_s[k]), k
+    e_g.close(); e_s.close()
