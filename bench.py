@@ -351,12 +351,32 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # the following steps instead of being the last thing the timer waits for.
     phase0 = (-(Wn + (K + 1) // 2)) % EPISODE
 
+    graphs = {}                                   # --graph: (phase, steps) -> captured fm_step_many launch sequence
+
+    def rollout_chunk(phase, t):
+        if not args.graph:
+            env.rollout_tensor(actions[phase:phase + t])
+            return
+        key = (phase, t, env._slot)
+        g = graphs.get(key)
+        if g is None:                             # captured during the dry run, replayed in the timed region
+            torch.cuda.synchronize(dev)
+            slot0 = env._slot
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                env.rollout_tensor(actions[phase:phase + t])
+            graphs[key] = (g, env._slot)
+            env._slot = slot0
+            g = graphs[key]
+        g[0].replay()
+        env._slot = g[1]
+
     def run_steps(n, phase):
         """n env steps from episode phase `phase`, in chunks that end at episode boundaries; every terminal step is
         followed by the statistics reduction and its all-reduce (side stream).  Returns the new phase."""
         while n > 0:
             t = min(n, EPISODE - phase)
-            env.rollout_tensor(actions[phase:phase + t])
+            rollout_chunk(phase, t)
             n -= t
             phase = (phase + t) % EPISODE
             if phase == 0:
@@ -365,6 +385,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     def prepare():
         env.reset_tensor()
+        env._slot = 0                             # same walk through the slab ring in the dry run and in the measured run
         return run_steps(phase0, 0)
 
     # dry run of the exact call sequence (plans, lazily created streams / buffers, NCCL channels), then the real one
@@ -532,8 +553,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "stats_allreduce": ("after every terminal step, side stream, joined before the timer stops" if world > 1
                                            else "local reduce after every terminal step"),
                        "episode_phase_at_start": (phase0 + Wn) % EPISODE,
-                       "launch": "fm_step_many: one persistent kernel per chunk of steps (chunks end at episode boundaries)"
-                                 if env.mapping == "aw" else "fm_step_many: env-range lanes on side streams"},
+                       "launch": ("fm_step_many: one persistent kernel per chunk of steps (chunks end at episode boundaries)"
+                                  if env.mapping == "aw" and not os.environ.get("FM_ROLL") == "0" else
+                                  "fm_step_many: env-range lanes on side streams") + (", chunks replayed as CUDA graphs" if args.graph else "")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "closed_loop": closed_loop, "edge_list": edge_list,
             "gpu_launches": launches, "clocks": clocks,
             "episode_stats": {"episodes": total_stats["episodes"], "env_steps": total_stats["env_steps"]},
@@ -560,6 +582,7 @@ def main():
     ap.add_argument("--edge-list", action="store_true", help="also time step + policy-side edge list (default on for c3)")
     ap.add_argument("--walls", type=int, default=0, choices=[0, 1, 2], help="diagnostic: num_walls (wall kernels, SURVEY N4)")
     ap.add_argument("--no-graph", action="store_true", help="c5: time the eager loop instead of the captured CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="replay every fm_step_many chunk of the timed region as a captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

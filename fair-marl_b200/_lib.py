@@ -71,6 +71,12 @@ class FmFormationState(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in FORMATION_STATE_FIELDS]
 
 
+class FmGnnConfig(C.Structure):
+    _fields_ = [("num_graphs", C.c_int32), ("graphs_per_adj", C.c_int32), ("num_entities", C.c_int32),
+                ("node_feat_dim", C.c_int32), ("embed_layers", C.c_int32), ("conv_layers", C.c_int32), ("aggr", C.c_int32),
+                ("relu", C.c_int32), ("layer_norm", C.c_int32), ("reserved_", C.c_int32), ("max_edge_dist", C.c_double)]
+
+
 class FairMarlError(RuntimeError):
     pass
 
@@ -120,6 +126,9 @@ def load():
         "fm_formation_step": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_formation_set_state": ([vp, C.POINTER(FmFormationState), vp], C.c_int),
         "fm_formation_get_state": ([vp, C.POINTER(FmFormationState), vp], C.c_int),
+        "fm_gnn_weight_floats": ([C.POINTER(FmGnnConfig)], i64),
+        "fm_gnn_supported": ([i32, i32], C.c_int),
+        "fm_gnn_forward": ([C.c_int, C.POINTER(FmGnnConfig), vp, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the ABI
@@ -134,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "fm_assign_costs", "fm_assign_positions", "fm_pair_dist", "fm_edge_list", "fm_stats_read", "fm_num_entities", "fm_mapping",
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",
     "fm_formation_create", "fm_formation_destroy", "fm_formation_reset", "fm_formation_step", "fm_formation_set_state",
-    "fm_formation_get_state",
+    "fm_formation_get_state", "fm_gnn_weight_floats", "fm_gnn_supported", "fm_gnn_forward",
 )
 
 

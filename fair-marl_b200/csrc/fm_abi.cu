@@ -64,7 +64,7 @@ struct FmHandle {
   int lockstep, host_step;
   // agent-warp mapping: persistent rollout kernel (fm_roll.cu).  Control block (zero between launches), one wave of CTAs.
   void* roll_ctl;
-  int roll_on, roll_max_ctas;
+  int roll_on, roll_max_ctas, roll_stagger_ns, roll_stagger1_ns;
   int lanes_override;        // FM_LANES (diagnostic), read once at fm_create; 0 = automatic
   // device staging for the *_host entry points (allocated on first use)
   float* st_onehot;
@@ -262,6 +262,10 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     }
     h->roll_max_ctas = per_sm * sms;
     if (const char* ev2 = getenv("FM_ROLL_CTAS")) { const int v = atoi(ev2); if (v >= 1) h->roll_max_ctas = v; }   // diagnostic
+    // start-up stagger of the CTAs of an SM (fm_roll.cu), only when the launch has several items per CTA
+    h->roll_stagger_ns = 0; h->roll_stagger1_ns = 0;
+    if (const char* ev3 = getenv("FM_ROLL_STAGGER_NS")) h->roll_stagger_ns = atoi(ev3);
+    if (const char* ev4 = getenv("FM_ROLL_STAGGER1_NS")) h->roll_stagger1_ns = atoi(ev4);
   }
   e = fm::launch_state_init(p, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
@@ -408,7 +412,8 @@ static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, con
   if (rc) return rc;
   if (h->roll_on) {                                  // agent-warp mapping: one-step launch of the persistent kernel
     FmOutputs o{p.o_obs, p.o_node, p.o_adj, p.o_rew, p.o_done, p.o_info};
-    fm::RollLaunch r{1, 1, h->roll_max_ctas, h->roll_ctl, idx, onehot, 0, &o};
+    const int tiles = (h->p.B + 31) / 32;
+    fm::RollLaunch r{1, 1, h->roll_max_ctas, tiles > h->roll_max_ctas ? h->roll_stagger1_ns : 0, h->roll_ctl, idx, onehot, 0, &o};
     FM_CUDA(fm::roll_launch(p, r, (cudaStream_t)stream));
   } else {
     FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, false));
@@ -449,7 +454,9 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
       DevParams p = h->p;
       set_outputs(p, nullptr);
       p.act_idx = nullptr; p.act_onehot = nullptr; p.reset_mask = nullptr;
-      fm::RollLaunch r{n, early, h->roll_max_ctas, h->roll_ctl, actions + (size_t)t0 * stride, nullptr, (long long)stride, outs + t0};
+      const long long items = (long long)n * ((h->p.B + 31) / 32);
+      fm::RollLaunch r{n, early, h->roll_max_ctas, items > 2LL * h->roll_max_ctas ? h->roll_stagger_ns : 0, h->roll_ctl,
+                       actions + (size_t)t0 * stride, nullptr, (long long)stride, outs + t0};
       FM_CUDA(fm::roll_launch(p, r, (cudaStream_t)stream));
       h->launches += 1;
       for (int t = 0; t < n; ++t) advance_phase(h, step_is_terminal(h));
@@ -808,6 +815,31 @@ int fm_formation_set_state(FmFormation* h, const FmFormationState* st, void* str
 
 int fm_formation_get_state(FmFormation* h, const FmFormationState* st, void* stream) {
   return formation_state_copy(h, st, false, stream, "fm_formation_get_state");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused graph-network forward (fm_policy.cu).
+int64_t fm_gnn_weight_floats(const FmGnnConfig* cfg) {
+  if (!cfg) return 0;
+  return fm::gnn_weight_count(cfg->embed_layers, cfg->conv_layers);
+}
+
+int fm_gnn_supported(int32_t num_entities, int32_t node_feat_dim) {
+  return fm::gnn_supported_entities(num_entities) && node_feat_dim >= 2 && node_feat_dim <= 17 ? 1 : 0;
+}
+
+int fm_gnn_forward(int device, const FmGnnConfig* cfg, const float* weights, const float* node_obs, const float* adj,
+                   const int32_t* agent_id, float* out, void* stream) {
+  if (!cfg || !weights || !node_obs || !adj || !out) return fail(FM_ERR_INVALID_ARG, "fm_gnn_forward: null argument");
+  if (cfg->num_graphs < 0 || cfg->graphs_per_adj < 1) return fail(FM_ERR_INVALID_ARG, "fm_gnn_forward: bad graph counts");
+  if (!fm_gnn_supported(cfg->num_entities, cfg->node_feat_dim))
+    return fail(FM_ERR_UNSUPPORTED, "fm_gnn_forward: not compiled for %d entities x %d features", cfg->num_entities, cfg->node_feat_dim);
+  if (cfg->embed_layers < 0 || cfg->embed_layers > 2 || cfg->conv_layers < 1 || cfg->conv_layers > 8 || cfg->aggr < 0 || cfg->aggr > 3)
+    return fail(FM_ERR_UNSUPPORTED, "fm_gnn_forward: embed_layers %d / conv_layers %d / aggr %d", cfg->embed_layers, cfg->conv_layers, cfg->aggr);
+  int rc = use_device(device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_gnn(*cfg, weights, node_obs, adj, agent_id, out, (cudaStream_t)stream));
+  return FM_OK;
 }
 
 }  // extern "C"

@@ -622,10 +622,7 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
     o[0] = vx; o[1] = vy; o[2] = px; o[3] = py; o[4] = gx - px; o[5] = gy - py; o[6] = fobs;
   }
   __syncthreads();                                // #3: image of the small outputs + TP / TV / TG complete; state written back
-  if (ROLL && rs.multi && rs.early && tid == 0) {  // step t of this tile is in the state block: step t + 1 may start
-    __threadfence();
-    st_release_gpu(rs.flags + rs.tile, rs.t + 1);
-  }
+  const bool release_now = ROLL && rs.multi && rs.early;   // step t of this tile is in the state block: step t + 1 may start
   // A full tile whose slices of the output arrays are 16-byte aligned (always, when the arrays are) goes out
   // as TMA bulk stores issued by one thread; ragged or unaligned tiles use vectorised st.global.cs.
   float* g_adj = (float*)io.out->adj ? (float*)io.out->adj + (size_t)env0 * L::ADJ_W : nullptr;
@@ -644,9 +641,11 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
       if (g_rew) bulk_store(g_rew, ST + L::S_REW, 32 * N * 4, pol);
       if (g_done) bulk_store(g_done, ST + L::S_DONE, 32 * N, pol);
       bulk_commit();
+      if (release_now) { __threadfence(); st_release_gpu(rs.flags + rs.tile, rs.t + 1); }   // behind the copy engine's reads
       if (g_node || !ROLL) bulk_wait_read<0>();   // the node_obs image is about to overwrite these
     }
   } else {
+    if (release_now && tid == 0) { __threadfence(); st_release_gpu(rs.flags + rs.tile, rs.t + 1); }
     if (g_adj) cta_copy_out<L::THREADS, 32 * L::ADJ_W>(g_adj, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
     if (g_obs) cta_copy_out<L::THREADS, 32 * L::OBS_W>(g_obs, ST + L::S_OBS, nenv * L::OBS_W, tid);
     if (g_rew) cta_copy_out<L::THREADS, 32 * N>(g_rew, ST + L::S_REW, nenv * N, tid);

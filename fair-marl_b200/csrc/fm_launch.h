@@ -24,6 +24,7 @@ struct RollLaunch {
   int num_steps;
   int early;                 // every step writes its own output arrays: a tile is released right after its state write-back
   int max_ctas;              // one wave: SMs x resident CTAs per SM
+  int stagger_ns;            // start-up delay per CTA slot of an SM (0: none)
   void* ctl;                 // device control block (roll_ctl_bytes), zero between launches
   const int* act_idx;        // step t reads act_idx + t * act_stride, or act_onehot + t * act_stride
   const float* act_onehot;
@@ -60,5 +61,10 @@ struct FormParams {
   const uint8_t* mask;       // reset
 };
 cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st);
+// fused graph-network forward of the rollout policy (fm_policy.cu)
+bool gnn_supported_entities(int E);
+int gnn_weight_count(int embed_layers, int conv_layers);
+cudaError_t launch_gnn(const FmGnnConfig& c, const float* weights, const float* node, const float* adj, const int* agent_id,
+                       float* out, cudaStream_t st);
 int set_error(int code, const char* fmt, ...);   // fm_last_error text (fm_abi.cu)
 }  // namespace fm

@@ -16,16 +16,19 @@
 
 namespace fm {
 
+constexpr int ROLL_MAX_SMS = 256;
 struct RollCtl {
-  unsigned long long next;   // items claimed beyond the first wave
+  unsigned long long next;   // items claimed so far
   unsigned int done;         // CTAs that have left
   unsigned int pad;
+  unsigned int sm_slot[ROLL_MAX_SMS];   // CTAs of this launch that have started on each SM (start-up stagger)
   int flags[1];              // [tiles] steps of this launch completed per tile
 };
 
 struct RollArgs {
   DevParams p;
   int T, ntiles, early;
+  int stagger_ns;            // start-up delay per CTA slot of an SM (see the kernel)
   RollCtl* ctl;
   const int* act_idx;        // step t reads act_idx + t * act_stride ([B, N] each), or
   const float* act_onehot;   //             act_onehot + t * act_stride ([B, N, 5] each)
@@ -43,23 +46,35 @@ aw_roll_kernel(const __grid_constant__ RollArgs a) {
   const int tid = threadIdx.x;
   const int total = a.T * a.ntiles;
   const bool late = a.T > 1 && a.early == 0;
-  // First wave: static (item = blockIdx.x) when all of it belongs to step 0; otherwise claimed like every other item,
-  // so that "claimed" always implies "held by a running CTA" (an item only ever waits for claimed items).
-  const bool first_static = a.ntiles >= (int)gridDim.x;
-  const int claim_base = first_static ? (int)gridDim.x : 0;
+  // Every item is claimed from the counter -- also the first one of a CTA -- so that "claimed" implies "held by a running
+  // CTA": an item only ever waits for claimed items, whatever else occupies the GPU or however large the grid is.
   AwRoll rs;
   rs.flags = a.ctl->flags; rs.prev_tile = -1; rs.prev_t = 0; rs.early = a.early != 0; rs.multi = a.T > 1;
   rs.s_next = &s_next[0]; rs.nx = 0;
   for (int k = tid; k < a.T; k += blockDim.x) s_outs[k] = a.outs[k];
-  if (!first_static && tid == 0) s_next[1] = (int)atomicAdd(&a.ctl->next, 1ull);
+  if (tid == 0) {
+    // Start-up stagger.  All CTAs of the wave start together and every item costs the same, so without it the CTAs of
+    // an SM stay in phase for the whole launch: they all compute (HBM idle), then all store (SM idle).  The k-th CTA
+    // to start on an SM waits k x stagger_ns; the phases stay spread because each CTA chains its items back to back.
+    if (a.stagger_ns > 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const unsigned k = atomicAdd(&a.ctl->sm_slot[smid % ROLL_MAX_SMS], 1u);
+      const unsigned long long wait = (unsigned long long)k * (unsigned)a.stagger_ns;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do { __nanosleep(128); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (wait > 0 && t1 - t0 < wait);
+    }
+    s_next[1] = (int)atomicAdd(&a.ctl->next, 1ull);
+  }
   __syncthreads();
-  int item = first_static ? (int)blockIdx.x : s_next[1];
+  int item = s_next[1];
   int it = 0;
   while (item < total) {
     const int t = item / a.ntiles, tile = item - t * a.ntiles;
     rs.t = t; rs.tile = tile;
     rs.s_next = &s_next[it & 1];                  // double buffered: a slow reader of the previous item's word is never overtaken
-    if (tid == 0) rs.nx = claim_base + (int)atomicAdd(&a.ctl->next, 1ull);   // consumed at barrier #0 (latency hidden behind the state loads)
+    if (tid == 0) rs.nx = (int)atomicAdd(&a.ctl->next, 1ull);   // consumed at barrier #0 (latency hidden behind the state loads)
     if (late) {
       // Late release (some steps of the launch share output arrays): the previous item's outputs must be in global
       // memory before its tile's next step may run -- and BEFORE this CTA waits, since its next item may be that step.
@@ -102,6 +117,8 @@ aw_roll_kernel(const __grid_constant__ RollArgs a) {
   if (s_last) {
     if (rs.multi)
       for (int k = tid; k < a.ntiles; k += blockDim.x) a.ctl->flags[k] = 0;
+    if (a.stagger_ns > 0)
+      for (int k = tid; k < ROLL_MAX_SMS; k += blockDim.x) a.ctl->sm_slot[k] = 0u;
     if (tid == 0) { a.ctl->next = 0ull; a.ctl->done = 0u; }
   }
 }
@@ -129,6 +146,7 @@ static cudaError_t roll_launch_no(const DevParams& p, const RollLaunch& r, cudaS
   a.T = r.num_steps;
   a.ntiles = (p.env_end - p.env_begin + 31) / 32;
   a.early = r.early;
+  a.stagger_ns = r.stagger_ns;
   a.ctl = reinterpret_cast<RollCtl*>(r.ctl);
   a.act_idx = r.act_idx; a.act_onehot = r.act_onehot; a.act_stride = r.act_stride;
   for (int t = 0; t < r.num_steps; ++t) a.outs[t] = r.outs[t];

@@ -165,9 +165,60 @@ class DenseTransformerConv(nn.Module):
         return out + self.lin_skip(x)
 
 
+_AGGR_CODE = {"node": 0, "mean": 1, "max": 2, "add": 3}
+
+
+def fused_gnn_supported(cfg: PolicyConfig, num_entities: int, graph_aggr: str) -> bool:
+    """Shape family of the fused CUDA forward (csrc/fm_policy.cu): the configuration of the shipped model_weights."""
+    from fair_marl_b200 import _lib
+    ok = (cfg.embed_hidden_size == 16 and cfg.gnn_hidden_size == 16 and cfg.gnn_num_heads == 3 and not cfg.gnn_concat_heads
+          and cfg.embed_layer_N <= 2 and cfg.num_embeddings <= 4 and cfg.embed_use_ReLU == cfg.gnn_use_ReLU
+          and (graph_aggr == "node" or cfg.global_aggr_type in ("mean", "max", "add")))
+    return bool(ok and _lib.load().fm_gnn_supported(int(num_entities), int(cfg.node_feat_dim)))
+
+
+def pack_gnn_weights(gnn: "DenseGNNBase") -> Tensor:
+    """The weight blob ``fm_gnn_forward`` reads (layout: include/fairmarl.h ``FmGnnConfig``): lin1 split into its
+    node-feature part (transposed, padded to 16 rows), the per-entity-type constant ``W_emb . embed(type) + b`` and the
+    edge-attribute column; every later matrix transposed to [in][out]; query | key | value | skip of a conv side by side."""
+    cfg, emb = gnn.cfg, gnn.embed_layer
+    H, KF = cfg.embed_hidden_size, cfg.node_feat_dim - 1
+    dev, dt = emb.lin1.weight.device, torch.float32
+    W1 = emb.lin1.weight.detach().to(dt)                                  # [H, KF + emb + 1]
+    es = cfg.embedding_size
+    parts = []
+    wn = torch.zeros(16, H, dtype=dt, device=dev)
+    wn[:KF] = W1[:, :KF].t()
+    parts.append(wn.reshape(-1))
+    ty = torch.zeros(4, H, dtype=dt, device=dev)
+    table = emb.entity_embed.weight.detach().to(dt)                        # [num_embeddings, es]
+    ty[:table.shape[0]] = table @ W1[:, KF:KF + es].t() + emb.lin1.bias.detach().to(dt)
+    parts.append(ty.reshape(-1))
+    parts.append(W1[:, KF + es].contiguous())
+
+    def ln_params(norm):
+        if isinstance(norm, nn.LayerNorm):
+            return [norm.weight.detach().to(dt), norm.bias.detach().to(dt)]
+        return [torch.ones(H, dtype=dt, device=dev), torch.zeros(H, dtype=dt, device=dev)]
+
+    parts += ln_params(emb.norm1)
+    for lin, norm in zip(emb.hidden, emb.hidden_norm):
+        parts += [lin.weight.detach().to(dt).t().reshape(-1), lin.bias.detach().to(dt)] + ln_params(norm)
+    for conv in [gnn.gnn1] + list(gnn.gnn2):
+        Wc = torch.cat([conv.lin_query.weight, conv.lin_key.weight, conv.lin_value.weight, conv.lin_skip.weight], dim=0).detach().to(dt)
+        bc = torch.cat([conv.lin_query.bias, conv.lin_key.bias, conv.lin_value.bias, conv.lin_skip.bias]).detach().to(dt)
+        parts += [Wc.t().reshape(-1), bc, conv.lin_edge.weight.detach().to(dt).reshape(-1)]
+    return torch.cat([x.reshape(-1) for x in parts]).contiguous()
+
+
 class DenseGNNBase(nn.Module):
     """``GNNBase.forward`` (gnn_new.py:555-575) = process_adj -> EmbedConv -> act(TransformerConv) x (1 + layer_N)
-    -> node gather (``graph_aggr='node'``) or global pool."""
+    -> node gather (``graph_aggr='node'``) or global pool.
+
+    Two implementations of the same function: ``forward`` with ``adj_env=None`` is plain PyTorch (any configuration,
+    any device); with ``adj_env=(adj [B, E, E], graphs_per_adj)`` on a CUDA device and a supported configuration
+    (``fused_gnn_supported``) the whole base is ONE launch of the fused kernel ``fm_gnn_forward`` (csrc/fm_policy.cu),
+    which reads the adjacency once per env.  Inference only (no autograd through the fused path)."""
 
     def __init__(self, cfg: PolicyConfig, graph_aggr: str):
         super().__init__()
@@ -180,9 +231,49 @@ class DenseGNNBase(nn.Module):
         self.act = _act(cfg.gnn_use_ReLU)
         self.out_dim = cfg.gnn_out_dim
 
-    def forward(self, node_obs: Tensor, adj: Tensor, agent_id: Tensor) -> Tensor:
+    def fused_available(self, node_obs: Tensor) -> bool:
+        return (node_obs.is_cuda and not torch.is_grad_enabled() and node_obs.dtype == torch.float32
+                and fused_gnn_supported(self.cfg, node_obs.shape[1], self.graph_aggr))
+
+    def _packed(self) -> Tensor:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_pack_key", None) != key:
+            self._pack_key, self._pack = key, pack_gnn_weights(self)
+        return self._pack
+
+    def forward_fused(self, node_obs: Tensor, adj_env: Tensor, graphs_per_adj: int, agent_id: Optional[Tensor]) -> Tensor:
+        """One launch of ``fm_gnn_forward``.  node_obs [M, E, F] contiguous fp32; adj_env [M / graphs_per_adj, E, E];
+        agent_id [M] or [M, 1] node indices (aggr 'node')."""
+        import ctypes as C
+        from fair_marl_b200 import _lib
+        cfg = self.cfg
+        M, E, F = node_obs.shape
+        if not node_obs.is_contiguous() or not adj_env.is_contiguous() or adj_env.shape[0] * graphs_per_adj != M:
+            raise ValueError("forward_fused: node_obs / adj_env must be contiguous and adj_env.shape[0] * graphs_per_adj == M")
+        aggr = 0 if self.graph_aggr == "node" else _AGGR_CODE[cfg.global_aggr_type]
+        c = _lib.FmGnnConfig(num_graphs=M, graphs_per_adj=int(graphs_per_adj), num_entities=E, node_feat_dim=F,
+                             embed_layers=cfg.embed_layer_N, conv_layers=1 + cfg.gnn_layer_N, aggr=aggr,
+                             relu=int(cfg.gnn_use_ReLU), layer_norm=int(cfg.use_feature_normalization),
+                             max_edge_dist=float(cfg.max_edge_dist))
+        w = self._packed()
+        aid = None
+        if aggr == 0:
+            if agent_id is None or agent_id.numel() != M:
+                raise ValueError("forward_fused: aggr 'node' gathers ONE node per graph (agent_id [M])")
+            aid = agent_id.reshape(M).to(torch.int32).contiguous()
+        out = torch.empty((M, cfg.gnn_hidden_size), dtype=torch.float32, device=node_obs.device)
+        stream = torch.cuda.current_stream(node_obs.device).cuda_stream
+        _lib.check(_lib.load().fm_gnn_forward(node_obs.device.index, C.byref(c), w.data_ptr(), node_obs.data_ptr(),
+                                              adj_env.data_ptr(), aid.data_ptr() if aid is not None else None,
+                                              out.data_ptr(), stream), "fm_gnn_forward")
+        return out
+
+    def forward(self, node_obs: Tensor, adj: Tensor, agent_id: Tensor, adj_env: Optional[Tuple[Tensor, int]] = None) -> Tensor:
         """node_obs [M, E, F]; adj [M, E, E] (any stride, e.g. the env's matrix expanded over its agents);
-        agent_id [M, k] integer node indices."""
+        agent_id [M, k] integer node indices.  ``adj_env``: see the class docstring."""
+        if adj_env is not None and (self.graph_aggr != "node" or agent_id.numel() == node_obs.shape[0]) \
+                and self.fused_available(node_obs):
+            return self.forward_fused(node_obs.contiguous(), adj_env[0], adj_env[1], agent_id)
         mask = edge_mask(adj, self.cfg.max_edge_dist)
         x = self.embed_layer(node_obs, adj, mask)
         x = self.act(self.gnn1(x, adj, mask))
@@ -267,8 +358,8 @@ class DenseGraphActor(_Trunk):
         super().__init__(cfg, cfg.actor_graph_aggr, cfg.obs_dim)
         self.action_out = nn.Linear(cfg.hidden_size, cfg.action_dim)
 
-    def features(self, obs, node_obs, adj, agent_id, rnn_states, masks):
-        nbd = self.gnn_base(node_obs, adj, agent_id)
+    def features(self, obs, node_obs, adj, agent_id, rnn_states, masks, adj_env=None):
+        nbd = self.gnn_base(node_obs, adj, agent_id, adj_env=adj_env)
         x = self.base(torch.cat([obs, nbd], dim=1))
         if self.recurrent:
             x, rnn_states = self.rnn(x, rnn_states, masks)
@@ -276,9 +367,11 @@ class DenseGraphActor(_Trunk):
 
     def forward(self, obs: Tensor, node_obs: Tensor, adj: Tensor, agent_id: Tensor, rnn_states: Tensor, masks: Tensor,
                 available_actions: Optional[Tensor] = None, deterministic: bool = False,
-                generator: Optional[torch.Generator] = None) -> Tuple[Tensor, Tensor, Tensor]:
-        """-> (actions [M,1] int64, action_log_probs [M,1], rnn_states [M,recurrent_N,hidden])."""
-        x, rnn_states = self.features(obs, node_obs, adj, agent_id, rnn_states, masks)
+                generator: Optional[torch.Generator] = None,
+                adj_env: Optional[Tuple[Tensor, int]] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """-> (actions [M,1] int64, action_log_probs [M,1], rnn_states [M,recurrent_N,hidden]).
+        ``adj_env = (adj [B, E, E], graphs_per_adj)`` selects the fused CUDA graph network (``DenseGNNBase``)."""
+        x, rnn_states = self.features(obs, node_obs, adj, agent_id, rnn_states, masks, adj_env=adj_env)
         logits = self.action_out(x)
         if available_actions is not None:                                   # distributions.py:86-88
             logits = logits.masked_fill(available_actions == 0, -1e10)
@@ -300,8 +393,8 @@ class DenseGraphCritic(_Trunk):
         self.v_out = nn.Linear(cfg.hidden_size, 1)
 
     def forward(self, cent_obs: Optional[Tensor], node_obs: Tensor, adj: Tensor, agent_id: Tensor, rnn_states: Tensor,
-                masks: Tensor) -> Tuple[Tensor, Tensor]:
-        nbd = self.gnn_base(node_obs, adj, agent_id)
+                masks: Tensor, adj_env: Optional[Tuple[Tensor, int]] = None) -> Tuple[Tensor, Tensor]:
+        nbd = self.gnn_base(node_obs, adj, agent_id, adj_env=adj_env)
         x = torch.cat([cent_obs, nbd], dim=1) if self.cfg.use_cent_obs else nbd
         x = self.base(x)
         if self.recurrent:

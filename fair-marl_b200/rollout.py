@@ -131,7 +131,8 @@ class RolloutCollector:
     ``[graphs, E, E, hidden]`` activations)."""
 
     def __init__(self, env, actor, critic, buffer: Optional[DeviceRolloutBuffer] = None, deterministic: bool = False,
-                 max_graphs: int = 1 << 17, generator: Optional[torch.Generator] = None, **buffer_kw):
+                 max_graphs: int = 1 << 17, generator: Optional[torch.Generator] = None, fused: Optional[bool] = None,
+                 **buffer_kw):
         self.env, self.actor, self.critic = env, actor, critic
         cfg = actor.cfg
         if buffer is None:
@@ -141,6 +142,17 @@ class RolloutCollector:
         self.buffer = buffer
         self.deterministic, self.max_graphs, self.generator = deterministic, int(max_graphs), generator
         self._graph = None
+        # fused CUDA graph network (csrc/fm_policy.cu) when both bases are in its shape family; else the dense torch modules
+        from fair_marl_b200.policy import fused_gnn_supported
+        E = env.num_entities
+        self.fused = bool(fused) if fused is not None else (
+            env.device.type == "cuda" and fused_gnn_supported(actor.cfg, E, actor.gnn_base.graph_aggr)
+            and fused_gnn_supported(critic.cfg, E, critic.gnn_base.graph_aggr)
+            and not (critic.cfg.critic_graph_aggr == "node"))
+        if cfg.use_cent_obs or critic.cfg.critic_graph_aggr == "node":
+            # GR_Critic concatenates cent_obs / gathers the N agents' rows via share_agent_id (graph_actor_critic.py:323-397);
+            # this loop feeds neither: refuse instead of crashing inside the MLP
+            raise NotImplementedError("RolloutCollector: use_cent_obs / critic_graph_aggr='node' are not wired into the device loop")
 
     def warmup(self) -> None:
         """``GMPERunner.warmup`` (:178-203): reset the envs; the observation lands in slab 0."""
@@ -163,10 +175,11 @@ class RolloutCollector:
         per = max(N, (self.max_graphs // N) * N)
         for lo in range(0, M, per):
             hi = min(M, lo + per)
-            adj_c = adj[lo // N:hi // N].reshape(hi - lo, E, E)
+            adj_c = adj[lo // N:hi // N].reshape(hi - lo, E, E) if not self.fused else None   # stride-0 view materialised only for the torch path
+            adj_e = (b.adj_env[t][lo // N:hi // N], N) if self.fused else None               # fused graph network: adj once per env
             a, lp, h = self.actor(obs[lo:hi], node[lo:hi], adj_c, aid[lo:hi], rnn[lo:hi], masks[lo:hi],
-                                  deterministic=self.deterministic, generator=self.generator)
-            v, hc = self.critic(None, node[lo:hi], adj_c, aid[lo:hi], rnn_c[lo:hi], masks[lo:hi])
+                                  deterministic=self.deterministic, generator=self.generator, adj_env=adj_e)
+            v, hc = self.critic(None, node[lo:hi], adj_c, aid[lo:hi], rnn_c[lo:hi], masks[lo:hi], adj_env=adj_e)
             outs.append((v, a, lp, h, hc))
         if len(outs) == 1:
             return outs[0]
@@ -218,5 +231,6 @@ class RolloutCollector:
         M = B * N
         adj = b.adj_env[-1].unsqueeze(1).expand(B, N, E, E).reshape(M, E, E)
         v, _ = self.critic(None, b.node_obs[-1].view(M, E, -1), adj, b.agent_id[-1].reshape(M, 1),
-                           b.rnn_states_critic[-1].view(M, *b.rnn_states.shape[3:]), b.masks[-1].view(M, 1))
+                           b.rnn_states_critic[-1].view(M, *b.rnn_states.shape[3:]), b.masks[-1].view(M, 1),
+                           adj_env=(b.adj_env[-1], N) if self.fused else None)
         b.compute_returns(v)

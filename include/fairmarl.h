@@ -261,6 +261,39 @@ int fm_formation_step(FmFormation* h, const int32_t* actions, const FmOutputs* o
 int fm_formation_set_state(FmFormation* h, const FmFormationState* st, void* stream);
 int fm_formation_get_state(FmFormation* h, const FmFormationState* st, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused graph-network forward of the rollout policy.
+ * Replaces GNNBase.forward (onpolicy/algorithms/utils/gnn_new.py:555-575): process_adj (:381-413) -> EmbedConv
+ * (:23-141) -> act(TransformerConv) x conv_layers (:252-271) -> node gather / global pool, for `num_graphs` graphs of
+ * `num_entities` nodes each, in one kernel launch.  Shape family: embed_hidden_size = gnn_hidden_size = 16,
+ * gnn_num_heads = 3, gnn_concat_heads = False (every shipped model_weights config).
+ *   weights   device, fm_gnn_weight_floats() floats, packed as (row-major, H = 16):
+ *               Wn[16][H]   lin1 weight, node-feature part, transposed; rows >= node_feat_dim - 1 zero
+ *               T[4][H]     lin1[:, emb part] . entity_embed[type] + lin1 bias
+ *               wd[H]       lin1 weight column of the edge attribute
+ *               ln1 gamma[H], beta[H]
+ *               embed_layers x { Wh[H in][H out], b[H], gamma[H], beta[H] }
+ *               conv_layers  x { W[H][160] = [query | key | value | skip] transposed, b[160], w_edge[48] }
+ *   node_obs  device [num_graphs, E, node_feat_dim]  (last column: entity type)
+ *   adj       device [num_graphs / graphs_per_adj, E, E]: graph m reads matrix m / graphs_per_adj
+ *   agent_id  device int32 [num_graphs] node gathered when aggr == 0 (NULL: m % graphs_per_adj)
+ *   out       device [num_graphs, 16]
+ */
+typedef struct FmGnnConfig {
+  int32_t num_graphs, graphs_per_adj, num_entities, node_feat_dim;
+  int32_t embed_layers;     /* embed_layer_N (hidden layers of EmbedConv after lin1), 0..2 */
+  int32_t conv_layers;      /* 1 + gnn_layer_N */
+  int32_t aggr;             /* 0 node gather, 1 global mean, 2 global max, 3 global add */
+  int32_t relu;             /* 1 ReLU, 0 Tanh (embed_use_ReLU == gnn_use_ReLU) */
+  int32_t layer_norm;       /* use_feature_normalization */
+  int32_t reserved_;
+  double max_edge_dist;
+} FmGnnConfig;
+int64_t fm_gnn_weight_floats(const FmGnnConfig* cfg);
+int fm_gnn_supported(int32_t num_entities, int32_t node_feat_dim);   /* 1 if the kernel is compiled for this graph size */
+int fm_gnn_forward(int device, const FmGnnConfig* cfg, const float* weights, const float* node_obs, const float* adj,
+                   const int32_t* agent_id, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,8 +17,8 @@ def pytest_configure(config):
 def pytest_generate_tests(metafunc):
     """Every GPU test runs under both kernel mappings: 'auto' (agent-warp where compiled, i.e. the
     product default) and 'group' (group-per-env kernels forced)."""
-    if metafunc.module.__name__.endswith("test_gpu_formation"):
-        return                                  # the formation kernels have one mapping (thread per env)
+    if metafunc.module.__name__.endswith(("test_gpu_formation", "test_gpu_policy")):
+        return                                  # kernels with a single mapping
     if metafunc.definition.get_closest_marker("gpu") and "kernel_mapping" in metafunc.fixturenames:
         metafunc.parametrize("kernel_mapping", ["auto", "group"], indirect=True)
 
@@ -31,11 +31,22 @@ def kernel_mapping(request):
     parity_util.MAPPING = "auto"
 
 
+def _gpu_ready() -> bool:
+    try:
+        import torch
+        from fair_marl_b200.build import library_path
+        return torch.cuda.is_available() and os.path.isfile(library_path())
+    except Exception:
+        return False
+
+
 def pytest_collection_modifyitems(config, items):
     from oracle.reference_shim import reference_available
-    if reference_available():
-        return
-    skip = pytest.mark.skip(reason="/root/reference not present")
+    have_ref, have_gpu = reference_available(), _gpu_ready()
+    skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    skip_gpu = pytest.mark.skip(reason="no CUDA device (or libfairmarl.so not built): GPU parity tests run on the B200 box")
     for item in items:
-        if "reference" in item.keywords:
-            item.add_marker(skip)
+        if not have_ref and "reference" in item.keywords:
+            item.add_marker(skip_ref)
+        if not have_gpu and "gpu" in item.keywords:
+            item.add_marker(skip_gpu)
