@@ -51,6 +51,9 @@ CONFIGS = {
     "c4": dict(agents=16, obstacles=3, envs=131072, rew=5.0, fairness=True,
                workload="navigation_graph 16 agents / 16 goals / 3 obstacles, FA+FR, 131072 envs per GPU (1M over 8), random actions"),
     # config 5: the rollout loop (policy forward in torch + simulator step + buffer insert), all on the device
+    # widened row N3 (diagnostic): the formation-family scenario of BASELINE config 2's wording, on its own kernels
+    "form": dict(agents=3, obstacles=3, envs=65536, rew=30.0, fairness=True,
+                 workload="nav_fairassign_fairrew_formation_graph 3 agents / 3 goals / 3 obstacles, FA+FR, 65536 envs, random actions"),
     "c5": dict(agents=3, obstacles=3, envs=65536, rew=30.0, fairness=True,
                workload="rmappo rollout loop at 3 agents: dense GNN actor + critic forward (torch) -> fused simulator step writing "
                         "the device-resident rollout buffer -> insert; sampled actions"),
@@ -312,6 +315,81 @@ def run_rollout(args, rank: int, local_rank: int, world: int):
                                 "api": "step_tensor(out=buffer slab): one launch per step"},
             "gpu_launches": launches, "clocks": clocks,
             "mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_formation(args, rank: int, local_rank: int, world: int):
+    """Widened row N3 (diagnostic line, not the headline): the formation-family scenario the shipped weights were trained on
+    (nav_fairassign_fairrew_formation_graph, 3 agents / 3 goals / 3 obstacles, FA+FR, reward 30, per-step lexifair
+    re-assignment) -- one fm_formation_step launch per step, random actions, auto-reset inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    import fair_marl_b200 as fm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.envs, args.steps, max(args.warmup, 3)
+    N, O = N_AGENTS, N_OBST
+    E = 2 * N + O
+    cfg = fm.FormationSimConfig(num_agents=N, num_obstacles=O, goal_rew=GOAL_REW, collision_rew=COLL_REW, episode_length=EPISODE,
+                                fairness_reward=FAIRNESS, info_every_step=False)
+    env = fm.B200FormationVecEnv(cfg, num_envs=B, device=local_rank, seed=0, env_offset=rank * B, num_slots=args.form_slots)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.randint(0, 5, (EPISODE, B, N), generator=g, device=dev, dtype=torch.int32)
+    env.reset_tensor()
+    for k in range(W):
+        env.step_tensor(actions[k % EPISODE])
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank, period=0.0005)
+    sampler.start()
+    time.sleep(0.02)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(K):
+        env.step_tensor(actions[(W + k) % EPISODE])
+    ev1.record()
+    sampler.sample_now()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary(t0, t1)
+    sampler.stop()
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    # algorithmic bytes per env-step, counted like SURVEY 8(d): state read once + dynamic state written once + every output once
+    words = (17 * N + 2 * O + 4 + N / 4) + (14 * N + 3 + N / 4) + (11 * N + 13 * N * E + E * E + N + N / 4)
+    alg_bytes = int(words * 4 * B)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.isfile(peaks_path) else 6650.0
+    achieved = alg_bytes / (elapsed_ms / K * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "agent-steps/sec, formation-family step+obs+reward+per-step assignment", "value": B * world * N * K / (elapsed_ms * 1e-3),
+            "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 logic / f32 state", "data": "synthetic",
+            "config": {"workload": "nav_fairassign_fairrew_formation_graph 3 agents / 3 goals / 3 obstacles, FA+FR, goal_rew=collision_rew=30, "
+                                   "episode_length 25 with auto-reset, lexifair re-assignment every step, random actions",
+                       "envs_per_gpu": B, "envs_total": B * world, "agents": N, "entities": E,
+                       "l2": f"outputs cycle through {args.form_slots} buffer sets ({args.form_slots * B * (11 * N + 13 * N * E + E * E + N) * 4 / 1e9:.2f} GB > 126 MB L2)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": f"fm::formation_kernel<{N}, 0>", "algorithmic_bytes_per_step": alg_bytes},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     env.close()
@@ -582,6 +660,7 @@ def main():
     ap.add_argument("--edge-list", action="store_true", help="also time step + policy-side edge list (default on for c3)")
     ap.add_argument("--walls", type=int, default=0, choices=[0, 1, 2], help="diagnostic: num_walls (wall kernels, SURVEY N4)")
     ap.add_argument("--no-graph", action="store_true", help="c5: time the eager loop instead of the captured CUDA graph")
+    ap.add_argument("--form-slots", type=int, default=8, help="form: output buffer sets the steps cycle through")
     ap.add_argument("--graph", action="store_true", help="replay every fm_step_many chunk of the timed region as a captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -599,6 +678,9 @@ def main():
         raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus}")
     if args.config == "c5":
         run_rollout(args, rank, local_rank, world)
+        return
+    if args.config == "form":
+        run_formation(args, rank, local_rank, world)
         return
     run_ours(args, rank, local_rank, world)
 

@@ -56,7 +56,8 @@ class FmFormationConfig(C.Structure):
         ("env_offset", C.c_int64), ("seed", C.c_uint64),
         ("world_size", C.c_double), ("max_speed", C.c_double), ("collision_rew", C.c_double), ("goal_rew", C.c_double),
         ("min_dist_thresh", C.c_double), ("min_obs_dist", C.c_double), ("fair_rew", C.c_double), ("zeroshift", C.c_double),
-        ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32), ("reserved_", C.c_int32),
+        ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32), ("assignment", C.c_int32),
+        ("info_every_step", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -75,6 +76,11 @@ class FmGnnConfig(C.Structure):
     _fields_ = [("num_graphs", C.c_int32), ("graphs_per_adj", C.c_int32), ("num_entities", C.c_int32),
                 ("node_feat_dim", C.c_int32), ("embed_layers", C.c_int32), ("conv_layers", C.c_int32), ("aggr", C.c_int32),
                 ("relu", C.c_int32), ("layer_norm", C.c_int32), ("reserved_", C.c_int32), ("max_edge_dist", C.c_double)]
+
+
+class FmHeadConfig(C.Structure):
+    _fields_ = [("num_rows", C.c_int32), ("obs_dim", C.c_int32), ("layers", C.c_int32), ("recurrent", C.c_int32),
+                ("feature_norm", C.c_int32), ("relu", C.c_int32), ("num_outputs", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class FairMarlError(RuntimeError):
@@ -129,6 +135,8 @@ def load():
         "fm_gnn_weight_floats": ([C.POINTER(FmGnnConfig)], i64),
         "fm_gnn_supported": ([i32, i32], C.c_int),
         "fm_gnn_forward": ([C.c_int, C.POINTER(FmGnnConfig), vp, vp, vp, vp, vp, vp], C.c_int),
+        "fm_head_weight_floats": ([C.POINTER(FmHeadConfig)], i64),
+        "fm_policy_head": ([C.c_int, C.POINTER(FmHeadConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the ABI
@@ -144,6 +152,7 @@ EXPORTED_SYMBOLS = (
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",
     "fm_formation_create", "fm_formation_destroy", "fm_formation_reset", "fm_formation_step", "fm_formation_set_state",
     "fm_formation_get_state", "fm_gnn_weight_floats", "fm_gnn_supported", "fm_gnn_forward",
+    "fm_head_weight_floats", "fm_policy_head",
 )
 
 

@@ -735,9 +735,14 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   if (!cfg || !out) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: null argument");
   *out = nullptr;
   if (cfg->num_envs <= 0) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_envs must be > 0 (got %d)", cfg->num_envs);
-  if (cfg->num_agents < 2 || cfg->num_agents > 4)
-    return fail(FM_ERR_UNSUPPORTED, "fm_formation_create: num_agents must be 2..4 (got %d): the observation needs a second goal, "
-                "and the per-thread lexifair enumerates permutations", cfg->num_agents);
+  if (cfg->num_agents < 2 || cfg->num_agents > fm::formation_max_agents())
+    return fail(FM_ERR_UNSUPPORTED, "fm_formation_create: num_agents must be 2..%d (got %d): the observation needs a second goal",
+                fm::formation_max_agents(), cfg->num_agents);
+  if (cfg->assignment < 0 || cfg->assignment > 2) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: assignment must be 0 (fair), 1 (optimal) or 2 (random)");
+  if (cfg->assignment != 0 && cfg->fairness_reward)
+    return fail(FM_ERR_INVALID_ARG, "fm_formation_create: the base formation scenarios (optimal / random assignment) have no fairness term");
+  if (cfg->assignment == 1 && cfg->num_agents > 5)
+    return fail(FM_ERR_UNSUPPORTED, "fm_formation_create: the min-sum matching enumerates permutations (num_agents <= 5, got %d)", cfg->num_agents);
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > FM_FORMATION_MAX_OBSTACLES)
     return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_obstacles must be in 0..%d (got %d)", FM_FORMATION_MAX_OBSTACLES, cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: episode_length must be >= 1");
@@ -753,6 +758,7 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   p.B = cfg->num_envs; p.N = cfg->num_agents; p.O = cfg->num_obstacles; p.episode_length = cfg->episode_length;
   p.fairness_reward = cfg->fairness_reward; p.collaborative = cfg->collaborative; p.auto_reset = cfg->auto_reset;
   p.has_max_speed = cfg->max_speed > 0.0; p.env_offset = cfg->env_offset;
+  p.assignment = cfg->assignment; p.info_every_step = cfg->info_every_step;
   p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
   p.world_size = cfg->world_size; p.max_speed = cfg->max_speed; p.collision_rew = cfg->collision_rew; p.goal_rew = cfg->goal_rew;
   p.min_dist_thresh = cfg->min_dist_thresh; p.min_obs_dist = cfg->min_obs_dist; p.fair_rew = cfg->fair_rew; p.zeroshift = cfg->zeroshift;
@@ -839,6 +845,25 @@ int fm_gnn_forward(int device, const FmGnnConfig* cfg, const float* weights, con
   int rc = use_device(device);
   if (rc) return rc;
   FM_CUDA(fm::launch_gnn(*cfg, weights, node_obs, adj, agent_id, out, (cudaStream_t)stream));
+  return FM_OK;
+}
+
+int64_t fm_head_weight_floats(const FmHeadConfig* cfg) {
+  if (!cfg) return 0;
+  return fm::head_weight_count(cfg->layers, cfg->recurrent);
+}
+
+int fm_policy_head(int device, const FmHeadConfig* cfg, const float* weights, const float* obs, const float* nbd,
+                   const float* rnn_in, const float* mask, const float* u, float* rnn_out, float* logp, int64_t* action,
+                   float* value, void* stream) {
+  if (!cfg || !weights || !nbd) return fail(FM_ERR_INVALID_ARG, "fm_policy_head: null argument");
+  if (cfg->obs_dim < 0 || cfg->obs_dim > 16 || (cfg->obs_dim > 0 && !obs)) return fail(FM_ERR_INVALID_ARG, "fm_policy_head: obs_dim must be 0..16 (with obs)");
+  if (cfg->layers < 0 || cfg->layers > 2 || cfg->num_outputs < 1 || cfg->num_outputs > 8) return fail(FM_ERR_UNSUPPORTED, "fm_policy_head: layers %d / outputs %d", cfg->layers, cfg->num_outputs);
+  if (cfg->recurrent && (!rnn_in || !mask || !rnn_out)) return fail(FM_ERR_INVALID_ARG, "fm_policy_head: recurrent head needs rnn_in, mask, rnn_out");
+  if (!value && (!logp || !action)) return fail(FM_ERR_INVALID_ARG, "fm_policy_head: actor head needs logp and action (or pass value for the critic)");
+  int rc = use_device(device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_head(*cfg, weights, obs, nbd, rnn_in, mask, u, rnn_out, logp, (long long*)action, value, (cudaStream_t)stream));
   return FM_OK;
 }
 

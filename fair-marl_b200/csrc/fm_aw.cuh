@@ -190,6 +190,8 @@ struct AwRoll {
   bool multi;        // the launch has more than one step (flags are in use)
   int* s_next;       // shared-memory word: the CTA's next item, published by thread 0 at barrier #0
   int nx;            // thread 0: the item it claimed for the next iteration
+  int total, ntiles; // items of the launch, tiles per step
+  bool next_ready;   // this thread has already seen the next item's dependency flag satisfied (polled early)
 };
 
 // The (N, O) pairs compiled for this mapping.  Everything else runs the group-per-env kernels.
@@ -389,6 +391,16 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
       static_block(sd0);
     }
     __syncthreads();                              // #1: new agent positions, static positions (env warp) visible
+    if (ROLL && rs.multi) {
+      // The next item of this CTA was published at barrier #0: look at its tile's flag NOW, so that the round trip of the
+      // acquire load is hidden behind this item's compute instead of sitting in front of the next item's state loads.
+      const int nitem = *rs.s_next;
+      rs.next_ready = true;
+      if (nitem < rs.total) {
+        const int nt = nitem / rs.ntiles, ntile = nitem - nt * rs.ntiles;
+        if (nt > 0) rs.next_ready = ld_acquire_gpu(rs.flags + ntile) >= nt;
+      }
+    }
     nstep = step + 1;                              // environment.py:819, :823
     done = nstep >= p.episode_length;              // environment.py:237-247 (agent.status is never set)
     do_reset = venv && done && (p.auto_reset != 0);
@@ -622,7 +634,9 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
     o[0] = vx; o[1] = vy; o[2] = px; o[3] = py; o[4] = gx - px; o[5] = gy - py; o[6] = fobs;
   }
   __syncthreads();                                // #3: image of the small outputs + TP / TV / TG complete; state written back
-  const bool release_now = ROLL && rs.multi && rs.early;   // step t of this tile is in the state block: step t + 1 may start
+  // Step t of this tile is in the state block: step t + 1 may start.  Released by the first lane of the env warp (which has
+  // nothing else to do here), so that thread 0 goes straight to the bulk stores instead of sitting in the fence.
+  if (ROLL && rs.multi && rs.early && tid == N * 32) { __threadfence(); st_release_gpu(rs.flags + rs.tile, rs.t + 1); }
   // A full tile whose slices of the output arrays are 16-byte aligned (always, when the arrays are) goes out
   // as TMA bulk stores issued by one thread; ragged or unaligned tiles use vectorised st.global.cs.
   float* g_adj = (float*)io.out->adj ? (float*)io.out->adj + (size_t)env0 * L::ADJ_W : nullptr;
@@ -641,11 +655,9 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
       if (g_rew) bulk_store(g_rew, ST + L::S_REW, 32 * N * 4, pol);
       if (g_done) bulk_store(g_done, ST + L::S_DONE, 32 * N, pol);
       bulk_commit();
-      if (release_now) { __threadfence(); st_release_gpu(rs.flags + rs.tile, rs.t + 1); }   // behind the copy engine's reads
       if (g_node || !ROLL) bulk_wait_read<0>();   // the node_obs image is about to overwrite these
     }
   } else {
-    if (release_now && tid == 0) { __threadfence(); st_release_gpu(rs.flags + rs.tile, rs.t + 1); }
     if (g_adj) cta_copy_out<L::THREADS, 32 * L::ADJ_W>(g_adj, ST + L::S_ADJ, nenv * L::ADJ_W, tid);
     if (g_obs) cta_copy_out<L::THREADS, 32 * L::OBS_W>(g_obs, ST + L::S_OBS, nenv * L::OBS_W, tid);
     if (g_rew) cta_copy_out<L::THREADS, 32 * N>(g_rew, ST + L::S_REW, nenv * N, tid);

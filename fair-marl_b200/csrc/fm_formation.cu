@@ -1,25 +1,41 @@
-// Formation-family scenarios on the device: a first, correctness-first CUDA path.
+// Formation-family scenarios on the device.
 //
-// Reference: multiagent/custom_scenarios/nav_fairassign_fairrew_formation_graph.py (FA+FR) and
-// nav_fairassign_nofairrew_formation_graph.py (FA), driven by MultiAgentGraphEnv.step (environment.py:816-877) over
-// World.step (core.py:250-404).  oracle/formation.py is the float64 restatement these kernels are tested against
-// (pinned to 755 steps of the unmodified reference).
+// Reference: multiagent/custom_scenarios/nav_fairassign_fairrew_formation_graph.py (FA+FR), its twin
+// nav_fairassign_nofairrew_formation_graph.py (FA), and the base scenarios nav_base_formation_graph_mask.py (OA: the reward
+// distance is the agent's entry of the min-sum matching re-solved in agent 0's reward call, :666-706) and
+// nav_base_formation_graph_randomgoal.py (RA: a random permutation drawn at reset, :258-259), driven by
+// MultiAgentGraphEnv.step (environment.py:816-877) over World.step (core.py:250-404).  oracle/formation.py is the float64
+// restatement these kernels are tested against (pinned to 1 733 steps of the unmodified reference).
 //
-// Mapping: ONE THREAD PER ENV.  The per-agent loop of MultiAgentGraphEnv.step is inherently sequential in this family
-// (agent i's observation rewrites the goal-occupancy table agent i + 1 reads, agent 0's reward call re-solves the
-// assignment, a latching agent's velocity is zeroed between its observation and its node rows), and teams are small
-// (N <= 4 here: lexifair by enumeration in registers, fm_small.cuh), so a thread walks the reference's own order with
-// the whole env in registers / local memory; lanes of a warp are 32 consecutive envs.  All arithmetic is float64 like
-// the reference; the state is stored as float32 in API layout (no transposes: fm_formation_get/set_state are plain
-// copies).  Outputs are written straight in API layout (per-thread contiguous runs; staging them through shared memory
-// for coalesced stores is the next step for this kernel -- it is not tuned).
+// Mapping.  The per-agent loop of MultiAgentGraphEnv.step is inherently sequential in this family (agent i's observation
+// rewrites the goal-occupancy table agent i + 1 reads, agent 0's reward call re-solves the assignment, a latching agent's
+// velocity is zeroed between its observation and its node rows), so the LOGIC runs one thread per env, lanes of a warp =
+// 32 consecutive envs, walking the reference's own order with the env in registers / local memory (float64 like the
+// reference, except the softplus contact terms, which are the fp32 hardware-approximation form of the navigation
+// kernels).  What a thread produces is not the output rows but their RECIPE, in warp-private shared memory:
+//   obs / adj / reward / done   lane = env images in API layout (the warp's slice of each array is one contiguous range)
+//   node_obs                    positions + per ego agent i the velocities and the goal picks (goal, occupied, history) of
+//                               the N agents as they stood when ego i's rows were built (6 N^2 + 2 E floats per env)
+// and the EMISSION is warp-cooperative: the images go out as TMA bulk stores; the 13-float node rows are rebuilt from the
+// recipe, 3 consecutive rows per lane into a 96-row staging buffer (lane stride 39 floats: conflict free) that the copy
+// engine streams out while the warp builds the next one (double buffered inside the adj image once that has been read).
+// Round 1's kernel wrote 468-byte row runs per lane (32 sectors per store instruction, 8.5 % of the HBM roofline).
+//
+// The device functions below are also compiled for the host by tests/test_kernel_source_host.py (g++, ASan + UBSan,
+// tests/host_emul/prelude.h stands in for the CUDA built-ins): the per-env logic and the row builder are checked against
+// the oracle on the CPU; only the warp-level emission (form_emit) is GPU-only.
 #include "fm_device.cuh"
 #include "fm_launch.h"
 #include "fm_small.cuh"
 
+#ifndef FM_SQRT64
+#define FM_SQRT64 dsqrt_fast      // correctly rounded, branch free (fm_device.cuh); the host build uses sqrt
+#endif
+
 namespace fm {
 
 constexpr int F_OBS = FM_FORMATION_OBS_DIM, F_NODE = FM_FORMATION_NODE_FEAT_DIM, F_MAXO = FM_FORMATION_MAX_OBSTACLES;
+constexpr int F_ROWS_PER_LANE = 3, F_CHUNK_ROWS = 32 * F_ROWS_PER_LANE, F_CHUNK_WORDS = F_CHUNK_ROWS * F_NODE;   // 96 rows, 1248 floats
 
 template <int N>
 struct FEnv {
@@ -31,8 +47,19 @@ struct FEnv {
   int step, episode;
 };
 
+// Where one env's thread writes (shared memory on the device, lane = env; plain arrays in the host harness).
+struct FOut {
+  float* obs;      // [N][11]
+  float* adj;      // [E][E]
+  float* rew;      // [N]
+  uint8_t* done;   // [N]
+  float* rec;      // recipe of the node rows: pos [E][2] | per ego i: vel [N][2], pick [N][4] (goal x, y, occupied, history)
+  float* info;     // [N][14]
+};
+__host__ __device__ inline int form_rec_floats(int N, int O) { return 2 * (2 * N + O) + 6 * N * N; }
+
 __device__ __forceinline__ double dn(double dx, double dy) {      // sqrt(dx*dx + dy*dy), no contraction (numpy has none)
-  return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  return FM_SQRT64(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
 template <int N>
@@ -84,7 +111,7 @@ __device__ void f_mean_std(const double (&v)[N], double& mean, double& sd) {
   mean = s / N;
   double q = 0.0;
   for (int j = 0; j < N; ++j) { const double d = v[j] - mean; q = __dadd_rn(q, __dmul_rn(d, d)); }
-  sd = sqrt(q / N);
+  sd = FM_SQRT64(q / N);
 }
 
 // Far branch shared by observation (:933-956) and the agent rows of the node features (:1256-1270): nearest goal not
@@ -152,16 +179,13 @@ __device__ void f_observation(const FormParams& p, FEnv<N>& e, int i, float* __r
   }
 }
 
-// graph_observation + _get_entity_feat_relative (:1083-1178, :1222-1340) for ego agent i: [E, 13].
+// graph_observation + _get_entity_feat_relative (:1083-1178, :1222-1340) for ego agent i, as a RECIPE: the velocities of
+// the N agents as they stand now (latched agents up to i have theirs zeroed) and, per agent, the goal it is shown heading
+// for with that goal's occupancy / history (the far branch may clear the occupancy table, :1266).  f_row turns it into rows.
 template <int N>
-__device__ void f_node_rows(const FormParams& p, FEnv<N>& e, int i, float* __restrict__ rows) {
-  const double x = e.px[i], y = e.py[i], vx = e.vx[i], vy = e.vy[i];
-  auto put = [&](int r, double rvx, double rvy, double rx, double ry, double gx, double gy, double occ, double hist, double type) {
-    if (!rows) return;
-    float* q = rows + (size_t)r * F_NODE;
-    q[0] = (float)rvx; q[1] = (float)rvy; q[2] = (float)rx; q[3] = (float)ry; q[4] = (float)gx; q[5] = (float)gy;
-    q[6] = (float)occ; q[7] = (float)hist; q[8] = (float)rx; q[9] = (float)ry; q[10] = (float)rx; q[11] = (float)ry; q[12] = (float)type;
-  };
+__device__ void f_node_recipe(const FormParams& p, FEnv<N>& e, int i, float* __restrict__ rec) {
+  float* v = rec + 2 * (2 * N + p.O) + i * 6 * N;
+  float* pk = v + 2 * N;
   for (int a = 0; a < N; ++a) {
     const double qx = e.px[a], qy = e.py[a];
     int first = 0; double mind = 0.0;
@@ -169,12 +193,38 @@ __device__ void f_node_rows(const FormParams& p, FEnv<N>& e, int i, float* __res
     double gx, gy, occ, hist;
     if (mind < p.min_obs_dist) { gx = e.lx[first]; gy = e.ly[first]; occ = e.occ[first]; hist = e.hist[first]; }
     else f_pick_goal<N>(e, qx, qy, a, gx, gy, occ, hist);
-    put(a, e.vx[a] - vx, e.vy[a] - vy, qx - x, qy - y, gx - x, gy - y, occ, hist, 0.0);
+    v[2 * a] = (float)e.vx[a]; v[2 * a + 1] = (float)e.vy[a];
+    pk[4 * a] = (float)gx; pk[4 * a + 1] = (float)gy; pk[4 * a + 2] = (float)occ; pk[4 * a + 3] = (float)hist;
   }
-  for (int a = 0; a < N; ++a)                                              // landmarks: occupied 1, history = landmark id
-    put(N + a, 0.0 - vx, 0.0 - vy, e.lx[a] - x, e.ly[a] - y, e.lx[a] - x, e.ly[a] - y, 1.0, (double)a, 1.0);
-  for (int k = 0; k < p.O; ++k)                                            // obstacles: id None -> history 0
-    put(2 * N + k, 0.0 - vx, 0.0 - vy, e.ox[k] - x, e.oy[k] - y, e.ox[k] - x, e.oy[k] - y, 1.0, 0.0, 2.0);
+}
+
+// positions of the E entities (agents, landmarks, obstacles) -> head of the recipe
+template <int N>
+__device__ void f_rec_positions(const FormParams& p, const FEnv<N>& e, float* __restrict__ rec) {
+  for (int a = 0; a < N; ++a) {
+    rec[2 * a] = (float)e.px[a]; rec[2 * a + 1] = (float)e.py[a];
+    rec[2 * (N + a)] = (float)e.lx[a]; rec[2 * (N + a) + 1] = (float)e.ly[a];
+  }
+  for (int k = 0; k < p.O; ++k) { rec[2 * (2 * N + k)] = (float)e.ox[k]; rec[2 * (2 * N + k) + 1] = (float)e.oy[k]; }
+}
+
+// One node_obs row (ego agent i, entity en) from an env's recipe (:1222-1340):
+//   [v_e - v_i (2), p_e - p_i (2), goal_e - p_i (2), goal occupied, goal history, p_e - p_i (2), p_e - p_i (2), type]
+// landmarks: occupied 1, history = landmark id; obstacles: occupied 1, history 0 (id None); both with v_e = 0, goal = p_e.
+__device__ __forceinline__ void f_row(const float* __restrict__ rec, int N, int O, int i, int en, float* __restrict__ q) {
+  const float* v = rec + 2 * (2 * N + O) + i * 6 * N;
+  const float* pk = v + 2 * N;
+  const float x = rec[2 * i], y = rec[2 * i + 1], vx = v[2 * i], vy = v[2 * i + 1];
+  const float rx = rec[2 * en] - x, ry = rec[2 * en + 1] - y;
+  float rvx = 0.0f - vx, rvy = 0.0f - vy, gx = rx, gy = ry, occ = 1.0f, hist = 0.0f, type = 2.0f;
+  if (en < N) {
+    rvx = v[2 * en] - vx; rvy = v[2 * en + 1] - vy;
+    gx = pk[4 * en] - x; gy = pk[4 * en + 1] - y; occ = pk[4 * en + 2]; hist = pk[4 * en + 3]; type = 0.0f;
+  } else if (en < 2 * N) {
+    hist = (float)(en - N); type = 1.0f;
+  }
+  q[0] = rvx; q[1] = rvy; q[2] = rx; q[3] = ry; q[4] = gx; q[5] = gy; q[6] = occ; q[7] = hist;
+  q[8] = rx; q[9] = ry; q[10] = rx; q[11] = ry; q[12] = type;
 }
 
 // cached_dist_mag (core.py:204-228) -> adj [E, E].
@@ -190,28 +240,117 @@ __device__ void f_adj(const FormParams& p, const FEnv<N>& e, float* __restrict__
   }
 }
 
+// Lexifair by sorted threshold descent for one thread (marl_fair_assign.py:16-55; oracle/lexifair.py lexifair_descent; the
+// group-parallel form is lexifair_group<G>, fm_device.cuh): entries are visited from the largest key (cost, i, j) down; an
+// entry is deleted unless the remaining entries would lose their perfect matching, in which case it is the bottleneck of
+// every remaining solution and its row / column freeze.  N <= 8: row masks are bytes, augmenting paths by depth-first search.
+template <int N>
+__device__ void lexifair_serial(const double (&c)[N * N], int (&out)[N]) {
+  unsigned char ord[N * N];
+  for (int k = 0; k < N * N; ++k) {                                        // insertion sort, descending by (cost, flat index)
+    int q = k;
+    while (q > 0 && (c[ord[q - 1]] < c[k] || (c[ord[q - 1]] == c[k] && ord[q - 1] < k))) { ord[q] = ord[q - 1]; --q; }
+    ord[q] = (unsigned char)k;
+  }
+  unsigned rowmask[N];
+  int match[N], colrow[N];
+  bool frozen[N];
+  for (int r = 0; r < N; ++r) { rowmask[r] = (1u << N) - 1u; match[r] = r; colrow[r] = r; frozen[r] = false; }
+  for (int t = 0; t < N * N; ++t) {
+    const int r = ord[t] / N, col = ord[t] % N;
+    if (!((rowmask[r] >> col) & 1u)) continue;
+    rowmask[r] &= ~(1u << col);
+    if (match[r] != col) continue;                                         // the matching survives the deletion
+    // row r and column col are free: look for an augmenting path r -> ... -> col (iterative DFS over rows)
+    int stack_row[N], stack_it[N], via[N];                                 // via[c]: row that reached column c
+    unsigned seen = 0;
+    int sp = 0;
+    stack_row[0] = r; stack_it[0] = 0;
+    bool found = false;
+    while (sp >= 0 && !found) {
+      const int rr = stack_row[sp];
+      int cc = stack_it[sp];
+      while (cc < N && (!((rowmask[rr] >> cc) & 1u) || ((seen >> cc) & 1u))) ++cc;
+      if (cc >= N) { --sp; continue; }
+      stack_it[sp] = cc + 1;
+      seen |= 1u << cc;
+      via[cc] = rr;
+      if (cc == col) { found = true; break; }
+      const int owner = colrow[cc];
+      if (frozen[owner]) continue;                                         // (a frozen row's column was removed from every mask)
+      ++sp; stack_row[sp] = owner; stack_it[sp] = 0;
+    }
+    if (found) {                                                           // flip the path back from `col`
+      int cc = col;
+      while (true) {
+        const int rr = via[cc];
+        const int prev = match[rr];                                        // column rr gives up (== -1 for the start row r)
+        match[rr] = cc; colrow[cc] = rr;
+        if (rr == r) break;
+        cc = prev;
+      }
+    } else {                                                               // critical entry: freeze row r / column col
+      rowmask[r] = 0u; frozen[r] = true; match[r] = col; colrow[col] = r;
+      for (int q = 0; q < N; ++q) if (q != r) rowmask[q] &= ~(1u << col);
+    }
+  }
+  for (int r = 0; r < N; ++r) out[r] = match[r];
+}
+
+template <int N>
+__device__ void f_costs(const FEnv<N>& e, double (&c)[N * N]) {              // cdist(agent_pos, goal_pos)
+  for (int a = 0; a < N; ++a)
+    for (int g = 0; g < N; ++g) c[a * N + g] = dn(e.px[a] - e.lx[g], e.py[a] - e.ly[g]);
+}
+
 template <int N>
 __device__ void f_assign(FEnv<N>& e) {                                     // cdist + lexifair (:704-721, :481-486)
   double c[N * N];
-  for (int a = 0; a < N; ++a)
-    for (int g = 0; g < N; ++g) c[a * N + g] = dn(e.px[a] - e.lx[g], e.py[a] - e.ly[g]);
-  lexifair_small<N>(c, e.gm);
+  f_costs<N>(e, c);
+  if constexpr (N <= 4) lexifair_small<N>(c, e.gm);
+  else lexifair_serial<N>(c, e.gm);
+}
+
+// Min-sum matching of the current agent -> goal distances by enumeration (scipy linear_sum_assignment in
+// nav_base_formation_graph_mask.py:255-260 and :686-689): match[i] = goal of agent i, delta[i] its distance.  N <= 5.
+template <int N>
+__device__ void f_min_sum(const FEnv<N>& e, int (&match)[N], double (&delta)[N]) {
+  double c[N * N];
+  f_costs<N>(e, c);
+  int perm[N], best[N];
+  for (int i = 0; i < N; ++i) { perm[i] = i; best[i] = i; }
+  double bs = 0.0;
+  bool have = false;
+  while (true) {                                                           // permutations in lexicographic order
+    double sum = 0.0;
+    for (int i = 0; i < N; ++i) sum += c[i * N + perm[i]];
+    if (!have || sum < bs) { bs = sum; have = true; for (int i = 0; i < N; ++i) best[i] = perm[i]; }
+    int k = N - 2;
+    while (k >= 0 && perm[k] > perm[k + 1]) --k;
+    if (k < 0) break;
+    int l = N - 1;
+    while (perm[l] < perm[k]) --l;
+    int t = perm[k]; perm[k] = perm[l]; perm[l] = t;
+    for (int a = k + 1, b = N - 1; a < b; ++a, --b) { t = perm[a]; perm[a] = perm[b]; perm[b] = t; }
+  }
+  for (int i = 0; i < N; ++i) { match[i] = best[i]; delta[i] = c[i * N + best[i]]; }
 }
 
 // env.reset()'s observation pass (environment.py:882-898): obs_i, then node rows_i, per agent.
 template <int N>
-__device__ void f_observe(const FormParams& p, int b, FEnv<N>& e) {
-  const int E = 2 * N + p.O;
+__device__ void f_observe(const FormParams& p, FEnv<N>& e, const FOut& o) {
+  f_rec_positions<N>(p, e, o.rec);
   for (int i = 0; i < N; ++i) {
-    f_observation<N>(p, e, i, p.out.obs ? p.out.obs + ((size_t)b * N + i) * F_OBS : nullptr);
-    f_node_rows<N>(p, e, i, p.out.node_obs ? p.out.node_obs + ((size_t)b * N + i) * E * F_NODE : nullptr);
+    f_observation<N>(p, e, i, o.obs + i * F_OBS);
+    f_node_recipe<N>(p, e, i, o.rec);
   }
-  f_adj<N>(p, e, p.out.adj ? p.out.adj + (size_t)b * E * E : nullptr);
+  f_adj<N>(p, e, o.adj);
 }
 
 // reset_world + random_scenario (:217-487) with the Philox draw scheme of the navigation kernels: draw counter per
 // (seed, global env, episode); obstacles 0.8 * U, agents U rejected vs obstacles (2.0x) / placed agents (1.05x), goals
-// 0.8 * U rejected vs obstacles (2.0x) / placed goals (1.2x).  Positions are float32 values, predicates float64.
+// 0.8 * U rejected vs obstacles (2.0x) / placed goals (1.2x; 1.5x in the base scenarios).  Positions are float32 values,
+// predicates float64.
 template <int N>
 __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
   const long long genv = p.env_offset + b;
@@ -228,7 +367,7 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
   const double r2 = 0.05 + 0.05;
   for (int pass = 0; pass < 2; ++pass) {
     double* X = pass ? e.lx : e.px; double* Y = pass ? e.ly : e.py;
-    const double dsame = pass ? 1.2 * r2 : 1.05 * r2;
+    const double dsame = pass ? (p.assignment == 0 ? 1.2 : 1.5) * r2 : 1.05 * r2;   // goals: :638-648; 1.5x in the base files
     for (int a = 0; a < N; ++a) {
       while (true) {
         float fx, fy; draw(fx, fy);
@@ -246,59 +385,77 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
     if (p.has_max_speed) e.mint[i] = dn(e.px[i] - e.lx[i], e.py[i] - e.ly[i]) / p.max_speed;   // goal_match = arange here (:229, :474-476)
   }
   e.step = 0;
-  f_assign<N>(e);
+  if (p.assignment == 0) {
+    f_assign<N>(e);
+  } else if (p.assignment == 1) {                                          // nav_base_formation_graph_mask.py:255-260
+    double delta[N];
+    f_min_sum<N>(e, e.gm, delta);
+  } else {                                                                 // np.random.shuffle(arange) (randomgoal :258-259):
+    for (int i = 0; i < N; ++i) e.gm[i] = i;                               // Fisher-Yates on the same draw stream
+    for (int k = N - 1; k > 0; --k) {
+      float x, y; draw(x, y);
+      const float u = __fdiv_rn(__fadd_rn(x, half), ws);
+      int j = (int)__fmul_rn(u, (float)(k + 1));
+      j = j < k ? j : k;
+      const int t = e.gm[k]; e.gm[k] = e.gm[j]; e.gm[j] = t;
+    }
+  }
   e.episode += 1;
 }
 
+// One softplus contact term (core.py:389-392, cached branch: dist_min = size + size): fp32 with hardware rsqrt / ex2 and
+// the polynomial log1p of the navigation kernels (fm_device.cuh contact_force: relative error of the term ~5e-7).
+__device__ __forceinline__ void f_pair_force(float dx, float dy, float& fx, float& fy) {
+  const float d2 = fmaf(dx, dx, __fmul_rn(dy, dy));
+  const float inv = rsqrt_approx(d2);
+  const float dist = __fmul_rn(d2, inv);
+  const float x = __fmul_rn(__fsub_rn(0.1f, dist), 50.0f);                 // -(dist - dist_min) / k,  k = 0.02
+  const float t = ex2_approx(__fmul_rn(-fabsf(x), 1.4426950408889634f));
+  const float sp = __fadd_rn(fmaxf(x, 0.0f), log1p_unit(t));
+  const float c = __fmul_rn(__fmul_rn(6.0f, sp), inv);                     // contact_force (300) * k * softplus / dist
+  fx = __fmul_rn(c, dx); fy = __fmul_rn(c, dy);
+}
+
+// reset() path for one env: optional reset, observation pass.
 template <int N>
-__global__ void __launch_bounds__(128) formation_reset_kernel(const FormParams p) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.B) return;
+__device__ void form_reset_env(const FormParams& p, int b, const FOut& o) {
   FEnv<N> e;
   f_load<N>(p, b, e);
   const bool doit = !p.mask || p.mask[b] != 0;
   if (doit) f_reset<N>(p, b, e);
-  f_observe<N>(p, b, e);
+  f_observe<N>(p, e, o);
   f_store<N>(p, b, e, doit);
 }
 
-// MultiAgentGraphEnv.step (environment.py:816-877) + graphworker auto-reset (env_wrappers.py:856-865).
+// MultiAgentGraphEnv.step (environment.py:816-877) + graphworker auto-reset (env_wrappers.py:856-865) for one env.
 template <int N>
-__global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.B) return;
+__device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
   FEnv<N> e;
   f_load<N>(p, b, e);
-  const int O = p.O, E = 2 * N + O;
+  const int O = p.O;
   e.step += 1;                                                             // :819, :823
-  // ---- World.step: action force (core.py:277-298), pair forces from the positions at step entry (:301-316, :370-404)
-  double Fx[N], Fy[N];
-  for (int i = 0; i < N; ++i) {
-    const int a = p.actions[(size_t)b * N + i];
-    Fx[i] = (((a == 1) ? 1.0 : 0.0) - ((a == 2) ? 1.0 : 0.0)) * 5.0;       // environment.py:301-311
-    Fy[i] = (((a == 3) ? 1.0 : 0.0) - ((a == 4) ? 1.0 : 0.0)) * 5.0;
-  }
-  const double km = 0.02, dmin = 0.05 + 0.05;
-  auto pair_force = [&](double dx, double dy, double& fx, double& fy) {
-    const double dist = dn(dx, dy);
-    const double z = -(dist - dmin) / km;
-    const double pen = (fmax(z, 0.0) + log1p(exp(-fabs(z)))) * km;         // np.logaddexp(0, z) * k  (:391)
-    fx = 300.0 * dx / dist * pen; fy = 300.0 * dy / dist * pen;            // :392
-  };
+  // ---- World.step: action force (core.py:277-298), pair forces from the positions at step entry (:301-316, :370-404),
+  // summed per agent in ascending partner order, joined to the float64 action force
+  float cfx[N], cfy[N];
+  for (int i = 0; i < N; ++i) { cfx[i] = 0.f; cfy[i] = 0.f; }
   for (int a = 0; a < N; ++a) {
     for (int c = a + 1; c < N; ++c) {
-      double fx, fy; pair_force(e.px[a] - e.px[c], e.py[a] - e.py[c], fx, fy);
-      if (!e.status[a]) { Fx[a] = fx + Fx[a]; Fy[a] = fy + Fy[a]; }        // core.py:397
-      if (!e.status[c]) { Fx[c] = -fx + Fx[c]; Fy[c] = -fy + Fy[c]; }      // core.py:398
+      float fx, fy; f_pair_force((float)e.px[a] - (float)e.px[c], (float)e.py[a] - (float)e.py[c], fx, fy);
+      if (!e.status[a]) { cfx[a] += fx; cfy[a] += fy; }                    // core.py:397
+      if (!e.status[c]) { cfx[c] -= fx; cfy[c] -= fy; }                    // core.py:398
     }
     for (int k = 0; k < O; ++k) {                                          // obstacles: whatever the status (:401)
-      double fx, fy; pair_force(e.px[a] - e.ox[k], e.py[a] - e.oy[k], fx, fy);
-      Fx[a] = fx + Fx[a]; Fy[a] = fy + Fy[a];
+      float fx, fy; f_pair_force((float)e.px[a] - (float)e.ox[k], (float)e.py[a] - (float)e.oy[k], fx, fy);
+      cfx[a] += fx; cfy[a] += fy;
     }
   }
   for (int i = 0; i < N; ++i) {                                            // integrate_state (:338-356): every agent
+    const int a = p.actions[(size_t)b * N + i];
+    const double ux = (((a == 1) ? 1.0 : 0.0) - ((a == 2) ? 1.0 : 0.0)) * 5.0;   // environment.py:301-311
+    const double uy = (((a == 3) ? 1.0 : 0.0) - ((a == 4) ? 1.0 : 0.0)) * 5.0;
+    const double Fx = __dadd_rn(ux, (double)cfx[i]), Fy = __dadd_rn(uy, (double)cfy[i]);
     double vx = __dmul_rn(e.vx[i], 0.75), vy = __dmul_rn(e.vy[i], 0.75);
-    vx = __dadd_rn(vx, __dmul_rn(Fx[i], 0.1)); vy = __dadd_rn(vy, __dmul_rn(Fy[i], 0.1));
+    vx = __dadd_rn(vx, __dmul_rn(Fx, 0.1)); vy = __dadd_rn(vy, __dmul_rn(Fy, 0.1));
     if (p.has_max_speed) {
       const double sp = dn(vx, vy);
       if (sp > p.max_speed) { vx = __dmul_rn(vx / sp, p.max_speed); vy = __dmul_rn(vy / sp, p.max_speed); }
@@ -308,21 +465,24 @@ __global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p)
     e.px[i] = __dadd_rn(e.px[i], sx); e.py[i] = __dadd_rn(e.py[i], sy);
     e.pd[i] = __dadd_rn(e.pd[i], dn(sx, sy));
   }
-  f_adj<N>(p, e, p.out.adj ? p.out.adj + (size_t)b * E * E : nullptr);
+  f_adj<N>(p, e, o.adj);
+  f_rec_positions<N>(p, e, o.rec);
 
   // ---- per-agent loop (environment.py:832-864): observation, reward, node rows, done, info -- in this order
-  double rew[N];
+  double rew[N], delta[N];
   bool done[N], all_done = true;
+  for (int i = 0; i < N; ++i) delta[i] = 0.0;
   const double th = p.min_dist_thresh, dcoll = 1.05 * (0.05 + 0.05);
   for (int i = 0; i < N; ++i) {
-    f_observation<N>(p, e, i, p.out.obs ? p.out.obs + ((size_t)b * N + i) * F_OBS : nullptr);
+    f_observation<N>(p, e, i, o.obs + i * F_OBS);
     // reward (:691-802)
     double fairness;
     if (e.dtg[i] == -1.0) { double m, s; f_mean_std<N>(e.pd, m, s); fairness = m / (s + 0.0001); }
     else fairness = e.dmean / (e.dstd + 0.0001);
-    if (i == 0) f_assign<N>(e);                                            // :704-721: re-assignment every step
+    if (i == 0 && p.assignment == 0) f_assign<N>(e);                       // :704-721: re-assignment every step
+    if (i == 0 && p.assignment == 1) { int m[N]; f_min_sum<N>(e, m, delta); }   // mask.py:666-706 (the stored match stays)
     const double x = e.px[i], y = e.py[i];
-    const double dg = dn(x - e.lx[e.gm[i]], y - e.ly[e.gm[i]]);
+    const double dg = p.assignment == 1 ? delta[i] : dn(x - e.lx[e.gm[i]], y - e.ly[e.gm[i]]);
     double r = 0.0;
     if (dg < th) {                                                         // :725-733
       if (!e.status[i]) { e.status[i] = true; e.vx[i] = 0.0; e.vy[i] = 0.0; r += p.goal_rew; }
@@ -340,7 +500,7 @@ __global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p)
     }
     r = fmin(fmax(r, -2.0 * p.collision_rew), p.goal_rew + p.fair_rew);
     rew[i] = r;
-    f_node_rows<N>(p, e, i, p.out.node_obs ? p.out.node_obs + ((size_t)b * N + i) * E * F_NODE : nullptr);
+    f_node_recipe<N>(p, e, i, o.rec);
     done[i] = e.status[i] || e.step >= p.episode_length;                   // environment.py:237-247
     all_done = all_done && done[i];
     // info_callback (:489-575)
@@ -356,9 +516,9 @@ __global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p)
       if (ohit) e.noc[i] += 1.0;                                                                                    // :521-523
       e.nac[i] += (double)hits;
       f_mean_std<N>(e.dtg, e.dmean, e.dstd);                                                                        // :534-535
-      if (p.out.info) {
+      if (o.info) {
         double tm, ts; f_mean_std<N>(e.treq, tm, ts);
-        float* q = p.out.info + ((size_t)b * N + i) * INFO_F;
+        float* q = o.info + i * INFO_F;
         q[0] = (float)r; q[1] = (float)e.dleft[i]; q[2] = (float)e.treq[i]; q[3] = (float)e.nac[i]; q[4] = (float)e.noc[i];
         q[5] = (float)e.dmean; q[6] = (float)e.dstd; q[7] = (float)(e.dmean / (e.dstd + 0.0001)); q[8] = (float)e.dtg[i];
         q[9] = (float)e.treq[i]; q[10] = (float)tm; q[11] = (float)ts; q[12] = (float)(tm / (ts + 0.0001)); q[13] = (float)e.mint[i];
@@ -368,27 +528,161 @@ __global__ void __launch_bounds__(128) formation_step_kernel(const FormParams p)
   double total = 0.0;
   for (int i = 0; i < N; ++i) total += rew[i];
   for (int i = 0; i < N; ++i) {
-    if (p.out.reward) p.out.reward[(size_t)b * N + i] = (float)(p.collaborative ? total : rew[i]);   // environment.py:867-870
-    if (p.out.done) p.out.done[(size_t)b * N + i] = done[i] ? 1 : 0;
+    o.rew[i] = (float)(p.collaborative ? total : rew[i]);                  // environment.py:867-870
+    o.done[i] = done[i] ? 1 : 0;
+  }
+  // info rows go straight to global memory, on the steps whose values the runner reads (every agent done; or every step)
+  if (o.info && p.out.info && (all_done || p.info_every_step)) {
+    float* g = p.out.info + (size_t)b * N * INFO_F;
+    for (int k = 0; k < N * INFO_F; ++k) g[k] = o.info[k];
   }
   const bool reset = p.auto_reset && all_done;                             // env_wrappers.py:859-865
-  if (reset) { f_reset<N>(p, b, e); f_observe<N>(p, b, e); }
+  if (reset) { f_reset<N>(p, b, e); f_observe<N>(p, e, o); }
   f_store<N>(p, b, e, reset);
 }
 
-cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st) {
-  const int blocks = (p.B + 127) / 128;
-#define FM_F_CASE(n)                                                            \
-  case n:                                                                       \
-    if (is_reset) formation_reset_kernel<n><<<blocks, 128, 0, st>>>(p);         \
-    else formation_step_kernel<n><<<blocks, 128, 0, st>>>(p);                   \
-    break;
-  switch (p.N) {
-    FM_F_CASE(2) FM_F_CASE(3) FM_F_CASE(4)
-    default: return cudaErrorInvalidValue;
+// ===================================================================================================================
+// Device only from here: shared-memory tile of a warp, warp-cooperative emission, kernels, launcher.
+#ifdef __CUDACC__
+
+struct FormTile {            // floats per warp; all offsets multiples of 4 floats
+  int obs, adj, rew, done, rec, info, rec_stride, info_stride, words;
+};
+__host__ __device__ inline FormTile form_tile(int N, int O, bool with_info) {
+  const int E = 2 * N + O;
+  FormTile t;
+  const int adj_words = 32 * E * E, stage_words = 2 * F_CHUNK_WORDS;       // the adj image doubles as the two row buffers
+  t.adj = 0;
+  t.obs = ((adj_words > stage_words ? adj_words : stage_words) + 3) & ~3;
+  t.rew = t.obs + ((32 * N * F_OBS + 3) & ~3);
+  t.done = t.rew + ((32 * N + 3) & ~3);
+  t.rec = t.done + ((8 * N + 3) & ~3);                                      // 32 N bytes
+  t.rec_stride = form_rec_floats(N, O) | 1;                                 // odd: lane = env accesses are conflict free
+  t.info = t.rec + ((32 * t.rec_stride + 3) & ~3);
+  t.info_stride = with_info ? ((N * INFO_F) | 1) : 0;
+  t.words = t.info + ((32 * t.info_stride + 3) & ~3);
+  return t;
+}
+
+// The warp's images -> global memory.  Full, 16-byte aligned tiles go through the copy engine; ragged / unaligned ones
+// are written by the lanes (coalesced for the images, per-lane rows for node_obs).
+template <int N>
+__device__ void form_emit(const FormParams& p, float* __restrict__ S, const FormTile& t, int env0, int nenv, int lane, bool with_step) {
+  const int O = p.O, E = 2 * N + O, NE = N * E;
+  float* g_obs = p.out.obs ? p.out.obs + (size_t)env0 * N * F_OBS : nullptr;
+  float* g_adj = p.out.adj ? p.out.adj + (size_t)env0 * E * E : nullptr;
+  float* g_rew = (with_step && p.out.reward) ? p.out.reward + (size_t)env0 * N : nullptr;
+  uint8_t* g_done = (with_step && p.out.done) ? p.out.done + (size_t)env0 * N : nullptr;
+  float* g_node = p.out.node_obs ? p.out.node_obs + (size_t)env0 * NE * F_NODE : nullptr;
+  const bool bulk = nenv == 32 && aligned16(g_obs) && aligned16(g_adj) && aligned16(g_rew) && aligned16(g_done) && aligned16(g_node);
+  uint64_t pol = 0;
+  if (bulk) {
+    if (lane == 0) {
+      pol = evict_first_policy();
+      fence_async_smem();
+      if (g_adj) bulk_store(g_adj, S + t.adj, 32 * E * E * 4, pol);
+      if (g_obs) bulk_store(g_obs, S + t.obs, 32 * N * F_OBS * 4, pol);
+      if (g_rew) bulk_store(g_rew, S + t.rew, 32 * N * 4, pol);
+      if (g_done) bulk_store(g_done, S + t.done, 32 * N, pol);
+      bulk_commit();
+    }
+  } else {
+    if (g_adj) for (int k = lane; k < nenv * E * E; k += 32) __stcs(g_adj + k, S[t.adj + k]);
+    if (g_obs) for (int k = lane; k < nenv * N * F_OBS; k += 32) __stcs(g_obs + k, S[t.obs + k]);
+    if (g_rew) for (int k = lane; k < nenv * N; k += 32) __stcs(g_rew + k, S[t.rew + k]);
+    if (g_done) for (int k = lane; k < nenv * N; k += 32) g_done[k] = reinterpret_cast<const uint8_t*>(S + t.done)[k];
   }
-#undef FM_F_CASE
+  if (!g_node) { if (bulk && lane == 0) bulk_wait_read<0>(); return; }
+  const int rows = nenv * NE;
+  if (!bulk) {
+    for (int r = lane; r < rows; r += 32) {
+      const int el = r / NE, q = r - el * NE, i = q / E, en = q - i * E;
+      float row[F_NODE];
+      f_row(S + t.rec + el * t.rec_stride, N, O, i, en, row);
+#pragma unroll
+      for (int f = 0; f < F_NODE; ++f) __stcs(g_node + (size_t)r * F_NODE + f, row[f]);
+    }
+    return;
+  }
+  if (lane == 0) bulk_wait_read<0>();                                       // the adj image becomes the two row buffers
+  __syncwarp();
+  int c = 0;
+  for (int r0 = 0; r0 < rows; r0 += F_CHUNK_ROWS, ++c) {
+    float* buf = S + t.adj + (c & 1) * F_CHUNK_WORDS;
+    if (c >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }       // the engine has read chunk c - 2 out of this buffer
+    int r = r0 + lane * F_ROWS_PER_LANE;
+    int el = r / NE, q = r - el * NE, i = q / E, en = q - i * E;
+#pragma unroll
+    for (int j = 0; j < F_ROWS_PER_LANE; ++j) {
+      if (r + j < rows) f_row(S + t.rec + el * t.rec_stride, N, O, i, en, buf + (lane * F_ROWS_PER_LANE + j) * F_NODE);
+      if (++en == E) { en = 0; if (++i == N) { i = 0; ++el; } }
+    }
+    __syncwarp();
+    const int nrow = min(F_CHUNK_ROWS, rows - r0);                          // 32 * N * E is a multiple of 4 rows: 16-byte sizes
+    if (lane == 0) {
+      fence_async_smem();
+      bulk_store(g_node + (size_t)r0 * F_NODE, buf, (uint32_t)nrow * F_NODE * 4u, pol);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();
+}
+
+constexpr int FORM_WARPS = 1;          // no block-level cooperation: one warp per CTA packs the SM's shared memory best
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(FORM_WARPS * 32) formation_kernel(const FormParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int env0 = (blockIdx.x * FORM_WARPS + wib) * 32;
+  if (env0 >= p.B) return;                                                  // warp-uniform
+  const int nenv = min(32, p.B - env0);
+  const FormTile t = form_tile(N, p.O, MODE == 0 && p.out.info != nullptr);
+  float* S = smem + (size_t)wib * t.words;
+  const int E = 2 * N + p.O;
+  if (lane < nenv) {
+    FOut o;
+    o.obs = S + t.obs + lane * N * F_OBS; o.adj = S + t.adj + lane * E * E; o.rew = S + t.rew + lane * N;
+    o.done = reinterpret_cast<uint8_t*>(S + t.done) + lane * N; o.rec = S + t.rec + lane * t.rec_stride;
+    o.info = t.info_stride ? S + t.info + lane * t.info_stride : nullptr;
+    if (MODE == 0) form_step_env<N>(p, env0 + lane, o); else form_reset_env<N>(p, env0 + lane, o);
+  }
+  __syncwarp();
+  form_emit<N>(p, S, t, env0, nenv, lane, MODE == 0);
+}
+
+int formation_max_agents() { return 7; }
+
+template <int N>
+static cudaError_t launch_formation_n(const FormParams& p, bool is_reset, cudaStream_t st) {
+  const FormTile t = form_tile(N, p.O, !is_reset && p.out.info != nullptr);
+  const size_t smem = (size_t)t.words * FORM_WARPS * sizeof(float);
+  const int blocks = (p.B + 32 * FORM_WARPS - 1) / (32 * FORM_WARPS);
+  cudaError_t e;
+  if (is_reset) {
+    e = cudaFuncSetAttribute(formation_kernel<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    formation_kernel<N, 1><<<blocks, FORM_WARPS * 32, smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(formation_kernel<N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    formation_kernel<N, 0><<<blocks, FORM_WARPS * 32, smem, st>>>(p);
+  }
   return cudaGetLastError();
 }
+
+cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st) {
+  switch (p.N) {
+    case 2: return launch_formation_n<2>(p, is_reset, st);
+    case 3: return launch_formation_n<3>(p, is_reset, st);
+    case 4: return launch_formation_n<4>(p, is_reset, st);
+    case 5: return launch_formation_n<5>(p, is_reset, st);
+    case 6: return launch_formation_n<6>(p, is_reset, st);
+    case 7: return launch_formation_n<7>(p, is_reset, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+#endif  // __CUDACC__
 
 }  // namespace fm

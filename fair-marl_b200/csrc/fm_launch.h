@@ -49,9 +49,11 @@ cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr,
 cudaError_t launch_pair_dist(const float* a, const float* b, long long num, double* out, cudaStream_t st);
 cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st);
 
-// formation family (fm_formation.cu): one thread per env, state in API layout
+// formation family (fm_formation.cu): per-env logic one thread per env, warp-cooperative emission; state in API layout
 struct FormParams {
   int B, N, O, episode_length, fairness_reward, collaborative, auto_reset, has_max_speed;
+  int assignment;            // 0 fair (lexifair every step), 1 optimal (min-sum every step), 2 random (permutation at reset)
+  int info_every_step;       // 0: info rows only on the steps on which every agent of the env is done
   long long env_offset;
   uint32_t seed_lo, seed_hi;
   double world_size, max_speed, collision_rew, goal_rew, min_dist_thresh, min_obs_dist, fair_rew, zeroshift;
@@ -66,5 +68,10 @@ bool gnn_supported_entities(int E);
 int gnn_weight_count(int embed_layers, int conv_layers);
 cudaError_t launch_gnn(const FmGnnConfig& c, const float* weights, const float* node, const float* adj, const int* agent_id,
                        float* out, cudaStream_t st);
+int head_weight_count(int layers, int recurrent);
+cudaError_t launch_head(const FmHeadConfig& c, const float* weights, const float* obs, const float* nbd, const float* rnn_in,
+                        const float* mask, const float* u, float* rnn_out, float* logp, long long* action, float* value,
+                        cudaStream_t st);
+int formation_max_agents();
 int set_error(int code, const char* fmt, ...);   // fm_last_error text (fm_abi.cu)
 }  // namespace fm

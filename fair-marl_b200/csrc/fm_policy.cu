@@ -415,4 +415,216 @@ cudaError_t launch_gnn(const FmGnnConfig& c, const float* weights, const float* 
 
 int gnn_weight_count(int embed_layers, int conv_layers) { return gnn_weight_floats(embed_layers, conv_layers); }
 
+// =====================================================================================================================
+// Fused policy HEAD (everything behind the graph network): GR_Actor.forward / GR_Critic.forward after gnn_base
+// (onpolicy/algorithms/graph_actor_critic.py:150-178, :380-397):
+//   x = [obs | nbd]  ->  MLPBase (utils/mlp.py: LayerNorm(in), then (Linear, act, LayerNorm) x (1 + layer_N))
+//     ->  RNNLayer, one step (utils/rnn.py:23-28, :57: GRU on h * mask, LayerNorm)
+//     ->  actor: Categorical head (utils/act.py, distributions.py:14-28): log-softmax, mode or an inverse-CDF draw from a
+//         caller-supplied uniform, log-prob of the action;   critic: v_out (a Linear; PopArt's forward is the same map).
+// One WARP per row (graph); hidden_size = 64: lane l owns hidden units l and l + 32.  All weights of the head (~32 K
+// floats) live in shared memory for the whole persistent CTA, stored k-quad interleaved ([k / 4][column][4]) so that one
+// LDS.128 feeds four FMAs and consecutive lanes read consecutive 16-byte words; the activation vector of the row sits in
+// a warp-private 64-float scratch and is read as broadcast LDS.128.  Replaces ~30 torch launches per network and step
+// (LayerNorm kernels with one CTA per 64-float row, GEMVs for the 5- and 1-wide output layers, multinomial).
+constexpr int HH = 64;                 // hidden_size
+constexpr int HD = 32;                 // padded input width (obs_dim + 16 <= 32)
+constexpr int HEAD_WARPS = 16;
+constexpr int HW_FN = 0;                               // feature_norm gamma[32], beta[32]
+constexpr int HW_FC1 = HW_FN + 2 * HD;                 // [8 quads][64][4], then b[64], ln gamma[64], beta[64]
+constexpr int HW_FC1_SZ = HD * HH + 3 * HH;
+constexpr int HW_FC_SZ = HH * HH + 3 * HH;             // per extra layer: [16 quads][64][4], b, gamma, beta
+constexpr int HW_GRU_SZ = 2 * HH * 3 * HH + 2 * 3 * HH + 2 * HH;   // Wih [16][192][4] | Whh | b_ih[192] | b_hh[192] | ln gamma, beta
+constexpr int HW_OUT_SZ = 8 * HH + 8;                  // Wo[8 rows][64] | bo[8]
+
+__host__ __device__ inline int head_weight_floats(int layers, int recurrent) {
+  return HW_FC1 + HW_FC1_SZ + layers * HW_FC_SZ + (recurrent ? HW_GRU_SZ : 0) + HW_OUT_SZ;
+}
+
+struct HeadArgs {
+  const float* w;
+  const float* obs;        // [M, obs_dim] or null (obs_dim 0)
+  const float* nbd;        // [M, 16]
+  const float* rnn_in;     // [M, 64]   (recurrent)
+  const float* mask;       // [M]       (recurrent)
+  const float* u;          // [M] uniforms in [0, 1) for the categorical draw; null: mode
+  float* rnn_out;          // [M, 64]
+  float* logp;             // [M]   actor
+  long long* action;       // [M]   actor
+  float* value;            // [M]   critic
+  int M, obs_dim, layers, recurrent, feat_norm, relu, A, wfloats;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// LayerNorm over the 64 values held two per lane
+__device__ __forceinline__ void head_ln(float& a, float& b, const float* __restrict__ g, int lane) {
+  const float mean = warp_sum(a + b) * (1.0f / HH);
+  a -= mean; b -= mean;
+  const float var = warp_sum(fmaf(a, a, b * b)) * (1.0f / HH);
+  const float inv = rsqrtf(var + 1e-5f);
+  a = fmaf(a * inv, g[lane], g[HH + lane]);
+  b = fmaf(b * inv, g[lane + 32], g[HH + lane + 32]);
+}
+
+// acc[c] += sum_k W[k][col_c] x[k] for NC columns of this lane; W k-quad interleaved with `ncol` columns, x in shared memory
+template <int NC>
+__device__ __forceinline__ void head_matvec(const float* __restrict__ Wq, int ncol, int quads, const float* __restrict__ xs,
+                                            const int (&col)[NC], float (&acc)[NC]) {
+#pragma unroll 4
+  for (int q = 0; q < quads; ++q) {
+    const float4 x4 = *reinterpret_cast<const float4*>(xs + 4 * q);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 w4 = *reinterpret_cast<const float4*>(Wq + ((size_t)q * ncol + col[c]) * 4);
+      acc[c] = fmaf(w4.x, x4.x, acc[c]); acc[c] = fmaf(w4.y, x4.y, acc[c]);
+      acc[c] = fmaf(w4.z, x4.z, acc[c]); acc[c] = fmaf(w4.w, x4.w, acc[c]);
+    }
+  }
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 1) head_kernel(const __grid_constant__ HeadArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;
+  const int wpad = (a.wfloats + 3) & ~3;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* xs = smem + wpad + wib * (2 * HH);                  // activation vector | masked hidden state
+  float* hs = xs + HH;
+  for (int k = threadIdx.x; k < a.wfloats; k += blockDim.x) W[k] = __ldg(a.w + k);
+  __syncthreads();
+  const int D = a.obs_dim + GH;
+  const float* w_gru = W + HW_FC1 + HW_FC1_SZ + a.layers * HW_FC_SZ;
+  const float* w_out = w_gru + (a.recurrent ? HW_GRU_SZ : 0);
+  const int c2[2] = {lane, lane + 32};
+  for (int m = blockIdx.x * HEAD_WARPS + wib; m < a.M; m += gridDim.x * HEAD_WARPS) {
+    // ---- input [obs | nbd], feature LayerNorm over D values --------------------------------------------------------
+    float x = 0.f;
+    if (lane < a.obs_dim) x = __ldcs(a.obs + (size_t)m * a.obs_dim + lane);
+    else if (lane < D) x = __ldcs(a.nbd + (size_t)m * GH + (lane - a.obs_dim));
+    if (a.feat_norm) {
+      const float mean = warp_sum(x) / (float)D;
+      const float d = lane < D ? x - mean : 0.f;
+      const float var = warp_sum(d * d) / (float)D;
+      x = lane < D ? fmaf(d * rsqrtf(var + 1e-5f), W[HW_FN + lane], W[HW_FN + HD + lane]) : 0.f;
+    }
+    xs[lane] = x;
+    __syncwarp();
+    // ---- fc1 and the layer_N hidden layers: Linear, act, LayerNorm ----------------------------------------------------
+    float h0, h1;
+    {
+      const float* wl = W + HW_FC1;
+      float acc[2] = {wl[HD * HH + lane], wl[HD * HH + lane + 32]};
+      head_matvec<2>(wl, HH, HD / 4, xs, c2, acc);
+      h0 = g_act<RELU>(acc[0]); h1 = g_act<RELU>(acc[1]);
+      head_ln(h0, h1, wl + HD * HH + HH, lane);
+    }
+    __syncwarp();
+    xs[lane] = h0; xs[lane + 32] = h1;
+    __syncwarp();
+    for (int l = 0; l < a.layers; ++l) {
+      const float* wl = W + HW_FC1 + HW_FC1_SZ + l * HW_FC_SZ;
+      float acc[2] = {wl[HH * HH + lane], wl[HH * HH + lane + 32]};
+      head_matvec<2>(wl, HH, HH / 4, xs, c2, acc);
+      h0 = g_act<RELU>(acc[0]); h1 = g_act<RELU>(acc[1]);
+      head_ln(h0, h1, wl + HH * HH + HH, lane);
+      __syncwarp();
+      xs[lane] = h0; xs[lane + 32] = h1;
+      __syncwarp();
+    }
+    // ---- one GRU step on h * mask (torch.nn.GRU gate order r | z | n), LayerNorm ----------------------------------------
+    if (a.recurrent) {
+      const float mk = a.mask[m];
+      const float p0 = __ldcs(a.rnn_in + (size_t)m * HH + lane) * mk, p1 = __ldcs(a.rnn_in + (size_t)m * HH + lane + 32) * mk;
+      hs[lane] = p0; hs[lane + 32] = p1;
+      __syncwarp();
+      const int c6[6] = {lane, lane + 32, HH + lane, HH + lane + 32, 2 * HH + lane, 2 * HH + lane + 32};
+      const float* bih = w_gru + 2 * HH * 3 * HH;
+      const float* bhh = bih + 3 * HH;
+      float gi[6], gh[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { gi[c] = bih[c6[c]]; gh[c] = bhh[c6[c]]; }
+      head_matvec<6>(w_gru, 3 * HH, HH / 4, xs, c6, gi);
+      head_matvec<6>(w_gru + HH * 3 * HH, 3 * HH, HH / 4, hs, c6, gh);
+      const float r0 = 1.0f / (1.0f + expf(-(gi[0] + gh[0]))), r1 = 1.0f / (1.0f + expf(-(gi[1] + gh[1])));
+      const float z0 = 1.0f / (1.0f + expf(-(gi[2] + gh[2]))), z1 = 1.0f / (1.0f + expf(-(gi[3] + gh[3])));
+      const float n0 = tanhf(gi[4] + r0 * gh[4]), n1 = tanhf(gi[5] + r1 * gh[5]);
+      h0 = (1.0f - z0) * n0 + z0 * p0; h1 = (1.0f - z1) * n1 + z1 * p1;
+      a.rnn_out[(size_t)m * HH + lane] = h0; a.rnn_out[(size_t)m * HH + lane + 32] = h1;
+      head_ln(h0, h1, bhh + 3 * HH, lane);
+    }
+    // ---- output layer -------------------------------------------------------------------------------------------------
+    float lg[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float v = 0.f;
+      if (o < a.A) v = warp_sum(fmaf(w_out[o * HH + lane], h0, w_out[o * HH + lane + 32] * h1)) + w_out[8 * HH + o];
+      lg[o] = v;
+    }
+    if (a.value) {
+      if (lane == 0) a.value[m] = lg[0];
+    } else {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) if (o < a.A) mx = fmaxf(mx, lg[o]);
+      float se = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) if (o < a.A) se += expf(lg[o] - mx);
+      const float lse = mx + logf(se);
+      int act = 0;
+      if (a.u) {                                             // inverse CDF of softmax(logits)
+        const float u = a.u[m];
+        float cdf = 0.f;
+        act = a.A - 1;
+        bool set = false;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) if (o < a.A) { cdf += expf(lg[o] - lse); if (!set && u < cdf) { act = o; set = true; } }
+      } else {                                               // FixedCategorical.mode: first maximum
+        float best = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) if (o < a.A && lg[o] > best) { best = lg[o]; act = o; }
+      }
+      float sel = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) if (o == act) sel = lg[o];
+      if (lane == 0) { a.action[m] = act; a.logp[m] = sel - lse; }
+    }
+    __syncwarp();
+  }
+}
+
+int head_weight_count(int layers, int recurrent) { return head_weight_floats(layers, recurrent); }
+
+cudaError_t launch_head(const FmHeadConfig& c, const float* weights, const float* obs, const float* nbd, const float* rnn_in,
+                        const float* mask, const float* u, float* rnn_out, float* logp, long long* action, float* value,
+                        cudaStream_t st) {
+  HeadArgs a;
+  a.w = weights; a.obs = obs; a.nbd = nbd; a.rnn_in = rnn_in; a.mask = mask; a.u = u; a.rnn_out = rnn_out; a.logp = logp;
+  a.action = action; a.value = value;
+  a.M = c.num_rows; a.obs_dim = c.obs_dim; a.layers = c.layers; a.recurrent = c.recurrent; a.feat_norm = c.feature_norm;
+  a.relu = c.relu; a.A = c.num_outputs; a.wfloats = head_weight_floats(c.layers, c.recurrent);
+  if (a.M <= 0) return cudaSuccess;
+  const size_t smem = (size_t)(((a.wfloats + 3) & ~3) + HEAD_WARPS * 2 * HH) * sizeof(float);
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  const int want = (a.M + HEAD_WARPS - 1) / HEAD_WARPS;
+  const int grid = want < sms ? want : sms;
+  if (a.relu) {
+    e = cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    head_kernel<true><<<grid, HEAD_WARPS * 32, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    head_kernel<false><<<grid, HEAD_WARPS * 32, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace fm

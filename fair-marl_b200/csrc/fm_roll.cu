@@ -50,7 +50,7 @@ aw_roll_kernel(const __grid_constant__ RollArgs a) {
   // CTA": an item only ever waits for claimed items, whatever else occupies the GPU or however large the grid is.
   AwRoll rs;
   rs.flags = a.ctl->flags; rs.prev_tile = -1; rs.prev_t = 0; rs.early = a.early != 0; rs.multi = a.T > 1;
-  rs.s_next = &s_next[0]; rs.nx = 0;
+  rs.s_next = &s_next[0]; rs.nx = 0; rs.total = total; rs.ntiles = a.ntiles; rs.next_ready = false;
   for (int k = tid; k < a.T; k += blockDim.x) s_outs[k] = a.outs[k];
   if (tid == 0) {
     // Start-up stagger.  All CTAs of the wave start together and every item costs the same, so without it the CTAs of
@@ -86,8 +86,9 @@ aw_roll_kernel(const __grid_constant__ RollArgs a) {
         rs.prev_tile = -1;
       }
     }
-    if (rs.multi && t > 0)
+    if (rs.multi && t > 0 && !rs.next_ready)       // (normally seen satisfied during the previous item, fm_aw.cuh barrier #1)
       while (ld_acquire_gpu(rs.flags + tile) < t) __nanosleep(64);
+    rs.next_ready = false;
     AwIo io;
     io.act_idx = a.act_idx ? a.act_idx + (size_t)t * a.act_stride : nullptr;
     io.act_onehot = a.act_onehot ? a.act_onehot + (size_t)t * a.act_stride : nullptr;

@@ -1,7 +1,9 @@
-"""Formation-family scenarios (``nav_fairassign_fairrew_formation_graph`` / ``..._nofairrew_...``) on the device:
-tensor-native env over ``fm_formation_*`` (include/fairmarl.h; kernels in csrc/fm_formation.cu).
+"""Formation-family scenarios on the device -- ``nav_fairassign_fairrew_formation_graph`` (FA+FR), ``..._nofairrew_...``
+(FA), ``nav_base_formation_graph_mask`` (OA) and ``nav_base_formation_graph_randomgoal`` (RA), i.e. the scenario files of the
+four shipped ``model_weights`` -- as a tensor-native env over ``fm_formation_*`` (include/fairmarl.h; kernels in
+csrc/fm_formation.cu: per-env logic one thread per env, warp-cooperative TMA emission; N = 2..7, no walls).
 
-A first, correctness-first path: device tensors in, device tensors out, the same dict keys
+SURVEY.md section 8f, N3: device tensors in, device tensors out, the same dict keys
 as ``B200GraphVecEnv.step_tensor`` with this family's shapes -- ``obs [B,N,11]`` (scenario ``observation``, :840-1015),
 ``node_obs [B,N,E,13]`` (``_get_entity_feat_relative``, :1222-1340), ``adj_env [B,E,E]``, ``reward [B,N]``,
 ``done [B,N]`` (per-agent early done, environment.py:240-242), ``info [B,N,14]``.  ``reset()`` / ``step()`` wrap the same
@@ -37,6 +39,8 @@ class FormationSimConfig:
     collaborative: bool = False
     fairness_reward: bool = True       # True: ..._fairrew_... scenario; False: ..._nofairrew_...
     auto_reset: bool = True
+    assignment: str = "fair"           # 'fair' (FA+FR, FA) | 'optimal' (OA: min-sum matching every step) | 'random' (RA)
+    info_every_step: bool = True       # False: info rows only on the steps where every agent of the env is done (rollouts)
 
     @property
     def num_entities(self) -> int:
@@ -46,9 +50,11 @@ class FormationSimConfig:
     def from_args(cls, args: Any, **overrides) -> "FormationSimConfig":
         kw = {f: getattr(args, f) for f in cls.__dataclass_fields__ if hasattr(args, f)}
         name = getattr(args, "scenario_name", "nav_fairassign_fairrew_formation_graph")
-        if name not in ("nav_fairassign_fairrew_formation_graph", "nav_fairassign_nofairrew_formation_graph"):
-            raise NotImplementedError(f"scenario {name!r} is not one of the two formation scenarios this path covers")
-        kw["fairness_reward"] = name == "nav_fairassign_fairrew_formation_graph"
+        modes = {"nav_fairassign_fairrew_formation_graph": ("fair", True), "nav_fairassign_nofairrew_formation_graph": ("fair", False),
+                 "nav_base_formation_graph_mask": ("optimal", False), "nav_base_formation_graph_randomgoal": ("random", False)}
+        if name not in modes:
+            raise NotImplementedError(f"scenario {name!r} is not one of the four formation scenarios this path covers")
+        kw["assignment"], kw["fairness_reward"] = modes[name]
         for unsupported in ("num_walls", "num_scripted_agents"):
             if getattr(args, unsupported, 0):
                 raise NotImplementedError(f"{unsupported} > 0 is not supported by the formation kernels")
@@ -106,7 +112,8 @@ class B200FormationVecEnv:
 
     closed = False
 
-    def __init__(self, cfg: FormationSimConfig, num_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0):
+    def __init__(self, cfg: FormationSimConfig, num_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
+                 num_slots: int = 1):
         torch = _lib.require_cuda()
         self.torch, self.lib, self.cfg = torch, _lib.load(), cfg
         self.num_envs, self.num_agents, self.num_entities = int(num_envs), cfg.num_agents, cfg.num_entities
@@ -117,17 +124,24 @@ class B200FormationVecEnv:
             world_size=cfg.world_size, max_speed=cfg.max_speed if cfg.max_speed is not None else -1.0,
             collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
             min_obs_dist=cfg.min_obs_dist, fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift,
-            fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative), auto_reset=int(cfg.auto_reset))
+            fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative), auto_reset=int(cfg.auto_reset),
+            assignment={"fair": 0, "optimal": 1, "random": 2}[cfg.assignment], info_every_step=int(cfg.info_every_step))
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_formation_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_formation_create")
         B, N, E = self.num_envs, self.num_agents, self.num_entities
         f32 = dict(dtype=torch.float32, device=self.device)
-        self._buf = {
+        # `num_slots` sets of output buffers, used round robin (1: every call overwrites the previous results)
+        info = torch.zeros((B, N, _lib.INFO_DIM), **f32)
+        self._slots = [{
             "obs": torch.zeros((B, N, _lib.FORMATION_OBS_DIM), **f32),
             "node_obs": torch.zeros((B, N, E, _lib.FORMATION_NODE_FEAT_DIM), **f32),
             "adj_env": torch.zeros((B, E, E), **f32), "reward": torch.zeros((B, N), **f32),
             "done": torch.zeros((B, N), dtype=torch.uint8, device=self.device),
-            "info": torch.zeros((B, N, _lib.INFO_DIM), **f32)}
+            "info": info} for _ in range(max(1, int(num_slots)))]
+        self._outs = [_lib.FmOutputs(b["obs"].data_ptr(), b["node_obs"].data_ptr(), b["adj_env"].data_ptr(),
+                                     b["reward"].data_ptr(), b["done"].data_ptr(), b["info"].data_ptr()) for b in self._slots]
+        self._slot = 0
+        self._buf = self._slots[0]
         inf, No, Nn = float("inf"), _lib.FORMATION_OBS_DIM, _lib.FORMATION_NODE_FEAT_DIM
         self.observation_space = [Box(-inf, inf, (No,)) for _ in range(N)]          # environment.py:117-120, :781-813
         self.share_observation_space = [Box(-inf, inf, (No * N,)) for _ in range(N)]
@@ -137,9 +151,7 @@ class B200FormationVecEnv:
         self.edge_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
         self.agent_id_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
         self.share_agent_id_observation_space = [Box(-inf, inf, (N,)) for _ in range(N)]
-        b = self._buf
-        self._out = _lib.FmOutputs(b["obs"].data_ptr(), b["node_obs"].data_ptr(), b["adj_env"].data_ptr(),
-                                   b["reward"].data_ptr(), b["done"].data_ptr(), b["info"].data_ptr())
+        self._out = self._outs[0]
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -162,6 +174,8 @@ class B200FormationVecEnv:
         if not (t.is_tensor(actions) and actions.is_cuda and actions.dtype == t.int32 and actions.is_contiguous()
                 and tuple(actions.shape) == (self.num_envs, self.num_agents)):
             raise ValueError(f"actions must be a contiguous int32 CUDA tensor [{self.num_envs},{self.num_agents}]")
+        self._slot = (self._slot + 1) % len(self._slots)
+        self._buf, self._out = self._slots[self._slot], self._outs[self._slot]
         _lib.check(self.lib.fm_formation_step(self._h, actions.data_ptr(), C.byref(self._out), self._stream()),
                    "fm_formation_step")
         out = dict(self._buf)

@@ -340,6 +340,15 @@ class _RNNStep(nn.Module):
         return self.norm(x), torch.stack(outs, dim=1)
 
 
+def _quad_interleave(w_t: Tensor, rows: int) -> Tensor:
+    """W^T [K, C] (zero padded to ``rows`` rows) -> [rows / 4][C][4], the layout the head kernel reads with one LDS.128 per
+    (k-quad, column)."""
+    K, Ccols = w_t.shape
+    pad = torch.zeros(rows, Ccols, dtype=w_t.dtype, device=w_t.device)
+    pad[:K] = w_t
+    return pad.view(rows // 4, 4, Ccols).permute(0, 2, 1).contiguous().reshape(-1)
+
+
 class _Trunk(nn.Module):
     def __init__(self, cfg: PolicyConfig, graph_aggr: str, extra_in: int, gnn_mult: int = 1):
         super().__init__()
@@ -349,6 +358,75 @@ class _Trunk(nn.Module):
         self.recurrent = cfg.use_recurrent_policy or cfg.use_naive_recurrent_policy
         if self.recurrent:
             self.rnn = _RNNStep(cfg)
+        self._head_in = self.gnn_base.out_dim * gnn_mult + extra_in
+
+    # ---- fused head (csrc/fm_policy.cu head_kernel, fm_policy_head) -------------------------------------------------
+    def head_supported(self) -> bool:
+        cfg = self.cfg
+        return (cfg.hidden_size == 64 and cfg.layer_N <= 2 and self.gnn_base.out_dim == 16 and 16 <= self._head_in <= 32
+                and (not self.recurrent or cfg.recurrent_N == 1))
+
+    def _out_linear(self) -> nn.Linear:
+        raise NotImplementedError
+
+    def pack_head_weights(self) -> Tensor:
+        """The weight blob ``fm_policy_head`` reads (layout: include/fairmarl.h ``FmHeadConfig``)."""
+        base, dt = self.base, torch.float32
+        dev = base.lins[0].weight.device
+        D, H = self._head_in, 64
+        g, b = torch.ones(32, dtype=dt, device=dev), torch.zeros(32, dtype=dt, device=dev)
+        if isinstance(base.feature_norm, nn.LayerNorm):
+            g[:D], b[:D] = base.feature_norm.weight.detach().to(dt), base.feature_norm.bias.detach().to(dt)
+        parts = [g, b]
+        for k, (lin, norm) in enumerate(zip(base.lins, base.norms)):
+            parts += [_quad_interleave(lin.weight.detach().to(dt).t(), 32 if k == 0 else H), lin.bias.detach().to(dt),
+                      norm.weight.detach().to(dt), norm.bias.detach().to(dt)]
+        if self.recurrent:
+            r = self.rnn.rnn
+            parts += [_quad_interleave(r.weight_ih_l0.detach().to(dt).t(), H), _quad_interleave(r.weight_hh_l0.detach().to(dt).t(), H),
+                      r.bias_ih_l0.detach().to(dt), r.bias_hh_l0.detach().to(dt),
+                      self.rnn.norm.weight.detach().to(dt), self.rnn.norm.bias.detach().to(dt)]
+        out = self._out_linear()
+        wo, bo = torch.zeros(8, H, dtype=dt, device=dev), torch.zeros(8, dtype=dt, device=dev)
+        wo[:out.weight.shape[0]], bo[:out.bias.shape[0]] = out.weight.detach().to(dt), out.bias.detach().to(dt)
+        parts += [wo.reshape(-1), bo]
+        return torch.cat([x.reshape(-1) for x in parts]).contiguous()
+
+    def _packed_head(self) -> Tensor:
+        ps = [p for n, p in self.named_parameters() if not n.startswith("gnn_base.")]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_head_key", None) != key:
+            self._head_key, self._head_pack = key, self.pack_head_weights()
+        return self._head_pack
+
+    def _run_head(self, obs: Optional[Tensor], nbd: Tensor, rnn_states: Tensor, masks: Tensor, u: Optional[Tensor], critic: bool):
+        import ctypes as C
+        from fair_marl_b200 import _lib
+        cfg = self.cfg
+        M = nbd.shape[0]
+        out_dim = self._out_linear().weight.shape[0]
+        c = _lib.FmHeadConfig(num_rows=M, obs_dim=0 if obs is None else obs.shape[1], layers=cfg.layer_N,
+                              recurrent=int(self.recurrent), feature_norm=int(cfg.use_feature_normalization),
+                              relu=int(cfg.use_ReLU), num_outputs=out_dim)
+        dev = nbd.device
+        w = self._packed_head()
+        rnn_in = rnn_states.reshape(M, -1).contiguous() if self.recurrent else None
+        rnn_out = torch.empty((M, 1, 64), dtype=torch.float32, device=dev) if self.recurrent else rnn_states
+        mk = masks.reshape(M).to(torch.float32).contiguous() if self.recurrent else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        if critic:
+            value = torch.empty((M, 1), dtype=torch.float32, device=dev)
+            logp = action = None
+        else:
+            value = None
+            logp = torch.empty((M, 1), dtype=torch.float32, device=dev)
+            action = torch.empty((M, 1), dtype=torch.int64, device=dev)
+        if obs is not None:
+            obs = obs.contiguous()
+        _lib.check(_lib.load().fm_policy_head(dev.index, C.byref(c), w.data_ptr(), ptr(obs), nbd.data_ptr(), ptr(rnn_in), ptr(mk),
+                                              ptr(u), ptr(rnn_out) if self.recurrent else None, ptr(logp), ptr(action), ptr(value),
+                                              torch.cuda.current_stream(dev).cuda_stream), "fm_policy_head")
+        return (value, rnn_out) if critic else (action, logp, rnn_out)
 
 
 class DenseGraphActor(_Trunk):
@@ -357,6 +435,9 @@ class DenseGraphActor(_Trunk):
     def __init__(self, cfg: PolicyConfig):
         super().__init__(cfg, cfg.actor_graph_aggr, cfg.obs_dim)
         self.action_out = nn.Linear(cfg.hidden_size, cfg.action_dim)
+
+    def _out_linear(self) -> nn.Linear:
+        return self.action_out
 
     def features(self, obs, node_obs, adj, agent_id, rnn_states, masks, adj_env=None):
         nbd = self.gnn_base(node_obs, adj, agent_id, adj_env=adj_env)
@@ -370,7 +451,13 @@ class DenseGraphActor(_Trunk):
                 generator: Optional[torch.Generator] = None,
                 adj_env: Optional[Tuple[Tensor, int]] = None) -> Tuple[Tensor, Tensor, Tensor]:
         """-> (actions [M,1] int64, action_log_probs [M,1], rnn_states [M,recurrent_N,hidden]).
-        ``adj_env = (adj [B, E, E], graphs_per_adj)`` selects the fused CUDA graph network (``DenseGNNBase``)."""
+        ``adj_env = (adj [B, E, E], graphs_per_adj)`` selects the fused CUDA graph network (``DenseGNNBase``) and, when the
+        head is in its shape family too, the fused head kernel (``fm_policy_head``): two launches for the whole forward."""
+        if (adj_env is not None and available_actions is None and self.cfg.actor_graph_aggr == "node" and self.head_supported()
+                and self.cfg.action_dim <= 8 and self.gnn_base.fused_available(node_obs) and agent_id.numel() == node_obs.shape[0]):
+            nbd = self.gnn_base.forward_fused(node_obs.contiguous(), adj_env[0], adj_env[1], agent_id)
+            u = None if deterministic else torch.rand(nbd.shape[0], device=nbd.device, generator=generator)
+            return self._run_head(obs, nbd, rnn_states, masks, u, critic=False)
         x, rnn_states = self.features(obs, node_obs, adj, agent_id, rnn_states, masks, adj_env=adj_env)
         logits = self.action_out(x)
         if available_actions is not None:                                   # distributions.py:86-88
@@ -392,8 +479,15 @@ class DenseGraphCritic(_Trunk):
         super().__init__(cfg, cfg.critic_graph_aggr, cfg.obs_dim * cfg.num_agents if cfg.use_cent_obs else 0, mult)
         self.v_out = nn.Linear(cfg.hidden_size, 1)
 
+    def _out_linear(self) -> nn.Linear:
+        return self.v_out
+
     def forward(self, cent_obs: Optional[Tensor], node_obs: Tensor, adj: Tensor, agent_id: Tensor, rnn_states: Tensor,
                 masks: Tensor, adj_env: Optional[Tuple[Tensor, int]] = None) -> Tuple[Tensor, Tensor]:
+        if (adj_env is not None and not self.cfg.use_cent_obs and self.cfg.critic_graph_aggr != "node" and self.head_supported()
+                and self.gnn_base.fused_available(node_obs)):
+            nbd = self.gnn_base.forward_fused(node_obs.contiguous(), adj_env[0], adj_env[1], None)
+            return self._run_head(None, nbd, rnn_states, masks, None, critic=True)
         nbd = self.gnn_base(node_obs, adj, agent_id, adj_env=adj_env)
         x = torch.cat([cent_obs, nbd], dim=1) if self.cfg.use_cent_obs else nbd
         x = self.base(x)

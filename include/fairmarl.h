@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FM_ABI_VERSION 4
+#define FM_ABI_VERSION 5
 #define FM_OBS_DIM 7         /* navigation_graph.py:826-857 */
 #define FM_NODE_FEAT_DIM 11  /* navigation_graph.py:1079-1124 (relative features) */
 #define FM_INFO_DIM 14       /* navigation_graph.py:625-647 + environment.py:857 */
@@ -204,9 +204,10 @@ const char* fm_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Formation-family scenarios: nav_fairassign_fairrew_formation_graph.py (fairness_reward 1)
- * and nav_fairassign_nofairrew_formation_graph.py (0) under MultiAgentGraphEnv.step (environment.py:816-877).  A first,
- * correctness-first device path with its own handle: one thread per env, num_agents 2..4, no walls, relative node
- * features.  Outputs use FmOutputs with obs [B, N, 11] (:840-1015), node_obs [B, N, E, 13] (:1222-1340), adj [B, E, E],
+ * and nav_fairassign_nofairrew_formation_graph.py (0) -- and, through `assignment`, the base scenarios of model_weights/OA
+ * and RA -- under MultiAgentGraphEnv.step (environment.py:816-877).  Own handle; num_agents 2..7, no walls, relative node
+ * features.  The sequential per-agent logic runs one thread per env; the outputs are emitted warp-cooperatively through
+ * shared-memory images and TMA bulk stores (csrc/fm_formation.cu).  Outputs use FmOutputs with obs [B, N, 11] (:840-1015), node_obs [B, N, E, 13] (:1222-1340), adj [B, E, E],
  * reward / done [B, N], info [B, N, 14] (terminal values survive the auto-reset). */
 #define FM_FORMATION_OBS_DIM 11
 #define FM_FORMATION_NODE_FEAT_DIM 13
@@ -222,6 +223,11 @@ typedef struct FmFormationConfig {
   int32_t fairness_reward; /* 1: ..._fairrew_... (tanh fairness term, :770-786); 0: ..._nofairrew_... */
   int32_t collaborative;   /* environment.py:867-870 */
   int32_t auto_reset;      /* graphworker, env_wrappers.py:859-865: reset once ALL agents of an env are done */
+  int32_t assignment;      /* which goal an agent is rewarded for: 0 'fair' lexifair re-solved every step (:704-721; FA+FR, FA);
+                              1 'optimal' min-sum matching re-solved every step (nav_base_formation_graph_mask.py:666-706; OA),
+                              num_agents <= 5; 2 'random' permutation drawn at reset (nav_base_formation_graph_randomgoal.py:
+                              258-259; RA).  1 and 2 use the base scenarios' 1.5x goal clearance and need fairness_reward 0. */
+  int32_t info_every_step; /* 0: info rows are written on the steps on which every agent of the env is done (what the runner reads) */
   int32_t reserved_;
 } FmFormationConfig;
 
@@ -293,6 +299,31 @@ int64_t fm_gnn_weight_floats(const FmGnnConfig* cfg);
 int fm_gnn_supported(int32_t num_entities, int32_t node_feat_dim);   /* 1 if the kernel is compiled for this graph size */
 int fm_gnn_forward(int device, const FmGnnConfig* cfg, const float* weights, const float* node_obs, const float* adj,
                    const int32_t* agent_id, float* out, void* stream);
+
+/* Fused policy head behind the graph network: GR_Actor.forward / GR_Critic.forward after gnn_base
+ * (onpolicy/algorithms/graph_actor_critic.py:150-178, :380-397): [obs | nbd] -> MLPBase (utils/mlp.py) -> one GRU step
+ * on h * mask + LayerNorm (utils/rnn.py:23-28, :57) -> Categorical head (utils/act.py; log-softmax, mode or a draw by
+ * inverse CDF from the caller's uniforms, log-prob of the action) or the value layer.  hidden_size = 64, recurrent_N = 1.
+ *   weights  device, fm_head_weight_floats() floats (W^T stored k-quad interleaved: [k / 4][column][4]):
+ *              feature_norm gamma[32], beta[32] (input width obs_dim + 16 <= 32, zero padded)
+ *              fc1 [8][64][4], b[64], ln gamma[64], beta[64];   layers x { [16][64][4], b, gamma, beta }
+ *              recurrent: W_ih [16][192][4], W_hh [16][192][4], b_ih[192], b_hh[192], ln gamma[64], beta[64]
+ *              output W[8 rows][64] (rows >= num_outputs zero), b[8]
+ *   obs [rows, obs_dim] (NULL when obs_dim == 0), nbd [rows, 16], rnn_in [rows, 64], mask [rows], u [rows] or NULL (mode)
+ *   rnn_out [rows, 64];  actor (value == NULL): action int64 [rows], logp [rows];  critic: value [rows] */
+typedef struct FmHeadConfig {
+  int32_t num_rows, obs_dim;
+  int32_t layers;           /* layer_N: hidden layers after fc1, 0..2 */
+  int32_t recurrent;        /* use_recurrent_policy or use_naive_recurrent_policy */
+  int32_t feature_norm;     /* use_feature_normalization (the input LayerNorm) */
+  int32_t relu;             /* use_ReLU */
+  int32_t num_outputs;      /* actions (<= 8) or 1 for the critic */
+  int32_t reserved_;
+} FmHeadConfig;
+int64_t fm_head_weight_floats(const FmHeadConfig* cfg);
+int fm_policy_head(int device, const FmHeadConfig* cfg, const float* weights, const float* obs, const float* nbd,
+                   const float* rnn_in, const float* mask, const float* u, float* rnn_out, float* logp, int64_t* action,
+                   float* value, void* stream);
 
 #ifdef __cplusplus
 }

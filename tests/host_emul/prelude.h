@@ -28,7 +28,14 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int max(int a, int b) { return a > b ? a : b; }      // CUDA's global int overloads
 static inline int min(int a, int b) { return a < b ? a : b; }
+using std::fmaf;   // fabsf / fmaxf come from <cmath> in the global namespace
 using std::exp; using std::fabs; using std::fmax; using std::fmin; using std::log1p; using std::sqrt; using std::tanh;
+#define __restrict__
+#define FM_SQRT64 sqrt                                  // the device uses dsqrt_fast (same bits: correctly rounded)
+namespace fm {                                          // hardware approximations of the device build (fm_device.cuh)
+static inline float rsqrt_approx(float x) { return 1.0f / std::sqrt(x); }
+static inline float ex2_approx(float x) { return std::exp2(x); }
+}
 
 namespace fm {
 constexpr int INFO_F = 14;          // fm_device.cuh

@@ -33,7 +33,7 @@ def test_binding_covers_header(lib_path):
     from fair_marl_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.load()
-    assert lib.fm_abi_version() == 4
+    assert lib.fm_abi_version() == 5
     assert lib.fm_stats_len(3) == 47
 
 
@@ -101,7 +101,7 @@ def test_formation_entry_points_reject_bad_configs_and_have_no_cpu_path(lib_path
     from fair_marl_b200 import _lib
     lib = _lib.load()
     h = ctypes.c_void_p()
-    cfg = _lib.FmFormationConfig(num_envs=4, num_agents=5, num_obstacles=3, episode_length=25)
+    cfg = _lib.FmFormationConfig(num_envs=4, num_agents=8, num_obstacles=3, episode_length=25)
     assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -3 and b"num_agents" in lib.fm_last_error()
     cfg = _lib.FmFormationConfig(num_envs=4, num_agents=3, num_obstacles=9, episode_length=25)
     assert lib.fm_formation_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1

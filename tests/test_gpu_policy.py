@@ -81,12 +81,18 @@ def test_fused_gnn_matches_dense_modules(E, NF, aggr, rep, kw):
     node = torch.randn(M, E, NF, generator=g, device="cuda")
     node[..., -1] = torch.randint(0, 3, (M, E), generator=g, device="cuda").float()
     aid = torch.randint(0, E, (M, 1), generator=g, device="cuda")
+    import copy
     with torch.no_grad():
-        ref = gnn(node, adj_env.repeat_interleave(rep, dim=0), aid)
+        adj_rep = adj_env.repeat_interleave(rep, dim=0)
+        ref32 = gnn(node, adj_rep, aid)
+        ref64 = copy.deepcopy(gnn).double()(node.double(), adj_rep.double(), aid)       # the same function in float64
         out = gnn(node, None, aid, adj_env=(adj_env, rep))
         out2 = gnn.forward_fused(node, adj_env, rep, aid)             # deterministic: bit-identical on a second launch
-    ok, err = _close(out.cpu().numpy(), ref.cpu().numpy(), 2e-5)      # two fp32 evaluations with different summation orders
-    assert ok, err
+    # The weights are perturbed away from the init, so the LayerNorms see small variances and fp32 round-off is amplified:
+    # the fused kernel is held to the float64 truth as tightly as torch's own fp32 evaluation is (x3, floor 1e-5).
+    err = lambda x: float((torch.abs(x.double() - ref64) / torch.clamp(ref64.abs(), min=1.0)).max())
+    e_fused, e_torch = err(out), err(ref32)
+    assert e_fused <= max(3.0 * e_torch, 1e-5), (e_fused, e_torch)
     assert torch.equal(out, out2)
 
 

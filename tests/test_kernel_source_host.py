@@ -39,11 +39,12 @@ def host_exe(tmp_path_factory):
     small = open(os.path.join(CSRC, "fm_small.cuh")).read()
     form = open(os.path.join(CSRC, "fm_formation.cu")).read()
     philox = _between(dev, "__device__ __forceinline__ void philox4x32_10(", "// U(-ws/2, ws/2)^2 draw number")
+    log1p_unit = _between(dev, "__device__ __forceinline__ float log1p_unit(float t) {", "// One contact-force term, core.py:389-392")
     params = _between(launch, "struct FormParams {", "cudaError_t launch_formation")
     small_body = _between(small, "// k-th permutation of 0..N-1", "}  // namespace fm")
-    form_body = _between(form, "constexpr int F_OBS", "cudaError_t launch_formation")
-    assert "u01_24" in philox and "lexifair_small" in small_body and "formation_step_kernel" in form_body
-    src = "\n".join(['#include "prelude.h"', "namespace fm {", philox, params, small_body, form_body, "}  // namespace fm",
+    form_body = _between(form, "constexpr int F_OBS", "// Device only from here")
+    assert "u01_24" in philox and "lexifair_small" in small_body and "form_step_env" in form_body and "fmaf" in log1p_unit
+    src = "\n".join(['#include "prelude.h"', "namespace fm {", philox, log1p_unit, params, small_body, form_body, "}  // namespace fm",
                      open(os.path.join(EMUL, "harness.inc")).read()])
     d = tmp_path_factory.mktemp("host_emul")
     cpp, exe = d / "formation_host.cpp", d / "formation_host"
@@ -82,7 +83,8 @@ def _run(exe, tmp, cfg: FormationConfig, st: FormationState, actions=None, is_re
     fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
     with open(fin, "wb") as f:
         np.array([B, N, O, cfg.episode_length, int(cfg.fairness_reward), int(cfg.collaborative), int(auto_reset), int(is_reset),
-                  int(mask is not None), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, env_offset], dtype=np.int32).tofile(f)
+                  int(mask is not None), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, env_offset,
+                  {"fair": 0, "optimal": 1, "random": 2}[cfg.assignment]], dtype=np.int32).tofile(f)
         np.array([cfg.world_size, cfg.max_speed if cfg.max_speed is not None else -1.0, cfg.collision_rew, cfg.goal_rew,
                   cfg.min_dist_thresh, cfg.min_obs_dist, cfg.fair_rew, cfg.zeroshift], dtype=np.float64).tofile(f)
         for name in STATE_ORDER:
@@ -125,7 +127,8 @@ def _compare(out, ref, post, rpost):
         assert_close(getattr(post, f), getattr(rpost, f), f)
 
 
-@pytest.mark.parametrize("name", ["formation_n3_o3_fafr", "formation_n4_o2_fa"])
+@pytest.mark.parametrize("name", ["formation_n3_o3_fafr", "formation_n4_o2_fa", "formation_n7_o3_fafr", "formation_n3_o3_oa",
+                                  "formation_n3_o3_ra"])
 def test_step_source_is_sanitizer_clean_and_matches_oracle(host_exe, tmp_path, name):
     cfg, g = load(name)
     pre = _fp32(state_from(g, "pre_"))
@@ -136,11 +139,15 @@ def test_step_source_is_sanitizer_clean_and_matches_oracle(host_exe, tmp_path, n
     _compare(out, ref, post, orc.get_state())
 
 
-@pytest.mark.parametrize("N,O,collab,fair", [(4, 2, True, False), (3, 3, False, True), (2, 1, False, True)])
-def test_reset_and_rollout_source_is_sanitizer_clean_and_matches_oracle(host_exe, tmp_path, N, O, collab, fair):
+@pytest.mark.parametrize("N,O,collab,fair,assignment", [
+    (4, 2, True, False, "fair"), (3, 3, False, True, "fair"), (2, 1, False, True, "fair"),
+    (5, 2, False, True, "fair"), (6, 1, False, False, "fair"), (7, 3, False, True, "fair"),     # serial lexifair descent (N > 4)
+    (3, 3, False, False, "optimal"), (4, 1, False, False, "optimal"), (5, 0, True, False, "optimal"),
+    (3, 3, False, False, "random"), (6, 2, False, False, "random")])
+def test_reset_and_rollout_source_is_sanitizer_clean_and_matches_oracle(host_exe, tmp_path, N, O, collab, fair, assignment):
     B = 24
     cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=8,
-                          collaborative=collab, fairness_reward=fair)
+                          collaborative=collab, fairness_reward=fair, assignment=assignment)
     orc = FormationOracle(cfg, B, seed=7, env_offset=3)
     ref = orc.reset()
     zero = FormationOracle(cfg, B).get_state()
