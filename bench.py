@@ -429,7 +429,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # the following steps instead of being the last thing the timer waits for.
     phase0 = (-(Wn + (K + 1) // 2)) % EPISODE
 
-    graphs = {}                                   # --graph: (phase, steps) -> captured fm_step_many launch sequence
+    graphs = {}                                   # (phase, steps, slot) -> captured fm_step_many launch sequence
+    replayed = [0]                                # kernels launched through graph replays (the handle counts eager launches only)
 
     def rollout_chunk(phase, t):
         if not args.graph:
@@ -439,15 +440,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         g = graphs.get(key)
         if g is None:                             # captured during the dry run, replayed in the timed region
             torch.cuda.synchronize(dev)
-            slot0 = env._slot
+            slot0, n0 = env._slot, env.kernel_launches
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 env.rollout_tensor(actions[phase:phase + t])
-            graphs[key] = (g, env._slot)
+            graphs[key] = (g, env._slot, env.kernel_launches - n0)
             env._slot = slot0
             g = graphs[key]
         g[0].replay()
         env._slot = g[1]
+        replayed[0] += g[2]
 
     def run_steps(n, phase):
         """n env steps from episode phase `phase`, in chunks that end at episode boundaries; every terminal step is
@@ -466,11 +468,34 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         env._slot = 0                             # same walk through the slab ring in the dry run and in the measured run
         return run_steps(phase0, 0)
 
-    # dry run of the exact call sequence (plans, lazily created streams / buffers, NCCL channels), then the real one
+    # One GPU: the whole timed sequence (rollout chunks, statistics reductions) is ONE captured graph.  Several GPUs: one
+    # graph per rollout chunk; the NCCL all-reduce between them stays an eager launch on the side stream.
+    region = {}
+
+    def timed_sequence(phase):
+        if not (args.graph and world == 1):
+            run_steps(K, phase)
+            stats.join()
+            return
+        if "g" not in region:                     # captured in the dry run below, replayed in the timed region
+            torch.cuda.synchronize(dev)
+            slot0, n0 = env._slot, env.kernel_launches
+            saved, args.graph = args.graph, False          # the region graph holds the eager launches themselves
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run_steps(K, phase)
+                stats.join()
+            args.graph = saved
+            region["g"], region["slot"], region["kernels"] = g, env._slot, env.kernel_launches - n0
+            env._slot = slot0
+        region["g"].replay()
+        env._slot = region["slot"]
+        replayed[0] += region["kernels"]
+
+    # dry run of the exact call sequence (plans, lazily created streams / buffers, NCCL channels, graphs), then the real one
     ph = prepare()
     ph = run_steps(Wn, ph)
-    run_steps(K, ph)
-    stats.join()
+    timed_sequence(ph)
     torch.cuda.synchronize(dev)
     env.read_stats(clear=True, out=stats_vec)
     ph = prepare()
@@ -484,11 +509,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.barrier()
     torch.cuda.synchronize(dev)
     launches0 = env.kernel_launches
+    replayed[0] = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    run_steps(K, ph)
-    stats.join()                                  # the all-reduce of the region's terminal steps is inside the measurement
+    timed_sequence(ph)                            # incl. stats.join(): the all-reduce of the region's terminal steps is inside
     ev1.record()
     sampler.sample_now()                          # one NVML read by this thread while the GPU is still working on the region
     torch.cuda.synchronize(dev)
@@ -496,7 +521,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.barrier()
     t1 = time.perf_counter()
     sampler.period = 0.02
-    launches = env.kernel_launches - launches0
+    launches = (env.kernel_launches - launches0) + replayed[0]           # eager launches + kernels inside the replayed graphs
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary(t0, t1)
     if world > 1:
@@ -513,7 +538,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env.algorithmic_bytes_per_step
-    kernel_name = {"aw": f"fm::aw_roll_kernel<{N_AGENTS},{N_OBST},11> (agent-warp, persistent rollout)",
+    kernel_name = {"aw": (f"fm::aw_roll_kernel<{N_AGENTS},{N_OBST},11> (agent-warp, persistent rollout)"
+                          if os.environ.get("FM_ROLL", "0") not in ("", "0") else f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)"),
                    "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}{', true' if N_WALLS else ''}> (group-per-env)"}[env.mapping]
     # One step = the step kernel's work over the whole batch (agent-warp mapping: (step, tile) items of one persistent
     # launch per chunk of steps; group mapping: concurrent env-range launches on side streams); that kernel is > 99 %
@@ -632,8 +658,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                            else "local reduce after every terminal step"),
                        "episode_phase_at_start": (phase0 + Wn) % EPISODE,
                        "launch": ("fm_step_many: one persistent kernel per chunk of steps (chunks end at episode boundaries)"
-                                  if env.mapping == "aw" and not os.environ.get("FM_ROLL") == "0" else
-                                  "fm_step_many: env-range lanes on side streams") + (", chunks replayed as CUDA graphs" if args.graph else "")},
+                                  if env.mapping == "aw" and os.environ.get("FM_ROLL", "0") not in ("", "0") else
+                                  "fm_step_many: one-shot step kernels on env-range lanes (side streams)") +
+                                 ((", the region's call sequence replayed as ONE captured CUDA graph" if world == 1 else
+                                   ", every chunk replayed as a captured CUDA graph") if args.graph else ", eager launches")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "closed_loop": closed_loop, "edge_list": edge_list,
             "gpu_launches": launches, "clocks": clocks,
             "episode_stats": {"episodes": total_stats["episodes"], "env_steps": total_stats["env_steps"]},
@@ -661,7 +689,9 @@ def main():
     ap.add_argument("--walls", type=int, default=0, choices=[0, 1, 2], help="diagnostic: num_walls (wall kernels, SURVEY N4)")
     ap.add_argument("--no-graph", action="store_true", help="c5: time the eager loop instead of the captured CUDA graph")
     ap.add_argument("--form-slots", type=int, default=8, help="form: output buffer sets the steps cycle through")
-    ap.add_argument("--graph", action="store_true", help="replay every fm_step_many chunk of the timed region as a captured CUDA graph")
+    ap.add_argument("--no-step-graph", dest="graph", action="store_false",
+                    help="launch fm_step_many eagerly instead of replaying the captured CUDA graph of the region's call sequence")
+    ap.set_defaults(graph=True)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -109,6 +109,7 @@ def load():
         "fm_create": ([C.POINTER(FmConfig), C.c_int, C.POINTER(vp)], C.c_int),
         "fm_destroy": ([vp], C.c_int),
         "fm_reset": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_observe": ([vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_step": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_step_onehot": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_step_many": ([vp, vp, i32, C.POINTER(FmOutputs), vp], C.c_int),
@@ -146,7 +147,7 @@ def load():
 
 
 EXPORTED_SYMBOLS = (
-    "fm_abi_version", "fm_last_error", "fm_stats_len", "fm_create", "fm_destroy", "fm_reset", "fm_step",
+    "fm_abi_version", "fm_last_error", "fm_stats_len", "fm_create", "fm_destroy", "fm_reset", "fm_observe", "fm_step",
     "fm_step_onehot", "fm_step_many", "fm_step_host", "fm_reset_host", "fm_read_info_host", "fm_set_state", "fm_get_state",
     "fm_assign_costs", "fm_assign_positions", "fm_pair_dist", "fm_edge_list", "fm_stats_read", "fm_num_entities", "fm_mapping",
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",

@@ -248,9 +248,12 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     const int v = atoi(ev);
     if (v >= 1 && v <= FM_MAX_LANES) h->lanes_override = v;
   }
-  if (p.mapping == 1) {                               // persistent rollout kernel (FM_ROLL=0: one-shot launches, diagnostic)
+  if (p.mapping == 1) {
+    // Persistent rollout kernel (fm_roll.cu), opt-in with FM_ROLL=1.  Measured on B200 at C2 it reaches 70 % of the HBM
+    // roofline against 93 % for the one-shot kernels on two env-range lanes replayed from a CUDA graph (profiles/r02_*), so
+    // the one-shot kernels stay the default path; the rollout kernel is kept, tested, for single-launch use.
     const char* ev = getenv("FM_ROLL");
-    h->roll_on = !(ev && atoi(ev) == 0);
+    h->roll_on = ev && atoi(ev) != 0;
     int per_sm = 0, sms = 0;
     e = fm::roll_prepare(p, &per_sm);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -371,6 +374,19 @@ static void advance_phase(FmHandle* h, bool terminal) {
   if (h->p.auto_reset) h->host_step = 0; else h->lockstep = 0;
 }
 
+int fm_observe(FmHandle* h, const FmOutputs* out, void* stream) {
+  if (!h) return fail(FM_ERR_INVALID_ARG, "fm_observe: null handle");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  DevParams p = h->p;
+  set_outputs(p, out);
+  p.reset_mask = nullptr; p.observe_only = 1;
+  p.act_idx = nullptr; p.act_onehot = nullptr;
+  FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, true));
+  h->launches += 1;
+  return FM_OK;                                      // no state change: the episode phase the host tracks stays valid
+}
+
 int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* stream) {
   if (!h) return fail(FM_ERR_INVALID_ARG, "fm_reset: null handle");
   int rc = use_device(h->device);
@@ -407,6 +423,9 @@ static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, con
   DevParams p = h->p;
   set_outputs(p, out);
   p.act_idx = idx; p.act_onehot = onehot; p.reset_mask = nullptr;
+  // A captured launch is replayed without passing through here: the host's view of the episode phase would drift, so
+  // the next-episode prefetch (the only consumer of that view) stays off until the next full fm_reset.
+  if (stream_capturing((cudaStream_t)stream)) h->lockstep = 0;
   const bool terminal = step_is_terminal(h);
   rc = prefetch_before_step(h, p, (cudaStream_t)stream, terminal);
   if (rc) return rc;
@@ -438,6 +457,7 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
   int rc = use_device(h->device);
   if (rc) return rc;
   const size_t stride = (size_t)h->p.B * h->p.N;
+  if (stream_capturing((cudaStream_t)stream)) h->lockstep = 0;      // see step_common
   if (h->roll_on) {
     // Agent-warp mapping: the whole rollout is (step, tile) items of ONE persistent kernel per chunk of <=
     // FM_ROLL_MAX_STEPS steps (fm_roll.cu).  A tile's next step may start as soon as its state is written back when

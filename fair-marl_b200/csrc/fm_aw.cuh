@@ -572,7 +572,7 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
   } else {
     // =========================================================================================
     // MODE 1: reset() / observe
-    do_reset = venv && (io.reset_mask ? (io.reset_mask[env] != 0) : true);
+    do_reset = venv && !p.observe_only && (io.reset_mask ? (io.reset_mask[env] != 0) : true);
     if (is_agent) {
       const float* gi = gs + (size_t)i * Bp;
       px = __ldcg(gi + (size_t)L::PX * Bp); py = __ldcg(gi + (size_t)L::PY * Bp);

@@ -13,13 +13,15 @@
 // 32 consecutive envs, walking the reference's own order with the env in registers / local memory (float64 like the
 // reference, except the softplus contact terms, which are the fp32 hardware-approximation form of the navigation
 // kernels).  What a thread produces is not the output rows but their RECIPE, in warp-private shared memory:
-//   obs / adj / reward / done   lane = env images in API layout (the warp's slice of each array is one contiguous range)
-//   node_obs                    positions + per ego agent i the velocities and the goal picks (goal, occupied, history) of
-//                               the N agents as they stood when ego i's rows were built (6 N^2 + 2 E floats per env)
-// and the EMISSION is warp-cooperative: the images go out as TMA bulk stores; the 13-float node rows are rebuilt from the
-// recipe, 3 consecutive rows per lane into a 96-row staging buffer (lane stride 39 floats: conflict free) that the copy
-// engine streams out while the warp builds the next one (double buffered inside the adj image once that has been read).
-// Round 1's kernel wrote 468-byte row runs per lane (32 sectors per store instruction, 8.5 % of the HBM roofline).
+//   obs / reward / done   lane = env images in API layout (the warp's slice of each array is one contiguous range)
+//   adj, node_obs         fp32 positions + post-integration velocities + per agent the ego index from which its velocity
+//                         reads zero (it latched this step) + per (ego, agent) the goal it is shown heading for (landmark
+//                         index, occupied, history): 2 E + 3 N + 3 N^2 floats per env (55 at N = 3, O = 3)
+// and the EMISSION is warp-cooperative: the images go out as TMA bulk stores; adj (unique pairs spread over the lanes,
+// mirrored) and the 13-float node rows are rebuilt from the recipes into two small staging buffers, one being filled
+// while the copy engine streams the other.  14.7 KB of shared memory per warp at N = 3: 14 warps / SM -- the logic is a
+// latency-bound serial chain, so resident warps are what buys throughput (round 2, first version: whole-tile adj image +
+// 6 N^2-float recipes, 29.9 KB, 7 warps / SM, 20 % of the HBM roofline; round 1: 468-byte row runs per lane, 8.5 %).
 //
 // The device functions below are also compiled for the host by tests/test_kernel_source_host.py (g++, ASan + UBSan,
 // tests/host_emul/prelude.h stands in for the CUDA built-ins): the per-env logic and the row builder are checked against
@@ -35,7 +37,7 @@
 namespace fm {
 
 constexpr int F_OBS = FM_FORMATION_OBS_DIM, F_NODE = FM_FORMATION_NODE_FEAT_DIM, F_MAXO = FM_FORMATION_MAX_OBSTACLES;
-constexpr int F_ROWS_PER_LANE = 3, F_CHUNK_ROWS = 32 * F_ROWS_PER_LANE, F_CHUNK_WORDS = F_CHUNK_ROWS * F_NODE;   // 96 rows, 1248 floats
+constexpr int F_ROWS_PER_LANE = 1, F_CHUNK_ROWS = 32 * F_ROWS_PER_LANE, F_CHUNK_WORDS = F_CHUNK_ROWS * F_NODE;   // 32 rows, 416 floats (small: shared memory per warp bounds the occupancy)
 
 template <int N>
 struct FEnv {
@@ -50,13 +52,14 @@ struct FEnv {
 // Where one env's thread writes (shared memory on the device, lane = env; plain arrays in the host harness).
 struct FOut {
   float* obs;      // [N][11]
-  float* adj;      // [E][E]
   float* rew;      // [N]
   uint8_t* done;   // [N]
-  float* rec;      // recipe of the node rows: pos [E][2] | per ego i: vel [N][2], pick [N][4] (goal x, y, occupied, history)
-  float* info;     // [N][14]
+  float* rec;      // recipe of adj and the node rows:
+                   //   pos [E][2] | vel [N][2] after the integration | latch [N]: ego index from which agent a's velocity reads 0
+                   //   (it latched in this step's reward call of that ego; N + 1: never) | per ego i: pick [N][3] = (goal: landmark
+                   //   index, or -1 = the agent's own position; goal occupied; goal history) as shown in ego i's rows
 };
-__host__ __device__ inline int form_rec_floats(int N, int O) { return 2 * (2 * N + O) + 6 * N * N; }
+__host__ __device__ inline int form_rec_floats(int N, int O) { return 2 * (2 * N + O) + 3 * N + 3 * N * N; }
 
 __device__ __forceinline__ double dn(double dx, double dy) {      // sqrt(dx*dx + dy*dy), no contraction (numpy has none)
   return FM_SQRT64(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
@@ -117,7 +120,7 @@ __device__ void f_mean_std(const double (&v)[N], double& mean, double& sd) {
 // Far branch shared by observation (:933-956) and the agent rows of the node features (:1256-1270): nearest goal not
 // marked occupied (== 1); if every goal is, the entity itself and a cleared table.
 template <int N>
-__device__ void f_pick_goal(FEnv<N>& e, double qx, double qy, int slot, double& gx, double& gy, double& occ, double& hist) {
+__device__ int f_pick_goal(FEnv<N>& e, double qx, double qy, int slot, double& gx, double& gy, double& occ, double& hist) {
   int best = -1;
   double bd = 0.0;
   for (int g = 0; g < N; ++g) {
@@ -125,9 +128,10 @@ __device__ void f_pick_goal(FEnv<N>& e, double qx, double qy, int slot, double& 
     const double d = dn(qx - e.lx[g], qy - e.ly[g]);
     if (best < 0 || d < bd) { best = g; bd = d; }
   }
-  if (best >= 0) { gx = e.lx[best]; gy = e.ly[best]; occ = e.occ[best]; hist = e.hist[best]; return; }
+  if (best >= 0) { gx = e.lx[best]; gy = e.ly[best]; occ = e.occ[best]; hist = e.hist[best]; return best; }
   for (int g = 0; g < N; ++g) e.occ[g] = 0.0;                              // :951 / :1266
   gx = qx; gy = qy; occ = e.occ[slot]; hist = e.hist[slot];
+  return -1;
 }
 
 // Scenario.observation (:840-1015) of agent i: 11 values, updates the occupancy table and the goal history.
@@ -179,47 +183,53 @@ __device__ void f_observation(const FormParams& p, FEnv<N>& e, int i, float* __r
   }
 }
 
-// graph_observation + _get_entity_feat_relative (:1083-1178, :1222-1340) for ego agent i, as a RECIPE: the velocities of
-// the N agents as they stand now (latched agents up to i have theirs zeroed) and, per agent, the goal it is shown heading
-// for with that goal's occupancy / history (the far branch may clear the occupancy table, :1266).  f_row turns it into rows.
+// graph_observation + _get_entity_feat_relative (:1083-1178, :1222-1340) for ego agent i, as a RECIPE: per agent a the goal
+// it is shown heading for with that goal's occupancy / history (the far branch may clear the occupancy table, :1266).  The
+// velocities ego i sees are the post-integration ones with the agents that latched at ego index <= i zeroed (rec latch[]).
 template <int N>
 __device__ void f_node_recipe(const FormParams& p, FEnv<N>& e, int i, float* __restrict__ rec) {
-  float* v = rec + 2 * (2 * N + p.O) + i * 6 * N;
-  float* pk = v + 2 * N;
+  float* pk = rec + 2 * (2 * N + p.O) + 3 * N + i * 3 * N;
   for (int a = 0; a < N; ++a) {
     const double qx = e.px[a], qy = e.py[a];
     int first = 0; double mind = 0.0;
     for (int g = 0; g < N; ++g) { const double d = dn(qx - e.lx[g], qy - e.ly[g]); if (g == 0 || d < mind) { first = g; mind = d; } }
     double gx, gy, occ, hist;
-    if (mind < p.min_obs_dist) { gx = e.lx[first]; gy = e.ly[first]; occ = e.occ[first]; hist = e.hist[first]; }
-    else f_pick_goal<N>(e, qx, qy, a, gx, gy, occ, hist);
-    v[2 * a] = (float)e.vx[a]; v[2 * a + 1] = (float)e.vy[a];
-    pk[4 * a] = (float)gx; pk[4 * a + 1] = (float)gy; pk[4 * a + 2] = (float)occ; pk[4 * a + 3] = (float)hist;
+    int gi = first;
+    if (mind < p.min_obs_dist) { occ = e.occ[first]; hist = e.hist[first]; }
+    else gi = f_pick_goal<N>(e, qx, qy, a, gx, gy, occ, hist);
+    pk[3 * a] = (float)gi; pk[3 * a + 1] = (float)occ; pk[3 * a + 2] = (float)hist;
   }
 }
 
-// positions of the E entities (agents, landmarks, obstacles) -> head of the recipe
+// head of the recipe: positions of the E entities (agents, landmarks, obstacles), velocities, no latch yet
 template <int N>
-__device__ void f_rec_positions(const FormParams& p, const FEnv<N>& e, float* __restrict__ rec) {
+__device__ void f_rec_head(const FormParams& p, const FEnv<N>& e, float* __restrict__ rec) {
   for (int a = 0; a < N; ++a) {
     rec[2 * a] = (float)e.px[a]; rec[2 * a + 1] = (float)e.py[a];
     rec[2 * (N + a)] = (float)e.lx[a]; rec[2 * (N + a) + 1] = (float)e.ly[a];
   }
   for (int k = 0; k < p.O; ++k) { rec[2 * (2 * N + k)] = (float)e.ox[k]; rec[2 * (2 * N + k) + 1] = (float)e.oy[k]; }
+  float* v = rec + 2 * (2 * N + p.O);
+  for (int a = 0; a < N; ++a) { v[2 * a] = (float)e.vx[a]; v[2 * a + 1] = (float)e.vy[a]; v[2 * N + a] = (float)(N + 1); }
 }
 
 // One node_obs row (ego agent i, entity en) from an env's recipe (:1222-1340):
 //   [v_e - v_i (2), p_e - p_i (2), goal_e - p_i (2), goal occupied, goal history, p_e - p_i (2), p_e - p_i (2), type]
 // landmarks: occupied 1, history = landmark id; obstacles: occupied 1, history 0 (id None); both with v_e = 0, goal = p_e.
 __device__ __forceinline__ void f_row(const float* __restrict__ rec, int N, int O, int i, int en, float* __restrict__ q) {
-  const float* v = rec + 2 * (2 * N + O) + i * 6 * N;
-  const float* pk = v + 2 * N;
-  const float x = rec[2 * i], y = rec[2 * i + 1], vx = v[2 * i], vy = v[2 * i + 1];
+  const float* v = rec + 2 * (2 * N + O);
+  const float* latch = v + 2 * N;
+  const float* pk = latch + N + i * 3 * N;
+  const bool zi = latch[i] <= (float)i;
+  const float x = rec[2 * i], y = rec[2 * i + 1], vx = zi ? 0.0f : v[2 * i], vy = zi ? 0.0f : v[2 * i + 1];
   const float rx = rec[2 * en] - x, ry = rec[2 * en + 1] - y;
   float rvx = 0.0f - vx, rvy = 0.0f - vy, gx = rx, gy = ry, occ = 1.0f, hist = 0.0f, type = 2.0f;
   if (en < N) {
-    rvx = v[2 * en] - vx; rvy = v[2 * en + 1] - vy;
-    gx = pk[4 * en] - x; gy = pk[4 * en + 1] - y; occ = pk[4 * en + 2]; hist = pk[4 * en + 3]; type = 0.0f;
+    const bool ze = latch[en] <= (float)i;
+    rvx = (ze ? 0.0f : v[2 * en]) - vx; rvy = (ze ? 0.0f : v[2 * en + 1]) - vy;
+    const int gi = (int)pk[3 * en];
+    if (gi >= 0) { gx = rec[2 * (N + gi)] - x; gy = rec[2 * (N + gi) + 1] - y; }      // gi < 0: the agent's own position (rel pos)
+    occ = pk[3 * en + 1]; hist = pk[3 * en + 2]; type = 0.0f;
   } else if (en < 2 * N) {
     hist = (float)(en - N); type = 1.0f;
   }
@@ -227,17 +237,10 @@ __device__ __forceinline__ void f_row(const float* __restrict__ rec, int N, int 
   q[8] = rx; q[9] = ry; q[10] = rx; q[11] = ry; q[12] = type;
 }
 
-// cached_dist_mag (core.py:204-228) -> adj [E, E].
-template <int N>
-__device__ void f_adj(const FormParams& p, const FEnv<N>& e, float* __restrict__ adj) {
-  if (!adj) return;
-  const int E = 2 * N + p.O;
-  auto X = [&](int s) { return s < N ? e.px[s] : (s < 2 * N ? e.lx[s - N] : e.ox[s - 2 * N]); };
-  auto Y = [&](int s) { return s < N ? e.py[s] : (s < 2 * N ? e.ly[s - N] : e.oy[s - 2 * N]); };
-  for (int a = 0; a < E; ++a) {
-    adj[a * E + a] = 0.0f;
-    for (int c = a + 1; c < E; ++c) { const float d = (float)dn(X(a) - X(c), Y(a) - Y(c)); adj[a * E + c] = d; adj[c * E + a] = d; }
-  }
+// One entry of cached_dist_mag (core.py:204-228) = adj [E, E], from the recipe's fp32 positions (the positions the state
+// block stores), float64 distance rounded once.
+__device__ __forceinline__ float f_adj_elem(const float* __restrict__ rec, int a, int c) {
+  return a == c ? 0.0f : (float)dn((double)rec[2 * a] - (double)rec[2 * c], (double)rec[2 * a + 1] - (double)rec[2 * c + 1]);
 }
 
 // Lexifair by sorted threshold descent for one thread (marl_fair_assign.py:16-55; oracle/lexifair.py lexifair_descent; the
@@ -339,12 +342,11 @@ __device__ void f_min_sum(const FEnv<N>& e, int (&match)[N], double (&delta)[N])
 // env.reset()'s observation pass (environment.py:882-898): obs_i, then node rows_i, per agent.
 template <int N>
 __device__ void f_observe(const FormParams& p, FEnv<N>& e, const FOut& o) {
-  f_rec_positions<N>(p, e, o.rec);
+  f_rec_head<N>(p, e, o.rec);
   for (int i = 0; i < N; ++i) {
     f_observation<N>(p, e, i, o.obs + i * F_OBS);
     f_node_recipe<N>(p, e, i, o.rec);
   }
-  f_adj<N>(p, e, o.adj);
 }
 
 // reset_world + random_scenario (:217-487) with the Philox draw scheme of the navigation kernels: draw counter per
@@ -465,8 +467,10 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
     e.px[i] = __dadd_rn(e.px[i], sx); e.py[i] = __dadd_rn(e.py[i], sy);
     e.pd[i] = __dadd_rn(e.pd[i], dn(sx, sy));
   }
-  f_adj<N>(p, e, o.adj);
-  f_rec_positions<N>(p, e, o.rec);
+  f_rec_head<N>(p, e, o.rec);
+  float* latch = o.rec + 2 * (2 * N + O) + 2 * N;
+  float info[N * INFO_F];                                                  // rows of this step; written out below when wanted
+  const bool want_info = p.out.info != nullptr;
 
   // ---- per-agent loop (environment.py:832-864): observation, reward, node rows, done, info -- in this order
   double rew[N], delta[N];
@@ -485,7 +489,7 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
     const double dg = p.assignment == 1 ? delta[i] : dn(x - e.lx[e.gm[i]], y - e.ly[e.gm[i]]);
     double r = 0.0;
     if (dg < th) {                                                         // :725-733
-      if (!e.status[i]) { e.status[i] = true; e.vx[i] = 0.0; e.vy[i] = 0.0; r += p.goal_rew; }
+      if (!e.status[i]) { e.status[i] = true; e.vx[i] = 0.0; e.vy[i] = 0.0; latch[i] = (float)i; r += p.goal_rew; }
     } else {
       r -= dg;
     }
@@ -516,9 +520,9 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
       if (ohit) e.noc[i] += 1.0;                                                                                    // :521-523
       e.nac[i] += (double)hits;
       f_mean_std<N>(e.dtg, e.dmean, e.dstd);                                                                        // :534-535
-      if (o.info) {
+      if (want_info) {
         double tm, ts; f_mean_std<N>(e.treq, tm, ts);
-        float* q = o.info + i * INFO_F;
+        float* q = info + i * INFO_F;
         q[0] = (float)r; q[1] = (float)e.dleft[i]; q[2] = (float)e.treq[i]; q[3] = (float)e.nac[i]; q[4] = (float)e.noc[i];
         q[5] = (float)e.dmean; q[6] = (float)e.dstd; q[7] = (float)(e.dmean / (e.dstd + 0.0001)); q[8] = (float)e.dtg[i];
         q[9] = (float)e.treq[i]; q[10] = (float)tm; q[11] = (float)ts; q[12] = (float)(tm / (ts + 0.0001)); q[13] = (float)e.mint[i];
@@ -532,9 +536,9 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
     o.done[i] = done[i] ? 1 : 0;
   }
   // info rows go straight to global memory, on the steps whose values the runner reads (every agent done; or every step)
-  if (o.info && p.out.info && (all_done || p.info_every_step)) {
+  if (want_info && (all_done || p.info_every_step)) {
     float* g = p.out.info + (size_t)b * N * INFO_F;
-    for (int k = 0; k < N * INFO_F; ++k) g[k] = o.info[k];
+    for (int k = 0; k < N * INFO_F; ++k) g[k] = info[k];
   }
   const bool reset = p.auto_reset && all_done;                             // env_wrappers.py:859-865
   if (reset) { f_reset<N>(p, b, e); f_observe<N>(p, e, o); }
@@ -546,83 +550,109 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
 #ifdef __CUDACC__
 
 struct FormTile {            // floats per warp; all offsets multiples of 4 floats
-  int obs, adj, rew, done, rec, info, rec_stride, info_stride, words;
+  int obs, rew, done, rec, stage, rec_stride, words;
 };
-__host__ __device__ inline FormTile form_tile(int N, int O, bool with_info) {
-  const int E = 2 * N + O;
+__host__ __device__ inline FormTile form_tile(int N, int O) {
   FormTile t;
-  const int adj_words = 32 * E * E, stage_words = 2 * F_CHUNK_WORDS;       // the adj image doubles as the two row buffers
-  t.adj = 0;
-  t.obs = ((adj_words > stage_words ? adj_words : stage_words) + 3) & ~3;
+  t.stage = 0;                                                             // two staging buffers of F_CHUNK_WORDS
+  t.obs = 2 * F_CHUNK_WORDS;
   t.rew = t.obs + ((32 * N * F_OBS + 3) & ~3);
   t.done = t.rew + ((32 * N + 3) & ~3);
   t.rec = t.done + ((8 * N + 3) & ~3);                                      // 32 N bytes
   t.rec_stride = form_rec_floats(N, O) | 1;                                 // odd: lane = env accesses are conflict free
-  t.info = t.rec + ((32 * t.rec_stride + 3) & ~3);
-  t.info_stride = with_info ? ((N * INFO_F) | 1) : 0;
-  t.words = t.info + ((32 * t.info_stride + 3) & ~3);
+  t.words = t.rec + ((32 * t.rec_stride + 3) & ~3);
   return t;
 }
 
-// The warp's images -> global memory.  Full, 16-byte aligned tiles go through the copy engine; ragged / unaligned ones
-// are written by the lanes (coalesced for the images, per-lane rows for node_obs).
+// The warp's images -> global memory.  Full, 16-byte aligned tiles go through the copy engine (obs / reward / done images
+// as they are; adj and the node rows rebuilt from the recipes into two staging buffers, one being filled while the engine
+// streams the other); ragged / unaligned tiles are written by the lanes.
 template <int N>
 __device__ void form_emit(const FormParams& p, float* __restrict__ S, const FormTile& t, int env0, int nenv, int lane, bool with_step) {
-  const int O = p.O, E = 2 * N + O, NE = N * E;
+  const int O = p.O, E = 2 * N + O, NE = N * E, EE = E * E;
   float* g_obs = p.out.obs ? p.out.obs + (size_t)env0 * N * F_OBS : nullptr;
-  float* g_adj = p.out.adj ? p.out.adj + (size_t)env0 * E * E : nullptr;
+  float* g_adj = p.out.adj ? p.out.adj + (size_t)env0 * EE : nullptr;
   float* g_rew = (with_step && p.out.reward) ? p.out.reward + (size_t)env0 * N : nullptr;
   uint8_t* g_done = (with_step && p.out.done) ? p.out.done + (size_t)env0 * N : nullptr;
   float* g_node = p.out.node_obs ? p.out.node_obs + (size_t)env0 * NE * F_NODE : nullptr;
   const bool bulk = nenv == 32 && aligned16(g_obs) && aligned16(g_adj) && aligned16(g_rew) && aligned16(g_done) && aligned16(g_node);
-  uint64_t pol = 0;
-  if (bulk) {
-    if (lane == 0) {
-      pol = evict_first_policy();
-      fence_async_smem();
-      if (g_adj) bulk_store(g_adj, S + t.adj, 32 * E * E * 4, pol);
-      if (g_obs) bulk_store(g_obs, S + t.obs, 32 * N * F_OBS * 4, pol);
-      if (g_rew) bulk_store(g_rew, S + t.rew, 32 * N * 4, pol);
-      if (g_done) bulk_store(g_done, S + t.done, 32 * N, pol);
-      bulk_commit();
-    }
-  } else {
-    if (g_adj) for (int k = lane; k < nenv * E * E; k += 32) __stcs(g_adj + k, S[t.adj + k]);
+  const float* rec = S + t.rec;
+  if (!bulk) {
     if (g_obs) for (int k = lane; k < nenv * N * F_OBS; k += 32) __stcs(g_obs + k, S[t.obs + k]);
     if (g_rew) for (int k = lane; k < nenv * N; k += 32) __stcs(g_rew + k, S[t.rew + k]);
     if (g_done) for (int k = lane; k < nenv * N; k += 32) g_done[k] = reinterpret_cast<const uint8_t*>(S + t.done)[k];
-  }
-  if (!g_node) { if (bulk && lane == 0) bulk_wait_read<0>(); return; }
-  const int rows = nenv * NE;
-  if (!bulk) {
-    for (int r = lane; r < rows; r += 32) {
-      const int el = r / NE, q = r - el * NE, i = q / E, en = q - i * E;
-      float row[F_NODE];
-      f_row(S + t.rec + el * t.rec_stride, N, O, i, en, row);
+    if (g_adj)
+      for (int k = lane; k < nenv * EE; k += 32) {
+        const int el = k / EE, q = k - el * EE, a = q / E;
+        __stcs(g_adj + k, f_adj_elem(rec + el * t.rec_stride, a, q - a * E));
+      }
+    if (g_node)
+      for (int r = lane; r < nenv * NE; r += 32) {
+        const int el = r / NE, q = r - el * NE, i = q / E;
+        float row[F_NODE];
+        f_row(rec + el * t.rec_stride, N, O, i, q - i * E, row);
 #pragma unroll
-      for (int f = 0; f < F_NODE; ++f) __stcs(g_node + (size_t)r * F_NODE + f, row[f]);
-    }
+        for (int f = 0; f < F_NODE; ++f) __stcs(g_node + (size_t)r * F_NODE + f, row[f]);
+      }
     return;
   }
-  if (lane == 0) bulk_wait_read<0>();                                       // the adj image becomes the two row buffers
-  __syncwarp();
-  int c = 0;
-  for (int r0 = 0; r0 < rows; r0 += F_CHUNK_ROWS, ++c) {
-    float* buf = S + t.adj + (c & 1) * F_CHUNK_WORDS;
+  uint64_t pol = 0;
+  if (lane == 0) {
+    pol = evict_first_policy();
+    fence_async_smem();
+    if (g_obs) bulk_store(g_obs, S + t.obs, 32 * N * F_OBS * 4, pol);
+    if (g_rew) bulk_store(g_rew, S + t.rew, 32 * N * 4, pol);
+    if (g_done) bulk_store(g_done, S + t.done, 32 * N, pol);
+    bulk_commit();
+  }
+  int c = 0;                                                                // staging chunks issued so far
+  auto next_buffer = [&]() -> float* {
     if (c >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }       // the engine has read chunk c - 2 out of this buffer
-    int r = r0 + lane * F_ROWS_PER_LANE;
-    int el = r / NE, q = r - el * NE, i = q / E, en = q - i * E;
-#pragma unroll
-    for (int j = 0; j < F_ROWS_PER_LANE; ++j) {
-      if (r + j < rows) f_row(S + t.rec + el * t.rec_stride, N, O, i, en, buf + (lane * F_ROWS_PER_LANE + j) * F_NODE);
-      if (++en == E) { en = 0; if (++i == N) { i = 0; ++el; } }
-    }
+    return S + t.stage + (c & 1) * F_CHUNK_WORDS;
+  };
+  auto send = [&](float* gdst, const float* buf, int words) {
     __syncwarp();
-    const int nrow = min(F_CHUNK_ROWS, rows - r0);                          // 32 * N * E is a multiple of 4 rows: 16-byte sizes
-    if (lane == 0) {
-      fence_async_smem();
-      bulk_store(g_node + (size_t)r0 * F_NODE, buf, (uint32_t)nrow * F_NODE * 4u, pol);
-      bulk_commit();
+    if (lane == 0) { fence_async_smem(); bulk_store(gdst, buf, (uint32_t)words * 4u, pol); bulk_commit(); }
+    ++c;
+  };
+  if (g_adj) {
+    // k whole envs per chunk (k a multiple of 4: 16-byte sizes): the unique pairs a < c of each env are spread over the
+    // lanes and mirrored; k = 0 (E >= 15): element-wise, straight to global memory (coalesced)
+    const int k = 8 * EE <= F_CHUNK_WORDS ? 8 : (4 * EE <= F_CHUNK_WORDS ? 4 : 0);
+    if (k == 0) {
+      for (int q = lane; q < 32 * EE; q += 32) {
+        const int el = q / EE, w = q - el * EE, a = w / E;
+        __stcs(g_adj + q, f_adj_elem(rec + el * t.rec_stride, a, w - a * E));
+      }
+    } else {
+      const int P = E * (E - 1) / 2;
+      for (int e0 = 0; e0 < 32; e0 += k) {
+        float* buf = next_buffer();
+        for (int q = lane; q < k * E; q += 32) { const int el = q / E, a = q - el * E; buf[el * EE + a * E + a] = 0.0f; }
+        for (int q = lane; q < k * P; q += 32) {
+          const int el = q / P;
+          int w = q - el * P, a = 0;
+          while (w >= E - 1 - a) { w -= E - 1 - a; ++a; }                  // pair w of row a: (a, a + 1 + w)
+          const int cc = a + 1 + w;
+          const float d = f_adj_elem(rec + (e0 + el) * t.rec_stride, a, cc);
+          buf[el * EE + a * E + cc] = d; buf[el * EE + cc * E + a] = d;
+        }
+        send(g_adj + (size_t)e0 * EE, buf, k * EE);
+      }
+    }
+  }
+  if (g_node) {
+    const int rows = 32 * NE;                                               // a multiple of 4 rows: 16-byte chunk sizes
+    for (int r0 = 0; r0 < rows; r0 += F_CHUNK_ROWS) {
+      float* buf = next_buffer();
+      const int r = r0 + lane * F_ROWS_PER_LANE;
+      int el = r / NE, q = r - el * NE, i = q / E, en = q - i * E;
+#pragma unroll
+      for (int j = 0; j < F_ROWS_PER_LANE; ++j) {
+        if (r + j < rows) f_row(rec + el * t.rec_stride, N, O, i, en, buf + (lane * F_ROWS_PER_LANE + j) * F_NODE);
+        if (++en == E) { en = 0; if (++i == N) { i = 0; ++el; } }
+      }
+      send(g_node + (size_t)r0 * F_NODE, buf, min(F_CHUNK_ROWS, rows - r0) * F_NODE);
     }
   }
   if (lane == 0) bulk_wait_read<0>();
@@ -637,14 +667,12 @@ __global__ void __launch_bounds__(FORM_WARPS * 32) formation_kernel(const FormPa
   const int env0 = (blockIdx.x * FORM_WARPS + wib) * 32;
   if (env0 >= p.B) return;                                                  // warp-uniform
   const int nenv = min(32, p.B - env0);
-  const FormTile t = form_tile(N, p.O, MODE == 0 && p.out.info != nullptr);
+  const FormTile t = form_tile(N, p.O);
   float* S = smem + (size_t)wib * t.words;
-  const int E = 2 * N + p.O;
   if (lane < nenv) {
     FOut o;
-    o.obs = S + t.obs + lane * N * F_OBS; o.adj = S + t.adj + lane * E * E; o.rew = S + t.rew + lane * N;
+    o.obs = S + t.obs + lane * N * F_OBS; o.rew = S + t.rew + lane * N;
     o.done = reinterpret_cast<uint8_t*>(S + t.done) + lane * N; o.rec = S + t.rec + lane * t.rec_stride;
-    o.info = t.info_stride ? S + t.info + lane * t.info_stride : nullptr;
     if (MODE == 0) form_step_env<N>(p, env0 + lane, o); else form_reset_env<N>(p, env0 + lane, o);
   }
   __syncwarp();
@@ -655,7 +683,7 @@ int formation_max_agents() { return 7; }
 
 template <int N>
 static cudaError_t launch_formation_n(const FormParams& p, bool is_reset, cudaStream_t st) {
-  const FormTile t = form_tile(N, p.O, !is_reset && p.out.info != nullptr);
+  const FormTile t = form_tile(N, p.O);
   const size_t smem = (size_t)t.words * FORM_WARPS * sizeof(float);
   const int blocks = (p.B + 32 * FORM_WARPS - 1) / (32 * FORM_WARPS);
   cudaError_t e;

@@ -253,7 +253,12 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 
     int rgm = gm;
     // An entry of the pending block generated for this env's episode key (prefetch_kernel) replaces the rejection
     // sampling and the lexifair solve: same Philox stream, same bits.
-    const bool use_pend = do_reset && p.q_tag != nullptr && p.q_tag[env] == (int)episode;
+    bool use_pend = false;
+    if (do_reset && p.q_tag != nullptr) {            // acquire: the entry's data is visible once its tag is
+      int tag;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(tag) : "l"(p.q_tag + env) : "memory");
+      use_pend = tag == (int)episode;
+    }
     if (__any_sync(FULL, use_pend)) {
       int pgm = 0;
       if (use_pend) {
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(THREADS) reset_kernel(const __grid_constant__ 
   bool do_reset = false;
   if (venv) {
     episode = (uint32_t)p.episode[env]; dmean = p.dmean[env]; dstd = p.dstd[env];
-    do_reset = p.reset_mask ? (p.reset_mask[env] != 0) : true;
+    do_reset = p.observe_only ? false : (p.reset_mask ? (p.reset_mask[env] != 0) : true);
     for (int k = i; k < O; k += G) {
       const float x = p.ox[(size_t)k * p.Bp + env], y = p.oy[(size_t)k * p.Bp + env];
       ent_write(ent + (2 * N + k) * ENT_STRIDE, x, y, 0.f, 0.f, x, y, 2.0f);
@@ -423,7 +428,10 @@ __global__ void __launch_bounds__(THREADS) prefetch_kernel(const __grid_constant
     p.q_px[idx] = x; p.q_py[idx] = y; p.q_gm[idx] = gm;
   }
   __syncwarp();
-  if (need && i == 0) p.q_tag[env] = (int)episode;
+  if (need && i == 0) {                              // the entry is complete (every lane's stores, ordered by the warp barrier) before its tag
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p.q_tag + env), "r"((int)episode) : "memory");
+  }
 }
 
 // =============================================================================================

@@ -54,6 +54,22 @@ class LazyInfos(Sequence):
         return self._fetch()
 
 
+def make_spaces(num_agents: int, num_entities: int, node_feat_dim: int = _lib.NODE_FEAT_DIM, obs_dim: int = _lib.OBS_DIM) -> Dict[str, list]:
+    """The per-agent space lists ``GMPERunner`` / ``GraphReplayBuffer`` read from the vec env (environment.py:117-190,
+    :781-813; env_wrappers.py:951-980), as ``Box`` / ``Discrete`` stand-ins (``gym`` is not a dependency)."""
+    N, E, inf = num_agents, num_entities, float("inf")
+    return {
+        "observation_space": [Box(-inf, inf, (obs_dim,)) for _ in range(N)],
+        "share_observation_space": [Box(-inf, inf, (obs_dim * N,)) for _ in range(N)],
+        "action_space": [Discrete(5) for _ in range(N)],
+        "node_observation_space": [Box(-inf, inf, (E, node_feat_dim)) for _ in range(N)],
+        "adj_observation_space": [Box(-inf, inf, (E, E)) for _ in range(N)],
+        "edge_observation_space": [Box(-inf, inf, (1,)) for _ in range(N)],
+        "agent_id_observation_space": [Box(-inf, inf, (1,)) for _ in range(N)],
+        "share_agent_id_observation_space": [Box(-inf, inf, (N,)) for _ in range(N)],
+    }
+
+
 class B200GraphVecEnv:
     """ShareVecEnv-compatible batched ``navigation_graph`` simulator on one B200.
 
@@ -109,15 +125,8 @@ class B200GraphVecEnv:
         _lib.check(self.lib.fm_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_create")
 
         # spaces (environment.py:117-190, :781-813)
-        inf = float("inf")
-        self.observation_space = [Box(-inf, inf, (_lib.OBS_DIM,)) for _ in range(N)]
-        self.share_observation_space = [Box(-inf, inf, (_lib.OBS_DIM * N,)) for _ in range(N)]
-        self.action_space = [Discrete(5) for _ in range(N)]
-        self.node_observation_space = [Box(-inf, inf, (E, self.node_feat_dim)) for _ in range(N)]
-        self.adj_observation_space = [Box(-inf, inf, (E, E)) for _ in range(N)]
-        self.edge_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
-        self.agent_id_observation_space = [Box(-inf, inf, (1,)) for _ in range(N)]
-        self.share_agent_id_observation_space = [Box(-inf, inf, (N,)) for _ in range(N)]
+        for name, spaces in make_spaces(N, E, self.node_feat_dim).items():
+            setattr(self, name, spaces)
 
         # get_id (navigation_graph.py:875-876): global_id == agent index
         self._agent_id_host = np.tile(np.arange(N, dtype=np.int64)[None, :, None], (self.num_envs, 1, 1))
@@ -229,10 +238,14 @@ class B200GraphVecEnv:
         _lib.check(self.lib.fm_reset(self._h, mptr, C.byref(o), self._stream()), "fm_reset")
         return self._package_out(views, with_step=False) if out is not None else self._package(slot, with_step=False)
 
-    def observe_tensor(self) -> Dict[str, Any]:
-        """Observation of the current state without stepping or resetting."""
-        z = self.torch.zeros(self.num_envs, dtype=self.torch.uint8, device=self.device)
-        return self.reset_tensor(mask=z)
+    def observe_tensor(self, out: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """Observation of the current state without stepping or resetting (``fm_observe``)."""
+        s = self._ensure_slabs()
+        slot = self._slot
+        views = self._check_out(out, with_step=False) if out is not None else {k: s[k][slot] for k in ("obs", "node_obs", "adj")}
+        o = self._outputs_struct(views, with_step=False)
+        _lib.check(self.lib.fm_observe(self._h, C.byref(o), self._stream()), "fm_observe")
+        return self._package_out(views, with_step=False) if out is not None else self._package(slot, with_step=False)
 
     def step_tensor(self, actions, out: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
         """One env step.  ``actions``: int32 CUDA tensor [B, N] in {0..4}, or float32 [B, N, 5] one-hot.

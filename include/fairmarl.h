@@ -127,6 +127,9 @@ int fm_destroy(FmHandle* h);
  * lexifair goal assignment (navigation_graph.py:555-561).  mask: uint8 [B] or NULL (= all envs).
  * Envs with mask 0 keep their state; obs / node_obs / adj of ALL envs are written to `out`. */
 int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* stream);
+/* Observation of the CURRENT state into `out` (obs, node_obs, adj) without resetting or stepping anything
+ * (MultiAgentGraphEnv._get_obs / graph_observation on the live world, environment.py:882-898 minus the reset). */
+int fm_observe(FmHandle* h, const FmOutputs* out, void* stream);
 
 /* GraphSubprocVecEnv.step -> graphworker -> MultiAgentGraphEnv.step (env_wrappers.py:983-996,
  * :856-865, environment.py:816-877): action decode, World.step (core.py:250-274), observation /

@@ -104,22 +104,22 @@ def test_rollout_lanes_equal_single_steps(N, O, B):
     (4096, 33, 3, 4),        # late release across a chunk boundary
 ])
 def test_persistent_rollout_kernel_equals_single_steps(B, T, slots, episode_length):
-    """fm_step_many on the agent-warp mapping is ONE persistent kernel per <= 32 steps (fm_roll.cu: (step, tile) work
-    items, per-tile dependency flags).  Every output of every step still visible in the slab ring, the final state and
-    the episode statistics are bit-identical to stepping one fm_step at a time -- and to the one-shot kernels
-    (FM_ROLL=0), which share the tile body but none of the scheduling."""
+    """With FM_ROLL=1 fm_step_many on the agent-warp mapping is ONE persistent kernel per <= 32 steps (fm_roll.cu: (step,
+    tile) work items, per-tile dependency flags) and fm_step is its one-step launch.  Every output of every step still
+    visible in the slab ring, the final state and the episode statistics are bit-identical to the default path (one-shot
+    kernels, env-range lanes), which shares the tile body but none of the scheduling."""
     import os
     import fair_marl_b200 as fm
     import torch
     cfg = NavConfig(num_agents=3, num_obstacles=3, goal_rew=30.0, collision_rew=30.0, episode_length=episode_length)
     sim = sim_config_from(cfg, mapping="aw")
-    e_r = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)
-    e_s = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)
-    os.environ["FM_ROLL"] = "0"
+    os.environ["FM_ROLL"] = "1"
     try:
-        e_o = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)        # one-shot launches
+        e_r = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)        # persistent kernel: rollout + single steps
+        e_s = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)
     finally:
         del os.environ["FM_ROLL"]
+    e_o = fm.B200GraphVecEnv(sim, num_envs=B, seed=4, num_slots=slots)            # default: one-shot launches
     for e in (e_r, e_s, e_o):
         e.reset_tensor()
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -150,8 +150,13 @@ def test_persistent_rollout_kernel_in_a_cuda_graph():
     import fair_marl_b200 as fm
     import torch
     cfg = NavConfig(num_agents=3, num_obstacles=3, episode_length=6)
+    import os
     B, T = 2048, 6
-    e_g = fm.B200GraphVecEnv(sim_config_from(cfg, mapping="aw"), num_envs=B, seed=9, num_slots=T)
+    os.environ["FM_ROLL"] = "1"
+    try:
+        e_g = fm.B200GraphVecEnv(sim_config_from(cfg, mapping="aw"), num_envs=B, seed=9, num_slots=T)
+    finally:
+        del os.environ["FM_ROLL"]
     e_s = fm.B200GraphVecEnv(sim_config_from(cfg, mapping="aw"), num_envs=B, seed=9, num_slots=T)
     e_g.reset_tensor(); e_s.reset_tensor()
     acts = torch.randint(0, 5, (T, B, 3), device="cuda", dtype=torch.int32)
