@@ -158,11 +158,13 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 
     const double dp = __dsub_rn(pj, mean_p), da = __dsub_rn(aj, mean_a), dv = __dsub_rn((j < i) ? aj : bj, mean_v);
     q_p = sq_acc(q_p, dp); q_a = sq_acc(q_a, da); q_v = sq_acc(q_v, dv);
   }
-  const double std_p = std_from_q(q_p, inv_n), std_v = std_from_q(q_v, inv_n), std_a = std_from_q(q_a, inv_n);
-  float fparam;                                  // navigation_graph.py:764-769 / :849-853
-  if (dtg == -1.0f) fparam = ratio_eps(mean_p, std_p);
-  else if (i == 0) fparam = ratio_eps((double)dmean, (double)dstd);
-  else fparam = ratio_eps(mean_v, std_v);
+  // navigation_graph.py:764-769 / :849-853.  One float64 root and one quotient per lane: the (mean, squared deviations) pair
+  // the lane's fairness value comes from is selected first (first step of the episode: the travelled distances; agent 0:
+  // last step's statistics from the state; agent i >= 1: the set left by agent i - 1's info_callback).
+  const bool from_state = dtg != -1.0f && i == 0;
+  const double mean_sel = dtg == -1.0f ? mean_p : mean_v, q_sel = dtg == -1.0f ? q_p : q_v;
+  const float fparam = from_state ? ratio_eps((double)dmean, (double)dstd) : ratio_eps(mean_sel, std_from_q(q_sel, inv_n));
+  const float std_a = (i == 0) ? (float)std_from_q(q_a, inv_n) : 0.0f;   // written to the state by the group's first lane only
 
   // reward (navigation_graph.py:760-824)
   float rew = reached ? p.goal_rew : -(float)dgoal;
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 
   // ---- write back state; observation row --------------------------------------------------------
   float fobs = (float)fparam;
   float ndtg = (float)dtg_new, ntreq = (float)treq_new, ndleft = dleft_new;
-  float ndmean = (float)mean_a, ndstd = (float)std_a;     // after the last agent's info_callback
+  float ndmean = (float)mean_a, ndstd = std_a;            // after the last agent's info_callback
   int nstep_store = nstep;
   uint32_t nepisode = episode;
   if (__any_sync(FULL, do_reset)) {

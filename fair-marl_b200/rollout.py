@@ -172,7 +172,7 @@ class RolloutCollector:
         rnn, rnn_c = b.rnn_states[t].view(M, *b.rnn_states.shape[3:]), b.rnn_states_critic[t].view(M, *b.rnn_states.shape[3:])
         masks = b.masks[t].view(M, 1)
         outs = []
-        per = max(N, (self.max_graphs // N) * N)
+        per = M if self.fused else max(N, (self.max_graphs // N) * N)    # the fused kernels materialise nothing per edge: one launch
         for lo in range(0, M, per):
             hi = min(M, lo + per)
             adj_c = adj[lo // N:hi // N].reshape(hi - lo, E, E) if not self.fused else None   # stride-0 view materialised only for the torch path

@@ -24,6 +24,26 @@ from fair_marl_b200.config import SimConfig
 from fair_marl_b200.spaces import Box, Discrete
 
 
+class _Nvtx:
+    """NVTX ranges around the entry points (``FM_NVTX=1``): ``fm:reset``, ``fm:step``, ``fm:rollout``, ``fm:edge_list``,
+    ``fm:step_host`` show up on the nsys / ncu timeline next to the kernels they launch."""
+    enabled = __import__("os").environ.get("FM_NVTX", "0") not in ("", "0")
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.enabled:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Nvtx.enabled:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class LazyInfos(Sequence):
     """``infos`` as the reference returns it -- a length-B sequence of length-N lists of dicts
     (env_wrappers.py:988-996) -- materialised from the device info rows only when indexed
@@ -235,7 +255,8 @@ class B200GraphVecEnv:
         if mask is not None:
             mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
             mptr = mask.data_ptr()
-        _lib.check(self.lib.fm_reset(self._h, mptr, C.byref(o), self._stream()), "fm_reset")
+        with _Nvtx("fm:reset"):
+            _lib.check(self.lib.fm_reset(self._h, mptr, C.byref(o), self._stream()), "fm_reset")
         return self._package_out(views, with_step=False) if out is not None else self._package(slot, with_step=False)
 
     def observe_tensor(self, out: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
@@ -268,14 +289,15 @@ class B200GraphVecEnv:
                 cached = self._plans[("slot", slot)] = (self._outputs_struct(views, with_step=True), self._package(slot, with_step=True))
             o, result = cached
         B, N = self.num_envs, self.num_agents
-        if actions.dim() == 2:
-            if actions.dtype != t.int32 or not actions.is_contiguous() or actions.shape != (B, N):
-                actions = actions.to(t.int32).contiguous().view(B, N)
-            rc = self.lib.fm_step(self._h, actions.data_ptr(), C.byref(o), self._stream())
-        else:
-            if actions.dtype != t.float32 or not actions.is_contiguous() or actions.shape != (B, N, 5):
-                actions = actions.to(t.float32).contiguous().view(B, N, 5)
-            rc = self.lib.fm_step_onehot(self._h, actions.data_ptr(), C.byref(o), self._stream())
+        with _Nvtx("fm:step"):
+            if actions.dim() == 2:
+                if actions.dtype != t.int32 or not actions.is_contiguous() or actions.shape != (B, N):
+                    actions = actions.to(t.int32).contiguous().view(B, N)
+                rc = self.lib.fm_step(self._h, actions.data_ptr(), C.byref(o), self._stream())
+            else:
+                if actions.dtype != t.float32 or not actions.is_contiguous() or actions.shape != (B, N, 5):
+                    actions = actions.to(t.float32).contiguous().view(B, N, 5)
+                rc = self.lib.fm_step_onehot(self._h, actions.data_ptr(), C.byref(o), self._stream())
         _lib.check(rc, "fm_step")
         self._step_version += 1
         self._last_step_api = "tensor"
@@ -337,7 +359,8 @@ class B200GraphVecEnv:
         arr = ring[0]
         first = C.cast(C.addressof(arr) + start * C.sizeof(_lib.FmOutputs), C.POINTER(_lib.FmOutputs))
         slots = [(start + k) % S for k in range(T)]
-        _lib.check(self.lib.fm_step_many(self._h, actions.data_ptr(), T, first, self._stream()), "fm_step_many")
+        with _Nvtx("fm:rollout"):
+            _lib.check(self.lib.fm_step_many(self._h, actions.data_ptr(), T, first, self._stream()), "fm_step_many")
         self._slot = slots[-1] if slots else self._slot
         self._step_version += T
         self._last_step_api = "tensor"
@@ -396,7 +419,8 @@ class B200GraphVecEnv:
         else:
             raise ValueError(f"actions must be [B,N,5] one-hot (or [B,N] indices), got {a.shape}")
         cur, o = self._host_outputs(with_step=True)
-        _lib.check(self.lib.fm_step_host(self._h, h["onehot"].data_ptr(), C.byref(o), self._stream()), "fm_step_host")
+        with _Nvtx("fm:step_host"):
+            _lib.check(self.lib.fm_step_host(self._h, h["onehot"].data_ptr(), C.byref(o), self._stream()), "fm_step_host")
         self._step_version += 1
         self._last_step_api = "host"
         obs, ag_id, node, adj_n = self._numpy_obs(cur, copy)

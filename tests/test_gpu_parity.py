@@ -470,7 +470,9 @@ def test_outputs_at_any_alignment_and_partial_outputs(N, O, B):
                 assert torch.equal(a[k], b[k]), (keep, k)
 
 
-@pytest.mark.parametrize("N,O,W,B,prefetch", [(3, 3, 2, 192, "1"), (4, 2, 1, 100, "0"), (7, 3, 2, 64, "1")])
+@pytest.mark.parametrize("N,O,W,B,prefetch", [(3, 3, 2, 192, "1"), (4, 2, 1, 100, "0"), (7, 3, 2, 64, "1"),
+                                              (16, 3, 2, 24, "1"), (12, 0, 1, 20, "0"),       # step_kernel<16, true>
+                                              (20, 2, 2, 8, "1")])                            # step_kernel<32, true>
 def test_walls_reset_and_rollout_match_oracle(N, O, W, B, prefetch, monkeypatch):
     """num_walls > 0 (group-per-env kernels): the reset draws wall axis / orientation from the same Philox stream and
     rejects placements inside the wall boxes exactly like the oracle (bit-exact state), and a random-action rollout
