@@ -47,6 +47,10 @@ struct FEnv {
   bool status[N];
   double dmean, dstd;
   int step, episode;
+  // agent a -> landmark g distances at the current positions (f_dists): positions do not move inside the per-agent loop of
+  // a step, and observation, reward, node rows, info and the assignment all read this same matrix (the reference
+  // recomputes each entry up to N + 4 times per step)
+  double dal[N * N];
 };
 
 // Where one env's thread writes (shared memory on the device, lane = env; plain arrays in the host harness).
@@ -97,6 +101,12 @@ __device__ void f_store(const FormParams& p, int b, const FEnv<N>& e, bool stati
   p.st.dist_traveled_mean[b] = (float)e.dmean; p.st.dist_traveled_stddev[b] = (float)e.dstd; p.st.step[b] = e.step; p.st.episode[b] = e.episode;
 }
 
+template <int N>
+__device__ void f_dists(FEnv<N>& e) {
+  for (int a = 0; a < N; ++a)
+    for (int g = 0; g < N; ++g) e.dal[a * N + g] = dn(e.px[a] - e.lx[g], e.py[a] - e.ly[g]);
+}
+
 // is_obstacle_collision (:576-586, no walls): closer than 2.0 * (size + size) to any obstacle.
 template <int N>
 __device__ bool f_obstacle_hit(const FormParams& p, const FEnv<N>& e, double x, double y) {
@@ -120,12 +130,12 @@ __device__ void f_mean_std(const double (&v)[N], double& mean, double& sd) {
 // Far branch shared by observation (:933-956) and the agent rows of the node features (:1256-1270): nearest goal not
 // marked occupied (== 1); if every goal is, the entity itself and a cleared table.
 template <int N>
-__device__ int f_pick_goal(FEnv<N>& e, double qx, double qy, int slot, double& gx, double& gy, double& occ, double& hist) {
-  int best = -1;
+__device__ int f_pick_goal(FEnv<N>& e, int a, double qx, double qy, int slot, double& gx, double& gy, double& occ, double& hist) {
+  int best = -1;                                                           // (qx, qy) = position of agent a
   double bd = 0.0;
   for (int g = 0; g < N; ++g) {
     if (e.occ[g] == 1.0) continue;
-    const double d = dn(qx - e.lx[g], qy - e.ly[g]);
+    const double d = e.dal[a * N + g];
     if (best < 0 || d < bd) { best = g; bd = d; }
   }
   if (best >= 0) { gx = e.lx[best]; gy = e.ly[best]; occ = e.occ[best]; hist = e.hist[best]; return best; }
@@ -140,7 +150,7 @@ __device__ void f_observation(const FormParams& p, FEnv<N>& e, int i, float* __r
   const double x = e.px[i], y = e.py[i];
   double d[N];
   int first = 0;
-  for (int g = 0; g < N; ++g) { d[g] = dn(x - e.lx[g], y - e.ly[g]); if (d[g] < d[first]) first = g; }
+  for (int g = 0; g < N; ++g) { d[g] = e.dal[i * N + g]; if (d[g] < d[first]) first = g; }
   int second = first == 0 ? 1 : 0;                                         // np.argsort(dists)[1]
   for (int g = 0; g < N; ++g) if (g != first && d[g] < d[second]) second = g;
   const double sgx = e.lx[second], sgy = e.ly[second], socc = e.occ[second];   // read before the updates below
@@ -152,19 +162,19 @@ __device__ void f_observation(const FormParams& p, FEnv<N>& e, int i, float* __r
     for (int g = 0; g < N; ++g) {                                          // :866-879 nearby goals marked occupied
       if (!(d[g] < p.min_obs_dist) || e.occ[g] != 1.0) continue;
       bool any = false; double mn = 0.0;
-      for (int j = 0; j < N; ++j) { const double q = dn(e.lx[g] - e.px[j], e.ly[g] - e.py[j]); any = any || (q < th); mn = j == 0 ? q : fmin(mn, q); }
+      for (int j = 0; j < N; ++j) { const double q = e.dal[j * N + g]; any = any || (q < th); mn = j == 0 ? q : fmin(mn, q); }
       if (!any) e.occ[g] = mn;
     }
     if (mind < th) {                                                       // :882-885
       e.occ[chosen] = 1.0; e.hist[chosen] = (double)i;
     } else {
       bool any = false; double closest = 0.0;
-      for (int j = 0; j < N; ++j) { const double q = dn(gx - e.px[j], gy - e.py[j]); any = any || (q < th); closest = j == 0 ? q : fmin(closest, q); }
+      for (int j = 0; j < N; ++j) { const double q = e.dal[j * N + chosen]; any = any || (q < th); closest = j == 0 ? q : fmin(closest, q); }
       if (e.occ[chosen] == 1.0 && any) {                                   // :908-923: nearest FREE goal; `chosen` becomes its
         int k = 0, bestk = -1, bestg = -1; double bd = 0.0;                //   index in the free SUBSET (reference quirk, kept)
         for (int g = 0; g < N; ++g) {
           if (e.occ[g] == 1.0) continue;
-          const double q = dn(x - e.lx[g], y - e.ly[g]);
+          const double q = d[g];
           if (bestk < 0 || q < bd) { bestk = k; bestg = g; bd = q; }
           ++k;
         }
@@ -175,7 +185,7 @@ __device__ void f_observation(const FormParams& p, FEnv<N>& e, int i, float* __r
     }
     gocc = e.occ[chosen]; ghist = e.hist[chosen];                          // :930-931
   } else {
-    f_pick_goal<N>(e, x, y, i, gx, gy, gocc, ghist);
+    f_pick_goal<N>(e, i, x, y, i, gx, gy, gocc, ghist);
   }
   if (o) {
     o[0] = (float)e.vx[i]; o[1] = (float)e.vy[i]; o[2] = (float)x; o[3] = (float)y; o[4] = (float)(gx - x); o[5] = (float)(gy - y);
@@ -192,11 +202,11 @@ __device__ void f_node_recipe(const FormParams& p, FEnv<N>& e, int i, float* __r
   for (int a = 0; a < N; ++a) {
     const double qx = e.px[a], qy = e.py[a];
     int first = 0; double mind = 0.0;
-    for (int g = 0; g < N; ++g) { const double d = dn(qx - e.lx[g], qy - e.ly[g]); if (g == 0 || d < mind) { first = g; mind = d; } }
+    for (int g = 0; g < N; ++g) { const double d = e.dal[a * N + g]; if (g == 0 || d < mind) { first = g; mind = d; } }
     double gx, gy, occ, hist;
     int gi = first;
     if (mind < p.min_obs_dist) { occ = e.occ[first]; hist = e.hist[first]; }
-    else gi = f_pick_goal<N>(e, qx, qy, a, gx, gy, occ, hist);
+    else gi = f_pick_goal<N>(e, a, qx, qy, a, gx, gy, occ, hist);
     pk[3 * a] = (float)gi; pk[3 * a + 1] = (float)occ; pk[3 * a + 2] = (float)hist;
   }
 }
@@ -302,8 +312,7 @@ __device__ void lexifair_serial(const double (&c)[N * N], int (&out)[N]) {
 
 template <int N>
 __device__ void f_costs(const FEnv<N>& e, double (&c)[N * N]) {              // cdist(agent_pos, goal_pos)
-  for (int a = 0; a < N; ++a)
-    for (int g = 0; g < N; ++g) c[a * N + g] = dn(e.px[a] - e.lx[g], e.py[a] - e.ly[g]);
+  for (int k = 0; k < N * N; ++k) c[k] = e.dal[k];
 }
 
 template <int N>
@@ -381,10 +390,11 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
       }
     }
   }
+  f_dists<N>(e);
   for (int i = 0; i < N; ++i) {
     e.vx[i] = e.vy[i] = 0.0; e.pd[i] = 0.0; e.status[i] = false; e.treq[i] = e.dtg[i] = e.dleft[i] = -1.0;
     e.noc[i] = e.nac[i] = 0.0; e.hist[i] = -1.0; e.reached[i] = -1.0; e.occ[i] = 0.0;
-    if (p.has_max_speed) e.mint[i] = dn(e.px[i] - e.lx[i], e.py[i] - e.ly[i]) / p.max_speed;   // goal_match = arange here (:229, :474-476)
+    if (p.has_max_speed) e.mint[i] = e.dal[i * N + i] / p.max_speed;       // goal_match = arange here (:229, :474-476)
   }
   e.step = 0;
   if (p.assignment == 0) {
@@ -424,7 +434,7 @@ __device__ void form_reset_env(const FormParams& p, int b, const FOut& o) {
   FEnv<N> e;
   f_load<N>(p, b, e);
   const bool doit = !p.mask || p.mask[b] != 0;
-  if (doit) f_reset<N>(p, b, e);
+  if (doit) f_reset<N>(p, b, e); else f_dists<N>(e);
   f_observe<N>(p, e, o);
   f_store<N>(p, b, e, doit);
 }
@@ -467,6 +477,7 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
     e.px[i] = __dadd_rn(e.px[i], sx); e.py[i] = __dadd_rn(e.py[i], sy);
     e.pd[i] = __dadd_rn(e.pd[i], dn(sx, sy));
   }
+  f_dists<N>(e);
   f_rec_head<N>(p, e, o.rec);
   float* latch = o.rec + 2 * (2 * N + O) + 2 * N;
   float info[N * INFO_F];                                                  // rows of this step; written out below when wanted
@@ -486,7 +497,7 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
     if (i == 0 && p.assignment == 0) f_assign<N>(e);                       // :704-721: re-assignment every step
     if (i == 0 && p.assignment == 1) { int m[N]; f_min_sum<N>(e, m, delta); }   // mask.py:666-706 (the stored match stays)
     const double x = e.px[i], y = e.py[i];
-    const double dg = p.assignment == 1 ? delta[i] : dn(x - e.lx[e.gm[i]], y - e.ly[e.gm[i]]);
+    const double dg = p.assignment == 1 ? delta[i] : e.dal[i * N + e.gm[i]];
     double r = 0.0;
     if (dg < th) {                                                         // :725-733
       if (!e.status[i]) { e.status[i] = true; e.vx[i] = 0.0; e.vy[i] = 0.0; latch[i] = (float)i; r += p.goal_rew; }
@@ -510,7 +521,7 @@ __device__ void form_step_env(const FormParams& p, int b, const FOut& o) {
     // info_callback (:489-575)
     {
       int near = 0; double d = 0.0;
-      for (int g = 0; g < N; ++g) { const double q = dn(x - e.lx[g], y - e.ly[g]); if (g == 0 || q < d) { near = g; d = q; } }
+      for (int g = 0; g < N; ++g) { const double q = e.dal[i * N + g]; if (g == 0 || q < d) { near = g; d = q; } }
       const double now = (double)e.step * 0.1, nr = (double)near;
       if (d < th && (nr != e.reached[i] && e.reached[i] != -1.0)) { e.reached[i] = nr; e.dleft[i] = d; }          // :497-499
       if (d < th && e.treq[i] == -1.0) { e.treq[i] = now; e.dtg[i] = e.pd[i]; e.dleft[i] = d; e.reached[i] = nr; }   // :501-505
@@ -618,24 +629,34 @@ __device__ void form_emit(const FormParams& p, float* __restrict__ S, const Form
   if (g_adj) {
     // k whole envs per chunk (k a multiple of 4: 16-byte sizes): the unique pairs a < c of each env are spread over the
     // lanes and mirrored; k = 0 (E >= 15): element-wise, straight to global memory (coalesced)
-    const int k = 8 * EE <= F_CHUNK_WORDS ? 8 : (4 * EE <= F_CHUNK_WORDS ? 4 : 0);
+    const int k = (E * (E - 1) / 2 > 96) ? 0 : (8 * EE <= F_CHUNK_WORDS ? 8 : (4 * EE <= F_CHUNK_WORDS ? 4 : 0));
     if (k == 0) {
       for (int q = lane; q < 32 * EE; q += 32) {
         const int el = q / EE, w = q - el * EE, a = w / E;
         __stcs(g_adj + q, f_adj_elem(rec + el * t.rec_stride, a, w - a * E));
       }
     } else {
+      // pair w -> (a, c), a < c, decoded once per launch into the lane's registers (P <= 3 x 32 for the E that get here)
       const int P = E * (E - 1) / 2;
+      int pa[3], pc[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        int w = lane + 32 * u, a = 0;
+        if (w < P) { while (w >= E - 1 - a) { w -= E - 1 - a; ++a; } }
+        pa[u] = a; pc[u] = a + 1 + w;
+      }
       for (int e0 = 0; e0 < 32; e0 += k) {
         float* buf = next_buffer();
-        for (int q = lane; q < k * E; q += 32) { const int el = q / E, a = q - el * E; buf[el * EE + a * E + a] = 0.0f; }
-        for (int q = lane; q < k * P; q += 32) {
-          const int el = q / P;
-          int w = q - el * P, a = 0;
-          while (w >= E - 1 - a) { w -= E - 1 - a; ++a; }                  // pair w of row a: (a, a + 1 + w)
-          const int cc = a + 1 + w;
-          const float d = f_adj_elem(rec + (e0 + el) * t.rec_stride, a, cc);
-          buf[el * EE + a * E + cc] = d; buf[el * EE + cc * E + a] = d;
+        for (int el = 0; el < k; ++el) {
+          const float* r = rec + (e0 + el) * t.rec_stride;
+          float* img = buf + el * EE;
+          if (lane < E) img[lane * E + lane] = 0.0f;
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+            if (lane + 32 * u < P) {
+              const float d = f_adj_elem(r, pa[u], pc[u]);
+              img[pa[u] * E + pc[u]] = d; img[pc[u] * E + pa[u]] = d;
+            }
         }
         send(g_adj + (size_t)e0 * EE, buf, k * EE);
       }
@@ -643,15 +664,16 @@ __device__ void form_emit(const FormParams& p, float* __restrict__ S, const Form
   }
   if (g_node) {
     const int rows = 32 * NE;                                               // a multiple of 4 rows: 16-byte chunk sizes
+    // row r of the warp = (env el, ego i, entity en); the lane's row advances by one chunk per iteration: carried, not divided
+    static_assert(F_ROWS_PER_LANE == 1, "one row per lane and chunk");
+    const int adv_i = F_CHUNK_ROWS / E, adv_e = F_CHUNK_ROWS - adv_i * E;
+    int el = lane / NE, i = (lane - el * NE) / E, en = lane - el * NE - i * E;
     for (int r0 = 0; r0 < rows; r0 += F_CHUNK_ROWS) {
       float* buf = next_buffer();
-      const int r = r0 + lane * F_ROWS_PER_LANE;
-      int el = r / NE, q = r - el * NE, i = q / E, en = q - i * E;
-#pragma unroll
-      for (int j = 0; j < F_ROWS_PER_LANE; ++j) {
-        if (r + j < rows) f_row(rec + el * t.rec_stride, N, O, i, en, buf + (lane * F_ROWS_PER_LANE + j) * F_NODE);
-        if (++en == E) { en = 0; if (++i == N) { i = 0; ++el; } }
-      }
+      if (r0 + lane < rows) f_row(rec + el * t.rec_stride, N, O, i, en, buf + lane * F_NODE);
+      en += adv_e; i += adv_i;
+      if (en >= E) { en -= E; ++i; }
+      while (i >= N) { i -= N; ++el; }
       send(g_node + (size_t)r0 * F_NODE, buf, min(F_CHUNK_ROWS, rows - r0) * F_NODE);
     }
   }
