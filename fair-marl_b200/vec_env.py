@@ -49,8 +49,10 @@ class LazyInfos(Sequence):
     (env_wrappers.py:988-996) -- materialised from the device info rows only when indexed
     (the runner touches it at log time only, graph_mpe_runner.py:143-146)."""
 
-    def __init__(self, env: "B200GraphVecEnv", version: int):
-        self._env, self._version, self._rows = env, version, None
+    def __init__(self, env: "B200GraphVecEnv", version: int, fresh=None):
+        # fresh: [B] bool, envs whose info rows were written by THIS step (the kernels write them on the step every agent
+        # is done, or on every step with SimConfig.info_every_step); None = all of them
+        self._env, self._version, self._rows, self._fresh = env, version, None, fresh
 
     def _fetch(self) -> np.ndarray:
         if self._rows is None:
@@ -65,12 +67,16 @@ class LazyInfos(Sequence):
     def __getitem__(self, b):
         if isinstance(b, slice):
             return [self[i] for i in range(*b.indices(len(self)))]
+        if self._fresh is not None and not bool(self._fresh[b]):
+            raise RuntimeError("info rows are written on terminal steps only; construct the env with "
+                               "SimConfig(info_every_step=True) to read infos on every step (eval / render loops)")
         rows = self._fetch()[b]
         keys = _lib.INFO_KEYS if self._env.cfg.max_speed is not None else _lib.INFO_KEYS[:-1]
         return [{k: float(rows[i, j]) for j, k in enumerate(keys)} for i in range(rows.shape[0])]
 
     def as_array(self) -> np.ndarray:
-        """[B, N, 14] float32, columns in ``INFO_KEYS`` order."""
+        """[B, N, 14] float32, columns in ``INFO_KEYS`` order (rows of envs that were not terminal at this step hold the
+        values of their last terminal step unless ``info_every_step`` is set)."""
         return self._fetch()
 
 
@@ -428,10 +434,11 @@ class B200GraphVecEnv:
         done = cur["done"].numpy().astype(bool)
         if copy:
             rew = rew.copy()
+        fresh = None if self.cfg.info_every_step else done.all(axis=1)
         if self.dummy_vec_env:                                        # env_wrappers.py:917-928
             reset_count = 1 if bool(done.all(axis=1).any()) else 0
-            return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version), reset_count
-        return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version)
+            return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version, fresh), reset_count
+        return obs, ag_id, node, adj_n, rew, done, LazyInfos(self, self._step_version, fresh)
 
     def step(self, actions, copy: bool = False):
         """``(obs, agent_id, node_obs, adj, rewards [B,N], dones [B,N] bool, infos)`` -- the 7-tuple of

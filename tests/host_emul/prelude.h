@@ -16,6 +16,7 @@
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __noinline__
 struct Dim3 { int x = 0, y = 0, z = 0; };
 static Dim3 blockIdx, blockDim, threadIdx;
 

@@ -36,6 +36,10 @@ def test_reference_api_shapes_dtypes_and_autoreset():
         obs, ag_id, node, adj, rew, done, infos = env.step(acts)
         assert rew.shape == (B, N) and done.shape == (B, N) and done.dtype == bool
         assert done.all() == (t == 24) and done.any() == (t == 24)
+        if t == 3:                                                    # info rows are written on terminal steps only:
+            with pytest.raises(RuntimeError, match="info_every_step"):    # stale values must not look like this step's
+                infos[0]
+            assert infos.as_array().shape[:2] == (B, N)
     # terminal step: obs are the NEW episode's (velocity 0, fairness 0), infos are terminal
     assert (obs[..., 0:2] == 0).all() and (obs[..., 6] == 0).all()
     assert len(infos) == B and len(infos[0]) == N and set(infos[0][0]) == set(INFO_KEYS)

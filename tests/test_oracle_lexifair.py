@@ -37,13 +37,17 @@ def test_ties_follow_cost_i_j_order(n):
         assert (lf.lexifair_descent(c[k]) == bf[k]).all()
 
 
-@pytest.mark.parametrize("n", [3, 5])
-def test_milp_restatement_equals_bruteforce(n):
+@pytest.mark.parametrize("n,count", [(3, 130), (5, 120), (7, 100)])
+def test_milp_restatement_equals_bruteforce(n, count):
+    """350 instances at n = 3, 5, 7 (the survey's own cross-check ran 340): the literal restatement of the reference's
+    MILP sequence (marl_fair_assign.py:16-58) on HiGHS picks the assignment the enumeration picks.  Continuous costs only:
+    with exact ties the reference's np.argmin(|costs - z|) (:39) may freeze a row that is not in the matching, so its
+    answer is solver dependent there (oracle/lexifair.py header); ties have probability ~0 for sampled positions."""
     rng = np.random.default_rng(7 + n)
-    for _ in range(6):
+    for k in range(count):
         c = rng.random((n, n)) * 2.0
         x, _ = lf.lexifair_milp(c)
-        assert (np.argmax(x, axis=1) == lf.lexifair_bruteforce(c)).all()
+        assert (np.argmax(x, axis=1) == lf.lexifair_bruteforce(c)).all(), (k, c)
 
 
 def test_descent_n16_is_lexicographically_minimal_against_random_swaps():

@@ -8,9 +8,9 @@ for n in 1 2 4 8; do
   [ $n -le $N ] || continue
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 tools/pcie_probe_multi.py 2> $OUT/probe_$n.err | tail -1 | tee -a $OUT/pcie_probe.jsonl | cut -c1-400
 done
-for n in 2 4 8; do
+for n in 2 8; do
   [ $n -le $N ] || continue
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $n --steps 20 --warmup 5 > $OUT/bench_driver_${n}gpu.json 2> $OUT/bench_driver_${n}gpu.err
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $n --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_driver_${n}gpu.json 2> $OUT/bench_driver_${n}gpu.err
   python - <<PY
 import json
 try:
@@ -20,6 +20,4 @@ except Exception as e:
     print("$n failed", e, open("$OUT/bench_driver_${n}gpu.err").read()[-1500:])
 PY
 done
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus $N > $OUT/bench_long_${N}gpu.json 2> $OUT/bench_long_${N}gpu.err; cut -c1-250 $OUT/bench_long_${N}gpu.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $N --config c5 --envs 65536 --steps 50 > $OUT/bench_c5_${N}gpu.json 2> $OUT/bench_c5_${N}gpu.err; cut -c1-300 $OUT/bench_c5_${N}gpu.json
 ls $OUT
