@@ -692,17 +692,26 @@ int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, do
   if (num_graphs > 0 && !adj) return fail(FM_ERR_INVALID_ARG, "fm_edge_list: null adj");
   int rc = use_device(device);
   if (rc) return rc;
-  // scratch (stream-ordered): per-CTA sums / offsets (int64) followed by the per-graph counts (int32)
-  const int nb = fm::edge_list_blocks(num_graphs);
   cudaStream_t st = (cudaStream_t)stream;
   void* scratch = nullptr;
-  const size_t bs_bytes = sizeof(long long) * (size_t)(nb > 0 ? nb : 1);
-  FM_CUDA(cudaMallocAsync(&scratch, bs_bytes + sizeof(int) * (size_t)(num_graphs > 0 ? num_graphs : 1), st));
-  long long* blocksums = (long long*)scratch;
-  int* counts = (int*)((char*)scratch + bs_bytes);
-  cudaError_t e = fm::launch_edge_list(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity,
-                                       counts, blocksums, (long long*)graph_offsets, (long long*)edge_index, edge_attr,
-                                       (long long*)nnz_out, st);
+  cudaError_t e;
+  static const bool three_pass = [] { const char* v = getenv("FM_EDGE_FUSED"); return v && v[0] == '0'; }();   // diagnostic / A-B
+  if (!three_pass && fm::edge_fused_smem(E) <= 96 * 1024) {
+    // single pass (fm_edges.cu): adj read once, look-back scan; scratch = one status word per CTA + the tile counter
+    FM_CUDA(cudaMallocAsync(&scratch, fm::edge_fused_scratch_bytes(num_graphs), st));
+    e = fm::launch_edge_list_fused(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity, scratch,
+                                   (long long*)graph_offsets, (long long*)edge_index, edge_attr, (long long*)nnz_out, st);
+  } else {
+    // count / scan / emit (fm_kernels.cu); scratch: per-CTA sums / offsets (int64) followed by the per-graph counts (int32)
+    const int nb = fm::edge_list_blocks(num_graphs);
+    const size_t bs_bytes = sizeof(long long) * (size_t)(nb > 0 ? nb : 1);
+    FM_CUDA(cudaMallocAsync(&scratch, bs_bytes + sizeof(int) * (size_t)(num_graphs > 0 ? num_graphs : 1), st));
+    long long* blocksums = (long long*)scratch;
+    int* counts = (int*)((char*)scratch + bs_bytes);
+    e = fm::launch_edge_list(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity,
+                             counts, blocksums, (long long*)graph_offsets, (long long*)edge_index, edge_attr,
+                             (long long*)nnz_out, st);
+  }
   cudaFreeAsync(scratch, st);
   if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_edge_list: %s", cudaGetErrorString(e));
   return FM_OK;
@@ -785,12 +794,17 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   formation_fields(p.N, p.O, (size_t)p.B, h->field_bytes);
   size_t total = 0;
   for (int k = 0; k < 20; ++k) total += (h->field_bytes[k] + 255) & ~(size_t)255;
+  const size_t state_bytes = total;
+  total += fm::formation_recipe_floats(p.N, p.O, p.B) * sizeof(float);               // recipes of the split step path
   cudaError_t e = cudaMalloc(&h->block, total);
   if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_formation_create: cudaMalloc(%zu B): %s", total, cudaGetErrorString(e)); }
   cudaMemset(h->block, 0, total);
   char* q = (char*)h->block;
   void** member = reinterpret_cast<void**>(&p.st);                                 // 20 pointers, declaration order
   for (int k = 0; k < 20; ++k) { member[k] = q; q += (h->field_bytes[k] + 255) & ~(size_t)255; }
+  p.rec = reinterpret_cast<float*>((char*)h->block + state_bytes);
+  const char* fused = getenv("FM_FORM_FUSED");
+  p.fused = fused && fused[0] == '1';
   *out = h;
   return FM_OK;
 }

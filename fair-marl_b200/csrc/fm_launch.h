@@ -46,6 +46,12 @@ int edge_list_blocks(int num_graphs);             // CTAs of the edge-list kerne
 cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
                              long long capacity, int* counts, long long* blocksums, long long* graph_offsets,
                              long long* edge_index, float* edge_attr, long long* nnz_out, cudaStream_t st);
+// single-pass form (fm_edges.cu)
+size_t edge_fused_smem(int E);
+size_t edge_fused_scratch_bytes(int num_graphs);
+cudaError_t launch_edge_list_fused(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
+                                   long long capacity, void* scratch, long long* graph_offsets, long long* edge_index,
+                                   float* edge_attr, long long* nnz_out, cudaStream_t st);
 cudaError_t launch_pair_dist(const float* a, const float* b, long long num, double* out, cudaStream_t st);
 cudaError_t launch_stats_reduce(double* partial, int rows, int K, double* out, int clear, cudaStream_t st);
 
@@ -61,7 +67,11 @@ struct FormParams {
   FmOutputs out;             // this launch
   const int32_t* actions;    // step
   const uint8_t* mask;       // reset
+  float* rec;                // handle-owned recipe block of the split step path ([tiles][32][rec_stride] floats); null: fused kernel
+  int fused;                 // 1: always the fused kernel (FM_FORM_FUSED=1, diagnostic / A-B)
 };
+size_t formation_recipe_floats(int N, int O, int B);
+cudaError_t launch_formation_image(const FormParams& p, cudaStream_t st);   // fm_form_image.cu: node_obs / adj from p.rec
 cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st);
 // fused graph-network forward of the rollout policy (fm_policy.cu)
 bool gnn_supported_entities(int E);

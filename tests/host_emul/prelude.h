@@ -1,4 +1,4 @@
-// Host prelude for running the DEVICE FUNCTIONS of csrc/fm_formation.cu on the CPU under ASan / UBSan.  Tests only: a
+// Host prelude for running the DEVICE FUNCTIONS of csrc/fm_form.cuh on the CPU under ASan / UBSan.  Tests only: a
 // sanitiser + parity pass over the kernel SOURCE (tests/test_kernel_source_host.py assembles the translation unit from
 // the real csrc files); it is not a CPU path of the product and nothing in fair_marl_b200 links it.
 #include <cmath>
@@ -32,6 +32,7 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 using std::fmaf;   // fabsf / fmaxf come from <cmath> in the global namespace
 using std::exp; using std::fabs; using std::fmax; using std::fmin; using std::log1p; using std::sqrt; using std::tanh;
 #define __restrict__
+#define FM_DIV64(a, b) ((a) / (b))
 #define FM_SQRT64 sqrt                                  // the device uses dsqrt_fast (same bits: correctly rounded)
 namespace fm {                                          // hardware approximations of the device build (fm_device.cuh)
 static inline float rsqrt_approx(float x) { return 1.0f / std::sqrt(x); }

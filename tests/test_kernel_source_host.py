@@ -1,4 +1,4 @@
-"""The DEVICE FUNCTIONS of csrc/fm_formation.cu compiled for the host (g++, ASan + UBSan, -ffp-contract=off) and run on
+"""The DEVICE FUNCTIONS of csrc/fm_form.cuh compiled for the host (g++, ASan + UBSan, -ffp-contract=off) and run on
 the formation fixtures: a sanitiser pass (out-of-bounds / uninitialised-index bugs in the per-thread local arrays show up
 here, not as layout-dependent wrong answers on the GPU) plus a CPU-side parity check of the kernel SOURCE against the
 oracle.  The translation unit is assembled from the real csrc files (tests/host_emul/prelude.h stands in for the CUDA
@@ -37,12 +37,12 @@ def host_exe(tmp_path_factory):
     dev = open(os.path.join(CSRC, "fm_device.cuh")).read()
     launch = open(os.path.join(CSRC, "fm_launch.h")).read()
     small = open(os.path.join(CSRC, "fm_small.cuh")).read()
-    form = open(os.path.join(CSRC, "fm_formation.cu")).read()
+    form = open(os.path.join(CSRC, "fm_form.cuh")).read()
     philox = _between(dev, "__device__ __forceinline__ void philox4x32_10(", "// U(-ws/2, ws/2)^2 draw number")
     log1p_unit = _between(dev, "__device__ __forceinline__ float log1p_unit(float t) {", "// One contact-force term, core.py:389-392")
     params = _between(launch, "struct FormParams {", "cudaError_t launch_formation")
     small_body = _between(small, "// k-th permutation of 0..N-1", "}  // namespace fm")
-    form_body = _between(form, "constexpr int F_OBS", "// Device only from here")
+    form_body = _between(form, "constexpr int F_OBS", "#ifdef __CUDACC__")
     assert "u01_24" in philox and "lexifair_small" in small_body and "form_step_env" in form_body and "fmaf" in log1p_unit
     src = "\n".join(['#include "prelude.h"', "namespace fm {", philox, log1p_unit, params, small_body, form_body, "}  // namespace fm",
                      open(os.path.join(EMUL, "harness.inc")).read()])

@@ -1,0 +1,29 @@
+import time, torch, sys
+sys.path.insert(0, "/root/repo")
+import fair_marl_b200 as fm
+cfg = fm.FormationSimConfig(num_agents=3, num_obstacles=3, goal_rew=30.0, collision_rew=30.0, episode_length=25, fairness_reward=True, info_every_step=False)
+for B in (256, 65536):
+    env = fm.B200FormationVecEnv(cfg, num_envs=B, device=0, seed=0, num_slots=8)
+    a = torch.randint(0, 5, (25, B, 3), device="cuda", dtype=torch.int32)
+    env.reset_tensor()
+    for k in range(30): env.step_tensor(a[k % 25])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(300): env.step_tensor(a[k % 25])
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(B, "host issue us/step", (t1 - t0) / 300 * 1e6, "total us/step", (t2 - t0) / 300 * 1e6)
+    # graph replay
+    g = torch.cuda.CUDAGraph()
+    s0 = env._slot
+    with torch.cuda.graph(g):
+        for k in range(25): env.step_tensor(a[k])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.replay(); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(12): g.replay()
+    ev1.record(); torch.cuda.synchronize()
+    print(B, "graph us/step", ev0.elapsed_time(ev1) / 300 * 1e3)
+    env.close()
