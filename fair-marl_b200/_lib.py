@@ -57,15 +57,15 @@ class FmFormationConfig(C.Structure):
         ("world_size", C.c_double), ("max_speed", C.c_double), ("collision_rew", C.c_double), ("goal_rew", C.c_double),
         ("min_dist_thresh", C.c_double), ("min_obs_dist", C.c_double), ("fair_rew", C.c_double), ("zeroshift", C.c_double),
         ("fairness_reward", C.c_int32), ("collaborative", C.c_int32), ("auto_reset", C.c_int32), ("assignment", C.c_int32),
-        ("info_every_step", C.c_int32), ("reserved_", C.c_int32),
+        ("info_every_step", C.c_int32), ("num_walls", C.c_int32),
     ]
 
 
 FORMATION_STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_match", "dists_to_goal",
                           "times_required", "dist_left_to_goal", "num_agent_collisions", "num_obstacle_collisions",
                           "dist_traveled_mean", "dist_traveled_stddev", "step", "min_time", "episode", "status",
-                          "goal_reached", "occupied", "goal_history")
-FORMATION_STATE_INT_FIELDS = ("goal_match", "step", "episode")
+                          "goal_reached", "occupied", "goal_history", "wall_axis", "wall_orient", "wall_len")
+FORMATION_STATE_INT_FIELDS = ("goal_match", "step", "episode", "wall_orient")
 
 
 class FmFormationState(C.Structure):

@@ -695,9 +695,13 @@ int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, do
   cudaStream_t st = (cudaStream_t)stream;
   void* scratch = nullptr;
   cudaError_t e;
-  static const bool three_pass = [] { const char* v = getenv("FM_EDGE_FUSED"); return v && v[0] == '0'; }();   // diagnostic / A-B
-  if (!three_pass && fm::edge_fused_smem(E) <= 96 * 1024) {
-    // single pass (fm_edges.cu): adj read once, look-back scan; scratch = one status word per CTA + the tile counter
+  // The single-pass form (fm_edges.cu) is opt-in (FM_EDGE_FUSED=1): it is bit-identical and reads adj once, but measured no
+  // faster than count / scan / emit at config 3 (448 vs 452 us of kernel time, profiles/r02_j: both are bound by the
+  // compaction's instruction count, and the look-back keeps whole CTAs at a barrier).
+  const char* fused_env = getenv("FM_EDGE_FUSED");        // read per call (tests flip it); ~50 ns beside two to three launches
+  const bool single_pass = fused_env && fused_env[0] == '1';
+  if (single_pass && fm::edge_fused_smem(E) <= 96 * 1024) {
+    // adj read once, look-back scan; scratch = one status word per CTA + the tile counter
     FM_CUDA(cudaMallocAsync(&scratch, fm::edge_fused_scratch_bytes(num_graphs), st));
     e = fm::launch_edge_list_fused(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity, scratch,
                                    (long long*)graph_offsets, (long long*)edge_index, edge_attr, (long long*)nnz_out, st);
@@ -750,14 +754,14 @@ struct FmFormation {
   int device;
   fm::FormParams p;
   void* block;
-  size_t field_bytes[20];
+  size_t field_bytes[23];
 };
 
-// the 20 members of FmFormationState, in declaration order: (words per env, element size)
-static void formation_fields(int N, int O, size_t B, size_t (&bytes)[20]) {
-  const size_t n = (size_t)N, o = (size_t)O;
-  const size_t words[20] = {2 * n, 2 * n, n, 2 * n, 2 * o, n, n, n, n, n, n, 1, 1, 1, n, 1, n, n, n, n};
-  for (int k = 0; k < 20; ++k) bytes[k] = words[k] * B * (k == 16 ? 1 : 4);      // status is uint8
+// the 23 members of FmFormationState, in declaration order: (words per env, element size)
+static void formation_fields(int N, int O, int W, size_t B, size_t (&bytes)[23]) {
+  const size_t n = (size_t)N, o = (size_t)O, w = (size_t)W;
+  const size_t words[23] = {2 * n, 2 * n, n, 2 * n, 2 * o, n, n, n, n, n, n, 1, 1, 1, n, 1, n, n, n, n, w, w, (size_t)(W ? 1 : 0)};
+  for (int k = 0; k < 23; ++k) bytes[k] = words[k] * B * (k == 16 ? 1 : 4);      // status is uint8
 }
 
 int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** out) {
@@ -775,6 +779,8 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > FM_FORMATION_MAX_OBSTACLES)
     return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_obstacles must be in 0..%d (got %d)", FM_FORMATION_MAX_OBSTACLES, cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: episode_length must be >= 1");
+  if (cfg->num_walls < 0 || cfg->num_walls > 2)
+    return fail(FM_ERR_INVALID_ARG, "fm_formation_create: num_walls must be 0..2 (wall_axis has two entries, :304; got %d)", cfg->num_walls);
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(FM_ERR_NO_DEVICE, "fm_formation_create: no CUDA device (there is no CPU path)");
   if (device < 0 || device >= count) return fail(FM_ERR_INVALID_ARG, "fm_formation_create: device %d out of range (%d devices)", device, count);
@@ -787,21 +793,21 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   p.B = cfg->num_envs; p.N = cfg->num_agents; p.O = cfg->num_obstacles; p.episode_length = cfg->episode_length;
   p.fairness_reward = cfg->fairness_reward; p.collaborative = cfg->collaborative; p.auto_reset = cfg->auto_reset;
   p.has_max_speed = cfg->max_speed > 0.0; p.env_offset = cfg->env_offset;
-  p.assignment = cfg->assignment; p.info_every_step = cfg->info_every_step;
+  p.assignment = cfg->assignment; p.info_every_step = cfg->info_every_step; p.W = cfg->num_walls;
   p.seed_lo = (uint32_t)(cfg->seed & 0xffffffffull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
   p.world_size = cfg->world_size; p.max_speed = cfg->max_speed; p.collision_rew = cfg->collision_rew; p.goal_rew = cfg->goal_rew;
   p.min_dist_thresh = cfg->min_dist_thresh; p.min_obs_dist = cfg->min_obs_dist; p.fair_rew = cfg->fair_rew; p.zeroshift = cfg->zeroshift;
-  formation_fields(p.N, p.O, (size_t)p.B, h->field_bytes);
+  formation_fields(p.N, p.O, p.W, (size_t)p.B, h->field_bytes);
   size_t total = 0;
-  for (int k = 0; k < 20; ++k) total += (h->field_bytes[k] + 255) & ~(size_t)255;
+  for (int k = 0; k < 23; ++k) total += (h->field_bytes[k] + 255) & ~(size_t)255;
   const size_t state_bytes = total;
   total += fm::formation_recipe_floats(p.N, p.O, p.B) * sizeof(float);               // recipes of the split step path
   cudaError_t e = cudaMalloc(&h->block, total);
   if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_formation_create: cudaMalloc(%zu B): %s", total, cudaGetErrorString(e)); }
   cudaMemset(h->block, 0, total);
   char* q = (char*)h->block;
-  void** member = reinterpret_cast<void**>(&p.st);                                 // 20 pointers, declaration order
-  for (int k = 0; k < 20; ++k) { member[k] = q; q += (h->field_bytes[k] + 255) & ~(size_t)255; }
+  void** member = reinterpret_cast<void**>(&p.st);                                 // 23 pointers, declaration order
+  for (int k = 0; k < 23; ++k) { member[k] = q; q += (h->field_bytes[k] + 255) & ~(size_t)255; }
   p.rec = reinterpret_cast<float*>((char*)h->block + state_bytes);
   const char* fused = getenv("FM_FORM_FUSED");
   p.fused = fused && fused[0] == '1';
@@ -841,7 +847,7 @@ static int formation_state_copy(FmFormation* h, const FmFormationState* st, bool
   if (int rc = use_device(h->device)) return rc;
   void* const* mine = reinterpret_cast<void* const*>(&h->p.st);
   void* const* theirs = reinterpret_cast<void* const*>(st);
-  for (int k = 0; k < 20; ++k) {
+  for (int k = 0; k < 23; ++k) {
     if (!theirs[k] || h->field_bytes[k] == 0) continue;
     FM_CUDA(cudaMemcpyAsync(to_handle ? mine[k] : theirs[k], to_handle ? theirs[k] : mine[k], h->field_bytes[k],
                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

@@ -66,6 +66,8 @@ template <int N>
 struct FEnv {
   double px[N], py[N], vx[N], vy[N], pd[N];
   float lx[N], ly[N], ox[F_MAXO], oy[F_MAXO];
+  float wax[2], wlen;          // walls (0..2): axis position per wall, half-length per env (:233-234, :301-333)
+  int wor[2];                  // orientation per wall: 0 'H' (along x at y = axis), 1 'V'
   double occ[N], dtg[N], treq[N], dleft[N];
   float hist[N], reached[N], mint[N], nac[N], noc[N];
   int gm[N];
@@ -88,7 +90,8 @@ struct FOut {
                    //   (it latched in this step's reward call of that ego; N + 1: never) | per ego i: pick [N][3] = (goal: landmark
                    //   index, or -1 = the agent's own position; goal occupied; goal history) as shown in ego i's rows
 };
-__host__ __device__ inline int form_rec_floats(int N, int O) { return 2 * (2 * N + O) + 3 * N + 3 * N * N; }
+// with walls: their midpoints close the position list (E = 2 N + O + W), and (half-length, axis 0, axis 1) follow the picks
+__host__ __device__ inline int form_rec_floats(int N, int O, int W = 0) { return 2 * (2 * N + O + W) + 3 * N + 3 * N * N + (W ? 3 : 0); }
 
 __device__ __forceinline__ double dn(double dx, double dy) {      // sqrt(dx*dx + dy*dy), no contraction (numpy has none)
   return FM_SQRT64(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
@@ -110,6 +113,10 @@ __device__ __forceinline__ void f_load(const FormParams& p, int b, FEnv<N>& e) {
   FM_UNROLL_O
   for (int k = 0; k < O; ++k) { e.ox[k] = p.st.obstacle_pos[((size_t)b * O + k) * 2]; e.oy[k] = p.st.obstacle_pos[((size_t)b * O + k) * 2 + 1]; }
   e.dmean = p.st.dist_traveled_mean[b]; e.dstd = p.st.dist_traveled_stddev[b]; e.step = p.st.step[b]; e.episode = p.st.episode[b];
+  if constexpr (OT < 0) {                                                  // walls: generic instantiation only
+    for (int w = 0; w < p.W; ++w) { e.wax[w] = p.st.wall_axis[(size_t)b * p.W + w]; e.wor[w] = p.st.wall_orient[(size_t)b * p.W + w]; }
+    if (p.W) e.wlen = p.st.wall_len[b];
+  }
 }
 
 template <int N, int OT>
@@ -129,6 +136,10 @@ __device__ __forceinline__ void f_store(const FormParams& p, int b, const FEnv<N
   if (statics) {
     FM_UNROLL_O
     for (int k = 0; k < O; ++k) { p.st.obstacle_pos[((size_t)b * O + k) * 2] = e.ox[k]; p.st.obstacle_pos[((size_t)b * O + k) * 2 + 1] = e.oy[k]; }
+    if constexpr (OT < 0) {
+      for (int w = 0; w < p.W; ++w) { p.st.wall_axis[(size_t)b * p.W + w] = e.wax[w]; p.st.wall_orient[(size_t)b * p.W + w] = e.wor[w]; }
+      if (p.W) p.st.wall_len[b] = e.wlen;
+    }
   }
   p.st.dist_traveled_mean[b] = (float)e.dmean; p.st.dist_traveled_stddev[b] = (float)e.dstd; p.st.step[b] = e.step; p.st.episode[b] = e.episode;
 }
@@ -150,6 +161,12 @@ __device__ __forceinline__ bool f_obstacle_hit(const FormParams& p, const FEnv<N
   bool hit = false;
   FM_UNROLL_O
   for (int k = 0; k < O; ++k) hit = hit || (dn((double)e.ox[k] - x, (double)e.oy[k] - y) < dmin);
+  if constexpr (OT < 0) {                                                  // :588-600: inside a wall's box grown by 1.5 * size
+    for (int w = 0; w < p.W; ++w) {
+      const double prll = e.wor[w] == 0 ? x : y, perp = e.wor[w] == 0 ? y : x, ax = (double)e.wax[w], wl = (double)e.wlen, g = 1.5 * 0.05;
+      hit = hit || ((ax - g) <= perp && perp <= (ax + g) && (-wl - g) <= prll && prll <= (wl + g));
+    }
+  }
   return hit;
 }
 
@@ -250,8 +267,8 @@ __device__ __forceinline__ void f_observation(const FormParams& p, FEnv<N>& e, i
 // velocities ego i sees are the post-integration ones with the agents that latched at ego index <= i zeroed (rec latch[]).
 template <int N, int OT>
 __device__ __forceinline__ void f_node_recipe(const FormParams& p, FEnv<N>& e, int i, float* __restrict__ rec) {
-  const int O = OT >= 0 ? OT : p.O;
-  float* pk = rec + 2 * (2 * N + O) + 3 * N + i * 3 * N;
+  const int O = OT >= 0 ? OT : p.O, W = OT >= 0 ? 0 : p.W;
+  float* pk = rec + 2 * (2 * N + O + W) + 3 * N + i * 3 * N;
   FM_UNROLL_N
   for (int a = 0; a < N; ++a) {
     const double qx = e.px[a], qy = e.py[a];
@@ -278,7 +295,15 @@ __device__ __forceinline__ void f_rec_head(const FormParams& p, const FEnv<N>& e
   }
   FM_UNROLL_O
   for (int k = 0; k < O; ++k) { rec[2 * (2 * N + k)] = e.ox[k]; rec[2 * (2 * N + k) + 1] = e.oy[k]; }
-  float* v = rec + 2 * (2 * N + O);
+  int W = 0;
+  if constexpr (OT < 0) {
+    W = p.W;
+    for (int w = 0; w < W; ++w) {                                          // wall.state.p_pos (:316-333): the midpoint
+      rec[2 * (2 * N + O + w)] = e.wor[w] == 0 ? 0.0f : e.wax[w]; rec[2 * (2 * N + O + w) + 1] = e.wor[w] == 0 ? e.wax[w] : 0.0f;
+    }
+    if (W) { float* x = rec + 2 * (2 * N + O + W) + 3 * N + 3 * N * N; x[0] = e.wlen; x[1] = e.wax[0]; x[2] = W > 1 ? e.wax[1] : 0.0f; }
+  }
+  float* v = rec + 2 * (2 * N + O + W);
   FM_UNROLL_N
   for (int a = 0; a < N; ++a) { v[2 * a] = (float)e.vx[a]; v[2 * a + 1] = (float)e.vy[a]; v[2 * N + a] = (float)(N + 1); }
 }
@@ -286,14 +311,19 @@ __device__ __forceinline__ void f_rec_head(const FormParams& p, const FEnv<N>& e
 // One node_obs row (ego agent i, entity en) from an env's recipe (:1222-1340):
 //   [v_e - v_i (2), p_e - p_i (2), goal_e - p_i (2), goal occupied, goal history, p_e - p_i (2), p_e - p_i (2), type]
 // landmarks: occupied 1, history = landmark id; obstacles: occupied 1, history 0 (id None); both with v_e = 0, goal = p_e.
-__device__ __forceinline__ void f_row(const float* __restrict__ rec, int N, int O, int i, int en, float* __restrict__ q) {
-  const float* v = rec + 2 * (2 * N + O);
+// Walls (:1323-1334; W > 0, the last W entities): p_e = the midpoint, the two trailing pairs are the corner offsets
+// (-len, axis + width / 2) - p_i and (len, axis - width / 2) - p_i as (x, y) whatever the orientation, type 3, history =
+// wall id in the fair-assignment files (wall_hist 1) and 0 in the base scenarios.
+__device__ __forceinline__ void f_row(const float* __restrict__ rec, int N, int O, int i, int en, float* __restrict__ q,
+                                      int W = 0, int wall_hist = 0) {
+  const float* v = rec + 2 * (2 * N + O + W);
   const float* latch = v + 2 * N;
   const float* pk = latch + N + i * 3 * N;
   const bool zi = latch[i] <= (float)i;
   const float x = rec[2 * i], y = rec[2 * i + 1], vx = zi ? 0.0f : v[2 * i], vy = zi ? 0.0f : v[2 * i + 1];
   const float rx = rec[2 * en] - x, ry = rec[2 * en + 1] - y;
   float rvx = 0.0f - vx, rvy = 0.0f - vy, gx = rx, gy = ry, occ = 1.0f, hist = 0.0f, type = 2.0f;
+  float c0 = rx, c1 = ry, c2 = rx, c3 = ry;
   if (en < N) {
     const bool ze = latch[en] <= (float)i;
     rvx = (ze ? 0.0f : v[2 * en]) - vx; rvy = (ze ? 0.0f : v[2 * en + 1]) - vy;
@@ -302,9 +332,14 @@ __device__ __forceinline__ void f_row(const float* __restrict__ rec, int N, int 
     occ = pk[3 * en + 1]; hist = pk[3 * en + 2]; type = 0.0f;
   } else if (en < 2 * N) {
     hist = (float)(en - N); type = 1.0f;
+  } else if (en >= 2 * N + O) {
+    const int w = en - (2 * N + O);
+    const float* wx = pk - i * 3 * N + 3 * N * N;                          // (half-length, axis 0, axis 1)
+    c0 = -wx[0] - x; c1 = (wx[1 + w] + 0.05f) - y; c2 = wx[0] - x; c3 = (wx[1 + w] - 0.05f) - y;
+    hist = wall_hist ? (float)w : 0.0f; type = 3.0f;
   }
   q[0] = rvx; q[1] = rvy; q[2] = rx; q[3] = ry; q[4] = gx; q[5] = gy; q[6] = occ; q[7] = hist;
-  q[8] = rx; q[9] = ry; q[10] = rx; q[11] = ry; q[12] = type;
+  q[8] = c0; q[9] = c1; q[10] = c2; q[11] = c3; q[12] = type;
 }
 
 // One entry of cached_dist_mag (core.py:204-228) = adj [E, E], from the recipe's fp32 positions (the positions the state
@@ -446,6 +481,14 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
     ++d;
   };
   for (int k = 0; k < p.O; ++k) { float x, y; draw(x, y); e.ox[k] = __fmul_rn(0.8f, x); e.oy[k] = __fmul_rn(0.8f, y); }
+  if (p.W) {
+    // :233-234 wall_length = U(0.2, 0.8) * ws / 4 per reset; :301-304 axis = +-U(0.2, 0.9) * ws / 2 (wall 0 at +, wall 1 at -);
+    // :306 orientation per wall.  One draw each, the raw 24-bit uniform of its x component.
+    auto uni = [&]() { float x, y; draw(x, y); return __fdiv_rn(__fadd_rn(x, half), ws); };
+    e.wlen = __fmul_rn(__fadd_rn(0.2f, __fmul_rn(0.6f, uni())), (float)(p.world_size / 4));
+    const float wp = __fmul_rn(__fadd_rn(0.2f, __fmul_rn(0.7f, uni())), half);
+    for (int w = 0; w < p.W; ++w) { e.wax[w] = w == 0 ? wp : -wp; e.wor[w] = uni() >= 0.5f ? 1 : 0; }
+  }
   const double r2 = 0.05 + 0.05;
   for (int pass = 0; pass < 2; ++pass) {
     double X[N], Y[N];
@@ -492,15 +535,40 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
 
 // One softplus contact term (core.py:389-392, cached branch: dist_min = size + size): fp32 with hardware rsqrt / ex2 and
 // the polynomial log1p of the navigation kernels (fm_device.cuh contact_force: relative error of the term ~5e-7).
-__device__ __forceinline__ void f_pair_force(float dx, float dy, float& fx, float& fy) {
+__device__ __forceinline__ void f_pair_force(float dx, float dy, float& fx, float& fy, float dmin = 0.1f) {
   const float d2 = fmaf(dx, dx, __fmul_rn(dy, dy));
   const float inv = rsqrt_approx(d2);
   const float dist = __fmul_rn(d2, inv);
-  const float x = __fmul_rn(__fsub_rn(0.1f, dist), 50.0f);                 // -(dist - dist_min) / k,  k = 0.02
+  const float x = __fmul_rn(__fsub_rn(dmin, dist), 50.0f);                 // -(dist - dist_min) / k,  k = 0.02
   const float t = ex2_approx(__fmul_rn(-fabsf(x), 1.4426950408889634f));
   const float sp = __fadd_rn(fmaxf(x, 0.0f), log1p_unit(t));
   const float c = __fmul_rn(__fmul_rn(6.0f, sp), inv);                     // contact_force (300) * k * softplus / dist
   fx = __fmul_rn(c, dx); fy = __fmul_rn(c, dy);
+}
+
+// get_wall_collision_force (core.py:407-462) of an agent at (px, py): wall_contact_force 220, margin 0.024, entity size
+// 0.05, width 0.1; wall along x at y = axis ('H') or along y at x = axis, endpoints [-len, len].  float64 like the reference,
+// so that the end-cap branches (where the force is discontinuous) are taken on the same side.
+__device__ __forceinline__ void f_wall_force(double px, double py, bool horiz, float axis, float len, float& fx, float& fy) {
+  const double prll = horiz ? px : py, perp = horiz ? py : px;
+  const double l = (double)len, r = 0.05;
+  if (prll < -l - r || prll > l + r) return;                               // beyond the endpoints: None (:417-419)
+  double st = 0.0, ct = 1.0;                                               // sin / cos of theta
+  if (prll < -l || prll > l) {                                             // part of the entity is past an end (:420-428)
+    const double past = prll < -l ? prll + l : prll - l;
+    st = past / r;                                                         // theta = arcsin(past / size)
+    ct = sqrt(fmax(0.0, 1.0 - st * st));
+  }
+  const double dist_min = ct * r + 0.05;                                   // + 0.5 * width
+  const double delta = perp - (double)axis;                                // :435
+  const double dist = fabs(delta);
+  const double k = 0.024;
+  const double x = -(dist - dist_min) / k;
+  const double pen = (fmax(x, 0.0) + log1p(exp(-fabs(x)))) * k;            // logaddexp(0, x) * k (:439)
+  const double mag = 220.0 * delta / dist * pen;                           // :440
+  const double fperp = ct * mag, fprll = st * fabs(mag);                   // :444-445
+  fx += (float)(horiz ? fprll : fperp);
+  fy += (float)(horiz ? fperp : fprll);
 }
 
 // reset() path for one env: optional reset, observation pass.  Runs on the generic (runtime O) code: resets are rare.
@@ -552,6 +620,14 @@ __device__ __forceinline__ void form_step_env(const FormParams& p, int b, const 
       float fx, fy; f_pair_force((float)e.px[a] - e.ox[k], (float)e.py[a] - e.oy[k], fx, fy);
       cfx[a] += fx; cfy[a] += fy;
     }
+    if constexpr (OT < 0) {
+      for (int w = 0; w < p.W; ++w) {                                      // a wall is also a circle entity of size = its width
+        const float mx = e.wor[w] == 0 ? 0.0f : e.wax[w], my = e.wor[w] == 0 ? e.wax[w] : 0.0f;   // at its midpoint (core.py:186, :215)
+        float fx, fy; f_pair_force((float)e.px[a] - mx, (float)e.py[a] - my, fx, fy, 0.05f + 0.1f);
+        cfx[a] += fx; cfy[a] += fy;
+      }
+      for (int w = 0; w < p.W; ++w) f_wall_force(e.px[a], e.py[a], e.wor[w] == 0, e.wax[w], e.wlen, cfx[a], cfy[a]);   // core.py:317-327
+    }
   }
   FM_UNROLL_N
   for (int i = 0; i < N; ++i) {                                            // integrate_state (:338-356): every agent
@@ -572,7 +648,7 @@ __device__ __forceinline__ void form_step_env(const FormParams& p, int b, const 
   }
   f_dists<N>(e);
   f_rec_head<N, OT>(p, e, o.rec);
-  float* latch = o.rec + 2 * (2 * N + O) + 2 * N;
+  float* latch = o.rec + 2 * (2 * N + O + (OT >= 0 ? 0 : p.W)) + 2 * N;
   // info rows are written after the loop (only then is "every agent done" known): what a row holds is the agent's own
   // final state except the team statistics as they stood after ITS info_callback, kept here (6 floats per agent)
   float istat[N][6];
@@ -664,14 +740,14 @@ __device__ __forceinline__ void form_step_env(const FormParams& p, int b, const 
 struct FormTile {            // floats per warp; all offsets multiples of 4 floats
   int obs, rew, done, rec, stage, rec_stride, words;
 };
-__host__ __device__ inline FormTile form_tile(int N, int O) {
+__host__ __device__ inline FormTile form_tile(int N, int O, int W = 0) {
   FormTile t;
   t.stage = 0;                                                             // two staging buffers of F_CHUNK_WORDS
   t.obs = 2 * F_CHUNK_WORDS;
   t.rew = t.obs + ((32 * N * F_OBS + 3) & ~3);
   t.done = t.rew + ((32 * N + 3) & ~3);
   t.rec = t.done + ((8 * N + 3) & ~3);                                      // 32 N bytes
-  t.rec_stride = form_rec_floats(N, O) | 1;                                 // odd: lane = env accesses are conflict free
+  t.rec_stride = form_rec_floats(N, O, W) | 1;                                 // odd: lane = env accesses are conflict free
   t.words = t.rec + ((32 * t.rec_stride + 3) & ~3);
   return t;
 }

@@ -39,7 +39,7 @@ namespace fm {
 // streams the other); ragged / unaligned tiles are written by the lanes.
 template <int N>
 __device__ void form_emit(const FormParams& p, float* __restrict__ S, const FormTile& t, int env0, int nenv, int lane, bool with_step) {
-  const int O = p.O, E = 2 * N + O, NE = N * E, EE = E * E;
+  const int O = p.O, W = p.W, E = 2 * N + O + W, NE = N * E, EE = E * E, wall_hist = p.assignment == 0;
   float* g_obs = p.out.obs ? p.out.obs + (size_t)env0 * N * F_OBS : nullptr;
   float* g_adj = p.out.adj ? p.out.adj + (size_t)env0 * EE : nullptr;
   float* g_rew = (with_step && p.out.reward) ? p.out.reward + (size_t)env0 * N : nullptr;
@@ -60,7 +60,7 @@ __device__ void form_emit(const FormParams& p, float* __restrict__ S, const Form
       for (int r = lane; r < nenv * NE; r += 32) {
         const int el = r / NE, q = r - el * NE, i = q / E;
         float row[F_NODE];
-        f_row(rec + el * t.rec_stride, N, O, i, q - i * E, row);
+        f_row(rec + el * t.rec_stride, N, O, i, q - i * E, row, W, wall_hist);
 #pragma unroll
         for (int f = 0; f < F_NODE; ++f) __stcs(g_node + (size_t)r * F_NODE + f, row[f]);
       }
@@ -129,7 +129,7 @@ __device__ void form_emit(const FormParams& p, float* __restrict__ S, const Form
     int el = lane / NE, i = (lane - el * NE) / E, en = lane - el * NE - i * E;
     for (int r0 = 0; r0 < rows; r0 += F_CHUNK_ROWS) {
       float* buf = next_buffer();
-      if (r0 + lane < rows) f_row(rec + el * t.rec_stride, N, O, i, en, buf + lane * F_NODE);
+      if (r0 + lane < rows) f_row(rec + el * t.rec_stride, N, O, i, en, buf + lane * F_NODE, W, wall_hist);
       en += adv_e; i += adv_i;
       if (en >= E) { en -= E; ++i; }
       while (i >= N) { i -= N; ++el; }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(FORM_WARPS * 32, FM_FORM_MIN_BLOCKS) formation
   const int env0 = (blockIdx.x * FORM_WARPS + wib) * 32;
   if (env0 >= p.B) return;                                                  // warp-uniform
   const int nenv = min(32, p.B - env0);
-  const FormTile t = form_tile(N, p.O);
+  const FormTile t = form_tile(N, p.O, p.W);
   float* S = smem + (size_t)wib * t.words;
   if (lane < nenv) {
     FOut o;
@@ -239,7 +239,7 @@ static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st) 
 
 template <int N, int MODE, int OT>
 static cudaError_t launch_formation_k(const FormParams& p, cudaStream_t st) {
-  const FormTile t = form_tile(N, p.O);
+  const FormTile t = form_tile(N, p.O, p.W);
   const size_t smem = (size_t)t.words * FORM_WARPS * sizeof(float);
   const int blocks = (p.B + 32 * FORM_WARPS - 1) / (32 * FORM_WARPS);
   cudaError_t e = cudaFuncSetAttribute(formation_kernel<N, MODE, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -254,7 +254,7 @@ template <int N>
 static cudaError_t launch_formation_n(const FormParams& p, bool is_reset, cudaStream_t st) {
   if (is_reset) return launch_formation_k<N, 1, -1>(p, st);
   if constexpr (N <= 4) {
-    if (p.rec && !p.fused) {
+    if (p.rec && !p.fused && p.W == 0) {
       switch (p.O) {
         case 0: return launch_formation_split<N, 0>(p, st);
         case 1: return launch_formation_split<N, 1>(p, st);

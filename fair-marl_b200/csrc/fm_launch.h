@@ -69,6 +69,7 @@ struct FormParams {
   const uint8_t* mask;       // reset
   float* rec;                // handle-owned recipe block of the split step path ([tiles][32][rec_stride] floats); null: fused kernel
   int fused;                 // 1: always the fused kernel (FM_FORM_FUSED=1, diagnostic / A-B)
+  int W;                     // walls (0..2): fused generic kernel only; entities 2N+O .. E-1 are the wall midpoints
 };
 size_t formation_recipe_floats(int N, int O, int B);
 cudaError_t launch_formation_image(const FormParams& p, cudaStream_t st);   // fm_form_image.cu: node_obs / adj from p.rec

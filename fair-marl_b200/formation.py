@@ -1,7 +1,7 @@
 """Formation-family scenarios on the device -- ``nav_fairassign_fairrew_formation_graph`` (FA+FR), ``..._nofairrew_...``
 (FA), ``nav_base_formation_graph_mask`` (OA) and ``nav_base_formation_graph_randomgoal`` (RA), i.e. the scenario files of the
 four shipped ``model_weights`` -- as a tensor-native env over ``fm_formation_*`` (include/fairmarl.h; kernels in
-csrc/fm_formation.cu: per-env logic one thread per env, warp-cooperative TMA emission; N = 2..7, no walls).
+csrc/fm_formation.cu: per-env logic one thread per env, warp-cooperative TMA emission; N = 2..7, 0..2 walls).
 
 SURVEY.md section 8f, N3: device tensors in, device tensors out, the same dict keys
 as ``B200GraphVecEnv.step_tensor`` with this family's shapes -- ``obs [B,N,11]`` (scenario ``observation``, :840-1015),
@@ -41,10 +41,11 @@ class FormationSimConfig:
     auto_reset: bool = True
     assignment: str = "fair"           # 'fair' (FA+FR, FA) | 'optimal' (OA: min-sum matching every step) | 'random' (RA)
     info_every_step: bool = True       # False: info rows only on the steps where every agent of the env is done (rollouts)
+    num_walls: int = 0                 # 0..2 (:301-333): wall midpoints close the entity list, rows of type 3
 
     @property
     def num_entities(self) -> int:
-        return 2 * self.num_agents + self.num_obstacles
+        return 2 * self.num_agents + self.num_obstacles + self.num_walls
 
     @classmethod
     def from_args(cls, args: Any, **overrides) -> "FormationSimConfig":
@@ -55,7 +56,7 @@ class FormationSimConfig:
         if name not in modes:
             raise NotImplementedError(f"scenario {name!r} is not one of the four formation scenarios this path covers")
         kw["assignment"], kw["fairness_reward"] = modes[name]
-        for unsupported in ("num_walls", "num_scripted_agents"):
+        for unsupported in ("num_scripted_agents",):
             if getattr(args, unsupported, 0):
                 raise NotImplementedError(f"{unsupported} > 0 is not supported by the formation kernels")
         if getattr(args, "graph_feat_type", "relative") != "relative":
@@ -125,7 +126,7 @@ class B200FormationVecEnv:
             collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
             min_obs_dist=cfg.min_obs_dist, fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift,
             fairness_reward=int(cfg.fairness_reward), collaborative=int(cfg.collaborative), auto_reset=int(cfg.auto_reset),
-            assignment={"fair": 0, "optimal": 1, "random": 2}[cfg.assignment], info_every_step=int(cfg.info_every_step))
+            assignment={"fair": 0, "optimal": 1, "random": 2}[cfg.assignment], info_every_step=int(cfg.info_every_step), num_walls=int(cfg.num_walls))
         self._h = C.c_void_p()
         _lib.check(self.lib.fm_formation_create(C.byref(c), self.device_index, C.byref(self._h)), "fm_formation_create")
         B, N, E = self.num_envs, self.num_agents, self.num_entities
@@ -208,9 +209,10 @@ class B200FormationVecEnv:
 
     # ------------------------------------------------------------------ state
     def _shapes(self):
-        B, N, O = self.num_envs, self.num_agents, self.cfg.num_obstacles
+        B, N, O, W = self.num_envs, self.num_agents, self.cfg.num_obstacles, self.cfg.num_walls
         per = {"pos": (B, N, 2), "vel": (B, N, 2), "landmark_pos": (B, N, 2), "obstacle_pos": (B, O, 2),
-               "dist_traveled_mean": (B,), "dist_traveled_stddev": (B,), "step": (B,), "episode": (B,)}
+               "dist_traveled_mean": (B,), "dist_traveled_stddev": (B,), "step": (B,), "episode": (B,),
+               "wall_axis": (B, W), "wall_orient": (B, W), "wall_len": (B,) if W else (0,)}
         return {name: per.get(name, (B, N)) for name in _lib.FORMATION_STATE_FIELDS}
 
     def _dtype(self, name):

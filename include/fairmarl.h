@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FM_ABI_VERSION 5
+#define FM_ABI_VERSION 6
 #define FM_OBS_DIM 7         /* navigation_graph.py:826-857 */
 #define FM_NODE_FEAT_DIM 11  /* navigation_graph.py:1079-1124 (relative features) */
 #define FM_INFO_DIM 14       /* navigation_graph.py:625-647 + environment.py:857 */
@@ -208,7 +208,7 @@ const char* fm_last_error(void);
 /* ---------------------------------------------------------------------------------------------------------------
  * Formation-family scenarios: nav_fairassign_fairrew_formation_graph.py (fairness_reward 1)
  * and nav_fairassign_nofairrew_formation_graph.py (0) -- and, through `assignment`, the base scenarios of model_weights/OA
- * and RA -- under MultiAgentGraphEnv.step (environment.py:816-877).  Own handle; num_agents 2..7, no walls, relative node
+ * and RA -- under MultiAgentGraphEnv.step (environment.py:816-877).  Own handle; num_agents 2..7, 0..2 walls, relative node
  * features.  The sequential per-agent logic runs one thread per env; the outputs are emitted warp-cooperatively through
  * shared-memory images and TMA bulk stores (csrc/fm_formation.cu).  Outputs use FmOutputs with obs [B, N, 11] (:840-1015), node_obs [B, N, E, 13] (:1222-1340), adj [B, E, E],
  * reward / done [B, N], info [B, N, 14] (terminal values survive the auto-reset). */
@@ -231,7 +231,7 @@ typedef struct FmFormationConfig {
                               num_agents <= 5; 2 'random' permutation drawn at reset (nav_base_formation_graph_randomgoal.py:
                               258-259; RA).  1 and 2 use the base scenarios' 1.5x goal clearance and need fairness_reward 0. */
   int32_t info_every_step; /* 0: info rows are written on the steps on which every agent of the env is done (what the runner reads) */
-  int32_t reserved_;
+  int32_t num_walls;       /* 0..2 (:301-333; core.py:36-55, :407-462): E = 2 N + O + W, wall rows of type 3 (:1323-1334) */
 } FmFormationConfig;
 
 /* State in API layout; the handle keeps it in exactly this layout (device), get / set are copies.  NULL: skipped. */
@@ -256,6 +256,9 @@ typedef struct FmFormationState {
   float* goal_reached;             /* [B, N]  scenario.goal_reached, -1 = none */
   float* occupied;                 /* [B, N]  scenario.landmark_poses_occupied */
   float* goal_history;             /* [B, N]  scenario.goal_history, -1 = none */
+  float* wall_axis;                /* [B, W]  wall.axis_pos (:301-304) */
+  int32_t* wall_orient;            /* [B, W]  0 'H', 1 'V' (:306) */
+  float* wall_len;                 /* [B]     half-length, redrawn at every reset (:233-234) */
 } FmFormationState;
 
 typedef struct FmFormation FmFormation;

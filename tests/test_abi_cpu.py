@@ -33,7 +33,7 @@ def test_binding_covers_header(lib_path):
     from fair_marl_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.load()
-    assert lib.fm_abi_version() == 5
+    assert lib.fm_abi_version() == 6
     assert lib.fm_stats_len(3) == 47
 
 
@@ -59,7 +59,7 @@ def test_struct_layouts_match_header(tmp_path):
         for field, _ in cls._fields_:
             assert int(got[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
     assert ctypes.sizeof(_lib.FmOutputs) == 6 * 8 and ctypes.sizeof(_lib.FmState) == 19 * 8
-    assert ctypes.sizeof(_lib.FmFormationState) == 20 * 8       # fm_abi.cu walks it as 20 pointers
+    assert ctypes.sizeof(_lib.FmFormationState) == 23 * 8       # fm_abi.cu walks it as 23 pointers
 
 
 def test_library_is_sm100a_only(lib_path):
@@ -126,6 +126,9 @@ def test_formation_config_from_reference_namespace():
     with pytest.raises(NotImplementedError):
         FormationSimConfig.from_args(a)
     a.scenario_name, a.num_walls = "nav_fairassign_fairrew_formation_graph", 1
+    c = FormationSimConfig.from_args(a)
+    assert c.num_walls == 1 and c.num_entities == 10 and c.fairness_reward
+    a.num_scripted_agents = 1
     with pytest.raises(NotImplementedError):
         FormationSimConfig.from_args(a)
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle.formation import FormationConfig, FormationOracle, FormationState
-from oracle.make_formation_golden import load, state_from
+from oracle.make_formation_golden import load, set_walls, state_from
 from oracle.navgraph import INFO_KEYS
 from parity_util import assert_close, assert_fairness_close
 
@@ -22,7 +22,8 @@ def _sim(cfg: FormationConfig, **kw):
         num_agents=cfg.num_agents, num_obstacles=cfg.num_obstacles, world_size=cfg.world_size, max_speed=cfg.max_speed,
         collision_rew=cfg.collision_rew, goal_rew=cfg.goal_rew, min_dist_thresh=cfg.min_dist_thresh,
         min_obs_dist=cfg.min_obs_dist, episode_length=cfg.episode_length, fair_rew=cfg.fair_rew, zeroshift=cfg.zeroshift,
-        collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, assignment=cfg.assignment, **kw)
+        collaborative=cfg.collaborative, fairness_reward=cfg.fairness_reward, assignment=cfg.assignment,
+        num_walls=cfg.num_walls, **kw)
 
 
 def _fp32(st: FormationState) -> FormationState:
@@ -52,6 +53,21 @@ def _from_device(dev) -> FormationState:
     return FormationState(**d)
 
 
+def _walls_to_device(orc: FormationOracle):
+    """Wall geometry of the oracle (kept beside FormationState) as device state entries, rounded to fp32 like the rest."""
+    if not orc.cfg.num_walls:
+        return {}
+    return {"wall_axis": orc.wall_axis.astype(np.float32), "wall_orient": orc.wall_orient.astype(np.int32),
+            "wall_len": orc.wall_len.astype(np.float32)}
+
+
+def _walls_from_device(orc: FormationOracle, dev) -> None:
+    if orc.cfg.num_walls:
+        orc.wall_axis = dev["wall_axis"].cpu().numpy().astype(np.float64)
+        orc.wall_orient = dev["wall_orient"].cpu().numpy().astype(np.int64)
+        orc.wall_len = dev["wall_len"].cpu().numpy().astype(np.float64)
+
+
 def _np(out):
     return {k: v.cpu().numpy() for k, v in out.items()}
 
@@ -74,7 +90,7 @@ def _compare_step(out, ref, post: FormationState, rpost: FormationState):
 
 
 @pytest.mark.parametrize("name", ["formation_n3_o3_fafr", "formation_n4_o2_fa", "formation_n7_o3_fafr", "formation_n3_o3_oa",
-                                  "formation_n3_o3_ra"])
+                                  "formation_n3_o3_ra", "formation_n3_o2_w2", "formation_n3_o3_w1_oa"])
 def test_step_matches_oracle_on_reference_states(name):
     """One step from every recorded reference state (rounded to fp32): device vs float64 oracle, outputs, info and the
     whole post-step state -- status latches, occupancy table, goal history and nearest-landmark latches included."""
@@ -83,10 +99,13 @@ def test_step_matches_oracle_on_reference_states(name):
     pre = _fp32(state_from(g, "pre_"))
     T = pre.pos.shape[0]
     env = fm.B200FormationVecEnv(_sim(cfg, auto_reset=False), num_envs=T)
-    env.set_state(_to_device(pre))
-    out = _np(env.step_tensor(_actions(g["actions"])))
     orc = FormationOracle(cfg, T)
     orc.set_state(pre)
+    set_walls(orc, g, "pre_")
+    dev_walls = _walls_to_device(orc)
+    env.set_state({**_to_device(pre), **dev_walls})
+    _walls_from_device(orc, env.get_state())                  # the fp32 geometry the device holds
+    out = _np(env.step_tensor(_actions(g["actions"])))
     ref = orc.step(g["actions"], autoreset=False)
     post, rpost = _from_device(env.get_state()), orc.get_state()
     _compare_step(out, ref, post, rpost)
@@ -99,25 +118,34 @@ def test_step_matches_oracle_on_reference_states(name):
     assert orc.branch_hits.get("status_latched", 0) > 0
     if cfg.assignment == "fair":
         assert orc.branch_hits.get("subset_index_quirk", 0) > 0
+    if cfg.num_walls:
+        assert orc.branch_hits.get("wall_end_cap", 0) > 0 and orc.branch_hits.get("wall_box_hit", 0) > 0
+        assert (out["node_obs"][:, :, -cfg.num_walls:, 12] == 3.0).all()
     env.close()
 
 
-@pytest.mark.parametrize("N,O,B,collab,fair,assignment", [
-    (3, 3, 48, False, True, "fair"), (4, 2, 32, True, False, "fair"), (2, 1, 32, False, True, "fair"),
-    (3, 3, 70, False, True, "fair"),                                    # a ragged last warp: the lane-store emission path
-    (5, 2, 32, False, True, "fair"), (7, 3, 40, False, True, "fair"),   # N > 4: serial lexifair descent every step
-    (3, 3, 48, False, False, "optimal"), (4, 1, 32, True, False, "optimal"), (3, 3, 48, False, False, "random"),
-    (6, 2, 32, False, False, "random")])
-def test_reset_and_rollout_match_oracle(N, O, B, collab, fair, assignment):
+@pytest.mark.parametrize("N,O,B,collab,fair,assignment,W", [
+    (3, 3, 48, False, True, "fair", 0), (4, 2, 32, True, False, "fair", 0), (2, 1, 32, False, True, "fair", 0),
+    (3, 3, 70, False, True, "fair", 0),                                 # a ragged last warp: the lane-store emission path
+    (5, 2, 32, False, True, "fair", 0), (7, 3, 40, False, True, "fair", 0),   # N > 4: serial lexifair descent every step
+    (3, 3, 48, False, False, "optimal", 0), (4, 1, 32, True, False, "optimal", 0), (3, 3, 48, False, False, "random", 0),
+    (6, 2, 32, False, False, "random", 0),
+    (3, 2, 40, False, True, "fair", 2), (4, 3, 32, False, False, "optimal", 1), (5, 1, 32, False, True, "fair", 2)])   # walls
+def test_reset_and_rollout_match_oracle(N, O, B, collab, fair, assignment, W):
     """Device reset == oracle reset bit for bit (same Philox draws, same acceptance rules, same lexifair), then a rollout
     that steers at the goals (so agents latch and envs finish early) across auto-resets, compared step by step."""
     import fair_marl_b200 as fm
     cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=15,
-                          collaborative=collab, fairness_reward=fair, assignment=assignment)
+                          collaborative=collab, fairness_reward=fair, assignment=assignment, num_walls=W)
     env = fm.B200FormationVecEnv(_sim(cfg), num_envs=B, seed=7, env_offset=3)
     orc = FormationOracle(cfg, B, seed=7, env_offset=3)
     out, ref = _np(env.reset_tensor()), orc.reset()
     st, rs = _from_device(env.get_state()), orc.get_state()
+    if W:                                         # same draws, same fp32 arithmetic: the wall geometry is bit-identical
+        dev = env.get_state()
+        assert (dev["wall_axis"].cpu().numpy() == orc.wall_axis.astype(np.float32)).all()
+        assert (dev["wall_orient"].cpu().numpy() == orc.wall_orient).all()
+        assert (dev["wall_len"].cpu().numpy() == orc.wall_len.astype(np.float32)).all()
     for f in ("pos", "landmark_pos", "obstacle_pos"):
         assert (getattr(st, f) == getattr(rs, f)).all(), f
     assert (st.goal_match == rs.goal_match).all() and (st.episode == 1).all() and not st.status.any()
@@ -129,8 +157,10 @@ def test_reset_and_rollout_match_oracle(N, O, B, collab, fair, assignment):
     rng = np.random.default_rng(5)
     resets = early = 0
     for t in range(32):
-        cur = _from_device(env.get_state())
+        dev = env.get_state()
+        cur = _from_device(dev)
         orc.set_state(cur)
+        _walls_from_device(orc, dev)
         d = np.take_along_axis(cur.landmark_pos, cur.goal_match[..., None], axis=1) - cur.pos
         seek = np.where(np.abs(d[..., 0]) > np.abs(d[..., 1]), np.where(d[..., 0] > 0, 1, 2), np.where(d[..., 1] > 0, 3, 4))
         a = np.where(rng.random((B, N)) < 0.25, rng.integers(0, 5, (B, N)), seek)

@@ -386,12 +386,15 @@ def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, T, monkeypat
         assert torch.equal(x, y), k
 
 
-def test_edge_list_corner_cases():
-    """process_adj on shapes the simulator never produces by itself: no edges at all, every edge, a single graph (2-D
+@pytest.mark.parametrize("single_pass", [False, True])
+def test_edge_list_corner_cases(single_pass, monkeypatch):
+    """Both forms of fm_edge_list (count / scan / emit, and the single-pass look-back kernel of fm_edges.cu, FM_EDGE_FUSED=1;
+    E = 35 x 8 lists needs 78 KB of shared memory, above 96 KB the call falls back).  process_adj on shapes the simulator never produces by itself: no edges at all, every edge, a single graph (2-D
     input), E = 35, more graph copies than lanes (repeat = 40), a graph count that is not a multiple of the 8 graphs
     a CTA handles, and 70 000 graphs (more CTAs than one scan segment)."""
     import torch
     import fair_marl_b200 as fm
+    monkeypatch.setenv("FM_EDGE_FUSED", "1" if single_pass else "0")
     rng = np.random.default_rng(3)
     dev = torch.device("cuda")
 

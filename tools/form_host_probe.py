@@ -27,3 +27,31 @@ for B in (256, 65536):
     ev1.record(); torch.cuda.synchronize()
     print(B, "graph us/step", ev0.elapsed_time(ev1) / 300 * 1e3)
     env.close()
+
+# logic kernel alone in steady state (FmOutputs without node_obs / adj: the image kernel is skipped)
+import ctypes as C
+from fair_marl_b200 import _lib
+B = 65536
+env = fm.B200FormationVecEnv(cfg, num_envs=B, device=0, seed=0, num_slots=8)
+a = torch.randint(0, 5, (25, B, 3), device="cuda", dtype=torch.int32)
+env.reset_tensor()
+outs = [_lib.FmOutputs(b["obs"].data_ptr(), None, None, b["reward"].data_ptr(), b["done"].data_ptr(), b["info"].data_ptr()) for b in env._slots]
+stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def logic_steps(n):
+    for k in range(n):
+        _lib.check(env.lib.fm_formation_step(env._h, a[k % 25].data_ptr(), C.byref(outs[k % 8]), stream), "step")
+logic_steps(30); torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record(); logic_steps(300); ev1.record(); torch.cuda.synchronize()
+print("logic kernel alone, steady state us/step", ev0.elapsed_time(ev1) / 300 * 1e3)
+
+# per-step durations over two episodes (logic kernel alone): where does the steady-state average come from?
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(61)]
+torch.cuda.synchronize()
+st = env.get_state(); print("episode phase (step of env 0):", int(st["step"][0]))
+evs[0].record()
+for k in range(60):
+    _lib.check(env.lib.fm_formation_step(env._h, a[k % 25].data_ptr(), C.byref(outs[k % 8]), stream), "step")
+    evs[k + 1].record()
+torch.cuda.synchronize()
+print("per-step us:", " ".join("%.0f" % (evs[k].elapsed_time(evs[k + 1]) * 1e3) for k in range(60)))
