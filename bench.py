@@ -325,7 +325,9 @@ def run_rollout(args, rank: int, local_rank: int, world: int):
 def run_formation(args, rank: int, local_rank: int, world: int):
     """Widened row N3 (diagnostic line, not the headline): the formation-family scenario the shipped weights were trained on
     (nav_fairassign_fairrew_formation_graph, 3 agents / 3 goals / 3 obstacles, FA+FR, reward 30, per-step lexifair
-    re-assignment) -- one fm_formation_step launch per step, random actions, auto-reset inside the timed region."""
+    re-assignment) -- fm_formation_step_many rollouts over pre-generated random actions (per step a logic kernel and an image
+    kernel), auto-reset inside the timed region; `closed_loop`: one fm_formation_step call
+    per step."""
     import torch
     import torch.distributed as dist
     import fair_marl_b200 as fm
@@ -344,9 +346,22 @@ def run_formation(args, rank: int, local_rank: int, world: int):
     env = fm.B200FormationVecEnv(cfg, num_envs=B, device=local_rank, seed=0, env_offset=rank * B, num_slots=args.form_slots)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = torch.randint(0, 5, (EPISODE, B, N), generator=g, device=dev, dtype=torch.int32)
+    def run_steps(n, phase):
+        """n steps from action-table phase `phase` as fm_formation_step_many rollouts (chunks end at the table's end)."""
+        while n > 0:
+            t = min(n, EPISODE - phase)
+            env.rollout_tensor(actions[phase:phase + t])
+            n -= t
+            phase = (phase + t) % EPISODE
+        return phase
+
+    # dry run of the exact call sequence (lane stream, kernel attributes), then the measured one from the same state
     env.reset_tensor()
-    for k in range(W):
-        env.step_tensor(actions[k % EPISODE])
+    ph = run_steps(W, 0)
+    run_steps(K, ph)
+    torch.cuda.synchronize(dev)
+    env.reset_tensor()
+    ph = run_steps(W, 0)
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(local_rank, period=0.0005)
     sampler.start()
@@ -357,8 +372,7 @@ def run_formation(args, rank: int, local_rank: int, world: int):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    for k in range(K):
-        env.step_tensor(actions[(W + k) % EPISODE])
+    run_steps(K, ph)
     ev1.record()
     sampler.sample_now()
     torch.cuda.synchronize(dev)
@@ -372,6 +386,18 @@ def run_formation(args, rank: int, local_rank: int, world: int):
         tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tt.item())
+    # closed loop: one fm_formation_step call per step (what a policy in the loop uses)
+    Kc = max(K, 100)
+    for k in range(10):
+        env.step_tensor(actions[k % EPISODE])
+    torch.cuda.synchronize(dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for k in range(Kc):
+        env.step_tensor(actions[k % EPISODE])
+    c1.record()
+    torch.cuda.synchronize(dev)
+    closed_ms = c0.elapsed_time(c1) / Kc
     # algorithmic bytes per env-step, counted like SURVEY 8(d): state read once + dynamic state written once + every output once
     words = (17 * N + 2 * O + 4 + N / 4) + (14 * N + 3 + N / 4) + (11 * N + 13 * N * E + E * E + N + N / 4)
     alg_bytes = int(words * 4 * B)
@@ -386,10 +412,18 @@ def run_formation(args, rank: int, local_rank: int, world: int):
             "config": {"workload": "nav_fairassign_fairrew_formation_graph 3 agents / 3 goals / 3 obstacles, FA+FR, goal_rew=collision_rew=30, "
                                    "episode_length 25 with auto-reset, lexifair re-assignment every step, random actions",
                        "envs_per_gpu": B, "envs_total": B * world, "agents": N, "entities": E,
-                       "l2": f"outputs cycle through {args.form_slots} buffer sets ({args.form_slots * B * (11 * N + 13 * N * E + E * E + N) * 4 / 1e9:.2f} GB > 126 MB L2)"},
+                       "launch": "fm_formation_step_many, one call per chunk of steps", "l2": f"outputs cycle through {args.form_slots} buffer sets ({args.form_slots * B * (11 * N + 13 * N * E + E * E + N) * 4 / 1e9:.2f} GB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": f"fm::formation_kernel<{N}, 0>", "algorithmic_bytes_per_step": alg_bytes},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clocks,
+                         "kernel": f"fm::formation_logic_kernel<{N}, {O}> + fm::formation_image_kernel<{N}, {O}>",
+                         "algorithmic_bytes_per_step": alg_bytes,
+                         "note": "a step is two launches per env-range lane: logic (thread per env) -> image (node_obs / adj from the "
+                                 "recipes; programmatic dependent launch); the "
+                                 "bytes are those of the whole step, the time is the whole step's"},
+            "cpu_baseline": None, "e2e": None,
+            "closed_loop": {"value": B * world * N / (closed_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": closed_ms, "steps": Kc,
+                            "frac": alg_bytes / (closed_ms * 1e-3) / 1e9 / peak,
+                            "api": "B200FormationVecEnv.step_tensor -> fm_formation_step, one call per step"},
+            "gpu_launches": 2 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     env.close()

@@ -131,6 +131,7 @@ def load():
         "fm_formation_destroy": ([vp], C.c_int),
         "fm_formation_reset": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_formation_step": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_formation_step_many": ([vp, vp, i32, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_formation_set_state": ([vp, C.POINTER(FmFormationState), vp], C.c_int),
         "fm_formation_get_state": ([vp, C.POINTER(FmFormationState), vp], C.c_int),
         "fm_gnn_weight_floats": ([C.POINTER(FmGnnConfig)], i64),
@@ -151,7 +152,8 @@ EXPORTED_SYMBOLS = (
     "fm_step_onehot", "fm_step_many", "fm_step_host", "fm_reset_host", "fm_read_info_host", "fm_set_state", "fm_get_state",
     "fm_assign_costs", "fm_assign_positions", "fm_pair_dist", "fm_edge_list", "fm_stats_read", "fm_num_entities", "fm_mapping",
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",
-    "fm_formation_create", "fm_formation_destroy", "fm_formation_reset", "fm_formation_step", "fm_formation_set_state",
+    "fm_formation_create", "fm_formation_destroy", "fm_formation_reset", "fm_formation_step", "fm_formation_step_many",
+    "fm_formation_set_state",
     "fm_formation_get_state", "fm_gnn_weight_floats", "fm_gnn_supported", "fm_gnn_forward",
     "fm_head_weight_floats", "fm_policy_head",
 )

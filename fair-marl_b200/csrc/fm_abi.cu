@@ -755,6 +755,11 @@ struct FmFormation {
   fm::FormParams p;
   void* block;
   size_t field_bytes[23];
+  fm::FormAsync async;       // side stream + fork / join events of the pending-reset prefetch (split step path)
+  bool has_async;
+  cudaStream_t lane_stream;  // second env-range lane of fm_formation_step_many (created on first use)
+  cudaEvent_t lane_fork, lane_join;
+  bool has_lane;
 };
 
 // the 23 members of FmFormationState, in declaration order: (words per env, element size)
@@ -787,7 +792,7 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   if (int rc = use_device(device)) return rc;
   FmFormation* h = new (std::nothrow) FmFormation();
   if (!h) return fail(FM_ERR_CUDA, "fm_formation_create: out of host memory");
-  h->cfg = *cfg; h->device = device;
+  h->cfg = *cfg; h->device = device; h->has_lane = false;
   fm::FormParams& p = h->p;
   memset(&p, 0, sizeof(p));
   p.B = cfg->num_envs; p.N = cfg->num_agents; p.O = cfg->num_obstacles; p.episode_length = cfg->episode_length;
@@ -802,6 +807,11 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   for (int k = 0; k < 23; ++k) total += (h->field_bytes[k] + 255) & ~(size_t)255;
   const size_t state_bytes = total;
   total += fm::formation_recipe_floats(p.N, p.O, p.B) * sizeof(float);               // recipes of the split step path
+  const size_t ready_off = total;
+  total += (2 * ((size_t)(p.B + 31) / 32) * sizeof(int) + 255) & ~(size_t)255;     // logic -> image flags (two per 32-env tile) of the split step path
+  const size_t pend_off = total;
+  const size_t pend_bytes = fm::formation_pending_floats(p.N, p.O, p.B) * sizeof(float);   // pending resets of the split step path
+  total += pend_bytes;
   cudaError_t e = cudaMalloc(&h->block, total);
   if (e != cudaSuccess) { delete h; return fail(FM_ERR_CUDA, "fm_formation_create: cudaMalloc(%zu B): %s", total, cudaGetErrorString(e)); }
   cudaMemset(h->block, 0, total);
@@ -811,6 +821,24 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   p.rec = reinterpret_cast<float*>((char*)h->block + state_bytes);
   const char* fused = getenv("FM_FORM_FUSED");
   p.fused = fused && fused[0] == '1';
+  p.Bp = ((p.B + 31) / 32) * 32;
+  h->has_async = false;
+  const char* nopdl = getenv("FM_FORM_PDL");                                       // FM_FORM_PDL=0: plain stream order (A-B)
+  const char* pf = getenv("FM_FORM_PREFETCH");
+  const bool prefetch = pf && pf[0] == '1';                                        // (an event record between the two launches would undo the dependent launch)
+  if (p.N <= 4 && p.O <= 3 && p.W == 0 && !p.fused && !prefetch && !(nopdl && nopdl[0] == '0'))
+    p.ready = reinterpret_cast<int*>((char*)h->block + ready_off);                  // zeroed with the block
+  // pending-reset prefetch: opt-in (FM_FORM_PREFETCH=1).  Bit-identical and tested, but measured slower (80 vs 74 us / step,
+  // profiles/r02_o): what an early reset costs is mostly the re-observation, which the prefetch does not remove.
+  if (p.N <= 4 && p.O <= 3 && p.W == 0 && !p.fused && prefetch) {
+    p.pend = reinterpret_cast<float*>((char*)h->block + pend_off);
+    cudaMemset(p.pend, 0xff, pend_bytes);                                          // tag -1: no block drawn yet
+    bool ok = cudaStreamCreateWithFlags(&h->async.side, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->async.fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->async.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaFree(h->block); delete h; return fail(FM_ERR_CUDA, "fm_formation_create: side stream / events: %s", cudaGetErrorString(cudaGetLastError())); }
+    h->has_async = true;
+  }
   *out = h;
   return FM_OK;
 }
@@ -819,6 +847,8 @@ int fm_formation_destroy(FmFormation* h) {
   if (!h) return FM_OK;
   if (int rc = use_device(h->device)) return rc;
   cudaDeviceSynchronize();
+  if (h->has_async) { cudaEventDestroy(h->async.fork); cudaEventDestroy(h->async.join); cudaStreamDestroy(h->async.side); }
+  if (h->has_lane) { cudaEventDestroy(h->lane_fork); cudaEventDestroy(h->lane_join); cudaStreamDestroy(h->lane_stream); }
   cudaFree(h->block);
   delete h;
   return FM_OK;
@@ -838,7 +868,63 @@ int fm_formation_step(FmFormation* h, const int32_t* actions, const FmOutputs* o
   if (int rc = use_device(h->device)) return rc;
   fm::FormParams p = h->p;
   p.out = *out; p.actions = actions; p.mask = nullptr;
-  FM_CUDA(fm::launch_formation(p, false, (cudaStream_t)stream));
+  FM_CUDA(fm::launch_formation(p, false, (cudaStream_t)stream, h->has_async ? &h->async : nullptr));
+  return FM_OK;
+}
+
+// The handle's launch parameters restricted to envs [start, start + count) (start a multiple of 32): every per-env pointer
+// moves by its own stride, the Philox key by `start`; tile-indexed blocks (recipes, ready flags) by whole tiles.
+static fm::FormParams formation_slice(const FmFormation* h, int start, int count, const FmOutputs& out, const int32_t* actions) {
+  fm::FormParams p = h->p;
+  const size_t B = (size_t)h->p.B;
+  void** member = reinterpret_cast<void**>(&p.st);
+  for (int k = 0; k < 23; ++k)
+    if (member[k]) member[k] = (char*)member[k] + h->field_bytes[k] / B * (size_t)start;
+  const size_t N = (size_t)p.N, E = 2 * N + (size_t)p.O + (size_t)p.W;
+  p.out = out;
+  if (p.out.obs) p.out.obs += (size_t)start * N * FM_FORMATION_OBS_DIM;
+  if (p.out.node_obs) p.out.node_obs += (size_t)start * N * E * FM_FORMATION_NODE_FEAT_DIM;
+  if (p.out.adj) p.out.adj += (size_t)start * E * E;
+  if (p.out.reward) p.out.reward += (size_t)start * N;
+  if (p.out.done) p.out.done += (size_t)start * N;
+  if (p.out.info) p.out.info += (size_t)start * N * FM_INFO_DIM;
+  p.actions = actions + (size_t)start * N;
+  p.mask = nullptr;
+  p.env_offset += start;
+  p.B = count;
+  if (p.rec) p.rec += fm::formation_recipe_floats(p.N, p.O, start);
+  if (p.ready) p.ready += 2 * (start / 32);
+  if (p.pend) p.pend += start;                          // SoA: the field stride stays the handle's Bp
+  return p;
+}
+
+int fm_formation_step_many(FmFormation* h, const int32_t* actions, int32_t T, const FmOutputs* outs, void* stream) {
+  if (!h || !actions || !outs) return fail(FM_ERR_INVALID_ARG, "fm_formation_step_many: null argument");
+  if (T < 0) return fail(FM_ERR_INVALID_ARG, "fm_formation_step_many: T must be >= 0");
+  if (int rc = use_device(h->device)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = h->p.B;
+  // One lane by default: two env-range lanes on two streams (FM_FORM_LANES=2) are bit-identical but measured 3 % slower
+  // (66.9 vs 65.0 us / step at 65 536 envs, profiles/r02_q) -- the logic kernels of both lanes fill the register file
+  // (16 warps x 128 registers per SM), so the other lane's image kernel finds no room to run beside them.
+  const char* lanes_env = getenv("FM_FORM_LANES");
+  const bool two = B >= 4096 && lanes_env && lanes_env[0] == '2';
+  if (two && !h->has_lane) {
+    bool ok = cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->lane_join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return fail(FM_ERR_CUDA, "fm_formation_step_many: lane stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    h->has_lane = true;
+  }
+  const int half = two ? ((B / 2 + 31) / 32) * 32 : B;
+  if (two) { FM_CUDA(cudaEventRecord(h->lane_fork, st)); FM_CUDA(cudaStreamWaitEvent(h->lane_stream, h->lane_fork, 0)); }
+  const size_t step_actions = (size_t)B * h->p.N;
+  for (int t = 0; t < T; ++t) {
+    const int32_t* a = actions + (size_t)t * step_actions;
+    FM_CUDA(fm::launch_formation(formation_slice(h, 0, half, outs[t], a), false, st, nullptr));
+    if (two) FM_CUDA(fm::launch_formation(formation_slice(h, half, B - half, outs[t], a), false, h->lane_stream, nullptr));
+  }
+  if (two) { FM_CUDA(cudaEventRecord(h->lane_join, h->lane_stream)); FM_CUDA(cudaStreamWaitEvent(st, h->lane_join, 0)); }
   return FM_OK;
 }
 

@@ -13,6 +13,8 @@
 //     distances between static entities are computed once per episode and kept in the state block,
 //     and every output is written lane = env into a shared-memory IMAGE of the API layout (odd strides:
 //     conflict free) which one thread hands to the copy engine (TMA bulk stores).
+#include <cstdlib>
+
 #include "fm_aw.cuh"
 
 namespace fm {
@@ -81,6 +83,10 @@ static cudaError_t aw_prepare_no() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 1, NODE_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 0, NODE_F_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 1, NODE_F_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (const char* v = getenv("FM_CARVEOUT"); v && v[0] == '1') {      // A/B: largest shared-memory carve-out instead of the driver's pick
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 0, NODE_F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 1, NODE_F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   return e;
 }
 

@@ -464,6 +464,16 @@ __device__ __forceinline__ void f_observe(const FormParams& p, FEnv<N>& e, const
   }
 }
 
+// what a reset leaves in the per-agent latches, counters and tables (:217-288)
+template <int N>
+__device__ __forceinline__ void f_reset_init(FEnv<N>& e) {
+  for (int i = 0; i < N; ++i) {
+    e.vx[i] = e.vy[i] = 0.0; e.pd[i] = 0.0; e.status[i] = false; e.treq[i] = e.dtg[i] = e.dleft[i] = -1.0;
+    e.noc[i] = e.nac[i] = 0.0f; e.hist[i] = -1.0f; e.reached[i] = -1.0f; e.occ[i] = 0.0;
+  }
+  e.step = 0;
+}
+
 // reset_world + random_scenario (:217-487) with the Philox draw scheme of the navigation kernels: draw counter per
 // (seed, global env, episode); obstacles 0.8 * U, agents U rejected vs obstacles (2.0x) / placed agents (1.05x), goals
 // 0.8 * U rejected vs obstacles (2.0x) / placed goals (1.2x; 1.5x in the base scenarios).  Positions are float32 values,
@@ -509,12 +519,9 @@ __device__ void f_reset(const FormParams& p, int b, FEnv<N>& e) {
     }
   }
   f_dists<N>(e);
-  for (int i = 0; i < N; ++i) {
-    e.vx[i] = e.vy[i] = 0.0; e.pd[i] = 0.0; e.status[i] = false; e.treq[i] = e.dtg[i] = e.dleft[i] = -1.0;
-    e.noc[i] = e.nac[i] = 0.0f; e.hist[i] = -1.0f; e.reached[i] = -1.0f; e.occ[i] = 0.0;
+  f_reset_init<N>(e);
+  for (int i = 0; i < N; ++i)
     if (p.has_max_speed) e.mint[i] = (float)(e.dal[i * N + i] / p.max_speed);   // goal_match = arange here (:229, :474-476)
-  }
-  e.step = 0;
   if (p.assignment == 0) {
     f_assign<N>(e);
   } else if (p.assignment == 1) {                                          // nav_base_formation_graph_mask.py:255-260
@@ -571,6 +578,49 @@ __device__ __forceinline__ void f_wall_force(double px, double py, bool horiz, f
   fy += (float)(horiz ? fperp : fprll);
 }
 
+// ---- pending resets (split step path) -----------------------------------------------------------------------------------
+// What a reset draws depends on (seed, global env, episode) only, so it can be computed AHEAD: formation_prefetch_kernel
+// (fm_form_image.cu) runs f_reset for every env whose pending block is stale, beside the image kernel, and leaves
+//   tag (the episode key the block was drawn for) | px py [N] | lx ly [N] | ox oy [O] | min_time [N] | goal_match [N]
+// in a handle-owned SoA block ([field][Bp], lane = env: coalesced).  The auto-reset inside the step then only copies the
+// block, clears the latches and re-observes.  Without this the step kernel's duration was set by the handful of warps in
+// which some env finished early: one lane walking the serial rejection sampling (about 12 000 instructions from local
+// memory) while 2 047 warps had long finished -- 53 us instead of 29 for the same instruction total (profiles/r02_n).
+__host__ __device__ inline int form_pending_floats(int N, int O) { return 1 + 6 * N + 2 * O; }
+
+#ifdef __CUDACC__
+template <int N>
+__device__ void f_pending_write(const FormParams& p, int b, const FEnv<N>& e, int key) {
+  float* q = p.pend + b;
+  const size_t S = (size_t)p.Bp;
+  int f = 1;
+  for (int i = 0; i < N; ++i) { q[f++ * S] = (float)e.px[i]; q[f++ * S] = (float)e.py[i]; }
+  for (int i = 0; i < N; ++i) { q[f++ * S] = e.lx[i]; q[f++ * S] = e.ly[i]; }
+  for (int k = 0; k < p.O; ++k) { q[f++ * S] = e.ox[k]; q[f++ * S] = e.oy[k]; }
+  for (int i = 0; i < N; ++i) q[f++ * S] = e.mint[i];
+  for (int i = 0; i < N; ++i) q[f++ * S] = __int_as_float(e.gm[i]);
+  q[0] = __int_as_float(key);
+}
+
+// The reset of env b for episode key e.episode from its pending block; false (nothing touched) if the block is stale.
+template <int N>
+__device__ bool f_pending_apply(const FormParams& p, int b, FEnv<N>& e) {
+  const float* q = p.pend + b;
+  const size_t S = (size_t)p.Bp;
+  if (__float_as_int(q[0]) != e.episode) return false;
+  int f = 1;
+  for (int i = 0; i < N; ++i) { e.px[i] = (double)q[f++ * S]; e.py[i] = (double)q[f++ * S]; }
+  for (int i = 0; i < N; ++i) { e.lx[i] = q[f++ * S]; e.ly[i] = q[f++ * S]; }
+  for (int k = 0; k < p.O; ++k) { e.ox[k] = q[f++ * S]; e.oy[k] = q[f++ * S]; }
+  for (int i = 0; i < N; ++i) { const float m = q[f++ * S]; if (p.has_max_speed) e.mint[i] = m; }
+  for (int i = 0; i < N; ++i) e.gm[i] = __float_as_int(q[f++ * S]);
+  f_dists<N>(e);
+  f_reset_init<N>(e);
+  e.episode += 1;
+  return true;
+}
+#endif  // __CUDACC__
+
 // reset() path for one env: optional reset, observation pass.  Runs on the generic (runtime O) code: resets are rare.
 template <int N>
 __device__ void form_reset_env(const FormParams& p, int b, const FOut& o) {
@@ -590,7 +640,11 @@ __device__ __noinline__ void form_reset_tail(const FormParams& p, int b, int epi
   FEnv<N> e;
   e.episode = episode; e.dmean = dmean; e.dstd = dstd;
   for (int i = 0; i < N; ++i) e.mint[i] = p.st.min_time[(size_t)b * N + i];   // kept when max_speed is None
-  f_reset<N>(p, b, e);
+  bool have = false;
+#ifdef __CUDACC__
+  if (p.pend) have = f_pending_apply<N>(p, b, e);
+#endif
+  if (!have) f_reset<N>(p, b, e);
   f_observe<N, -1>(p, e, o);
   f_store<N, -1>(p, b, e, true);
 }
@@ -740,10 +794,11 @@ __device__ __forceinline__ void form_step_env(const FormParams& p, int b, const 
 struct FormTile {            // floats per warp; all offsets multiples of 4 floats
   int obs, rew, done, rec, stage, rec_stride, words;
 };
-__host__ __device__ inline FormTile form_tile(int N, int O, int W = 0) {
+// with_stage: the fused kernel's two staging buffers (the logic kernel of the split path emits no rows: 3.3 KB less)
+__host__ __device__ inline FormTile form_tile(int N, int O, int W = 0, bool with_stage = true) {
   FormTile t;
   t.stage = 0;                                                             // two staging buffers of F_CHUNK_WORDS
-  t.obs = 2 * F_CHUNK_WORDS;
+  t.obs = with_stage ? 2 * F_CHUNK_WORDS : 0;
   t.rew = t.obs + ((32 * N * F_OBS + 3) & ~3);
   t.done = t.rew + ((32 * N + 3) & ~3);
   t.rec = t.done + ((8 * N + 3) & ~3);                                      // 32 N bytes

@@ -52,6 +52,17 @@ __global__ void __launch_bounds__(FI_WARPS * 32) formation_image_kernel(const Fo
   float* rec = smem;
   float* node = rec + ((REC_W + 3) & ~3);
   float* adj = node + FI_ENVS * NODE_W;
+  if (p.ready) {                                                            // programmatic dependent launch: wait for this CTA's 16 envs
+    if (tid == 0) {
+      const int* f = p.ready + blockIdx.x;
+      int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (!v) __nanosleep(200);
+      } while (!v);
+    }
+    __syncthreads();
+  }
   {                                                                         // this CTA's recipes: 16-byte loads, L2 hits
     const float4* src = reinterpret_cast<const float4*>(p.rec + (size_t)blockIdx.x * REC_W);
     float4* dst = reinterpret_cast<float4*>(rec);
@@ -59,6 +70,7 @@ __global__ void __launch_bounds__(FI_WARPS * 32) formation_image_kernel(const Fo
     for (int k = tid; k < (REC_W + 3) / 4; k += FI_WARPS * 32) dst[k] = __ldcs(src + k);
   }
   __syncthreads();
+  if (p.ready && tid == 0) p.ready[blockIdx.x] = 0;                         // consumed; the next step's producer runs after this grid
   float* g_node = p.out.node_obs ? p.out.node_obs + (size_t)env0 * NODE_W : nullptr;
   float* g_adj = p.out.adj ? p.out.adj + (size_t)env0 * EE : nullptr;
   const int el = lane & (FI_ENVS - 1);
@@ -107,10 +119,22 @@ static cudaError_t launch_image(const FormParams& p, cudaStream_t st) {
   if (dev != attr_device) {
     e = cudaFuncSetAttribute(formation_image_kernel<N, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(formation_image_kernel<N, OT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     attr_device = dev;
   }
-  formation_image_kernel<N, OT><<<(p.B + FI_ENVS - 1) / FI_ENVS, FI_WARPS * 32, smem, st>>>(p);
-  return cudaGetLastError();
+  const int blocks = (p.B + FI_ENVS - 1) / FI_ENVS;
+  if (!p.ready) {
+    formation_image_kernel<N, OT><<<blocks, FI_WARPS * 32, smem, st>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(FI_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, formation_image_kernel<N, OT>, p);
 }
 
 template <int N>
@@ -122,6 +146,32 @@ static cudaError_t launch_image_n(const FormParams& p, cudaStream_t st) {
     case 3: return launch_image<N, 3>(p, st);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// Pending resets (fm_form.cuh): every env whose block was not drawn for its current episode key gets a fresh one.  Almost
+// every thread leaves at once; the ones that stay walk the serial reset, off the step's critical path.
+template <int N>
+__global__ void __launch_bounds__(64) formation_prefetch_kernel(const FormParams p) {
+  const int b = blockIdx.x * 64 + threadIdx.x;
+  if (b >= p.B) return;
+  const int key = p.st.episode[b];
+  if (__float_as_int(p.pend[b]) == key) return;
+  FEnv<N> e;
+  e.episode = key;
+  for (int i = 0; i < N; ++i) e.mint[i] = 0.0f;
+  f_reset<N>(p, b, e);
+  f_pending_write<N>(p, b, e, key);
+}
+
+cudaError_t launch_formation_prefetch(const FormParams& p, cudaStream_t st) {
+  const int blocks = (p.B + 63) / 64;
+  switch (p.N) {
+    case 2: formation_prefetch_kernel<2><<<blocks, 64, 0, st>>>(p); break;
+    case 3: formation_prefetch_kernel<3><<<blocks, 64, 0, st>>>(p); break;
+    case 4: formation_prefetch_kernel<4><<<blocks, 64, 0, st>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
 }
 
 // node_obs / adj of one step from the recipes the logic kernel left in p.rec (N <= 4, O <= 3)

@@ -185,7 +185,12 @@ __global__ void __launch_bounds__(32, FM_FORM_LOGIC_BLOCKS) formation_logic_kern
   const int lane = threadIdx.x;
   const int env0 = blockIdx.x * 32;
   const int nenv = min(32, p.B - env0);
-  const FormTile t = form_tile(N, OT);
+  // The image kernel is a programmatic dependent launch: it may be scheduled as soon as every CTA of this grid is running,
+  // and each of its CTAs waits for the `ready` flag of its own 16 envs.  So rows are built while the few warps in which an
+  // env finished early are still walking the serial reset + re-observation (which set this kernel's duration: 29 us on the
+  // steps without an early reset, 55 with one -- same instruction total, profiles/r02_n, tools/form_tail_probe.py).
+  if (p.ready) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const FormTile t = form_tile(N, OT, 0, false);
   float* S = smem;
   if (lane < nenv) {
     FOut o;
@@ -199,10 +204,20 @@ __global__ void __launch_bounds__(32, FM_FORM_LOGIC_BLOCKS) formation_logic_kern
   uint8_t* g_done = p.out.done ? p.out.done + (size_t)env0 * N : nullptr;
   float* g_rec = p.rec + (size_t)blockIdx.x * 32 * t.rec_stride;           // handle-owned, whole tiles, 128-byte multiples
   const bool bulk = nenv == 32 && aligned16(g_obs) && aligned16(g_rew) && aligned16(g_done);
+  if (p.ready) {
+    // recipes by plain coalesced stores, then fence + flags: the consumer's acquire load orders its reads behind them
+    for (int k = lane; k < 32 * t.rec_stride; k += 32) g_rec[k] = S[t.rec + k];
+    __threadfence();
+    __syncwarp();
+    if (lane < 2) {
+      int* f = p.ready + 2 * blockIdx.x + lane;
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(f), "r"(1) : "memory");
+    }
+  }
   if (lane == 0) {
     const uint64_t pol = evict_first_policy();
     fence_async_smem();
-    bulk_store_plain(g_rec, S + t.rec, 32u * (uint32_t)t.rec_stride * 4u);  // read back by the image kernel: default L2 policy
+    if (!p.ready) bulk_store_plain(g_rec, S + t.rec, 32u * (uint32_t)t.rec_stride * 4u);  // read back by the image kernel: default L2 policy
     if (bulk) {
       if (g_obs) bulk_store(g_obs, S + t.obs, 32 * N * F_OBS * 4, pol);
       if (g_rew) bulk_store(g_rew, S + t.rew, 32 * N * 4, pol);
@@ -219,8 +234,8 @@ __global__ void __launch_bounds__(32, FM_FORM_LOGIC_BLOCKS) formation_logic_kern
 }
 
 template <int N, int OT>
-static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st) {
-  const FormTile t = form_tile(N, OT);
+static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st, const FormAsync* async) {
+  const FormTile t = form_tile(N, OT, 0, false);
   const size_t smem = (size_t)t.words * sizeof(float);
   static int attr_device = -1;                         // opt-in shared-memory size: once per device
   int dev = 0;
@@ -229,12 +244,27 @@ static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st) 
   if (dev != attr_device) {
     e = cudaFuncSetAttribute(formation_logic_kernel<N, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // 65 536 envs are 2 048 one-warp CTAs and 148 SMs x 14 resident CTAs is 2 072: with the carve-out the driver picked by
+    // itself some launches fitted one wave (27 us) and most did not (55 us; same instructions, profiles/r02_l).  Ask for
+    // the largest shared-memory carve-out so that the register file (16 CTAs / SM) is the only limit.
+    e = cudaFuncSetAttribute(formation_logic_kernel<N, OT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     attr_device = dev;
   }
   formation_logic_kernel<N, OT><<<(p.B + 31) / 32, 32, smem, st>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (!p.out.node_obs && !p.out.adj) return cudaSuccess;
-  return launch_formation_image(p, st);                // fm_form_image.cu
+  // the envs that reset in this step consumed their pending blocks: redraw them on the side stream, beside the image kernel
+  const bool pf = async && p.pend && p.auto_reset;
+  if (pf) {
+    if ((e = cudaEventRecord(async->fork, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(async->side, async->fork, 0)) != cudaSuccess) return e;
+    if ((e = launch_formation_prefetch(p, async->side)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(async->join, async->side)) != cudaSuccess) return e;
+  }
+  if (p.out.node_obs || p.out.adj)
+    if ((e = launch_formation_image(p, st)) != cudaSuccess) return e;                // fm_form_image.cu
+  if (pf) e = cudaStreamWaitEvent(st, async->join, 0);
+  return e;
 }
 
 template <int N, int MODE, int OT>
@@ -251,15 +281,15 @@ static cudaError_t launch_formation_k(const FormParams& p, cudaStream_t st) {
 // Steps of small teams (N <= 4) with at most 3 obstacles take the split path (env in registers, obstacle count a template
 // parameter, image kernel); everything else, and every reset, the fused generic kernel.
 template <int N>
-static cudaError_t launch_formation_n(const FormParams& p, bool is_reset, cudaStream_t st) {
+static cudaError_t launch_formation_n(const FormParams& p, bool is_reset, cudaStream_t st, const FormAsync* async) {
   if (is_reset) return launch_formation_k<N, 1, -1>(p, st);
   if constexpr (N <= 4) {
     if (p.rec && !p.fused && p.W == 0) {
       switch (p.O) {
-        case 0: return launch_formation_split<N, 0>(p, st);
-        case 1: return launch_formation_split<N, 1>(p, st);
-        case 2: return launch_formation_split<N, 2>(p, st);
-        case 3: return launch_formation_split<N, 3>(p, st);
+        case 0: return launch_formation_split<N, 0>(p, st, async);
+        case 1: return launch_formation_split<N, 1>(p, st, async);
+        case 2: return launch_formation_split<N, 2>(p, st, async);
+        case 3: return launch_formation_split<N, 3>(p, st, async);
         default: break;
       }
     }
@@ -267,16 +297,17 @@ static cudaError_t launch_formation_n(const FormParams& p, bool is_reset, cudaSt
   return launch_formation_k<N, 0, -1>(p, st);
 }
 
+size_t formation_pending_floats(int N, int O, int B) { return (size_t)form_pending_floats(N, O) * (size_t)(((B + 31) / 32) * 32); }
 size_t formation_recipe_floats(int N, int O, int B) { return (size_t)((B + 31) / 32) * 32 * form_tile(N, O).rec_stride; }
 
-cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st) {
+cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st, const FormAsync* async) {
   switch (p.N) {
-    case 2: return launch_formation_n<2>(p, is_reset, st);
-    case 3: return launch_formation_n<3>(p, is_reset, st);
-    case 4: return launch_formation_n<4>(p, is_reset, st);
-    case 5: return launch_formation_n<5>(p, is_reset, st);
-    case 6: return launch_formation_n<6>(p, is_reset, st);
-    case 7: return launch_formation_n<7>(p, is_reset, st);
+    case 2: return launch_formation_n<2>(p, is_reset, st, async);
+    case 3: return launch_formation_n<3>(p, is_reset, st, async);
+    case 4: return launch_formation_n<4>(p, is_reset, st, async);
+    case 5: return launch_formation_n<5>(p, is_reset, st, async);
+    case 6: return launch_formation_n<6>(p, is_reset, st, async);
+    case 7: return launch_formation_n<7>(p, is_reset, st, async);
     default: return cudaErrorInvalidValue;
   }
 }

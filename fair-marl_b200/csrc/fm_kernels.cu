@@ -11,6 +11,8 @@
 //   stats_reduce      fixed-order reduction of the per-warp statistic partial sums.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "fm_device.cuh"
 #include "fm_launch.h"
 
@@ -710,6 +712,10 @@ static cudaError_t prepare_g(const DevParams& p) {
   e = cudaFuncSetAttribute(prefetch_kernel<G, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            p.sm_pf_per_warp * (THREADS / 32) * (int)sizeof(float));
   if (e != cudaSuccess) return e;
+  if (const char* v = getenv("FM_CARVEOUT"); v && v[0] == '1') {      // A/B: largest shared-memory carve-out instead of the driver's pick
+    e = cudaFuncSetAttribute(step_kernel<G, WALLS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
   return cudaFuncSetAttribute(step_kernel<G, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 

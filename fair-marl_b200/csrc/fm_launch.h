@@ -70,10 +70,16 @@ struct FormParams {
   float* rec;                // handle-owned recipe block of the split step path ([tiles][32][rec_stride] floats); null: fused kernel
   int fused;                 // 1: always the fused kernel (FM_FORM_FUSED=1, diagnostic / A-B)
   int W;                     // walls (0..2): fused generic kernel only; entities 2N+O .. E-1 are the wall midpoints
+  float* pend;               // pending-reset blocks of the split step path ([form_pending_floats][Bp], fm_form.cuh); null: none
+  int Bp;                    // B rounded up to whole warps
+  int* ready;                // split step path: one flag per 16 envs, logic kernel -> image kernel (programmatic dependent launch); null: none
 };
 size_t formation_recipe_floats(int N, int O, int B);
 cudaError_t launch_formation_image(const FormParams& p, cudaStream_t st);   // fm_form_image.cu: node_obs / adj from p.rec
-cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st);
+struct FormAsync { cudaStream_t side; cudaEvent_t fork, join; };   // handle-owned: the prefetch kernel runs beside the image kernel
+size_t formation_pending_floats(int N, int O, int B);
+cudaError_t launch_formation_prefetch(const FormParams& p, cudaStream_t st);   // fm_form_image.cu
+cudaError_t launch_formation(const FormParams& p, bool is_reset, cudaStream_t st, const FormAsync* async = nullptr);
 // fused graph-network forward of the rollout policy (fm_policy.cu)
 bool gnn_supported_entities(int E);
 int gnn_weight_count(int embed_layers, int conv_layers);

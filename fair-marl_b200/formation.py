@@ -183,6 +183,29 @@ class B200FormationVecEnv:
         out["done"] = self._buf["done"].view(t.bool)
         return out
 
+    def rollout_tensor(self, actions):
+        """T consecutive steps with pre-generated actions int32 CUDA ``[T, B, N]`` in ONE ``fm_formation_step_many`` call
+        (``FM_FORM_LANES=2``: two env-range lanes on two streams).  Step t writes the output slot ``slots[t]`` of the ring (``num_slots`` sets,
+        round robin: with T > num_slots the early steps are overwritten); returns ``slots``.  ``slot_outputs(k)`` are the
+        tensors of slot k."""
+        t = self.torch
+        if not (t.is_tensor(actions) and actions.is_cuda and actions.dtype == t.int32 and actions.is_contiguous()
+                and actions.dim() == 3 and tuple(actions.shape[1:]) == (self.num_envs, self.num_agents)):
+            raise ValueError(f"actions must be a contiguous int32 CUDA tensor [T,{self.num_envs},{self.num_agents}]")
+        T = int(actions.shape[0])
+        slots = [(self._slot + 1 + k) % len(self._slots) for k in range(T)]
+        outs = (_lib.FmOutputs * max(T, 1))(*[self._outs[k] for k in slots])
+        _lib.check(self.lib.fm_formation_step_many(self._h, actions.data_ptr(), T, outs, self._stream()), "fm_formation_step_many")
+        if T:
+            self._slot = slots[-1]
+            self._buf, self._out = self._slots[self._slot], self._outs[self._slot]
+        return slots
+
+    def slot_outputs(self, k: int) -> Dict[str, Any]:
+        out = dict(self._slots[k])
+        out["done"] = self._slots[k]["done"].view(self.torch.bool)
+        return out
+
     # ------------------------------------------------------------------ ShareVecEnv interface (numpy)
     def reset(self):
         """``(obs, agent_id, node_obs, adj)`` (env_wrappers.py:997-1002)."""

@@ -270,6 +270,11 @@ int fm_formation_destroy(FmFormation* h);
 int fm_formation_reset(FmFormation* h, const uint8_t* mask, const FmOutputs* out, void* stream);
 /* actions: int32 [B, N] in {0..4} (0 no-op, 1 +x, 2 -x, 3 +y, 4 -y). */
 int fm_formation_step(FmFormation* h, const int32_t* actions, const FmOutputs* out, void* stream);
+/* T consecutive steps with pre-generated actions int32 [T, B, N] (random-action rollouts, replayed trajectories): step t
+ * writes outs[t] (host array of T FmOutputs of device pointers): one call, no host work between the steps.  With
+ * FM_FORM_LANES=2 the batch runs as two env-range lanes on two streams forked from / joined to `stream` (measured no faster
+ * for this family).  Bit-identical to T calls of fm_formation_step either way. */
+int fm_formation_step_many(FmFormation* h, const int32_t* actions, int32_t T, const FmOutputs* outs, void* stream);
 int fm_formation_set_state(FmFormation* h, const FmFormationState* st, void* stream);
 int fm_formation_get_state(FmFormation* h, const FmFormationState* st, void* stream);
 

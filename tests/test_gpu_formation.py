@@ -184,6 +184,41 @@ def test_reset_and_rollout_match_oracle(N, O, B, collab, fair, assignment, W):
     env.close()
 
 
+@pytest.mark.parametrize("N,O,B,T,slots", [(3, 3, 4096 + 70, 40, 40), (4, 2, 8192, 12, 12), (3, 3, 300, 30, 4), (5, 2, 4500, 9, 9)])
+@pytest.mark.parametrize("lanes", ["1", "2"])
+def test_rollout_lanes_equal_single_steps(N, O, B, T, slots, lanes, monkeypatch):
+    """fm_formation_step_many (one lane, or two env-range lanes on two streams for B >= 4096; pre-generated actions) against T calls of
+    fm_formation_step: every output of every step still in the ring, the final state and the info rows, bit for bit.
+    Short episodes, so that time-out resets fall inside the rollout; goal seeking, so that early resets do too."""
+    import torch
+    import fair_marl_b200 as fm
+    monkeypatch.setenv("FM_FORM_LANES", lanes)
+    cfg = FormationConfig(num_agents=N, num_obstacles=O, goal_rew=30.0, collision_rew=30.0, episode_length=7)
+    e_r = fm.B200FormationVecEnv(_sim(cfg, info_every_step=False), num_envs=B, seed=11, num_slots=slots)
+    e_s = fm.B200FormationVecEnv(_sim(cfg, info_every_step=False), num_envs=B, seed=11, num_slots=slots)
+    e_r.reset_tensor(); e_s.reset_tensor()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.randint(0, 5, (T, B, N), generator=g, device="cuda", dtype=torch.int32)
+    slot_of = e_r.rollout_tensor(acts)
+    for t in range(T):
+        o_s = e_s.step_tensor(acts[t])
+        if slot_of[t] not in slot_of[t + 1:]:
+            o_r = e_r.slot_outputs(slot_of[t])
+            for k in ("obs", "node_obs", "adj_env", "reward", "done"):
+                assert torch.equal(o_r[k], o_s[k]), (t, k)
+    s_r, s_s = e_r.get_state(), e_s.get_state()
+    for k in s_r:
+        assert torch.equal(s_r[k], s_s[k]), k
+    assert torch.equal(e_r._slots[0]["info"], e_s._slots[0]["info"])
+    assert int(s_r["episode"].max()) >= 1 + T // 7
+    # a second rollout continues the same trajectory
+    slot_of = e_r.rollout_tensor(acts[:3])
+    for t in range(3):
+        o_s = e_s.step_tensor(acts[t])
+        assert torch.equal(e_r.slot_outputs(slot_of[t])["node_obs"], o_s["node_obs"]), t
+    e_r.close(); e_s.close()
+
+
 def test_masked_reset_and_errors():
     import torch
     import fair_marl_b200 as fm

@@ -55,3 +55,19 @@ for k in range(60):
     evs[k + 1].record()
 torch.cuda.synchronize()
 print("per-step us:", " ".join("%.0f" % (evs[k].elapsed_time(evs[k + 1]) * 1e3) for k in range(60)))
+
+def per_step(label, act_of, n=60):
+    torch.cuda.synchronize()
+    evs[0].record()
+    for k in range(n):
+        _lib.check(env.lib.fm_formation_step(env._h, act_of(k).data_ptr(), C.byref(outs[k % 8]), stream), "step")
+        evs[k + 1].record()
+    torch.cuda.synchronize()
+    print(label, "phase", int(st["step"][0]), ":", " ".join("%.0f" % (evs[k].elapsed_time(evs[k + 1]) * 1e3) for k in range(n)))
+st = env.get_state()
+per_step("same action slice a[0]", lambda k: a[0])
+st = env.get_state()
+per_step("slices shifted by 7", lambda k: a[(k + 7) % 25])
+zero = torch.zeros_like(a[0])
+st = env.get_state()
+per_step("no-op actions", lambda k: zero)
