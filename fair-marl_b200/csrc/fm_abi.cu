@@ -759,6 +759,7 @@ struct FmFormation {
   bool has_async;
   cudaStream_t lane_stream;  // second env-range lane of fm_formation_step_many (created on first use)
   cudaEvent_t lane_fork, lane_join;
+  fm::FormAsync lane_async;  // the second lane's own prefetch stream / events
   bool has_lane;
 };
 
@@ -824,13 +825,11 @@ int fm_formation_create(const FmFormationConfig* cfg, int device, FmFormation** 
   p.Bp = ((p.B + 31) / 32) * 32;
   h->has_async = false;
   const char* nopdl = getenv("FM_FORM_PDL");                                       // FM_FORM_PDL=0: plain stream order (A-B)
-  const char* pf = getenv("FM_FORM_PREFETCH");
-  const bool prefetch = pf && pf[0] == '1';                                        // (an event record between the two launches would undo the dependent launch)
-  if (p.N <= 4 && p.O <= 3 && p.W == 0 && !p.fused && !prefetch && !(nopdl && nopdl[0] == '0'))
+  const char* nopf = getenv("FM_FORM_PREFETCH");                                   // FM_FORM_PREFETCH=0: every reset drawn inline (A-B)
+  const bool split = p.N <= 4 && p.O <= 3 && p.W == 0 && !p.fused;
+  if (split && !(nopdl && nopdl[0] == '0'))
     p.ready = reinterpret_cast<int*>((char*)h->block + ready_off);                  // zeroed with the block
-  // pending-reset prefetch: opt-in (FM_FORM_PREFETCH=1).  Bit-identical and tested, but measured slower (80 vs 74 us / step,
-  // profiles/r02_o): what an early reset costs is mostly the re-observation, which the prefetch does not remove.
-  if (p.N <= 4 && p.O <= 3 && p.W == 0 && !p.fused && prefetch) {
+  if (split && !(nopf && nopf[0] == '0')) {
     p.pend = reinterpret_cast<float*>((char*)h->block + pend_off);
     cudaMemset(p.pend, 0xff, pend_bytes);                                          // tag -1: no block drawn yet
     bool ok = cudaStreamCreateWithFlags(&h->async.side, cudaStreamNonBlocking) == cudaSuccess;
@@ -848,7 +847,10 @@ int fm_formation_destroy(FmFormation* h) {
   if (int rc = use_device(h->device)) return rc;
   cudaDeviceSynchronize();
   if (h->has_async) { cudaEventDestroy(h->async.fork); cudaEventDestroy(h->async.join); cudaStreamDestroy(h->async.side); }
-  if (h->has_lane) { cudaEventDestroy(h->lane_fork); cudaEventDestroy(h->lane_join); cudaStreamDestroy(h->lane_stream); }
+  if (h->has_lane) {
+    cudaEventDestroy(h->lane_fork); cudaEventDestroy(h->lane_join); cudaStreamDestroy(h->lane_stream);
+    if (h->has_async) { cudaEventDestroy(h->lane_async.fork); cudaEventDestroy(h->lane_async.join); cudaStreamDestroy(h->lane_async.side); }
+  }
   cudaFree(h->block);
   delete h;
   return FM_OK;
@@ -913,6 +915,11 @@ int fm_formation_step_many(FmFormation* h, const int32_t* actions, int32_t T, co
     bool ok = cudaStreamCreateWithFlags(&h->lane_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->lane_join, cudaEventDisableTiming) == cudaSuccess;
+    if (h->has_async) {
+      ok = ok && cudaStreamCreateWithFlags(&h->lane_async.side, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&h->lane_async.fork, cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&h->lane_async.join, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) return fail(FM_ERR_CUDA, "fm_formation_step_many: lane stream / events: %s", cudaGetErrorString(cudaGetLastError()));
     h->has_lane = true;
   }
@@ -921,8 +928,8 @@ int fm_formation_step_many(FmFormation* h, const int32_t* actions, int32_t T, co
   const size_t step_actions = (size_t)B * h->p.N;
   for (int t = 0; t < T; ++t) {
     const int32_t* a = actions + (size_t)t * step_actions;
-    FM_CUDA(fm::launch_formation(formation_slice(h, 0, half, outs[t], a), false, st, nullptr));
-    if (two) FM_CUDA(fm::launch_formation(formation_slice(h, half, B - half, outs[t], a), false, h->lane_stream, nullptr));
+    FM_CUDA(fm::launch_formation(formation_slice(h, 0, half, outs[t], a), false, st, h->has_async ? &h->async : nullptr));
+    if (two) FM_CUDA(fm::launch_formation(formation_slice(h, half, B - half, outs[t], a), false, h->lane_stream, h->has_async ? &h->lane_async : nullptr));
   }
   if (two) { FM_CUDA(cudaEventRecord(h->lane_join, h->lane_stream)); FM_CUDA(cudaStreamWaitEvent(st, h->lane_join, 0)); }
   return FM_OK;

@@ -599,23 +599,34 @@ __device__ void f_pending_write(const FormParams& p, int b, const FEnv<N>& e, in
   for (int k = 0; k < p.O; ++k) { q[f++ * S] = e.ox[k]; q[f++ * S] = e.oy[k]; }
   for (int i = 0; i < N; ++i) q[f++ * S] = e.mint[i];
   for (int i = 0; i < N; ++i) q[f++ * S] = __int_as_float(e.gm[i]);
+  __threadfence();                                                         // a concurrent step kernel that sees the tag sees the block
   q[0] = __int_as_float(key);
 }
 
 // The reset of env b for episode key e.episode from its pending block; false (nothing touched) if the block is stale.
-template <int N>
-__device__ bool f_pending_apply(const FormParams& p, int b, FEnv<N>& e) {
+template <int N, int OT>
+__device__ __forceinline__ bool f_pending_apply(const FormParams& p, int b, FEnv<N>& e) {
+  const int O = OT >= 0 ? OT : p.O;
   const float* q = p.pend + b;
   const size_t S = (size_t)p.Bp;
   if (__float_as_int(q[0]) != e.episode) return false;
-  int f = 1;
-  for (int i = 0; i < N; ++i) { e.px[i] = (double)q[f++ * S]; e.py[i] = (double)q[f++ * S]; }
-  for (int i = 0; i < N; ++i) { e.lx[i] = q[f++ * S]; e.ly[i] = q[f++ * S]; }
-  for (int k = 0; k < p.O; ++k) { e.ox[k] = q[f++ * S]; e.oy[k] = q[f++ * S]; }
-  for (int i = 0; i < N; ++i) { const float m = q[f++ * S]; if (p.has_max_speed) e.mint[i] = m; }
-  for (int i = 0; i < N; ++i) e.gm[i] = __float_as_int(q[f++ * S]);
+  FM_UNROLL_N
+  for (int i = 0; i < N; ++i) { e.px[i] = (double)q[(1 + 2 * i) * S]; e.py[i] = (double)q[(2 + 2 * i) * S]; }
+  FM_UNROLL_N
+  for (int i = 0; i < N; ++i) { e.lx[i] = q[(1 + 2 * N + 2 * i) * S]; e.ly[i] = q[(2 + 2 * N + 2 * i) * S]; }
+  FM_UNROLL_O
+  for (int k = 0; k < O; ++k) { e.ox[k] = q[(1 + 4 * N + 2 * k) * S]; e.oy[k] = q[(2 + 4 * N + 2 * k) * S]; }
+  FM_UNROLL_N
+  for (int i = 0; i < N; ++i) { const float m = q[(1 + 4 * N + 2 * O + i) * S]; if (p.has_max_speed) e.mint[i] = m; }
+  FM_UNROLL_N
+  for (int i = 0; i < N; ++i) e.gm[i] = __float_as_int(q[(1 + 5 * N + 2 * O + i) * S]);
   f_dists<N>(e);
-  f_reset_init<N>(e);
+  FM_UNROLL_N
+  for (int i = 0; i < N; ++i) {
+    e.vx[i] = e.vy[i] = 0.0; e.pd[i] = 0.0; e.status[i] = false; e.treq[i] = e.dtg[i] = e.dleft[i] = -1.0;
+    e.noc[i] = e.nac[i] = 0.0f; e.hist[i] = -1.0f; e.reached[i] = -1.0f; e.occ[i] = 0.0;
+  }
+  e.step = 0;
   e.episode += 1;
   return true;
 }
@@ -634,20 +645,30 @@ __device__ void form_reset_env(const FormParams& p, int b, const FOut& o) {
 
 // Auto-reset at the end of a step (env_wrappers.py:859-865), out of line with an env of its own: the step's env stays in
 // registers (a reference handed to a call would give it a home in local memory for the whole step).  dist_traveled_mean /
-// stddev are world attributes the reset does not touch.
+// stddev are world attributes the reset does not touch.  Two forms: the generic one draws the reset here (serial rejection
+// sampling, env in local memory); the fast one (split step path, pending block valid) copies the block and re-observes on the
+// unrolled register code -- this is the path whose latency sets the logic kernel's duration whenever some env finishes early.
 template <int N>
 __device__ __noinline__ void form_reset_tail(const FormParams& p, int b, int episode, double dmean, double dstd, const FOut& o) {
   FEnv<N> e;
   e.episode = episode; e.dmean = dmean; e.dstd = dstd;
   for (int i = 0; i < N; ++i) e.mint[i] = p.st.min_time[(size_t)b * N + i];   // kept when max_speed is None
-  bool have = false;
-#ifdef __CUDACC__
-  if (p.pend) have = f_pending_apply<N>(p, b, e);
-#endif
-  if (!have) f_reset<N>(p, b, e);
+  f_reset<N>(p, b, e);
   f_observe<N, -1>(p, e, o);
   f_store<N, -1>(p, b, e, true);
 }
+#ifdef __CUDACC__
+template <int N, int OT>
+__device__ __noinline__ void form_reset_tail_fast(const FormParams& p, int b, int episode, double dmean, double dstd, const FOut& o) {
+  FEnv<N> e;
+  e.episode = episode; e.dmean = dmean; e.dstd = dstd;
+  FM_UNROLL_N
+  for (int i = 0; i < N; ++i) e.mint[i] = p.st.min_time[(size_t)b * N + i];
+  f_pending_apply<N, OT>(p, b, e);                                          // the caller checked the tag
+  f_observe<N, OT>(p, e, o);
+  f_store<N, OT>(p, b, e, true);
+}
+#endif
 
 // MultiAgentGraphEnv.step (environment.py:816-877) + graphworker auto-reset (env_wrappers.py:856-865) for one env.
 template <int N, int OT = -1>
@@ -786,8 +807,15 @@ __device__ __forceinline__ void form_step_env(const FormParams& p, int b, const 
       q[9] = (float)e.treq[i]; q[10] = istat[i][3]; q[11] = istat[i][4]; q[12] = istat[i][5]; q[13] = e.mint[i];
     }
   }
-  if (p.auto_reset && all_done) form_reset_tail<N>(p, b, e.episode, e.dmean, e.dstd, o);   // env_wrappers.py:859-865
-  else f_store<N, OT>(p, b, e, false);
+  if (p.auto_reset && all_done) {                                          // env_wrappers.py:859-865
+#ifdef __CUDACC__
+    if (OT >= 0 && p.pend && __float_as_int(p.pend[b]) == e.episode) form_reset_tail_fast<N, OT>(p, b, e.episode, e.dmean, e.dstd, o);
+    else
+#endif
+      form_reset_tail<N>(p, b, e.episode, e.dmean, e.dstd, o);
+  } else {
+    f_store<N, OT>(p, b, e, false);
+  }
 }
 
 #ifdef __CUDACC__

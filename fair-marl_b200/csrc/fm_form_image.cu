@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(64) formation_prefetch_kernel(const FormParams
   e.episode = key;
   for (int i = 0; i < N; ++i) e.mint[i] = 0.0f;
   f_reset<N>(p, b, e);
-  f_pending_write<N>(p, b, e, key);
+  f_pending_write<N>(p, b, e, key);                                          // (tag last, behind a fence)
 }
 
 cudaError_t launch_formation_prefetch(const FormParams& p, cudaStream_t st) {

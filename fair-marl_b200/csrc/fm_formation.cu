@@ -251,9 +251,9 @@ static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st, 
     if (e != cudaSuccess) return e;
     attr_device = dev;
   }
-  formation_logic_kernel<N, OT><<<(p.B + 31) / 32, 32, smem, st>>>(p);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  // the envs that reset in this step consumed their pending blocks: redraw them on the side stream, beside the image kernel
+  // Pending resets: the envs that reset in EARLIER steps consumed their blocks; redraw them on the side stream while this
+  // step runs (forked before the logic launch, so that logic -> image stay adjacent for the dependent launch; joined behind
+  // the image kernel).  A block is therefore fresh again two steps after it was used; an env that resets sooner draws inline.
   const bool pf = async && p.pend && p.auto_reset;
   if (pf) {
     if ((e = cudaEventRecord(async->fork, st)) != cudaSuccess) return e;
@@ -261,6 +261,8 @@ static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st, 
     if ((e = launch_formation_prefetch(p, async->side)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(async->join, async->side)) != cudaSuccess) return e;
   }
+  formation_logic_kernel<N, OT><<<(p.B + 31) / 32, 32, smem, st>>>(p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (p.out.node_obs || p.out.adj)
     if ((e = launch_formation_image(p, st)) != cudaSuccess) return e;                // fm_form_image.cu
   if (pf) e = cudaStreamWaitEvent(st, async->join, 0);
