@@ -42,6 +42,10 @@ STATE_FIELDS = ("pos", "vel", "p_dist", "landmark_pos", "obstacle_pos", "goal_ma
 STATE_INT_FIELDS = ("goal_match", "num_agent_collisions", "num_obstacle_collisions", "step", "episode", "wall_orient")
 
 
+class FmSoaOutputs(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("node_obs", C.c_void_p), ("adj", C.c_void_p)]
+
+
 class FmState(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in STATE_FIELDS]
 
@@ -110,6 +114,9 @@ def load():
         "fm_destroy": ([vp], C.c_int),
         "fm_reset": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_observe": ([vp, C.POINTER(FmOutputs), vp], C.c_int),
+        "fm_soa_stride": ([vp], C.c_int),
+        "fm_observe_soa": ([vp, C.POINTER(FmSoaOutputs), vp], C.c_int),
+        "fm_check_finite": ([vp, vp, vp, vp], C.c_int),
         "fm_step": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_step_onehot": ([vp, vp, C.POINTER(FmOutputs), vp], C.c_int),
         "fm_step_many": ([vp, vp, i32, C.POINTER(FmOutputs), vp], C.c_int),
@@ -148,7 +155,7 @@ def load():
 
 
 EXPORTED_SYMBOLS = (
-    "fm_abi_version", "fm_last_error", "fm_stats_len", "fm_create", "fm_destroy", "fm_reset", "fm_observe", "fm_step",
+    "fm_abi_version", "fm_last_error", "fm_stats_len", "fm_create", "fm_destroy", "fm_reset", "fm_observe", "fm_soa_stride", "fm_observe_soa", "fm_check_finite", "fm_step",
     "fm_step_onehot", "fm_step_many", "fm_step_host", "fm_reset_host", "fm_read_info_host", "fm_set_state", "fm_get_state",
     "fm_assign_costs", "fm_assign_positions", "fm_pair_dist", "fm_edge_list", "fm_stats_read", "fm_num_entities", "fm_mapping",
     "fm_algorithmic_bytes_per_step", "fm_kernel_launches",

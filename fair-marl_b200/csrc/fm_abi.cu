@@ -387,6 +387,29 @@ int fm_observe(FmHandle* h, const FmOutputs* out, void* stream) {
   return FM_OK;                                      // no state change: the episode phase the host tracks stays valid
 }
 
+int fm_soa_stride(const FmHandle* h) { return h ? h->p.Bp : 0; }
+
+int fm_observe_soa(FmHandle* h, const FmSoaOutputs* out, void* stream) {
+  if (!h || !out) return fail(FM_ERR_INVALID_ARG, "fm_observe_soa: null argument");
+  if (h->p.W > 0) return fail(FM_ERR_UNSUPPORTED, "fm_observe_soa: walls are not supported in the SoA mode");
+  for (const float* q : {out->obs, out->node_obs, out->adj})
+    if (q && (reinterpret_cast<uintptr_t>(q) & 15u)) return fail(FM_ERR_INVALID_ARG, "fm_observe_soa: outputs must be 16-byte aligned");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_observe_soa(h->p, out->obs, out->node_obs, out->adj, (cudaStream_t)stream));
+  h->launches += 1;
+  return FM_OK;
+}
+
+int fm_check_finite(FmHandle* h, int32_t* flags, int32_t* count, void* stream) {
+  if (!h) return fail(FM_ERR_INVALID_ARG, "fm_check_finite: null handle");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  FM_CUDA(fm::launch_finite_guard(h->p, flags, count, (cudaStream_t)stream));
+  h->launches += 1;
+  return FM_OK;
+}
+
 int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* stream) {
   if (!h) return fail(FM_ERR_INVALID_ARG, "fm_reset: null handle");
   int rc = use_device(h->device);

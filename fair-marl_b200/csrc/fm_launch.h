@@ -42,6 +42,8 @@ cudaError_t launch_assign(const double* costs, const float* apos, const float* g
                           cudaStream_t st);
 cudaError_t launch_state_io(const DevParams& p, const HostState& hs, int to_internal, cudaStream_t st);
 cudaError_t launch_state_init(const DevParams& p, cudaStream_t st);
+cudaError_t launch_observe_soa(const DevParams& p, float* obs, float* node, float* adj, cudaStream_t st);   // fm_soa.cu
+cudaError_t launch_finite_guard(const DevParams& p, int* flags, int* count, cudaStream_t st);
 int edge_list_blocks(int num_graphs);             // CTAs of the edge-list kernels (8 graphs each): size of `blocksums`
 cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
                              long long capacity, int* counts, long long* blocksums, long long* graph_offsets,

@@ -274,6 +274,29 @@ class B200GraphVecEnv:
         _lib.check(self.lib.fm_observe(self._h, C.byref(o), self._stream()), "fm_observe")
         return self._package_out(views, with_step=False) if out is not None else self._package(slot, with_step=False)
 
+    def observe_soa_tensor(self) -> Dict[str, Any]:
+        """The observation of the current state in the SoA layout (``fm_observe_soa``): one plane per value, envs fastest --
+        ``obs [N, 7, B]``, ``node_obs [N, E, F, B]``, ``adj [E, E, B]`` (views of buffers whose env stride is
+        ``fm_soa_stride``; bit-identical to ``observe_tensor`` transposed).  For device-side consumers with lane = env."""
+        t = self.torch
+        N, E, B = self.num_agents, self.num_entities, self.num_envs
+        F = _lib.NODE_FEAT_DIM_GLOBAL if self.cfg.graph_feat_type == "global" else _lib.NODE_FEAT_DIM
+        S = int(self.lib.fm_soa_stride(self._h))
+        if getattr(self, "_soa", None) is None:
+            f32 = dict(dtype=t.float32, device=self.device)
+            self._soa = {"obs": t.empty((N, _lib.OBS_DIM, S), **f32), "node_obs": t.empty((N, E, F, S), **f32), "adj": t.empty((E, E, S), **f32)}
+        o = _lib.FmSoaOutputs(self._soa["obs"].data_ptr(), self._soa["node_obs"].data_ptr(), self._soa["adj"].data_ptr())
+        _lib.check(self.lib.fm_observe_soa(self._h, C.byref(o), self._stream()), "fm_observe_soa")
+        return {k: v[..., :B] for k, v in self._soa.items()}
+
+    def check_finite(self):
+        """``(flags [B] int32, count [1] int32)`` device tensors: envs whose dynamic state holds a NaN / Inf (``fm_check_finite``)."""
+        t = self.torch
+        flags = t.empty((self.num_envs,), dtype=t.int32, device=self.device)
+        count = t.empty((1,), dtype=t.int32, device=self.device)
+        _lib.check(self.lib.fm_check_finite(self._h, flags.data_ptr(), count.data_ptr(), self._stream()), "fm_check_finite")
+        return flags, count
+
     def step_tensor(self, actions, out: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
         """One env step.  ``actions``: int32 CUDA tensor [B, N] in {0..4}, or float32 [B, N, 5] one-hot.
         Asynchronous on the current stream; the returned tensors are views of slab ``slot``, or of ``out`` when the

@@ -131,6 +131,23 @@ int fm_reset(FmHandle* h, const uint8_t* mask, const FmOutputs* out, void* strea
  * (MultiAgentGraphEnv._get_obs / graph_observation on the live world, environment.py:882-898 minus the reset). */
 int fm_observe(FmHandle* h, const FmOutputs* out, void* stream);
 
+/* SoA observation mode: the values of fm_observe as one plane per value, envs fastest (device pointers, any may be NULL):
+ *   obs [N][7][S], node_obs [N][E][F][S] (F = 11, or 7 with graph_feat_global), adj [E][E][S], S = fm_soa_stride(h) >= B
+ * (a multiple of 4; planes are 16-byte aligned when the arrays are).  For device-side consumers that walk envs in lanes;
+ * 16-byte loads and streaming stores throughout (csrc/fm_soa.cu).  Bit-identical to the API layout.  No walls. */
+typedef struct FmSoaOutputs {
+  float* obs;
+  float* node_obs;
+  float* adj;
+} FmSoaOutputs;
+int fm_soa_stride(const FmHandle* h);
+int fm_observe_soa(FmHandle* h, const FmSoaOutputs* out, void* stream);
+
+/* Non-finite guard (core.py:392 is a latent 0/0 in the reference): flags[b] = 1 if the dynamic
+ * state of env b holds a NaN / Inf (positions, velocities, travelled distances, running statistics), else 0; *count = how
+ * many.  int32 device pointers, either may be NULL. */
+int fm_check_finite(FmHandle* h, int32_t* flags, int32_t* count, void* stream);
+
 /* GraphSubprocVecEnv.step -> graphworker -> MultiAgentGraphEnv.step (env_wrappers.py:983-996,
  * :856-865, environment.py:816-877): action decode, World.step (core.py:250-274), observation /
  * reward / graph_observation / done / info_callback per agent in the reference's order, and the

@@ -28,12 +28,17 @@ def assert_fairness_close(dev, ref, name="fairness_param"):
     the same distance: a relative perturbation e of one distance moves the ratio by about
     e * mean/std, i.e. by up to e * |ratio| * 1e4 * std ... <= ~e * |ratio| relative once std <~ 1e-4 (first steps
     of an episode: distances 0.05, 0.05, 0.0500389 -> ratio 423).  The travelled distance agrees to ~1e-7 (fp32
-    contact-force terms), so the tolerance is 1e-5 while |ref| <= 33, 3e-7 * |ref| beyond, capped at 1e-3; from
-    ratio 20 on tanh(ratio - 5) is 1 to 1e-13 and the reward does not see the difference."""
+    contact-force terms), so the tolerance is 1e-5 while |ref| <= 33, 3e-7 * |ref| beyond, capped at 3e-4; from
+    ratio 20 on tanh(ratio - 5) is 1 to 1e-13 and the reward does not see the difference.  Round 2 moved the root and the
+    quotient to float64 on the device and measured what is left (tools/fairness_error.py, 614 400 samples at
+    N = 3, 358 400 at N = 7, profiles/r02_a_fairness_error.jsonl): max error 2.3e-6 for |ref| <= 33, 3.3e-6 up to 100,
+    2.05e-5 = 4.8e-8 * |ref| up to 1000, 5e-6 beyond -- the residue is the float32 contact-force term inside p_dist, not the
+    statistics.  Round 1's cap was 1e-3; the slope stays, because the wall kernels (float64 wall force feeding p_dist) reach
+    1.08e-5 at a ratio between 36 and 67 (test_walls_reset_and_rollout_match_oracle failed a 1.5e-7 slope)."""
     dev = np.asarray(dev, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     err = np.abs(dev - ref) / np.maximum(np.abs(ref), 1.0)
-    tol = np.clip(3e-7 * np.abs(ref), RTOL, 1e-3)
+    tol = np.clip(3e-7 * np.abs(ref), RTOL, 3e-4)
     assert (err <= tol).all(), f"{name}: max err {err.max():.3e}"
 
 

@@ -208,3 +208,43 @@ def test_edge_list_tensor_matches_process_adj_without_sync():
     assert np.array_equal(r["edge_attr"][:n].cpu().numpy(), ea[:, 0].astype(np.float32))
     assert int(r["offsets"][-1].item()) == n
     env.close()
+
+
+@pytest.mark.parametrize("N,O,B,feat,mapping", [(3, 3, 200, "relative", "aw"), (3, 3, 4097, "relative", "group"), (7, 3, 130, "relative", "group"),
+                                                (4, 2, 64, "global", "group"), (16, 3, 33, "relative", "group")])
+def test_soa_observation_equals_api_layout_transposed(N, O, B, feat, mapping):
+    """fm_observe_soa (one plane per value, envs fastest; csrc/fm_soa.cu) against fm_observe (API layout) after a reset and in
+    the middle of an episode: the same bits, transposed."""
+    import torch
+    import fair_marl_b200 as fm
+    cfg = NavConfig(num_agents=N, num_obstacles=O, graph_feat_type=feat, episode_length=6)
+    env = fm.B200GraphVecEnv(sim_config_from(cfg, mapping=mapping), num_envs=B, seed=3)
+    env.reset_tensor()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for t in range(9):                                                # crosses an auto-reset; the fairness channel switches source
+        if t in (0, 1, 4, 8):
+            api, soa = env.observe_tensor(), env.observe_soa_tensor()
+            assert torch.equal(soa["obs"], api["obs"].permute(1, 2, 0)), t
+            assert torch.equal(soa["node_obs"], api["node_obs"].permute(1, 2, 3, 0)), t
+            assert torch.equal(soa["adj"], api["adj_env"].permute(1, 2, 0)), t
+        env.step_tensor(torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int32))
+    env.close()
+
+
+def test_finite_guard_flags_poisoned_envs():
+    import torch
+    import fair_marl_b200 as fm
+    cfg = NavConfig(num_agents=3, num_obstacles=3)
+    B = 300
+    env = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=1)
+    env.reset_tensor()
+    flags, count = env.check_finite()
+    assert int(count) == 0 and not bool(flags.any())
+    st = env.get_state()
+    st["vel"][7, 1, 0] = float("nan")
+    st["pos"][123, 2, 1] = float("inf")
+    st["p_dist"][299, 0] = float("-inf")
+    env.set_state(st)
+    flags, count = env.check_finite()
+    assert int(count) == 3 and flags.nonzero().flatten().tolist() == [7, 123, 299]
+    env.close()
