@@ -195,7 +195,13 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
   h->lockstep = 1; h->host_step = 0;
   {
     const char* ev = getenv("FM_PREFETCH");
-    h->pf_on = p.mapping == 0 && cfg->auto_reset && !(ev && atoi(ev) == 0);
+    // Group mapping: on unless FM_PREFETCH=0.  Agent-warp mapping: the kernels consume the same block (bit-identical,
+    // tested), but only with FM_PREFETCH=2: measured SLOWER at C2 (0.767 vs 0.861 of the roofline in the driver
+    // configuration, 0.80 vs 0.93 in long runs, profiles/r02_u_*).  There the inline reset costs 47 us per episode with
+    // lane = env (32 envs per warp in lockstep), while prefetch_kernel<4> spends 4 lanes per env on the same serial work and
+    // takes the SMs from the memory-bound step kernels it runs beside.
+    const int v = ev ? atoi(ev) : 1;
+    h->pf_on = cfg->auto_reset && (p.mapping == 0 ? v != 0 : v == 2);
   }
   if (h->pf_on) {
     const size_t rows = (size_t)(5 * N + 2 * O + 2 * W);
@@ -342,7 +348,11 @@ static int ensure_prefetch_streams(FmHandle* h) {
 // Before a step launch on stream s: the kernel may consume pending entries only when the host knows the episode
 // phase (lockstep) and the stream is not being captured; a terminal step waits for every prefetch in flight.
 static int prefetch_before_step(FmHandle* h, DevParams& p, cudaStream_t s, bool terminal) {
-  if (!h->pf_on || !h->lockstep || stream_capturing(s)) { p.q_tag = nullptr; return FM_OK; }
+  // The kernels take an entry only if its tag equals the env's episode key (acquire load), and an entry depends on (seed,
+  // global env, key) alone: consuming it needs no host knowledge.  What the host's view of the phase (lockstep, not
+  // capturing) adds is the wait that makes sure the prefetch launched after the last terminal step has finished.
+  if (!h->pf_on) { p.q_tag = nullptr; return FM_OK; }
+  if (!h->lockstep || stream_capturing(s)) return FM_OK;
   if (terminal)
     for (int k = 0; k < FM_MAX_LANES; ++k)
       if (h->pf_used[k]) FM_CUDA(cudaStreamWaitEvent(s, h->pf_ready[k], 0));
@@ -521,6 +531,28 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
     for (int k = 1; k < lanes; ++k) FM_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->lane_fork, 0));
   }
   const int per_lane = (((B + lanes - 1) / lanes) + 127) & ~127;      // lane boundaries at multiples of 128 envs
+  // Next-episode prefetch when the host does not drive it (stream capture, or the episode phase unknown to the host): one
+  // launch per lane at the START of the call, on the lane's prefetch stream, joined at the end of the call (so that a
+  // capture closes).  It redraws the entries whose tag is stale -- all of them right after a terminal step, none
+  // otherwise -- so a rollout issued in calls that start behind episode boundaries (bench.py, the rollout buffer) finds
+  // the entries at its terminal steps; any other call pattern falls back to the inline reset, entry by entry.
+  const bool pf_call = h->pf_on && num_steps > 0 && (!h->lockstep || stream_capturing(user));
+  if (pf_call) {
+    rc = ensure_prefetch_streams(h);
+    if (rc) return rc;
+    for (int k = 0; k < lanes; ++k) {
+      DevParams p = h->p;
+      p.env_begin = k * per_lane < B ? k * per_lane : B;
+      p.env_end = (k + 1) * per_lane < B ? (k + 1) * per_lane : B;
+      if (p.env_begin >= p.env_end) continue;
+      cudaStream_t ls = k == 0 ? user : h->lane_stream[k];
+      FM_CUDA(cudaEventRecord(h->pf_go[k], ls));
+      FM_CUDA(cudaStreamWaitEvent(h->pf_stream[k], h->pf_go[k], 0));
+      FM_CUDA(fm::launch_prefetch(p, h->pf_stream[k]));
+      FM_CUDA(cudaEventRecord(h->pf_ready[k], h->pf_stream[k]));
+      h->launches += 1;
+    }
+  }
   for (int t = 0; t < num_steps; ++t) {
     const bool terminal = step_is_terminal(h);
     for (int k = 0; k < lanes; ++k) {
@@ -539,6 +571,10 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
     }
     advance_phase(h, terminal);
   }
+  if (pf_call)
+    for (int k = 0; k < lanes; ++k)
+      if ((k * per_lane < B ? k * per_lane : B) < ((k + 1) * per_lane < B ? (k + 1) * per_lane : B))
+        FM_CUDA(cudaStreamWaitEvent(k == 0 ? user : h->lane_stream[k], h->pf_ready[k], 0));
   if (lanes > 1) {
     for (int k = 1; k < lanes; ++k) {
       FM_CUDA(cudaEventRecord(h->lane_join[k], h->lane_stream[k]));

@@ -169,6 +169,41 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
       sd[aw_spair(a, b, M)] = (float)dist64(PXY(N + a, 0), PXY(N + a, 1), PXY(N + b, 0), PXY(N + b, 1));
 }
 
+// The same reset from the env's entry of the pending block (prefetch_kernel, fm_kernels.cu: placement + assignment of the
+// NEXT episode drawn ahead of time from the same Philox stream; the caller has seen q_tag[env] == episode with an acquire
+// load).  Same outputs as aw_reset_env, same bits: what is left to do here is min_time against the previous goal_match and
+// the distances between the static entities.  The terminal step of an episode was 74 us against 26.5 for a regular one
+// (profiles/r02_final_launches_driver_config.csv) -- 9 % of a rollout -- because every env warp walked the serial
+// rejection sampling while its three agent warps waited.
+template <int N, int O>
+__device__ __forceinline__ void aw_reset_from_pending(const DevParams& p, int env, float* __restrict__ Tc, float* __restrict__ Sc,
+                                                      float* __restrict__ sd) {
+  using L = AwLayout<N, O>;
+  constexpr int RW = L::RW, M = L::M;
+  auto PXY = [&](int e, int c) -> float& { return Tc[(L::TP + 2 * e + c) * RW]; };
+  const size_t Bp = (size_t)p.Bp;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    PXY(i, 0) = __ldcg(p.q_px + i * Bp + env); PXY(i, 1) = __ldcg(p.q_py + i * Bp + env);
+    PXY(N + i, 0) = __ldcg(p.q_lx + i * Bp + env); PXY(N + i, 1) = __ldcg(p.q_ly + i * Bp + env);
+  }
+#pragma unroll
+  for (int k = 0; k < O; ++k) { PXY(2 * N + k, 0) = __ldcg(p.q_ox + k * Bp + env); PXY(2 * N + k, 1) = __ldcg(p.q_oy + k * Bp + env); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (p.has_max_speed) {                 // min_time with the PREVIOUS goal_match (:545-547, :719-728)
+      const int og = __float_as_int(Sc[(L::GMO + i) * RW]);
+      Sc[(L::RMINT + i) * RW] = (float)(dist64(PXY(i, 0), PXY(i, 1), PXY(N + og, 0), PXY(N + og, 1)) / p.max_speed);
+    }
+    Sc[(L::RGM + i) * RW] = __int_as_float(__ldcg(p.q_gm + i * Bp + env));
+  }
+#pragma unroll 1
+  for (int a = 0; a < M; ++a)
+#pragma unroll 1
+    for (int b = a + 1; b < M; ++b)
+      sd[aw_spair(a, b, M)] = (float)dist64(PXY(N + a, 0), PXY(N + a, 1), PXY(N + b, 0), PXY(N + b, 1));
+}
+
 // Per-launch (one-shot kernels) or per-step (rollout kernel) inputs and outputs of a tile.
 // The output pointers are read where they are used (one-shot kernels: a local built from the kernel parameters, i.e.
 // constant-bank operands; rollout kernel: the step's entry of a shared-memory table), so they hold no registers
@@ -300,7 +335,10 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
   };
   // Reset of this env by its env-warp thread: new placement -> tables, scratch and the state block.
   auto reset_static = [&](float* sd) {
-    aw_reset_env<N, O>(p, genv, (uint32_t)epis, Tc, Sc, sd);
+    bool pend = false;
+    if (p.q_tag != nullptr) pend = ld_acquire_gpu(p.q_tag + env) == epis;   // the entry's data is visible once its tag is
+    if (pend) aw_reset_from_pending<N, O>(p, env, Tc, Sc, sd);
+    else aw_reset_env<N, O>(p, genv, (uint32_t)epis, Tc, Sc, sd);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];

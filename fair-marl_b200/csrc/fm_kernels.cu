@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(THREADS, G == 8 ? (WALLS ? 5 : 6) : (G == 4 ? 
   if (__any_sync(FULL, do_reset)) {
     // graphworker auto-reset (env_wrappers.py:859-865): obs / node_obs / adj come from the new
     // episode; reward / done / info stay terminal.
+    __syncwarp();          // the entity table is rewritten below: every lane is past its distance_tile reads (racecheck)
     float rx = npx, ry = npy, rmint = act ? p.mintime[idx] : 0.f;
     int rgm = gm;
     // An entry of the pending block generated for this env's episode key (prefetch_kernel) replaces the rejection
@@ -724,7 +725,10 @@ int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); 
 int num_warps(int B, int N) { const int epw = 32 / group_size(N); return (B + epw - 1) / epw; }
 
 cudaError_t prepare_kernels(const DevParams& p) {
-  if (p.mapping == 1) return aw_prepare(p);
+  if (p.mapping == 1) {
+    cudaError_t e = aw_prepare(p);
+    if (e != cudaSuccess || !p.q_tag) return e;       // the agent-warp kernels consume the entries prefetch_kernel<G> produces
+  }
   FM_DISPATCH_G(prepare_g, p)
 }
 

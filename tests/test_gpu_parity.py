@@ -343,19 +343,22 @@ def test_group_kernel_staging_variants_are_bitwise_equal(variant, monkeypatch):
         assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("N,O,B,lanes,T", [(7, 3, 300, 1, 6), (16, 3, 70, 1, 6), (7, 3, 1024, 2, 6), (5, 0, 33, 1, 6), (7, 3, 64, 1, 1)])
-def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, T, monkeypatch):
-    """The group mapping produces the placement + assignment of every env's next episode ahead of time on a side
-    stream (prefetch_kernel) and the terminal step copies it.  Same Philox stream, same bits: a run with the
+@pytest.mark.parametrize("N,O,B,lanes,T,mapping", [
+    (7, 3, 300, 1, 6, "group"), (16, 3, 70, 1, 6, "group"), (7, 3, 1024, 2, 6, "group"), (5, 0, 33, 1, 6, "group"), (7, 3, 64, 1, 1, "group"),
+    (3, 3, 300, 1, 6, "aw"), (3, 3, 1100, 2, 6, "aw"), (4, 2, 70, 1, 1, "aw"), (3, 0, 33, 1, 5, "aw")])
+def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, T, mapping, monkeypatch):
+    """Both mappings take the placement + assignment of every env's next episode from a block produced ahead of time on a side
+    stream (prefetch_kernel); the terminal step copies its entry (and, after the masked reset below, keeps doing so entry by
+    entry: a tag that matches the env's episode key is all a kernel needs).  Same Philox stream, same bits: a run with the
     prefetch disabled (FM_PREFETCH=0: every reset is computed inside the step kernel) must be identical, through
     single steps, through fm_step_many with env-range lanes, and across a masked reset that breaks the lockstep."""
     import torch
     cfg = NavConfig(num_agents=N, num_obstacles=O, episode_length=T)    # T = 1: every step is terminal
     monkeypatch.setenv("FM_LANES", str(lanes))
     runs = []
-    for pf in ("1", "0"):
+    for pf in ("2", "0"):                                     # 2: also for the agent-warp mapping (off by default there: slower)
         monkeypatch.setenv("FM_PREFETCH", pf)
-        env = _env(cfg, B, seed=31, sim=dict(mapping="group"), num_slots=8)
+        env = _env(cfg, B, seed=31, sim=dict(mapping=mapping), num_slots=8)
         g = torch.Generator(device="cuda").manual_seed(5)
         rec = []
 
@@ -377,6 +380,23 @@ def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, T, monkeypat
         keep(env.reset_tensor())                              # lockstep again
         for t in range(8):
             keep(env.step_tensor(torch.randint(0, 5, (B, N), generator=g, device="cuda", dtype=torch.int32)))
+        # rollouts under stream capture: the prefetch is launched at the start of every fm_step_many call and joined at
+        # its end; two replays of (one call that ends at an episode boundary, one that starts behind it)
+        acts2 = torch.randint(0, 5, (2 * T + 3, B, N), generator=g, device="cuda", dtype=torch.int32)
+        env.reset_tensor()
+        env.rollout_tensor(acts2[:2])                         # eager: streams, plans
+        env.reset_tensor()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        slot0 = env._slot
+        with torch.cuda.graph(graph):
+            s1 = env.rollout_tensor(acts2[:T])
+            s2 = env.rollout_tensor(acts2[T:])
+        for rep in range(2):
+            env._slot = slot0
+            graph.replay()
+            for slot in (s1 + s2)[-5:]:
+                keep(env.slot_outputs(slot))
         st = env.get_state()
         rec.extend([st["goal_match"], st["landmark_pos"], st["obstacle_pos"], st["episode"], st["min_time"]])
         runs.append(rec)
