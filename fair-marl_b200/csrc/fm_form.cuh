@@ -818,6 +818,7 @@ __device__ __forceinline__ void form_step_env(const FormParams& p, int b, const 
   }
 }
 
+// ---- device only from here: the shared-memory tile of a warp (tests/test_kernel_source_host.py cuts the host unit above this line)
 #ifdef __CUDACC__
 struct FormTile {            // floats per warp; all offsets multiples of 4 floats
   int obs, rew, done, rec, stage, rec_stride, words;

@@ -42,7 +42,7 @@ def host_exe(tmp_path_factory):
     log1p_unit = _between(dev, "__device__ __forceinline__ float log1p_unit(float t) {", "// One contact-force term, core.py:389-392")
     params = _between(launch, "struct FormParams {", "cudaError_t launch_formation")
     small_body = _between(small, "// k-th permutation of 0..N-1", "}  // namespace fm")
-    form_body = _between(form, "constexpr int F_OBS", "#ifdef __CUDACC__")
+    form_body = _between(form, "constexpr int F_OBS", "// ---- device only from here")
     assert "u01_24" in philox and "lexifair_small" in small_body and "form_step_env" in form_body and "fmaf" in log1p_unit
     src = "\n".join(['#include "prelude.h"', "namespace fm {", philox, log1p_unit, params, small_body, form_body, "}  // namespace fm",
                      open(os.path.join(EMUL, "harness.inc")).read()])
