@@ -660,6 +660,74 @@ int fm_step_host(FmHandle* h, const float* onehot_host, const FmOutputs* out_hos
   return FM_OK;
 }
 
+static void host_lane_range(const FmHandle* h, int lane, int num_lanes, int& b0, int& b1) {
+  const int B = h->p.B;
+  const int per = (((B + num_lanes - 1) / num_lanes) + 127) & ~127;
+  b0 = lane * per < B ? lane * per : B;
+  b1 = (lane + 1) * per < B ? (lane + 1) * per : B;
+}
+
+int fm_host_lane_range(const FmHandle* h, int32_t lane, int32_t num_lanes, int32_t* env_begin, int32_t* env_end) {
+  if (!h || !env_begin || !env_end || num_lanes < 1 || num_lanes > FM_MAX_LANES || lane < 0 || lane >= num_lanes)
+    return fail(FM_ERR_INVALID_ARG, "fm_host_lane_range: bad arguments");
+  int b0, b1;
+  host_lane_range(h, lane, num_lanes, b0, b1);
+  *env_begin = b0; *env_end = b1;
+  return FM_OK;
+}
+
+int fm_step_host_lane(FmHandle* h, const float* onehot_host, const FmOutputs* out_host, int32_t lane, int32_t num_lanes, void* stream) {
+  if (!h || !onehot_host) return fail(FM_ERR_INVALID_ARG, "fm_step_host_lane: null argument");
+  if (num_lanes < 1 || num_lanes > FM_MAX_LANES || lane < 0 || lane >= num_lanes) return fail(FM_ERR_INVALID_ARG, "fm_step_host_lane: bad lane");
+  if (h->roll_on) return fail(FM_ERR_UNSUPPORTED, "fm_step_host_lane: not available with FM_ROLL=1");
+  int rc = use_device(h->device);
+  if (rc) return rc;
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  rc = ensure_lanes(h);
+  if (rc) return rc;
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t ls = lane == 0 ? user : h->lane_stream[lane];
+  if (lane == 0 && num_lanes > 1) FM_CUDA(cudaEventRecord(h->lane_fork, user));
+  if (lane > 0) FM_CUDA(cudaStreamWaitEvent(ls, h->lane_fork, 0));
+  int b0, b1;
+  host_lane_range(h, lane, num_lanes, b0, b1);
+  const bool terminal = step_is_terminal(h);
+  if (b0 < b1) {
+    const size_t N = h->p.N, E = h->p.E, n = (size_t)(b1 - b0), o = (size_t)b0;
+    FM_CUDA(cudaMemcpyAsync(h->st_onehot + o * N * 5, onehot_host + o * N * 5, n * N * 5 * sizeof(float), cudaMemcpyHostToDevice, ls));
+    DevParams p = h->p;
+    FmOutputs dev = h->st_out;
+    set_outputs(p, &dev);
+    p.act_idx = nullptr; p.act_onehot = h->st_onehot; p.reset_mask = nullptr;
+    p.env_begin = b0; p.env_end = b1;
+    rc = prefetch_before_step(h, p, ls, terminal);
+    if (rc) return rc;
+    FM_CUDA(fm::launch_step(p, ls, false));
+    h->launches += 1;
+    if (terminal && h->p.auto_reset) { rc = prefetch_after_reset(h, ls, lane, b0, b1); if (rc) return rc; }
+    if (out_host) {
+      const size_t F = h->p.feat_global ? fm::NODE_F_GLOBAL : fm::NODE_F;
+      auto d2h = [&](void* dst, const void* src, size_t per_env) -> cudaError_t {
+        return dst ? cudaMemcpyAsync((char*)dst + o * per_env, (const char*)src + o * per_env, n * per_env, cudaMemcpyDeviceToHost, ls) : cudaSuccess;
+      };
+      FM_CUDA(d2h(out_host->node_obs, h->st_out.node_obs, N * E * F * 4));
+      FM_CUDA(d2h(out_host->adj, h->st_out.adj, E * E * 4));
+      FM_CUDA(d2h(out_host->obs, h->st_out.obs, N * fm::OBS_F * 4));
+      FM_CUDA(d2h(out_host->reward, h->st_out.reward, N * 4));
+      FM_CUDA(d2h(out_host->done, h->st_out.done, N));
+      FM_CUDA(d2h(out_host->info, h->st_out.info, N * fm::INFO_F * 4));
+    }
+  }
+  if (lane > 0) FM_CUDA(cudaEventRecord(h->lane_join[lane], ls));
+  if (lane == num_lanes - 1) {
+    for (int k = 1; k < num_lanes; ++k) FM_CUDA(cudaStreamWaitEvent(user, h->lane_join[k], 0));
+    advance_phase(h, terminal);
+    FM_CUDA(cudaStreamSynchronize(user));
+  }
+  return FM_OK;
+}
+
 int fm_read_info_host(FmHandle* h, float* info_host, void* stream) {
   if (!h || !info_host) return fail(FM_ERR_INVALID_ARG, "fm_read_info_host: null argument");
   int rc = use_device(h->device);

@@ -15,6 +15,7 @@ Two call styles:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -185,6 +186,14 @@ class B200GraphVecEnv:
                 "info": t.empty((B, N, _lib.INFO_DIM), dtype=t.float32, **pin),
                 "flip": 0,
             }
+            # env-range lanes of the host step (FM_HOST_LANES overrides; the persistent kernel has no ranged launch)
+            lanes = int(os.environ.get("FM_HOST_LANES", "4" if B >= 16384 else "1"))
+            lanes = 1 if os.environ.get("FM_ROLL", "0") not in ("", "0") else max(1, min(8, lanes))
+            self._host_lanes, self._host_lane_bounds = lanes, []
+            for k in range(lanes):
+                b0, b1 = C.c_int32(), C.c_int32()
+                _lib.check(self.lib.fm_host_lane_range(self._h, k, lanes, C.byref(b0), C.byref(b1)), "fm_host_lane_range")
+                self._host_lane_bounds.append((b0.value, b1.value))
         return self._host
 
     def _ensure_slabs(self):
@@ -440,16 +449,28 @@ class B200GraphVecEnv:
         B, N = self.num_envs, self.num_agents
         a = np.asarray(actions)
         if a.shape == (B, N, 5):
-            h["onehot"].numpy()[...] = a                              # cast to float32 into pinned memory
+            onehot = True
         elif a.shape in ((B, N), (B, N, 1)):                          # convenience: action indices
-            oh = h["onehot"].numpy()
-            oh[...] = 0.0
-            np.put_along_axis(oh, a.reshape(B, N, 1).astype(np.int64), 1.0, axis=2)
+            onehot, a = False, a.reshape(B, N, 1).astype(np.int64)
         else:
             raise ValueError(f"actions must be [B,N,5] one-hot (or [B,N] indices), got {a.shape}")
         cur, o = self._host_outputs(with_step=True)
+        oh = h["onehot"].numpy()
+        # Large batches go as env-range lanes: the rows of lane k + 1 are converted into the pinned float32 buffer (the runner
+        # hands float64 one-hot, graph_mpe_runner.py:429-431) while lane k's results cross the bus (fm_step_host_lane).
+        lanes = self._host_lanes
         with _Nvtx("fm:step_host"):
-            _lib.check(self.lib.fm_step_host(self._h, h["onehot"].data_ptr(), C.byref(o), self._stream()), "fm_step_host")
+            for k in range(lanes):
+                b0, b1 = self._host_lane_bounds[k]
+                if onehot:
+                    oh[b0:b1] = a[b0:b1]                              # cast to float32 into pinned memory
+                else:
+                    oh[b0:b1] = 0.0
+                    np.put_along_axis(oh[b0:b1], a[b0:b1], 1.0, axis=2)
+                if lanes == 1:
+                    _lib.check(self.lib.fm_step_host(self._h, h["onehot"].data_ptr(), C.byref(o), self._stream()), "fm_step_host")
+                else:
+                    _lib.check(self.lib.fm_step_host_lane(self._h, h["onehot"].data_ptr(), C.byref(o), k, lanes, self._stream()), "fm_step_host_lane")
         self._step_version += 1
         self._last_step_api = "host"
         obs, ag_id, node, adj_n = self._numpy_obs(cur, copy)

@@ -166,6 +166,14 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
  * (pinned for full speed).  Copies actions in, steps, copies the requested outputs back and
  * synchronises `stream`.  This is the call a ShareVecEnv.step() drop-in makes. */
 int fm_step_host(FmHandle* h, const float* onehot_host, const FmOutputs* out_host, void* stream);
+/* The same step issued as `num_lanes` env-range lanes (1..8), one call per lane in the order 0 .. num_lanes - 1: lane k
+ * covers envs [k * L, min(B, (k + 1) * L)), L = ceil(B / num_lanes) rounded up to 128; fm_host_lane_range gives the range.
+ * A call enqueues its lane -- H2D of that range of `onehot_host`, the step kernel on that range, D2H of that range of every
+ * output -- and returns without waiting, except the last one, which waits for all lanes.  The caller fills the action rows
+ * of lane k + 1 (GMPERunner builds them as float64 one-hot, graph_mpe_runner.py:429-431: the conversion into the pinned
+ * float32 buffer costs as much as a fifth of the copies) while lane k's results cross the bus.  Pointers are the FULL arrays. */
+int fm_step_host_lane(FmHandle* h, const float* onehot_host, const FmOutputs* out_host, int32_t lane, int32_t num_lanes, void* stream);
+int fm_host_lane_range(const FmHandle* h, int32_t lane, int32_t num_lanes, int32_t* env_begin, int32_t* env_end);
 int fm_reset_host(FmHandle* h, const uint8_t* mask_host, const FmOutputs* out_host, void* stream);
 /* Info rows of the most recent fm_step_host call, copied to host on demand ([B, N, 14] floats).
  * The runner reads infos only at log time (graph_mpe_runner.py:143-146), so fm_step_host does not

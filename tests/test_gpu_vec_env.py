@@ -50,10 +50,14 @@ def test_reference_api_shapes_dtypes_and_autoreset():
     env.close()
 
 
-def test_host_api_equals_tensor_api_and_oracle():
+@pytest.mark.parametrize("N,B,lanes", [(4, 200, "1"), (4, 1000, "3"), (3, 700, "4"), (7, 300, "2")])
+def test_host_api_equals_tensor_api_and_oracle(N, B, lanes, monkeypatch):
+    """numpy in / numpy out (fm_step_host, or fm_step_host_lane: env-range lanes whose action rows are converted while the
+    previous lane's results cross the bus) against the tensor API and the oracle, across an auto-reset, one-hot and index
+    actions."""
     import fair_marl_b200 as fm
-    cfg = NavConfig(num_agents=4, num_obstacles=2)
-    B = 200
+    monkeypatch.setenv("FM_HOST_LANES", lanes)
+    cfg = NavConfig(num_agents=N, num_obstacles=2)
     e_host = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=9)
     e_dev = fm.B200GraphVecEnv(sim_config_from(cfg), num_envs=B, seed=9)
     orc = NavGraphOracle(cfg, B, seed=9)
@@ -64,8 +68,8 @@ def test_host_api_equals_tensor_api_and_oracle():
     import torch
     for t in range(28):
         orc.set_state(device_state_to_nav(e_dev.get_state()))
-        a = rng.integers(0, 5, (B, 4))
-        obs, ag, node, adj, rew, done, infos = e_host.step(np.eye(5)[a])
+        a = rng.integers(0, 5, (B, N))
+        obs, ag, node, adj, rew, done, infos = e_host.step(np.eye(5)[a] if t % 3 else a)
         d = e_dev.step_tensor(torch.as_tensor(a, dtype=torch.int32, device="cuda"))
         assert (obs == d["obs"].cpu().numpy()).all() and (node == d["node_obs"].cpu().numpy()).all()
         assert (adj == d["adj"].cpu().numpy()).all() and (rew == d["reward"].cpu().numpy()).all()
