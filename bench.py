@@ -414,16 +414,16 @@ def run_formation(args, rank: int, local_rank: int, world: int):
                        "envs_per_gpu": B, "envs_total": B * world, "agents": N, "entities": E,
                        "launch": "fm_formation_step_many, one call per chunk of steps", "l2": f"outputs cycle through {args.form_slots} buffer sets ({args.form_slots * B * (11 * N + 13 * N * E + E * E + N) * 4 / 1e9:.2f} GB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": f"fm::formation_logic_kernel<{N}, {O}> + fm::formation_image_kernel<{N}, {O}>",
+                         "kernel": f"fm::formation_logic_kernel<{N}, {O}> + fm::formation_image_kernel<{N}, {O}> (+ fm::formation_prefetch_kernel<{N}> on a side stream)",
                          "algorithmic_bytes_per_step": alg_bytes,
-                         "note": "a step is two launches per env-range lane: logic (thread per env) -> image (node_obs / adj from the "
-                                 "recipes; programmatic dependent launch); the "
+                         "note": "a step is three launches: logic (thread per env) -> image (node_obs / adj from the recipes; programmatic "
+                                 "dependent launch), and the pending-reset prefetch on a side stream; the "
                                  "bytes are those of the whole step, the time is the whole step's"},
             "cpu_baseline": None, "e2e": None,
             "closed_loop": {"value": B * world * N / (closed_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": closed_ms, "steps": Kc,
                             "frac": alg_bytes / (closed_ms * 1e-3) / 1e9 / peak,
                             "api": "B200FormationVecEnv.step_tensor -> fm_formation_step, one call per step"},
-            "gpu_launches": 2 * K, "clocks": clocks,
+            "gpu_launches": 3 * K, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     env.close()
