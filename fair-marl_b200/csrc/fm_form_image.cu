@@ -3,7 +3,10 @@
 
 namespace fm {
 
-constexpr int FI_WARPS = 4, FI_ENVS = 16, FI_PARTS = FI_WARPS * (32 / FI_ENVS);
+#ifndef FM_FI_WARPS
+#define FM_FI_WARPS 4                  // A-B knob: warps per image CTA (4 or 8)
+#endif
+constexpr int FI_WARPS = FM_FI_WARPS, FI_ENVS = 16, FI_PARTS = FI_WARPS * (32 / FI_ENVS);
 
 // The share of PART in one env's images: every (ego, entity) row and adj pair whose running index is PART modulo the
 // part count, with all indices compile-time values (f_row / f_adj_elem fold to immediate shared-memory offsets, the row
@@ -86,7 +89,15 @@ __global__ void __launch_bounds__(FI_WARPS * 32) formation_image_kernel(const Fo
       case 4: image_part<N, O, 4>(r, nimg, aimg); break;
       case 5: image_part<N, O, 5>(r, nimg, aimg); break;
       case 6: image_part<N, O, 6>(r, nimg, aimg); break;
-      default: image_part<N, O, 7>(r, nimg, aimg); break;
+      case 7: image_part<N, O, 7>(r, nimg, aimg); break;
+      case 8: image_part<N, O, 8>(r, nimg, aimg); break;
+      case 9: image_part<N, O, 9>(r, nimg, aimg); break;
+      case 10: image_part<N, O, 10>(r, nimg, aimg); break;
+      case 11: image_part<N, O, 11>(r, nimg, aimg); break;
+      case 12: image_part<N, O, 12>(r, nimg, aimg); break;
+      case 13: image_part<N, O, 13>(r, nimg, aimg); break;
+      case 14: image_part<N, O, 14>(r, nimg, aimg); break;
+      default: image_part<N, O, 15>(r, nimg, aimg); break;
     }
   }
   __syncthreads();
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(FI_WARPS * 32) formation_image_kernel(const Fo
 template <int N, int OT>
 static cudaError_t launch_image(const FormParams& p, cudaStream_t st) {
   constexpr int E = 2 * N + OT;
-  static_assert(FI_PARTS == 8, "formation_image_kernel dispatches 8 parts");
+  static_assert(FI_PARTS == 8 || FI_PARTS == 16, "formation_image_kernel dispatches up to 16 parts");
   const FormTile t = form_tile(N, OT);
   const size_t smem = (size_t)(((FI_ENVS * t.rec_stride + 3) & ~3) + FI_ENVS * (N * E * F_NODE + E * E)) * sizeof(float);
   static int attr_device = -1;                         // opt-in shared-memory size: once per device

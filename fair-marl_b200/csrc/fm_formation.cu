@@ -261,9 +261,12 @@ static cudaError_t launch_formation_split(const FormParams& p, cudaStream_t st, 
     if ((e = launch_formation_prefetch(p, async->side)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(async->join, async->side)) != cudaSuccess) return e;
   }
-  formation_logic_kernel<N, OT><<<(p.B + 31) / 32, 32, smem, st>>>(p);
+  const bool images = p.out.node_obs || p.out.adj;
+  FormParams lp = p;
+  if (!images) lp.ready = nullptr;                    // no image kernel behind this step: nobody would consume (and clear) the flags
+  formation_logic_kernel<N, OT><<<(p.B + 31) / 32, 32, smem, st>>>(lp);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (p.out.node_obs || p.out.adj)
+  if (images)
     if ((e = launch_formation_image(p, st)) != cudaSuccess) return e;                // fm_form_image.cu
   if (pf) e = cudaStreamWaitEvent(st, async->join, 0);
   return e;

@@ -260,3 +260,32 @@ def test_info_rows_only_when_every_agent_is_done():
         if t < 5:
             assert (o_end["info"] == 0).all()                           # untouched before the first terminal step
     e_all.close(); e_end.close()
+
+
+def test_partial_outputs_do_not_leave_ready_flags_behind():
+    """A step without node_obs / adj runs the logic kernel alone (no image kernel to consume the per-16-env ready flags of the
+    dependent launch); the steps after it must still build their rows from THEIR recipes."""
+    import ctypes as C
+    import torch
+    import fair_marl_b200 as fm
+    from fair_marl_b200 import _lib
+    cfg = FormationConfig(num_agents=3, num_obstacles=3, episode_length=9)
+    B = 4096
+    e_a = fm.B200FormationVecEnv(_sim(cfg), num_envs=B, seed=5)
+    e_b = fm.B200FormationVecEnv(_sim(cfg), num_envs=B, seed=5)
+    e_a.reset_tensor(); e_b.reset_tensor()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for t in range(12):
+        a = torch.randint(0, 5, (B, 3), generator=g, device="cuda", dtype=torch.int32)
+        o_b = e_b.step_tensor(a)
+        if t % 3 == 1:                                  # logic kernel alone
+            s = e_a._slots[0]
+            o = _lib.FmOutputs(s["obs"].data_ptr(), None, None, s["reward"].data_ptr(), s["done"].data_ptr(), s["info"].data_ptr())
+            _lib.check(e_a.lib.fm_formation_step(e_a._h, a.data_ptr(), C.byref(o), stream), "fm_formation_step")
+            assert torch.equal(s["obs"], o_b["obs"]), t
+        else:
+            o_a = e_a.step_tensor(a)
+            for k in ("obs", "node_obs", "adj_env", "reward"):
+                assert torch.equal(o_a[k], o_b[k]), (t, k)
+    e_a.close(); e_b.close()
