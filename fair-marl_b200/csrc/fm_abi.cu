@@ -173,6 +173,12 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     }
     p.speed2_max = t;
   }
+  {                                                          // smallest double whose sqrt is >= dcoll: sqrt_rn(x) < dcoll  <=>  x < dcoll2_lt
+    double t = p.dcoll * p.dcoll;
+    while (sqrt(t) < p.dcoll) t = nextafter(t, INFINITY);
+    while (sqrt(nextafter(t, 0.0)) >= p.dcoll) t = nextafter(t, 0.0);
+    p.dcoll2_lt = t;
+  }
   p.episode_length = cfg->episode_length;
   p.fairness_reward = cfg->fairness_reward;
   p.collaborative = cfg->collaborative;

@@ -139,9 +139,10 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
       if (goal) { x = __fmul_rn(0.8f, x); y = __fmul_rn(0.8f, y); }
       bool bad = false;
 #pragma unroll 1
-      for (int k = 0; k < O; ++k) bad = bad || (dist64(PXY(2 * N + k, 0), PXY(2 * N + k, 1), x, y) < p.dcoll);
+      // |c - q| < dcoll as |c - q|^2 < dcoll2_lt (the square root is correctly rounded and monotone: same decision, no root)
+      for (int k = 0; k < O; ++k) bad = bad || (dist64_sq(PXY(2 * N + k, 0), PXY(2 * N + k, 1), x, y) < p.dcoll2_lt);
 #pragma unroll 1
-      for (int j = base; j < slot; ++j) bad = bad || (dist64(PXY(j, 0), PXY(j, 1), x, y) < p.dcoll);
+      for (int j = base; j < slot; ++j) bad = bad || (dist64_sq(PXY(j, 0), PXY(j, 1), x, y) < p.dcoll2_lt);
       if (!bad || d >= (uint32_t)MAX_DRAWS) break;
     }
     PXY(slot, 0) = x;
