@@ -120,33 +120,48 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
   using L = AwLayout<N, O>;
   constexpr int RW = L::RW, M = L::M;
   auto PXY = [&](int e, int c) -> float& { return Tc[(L::TP + 2 * e + c) * RW]; };
-#pragma unroll 1
+  // The obstacles and the entities of the kind being placed are kept in registers as doubles (O <= 3, N <= 4: the loops
+  // below unroll): the rejection tests are then independent float64 multiply-adds with no shared-memory load or conversion
+  // in the chain, compared as SQUARES -- |c - q| < dcoll  <=>  |c - q|^2 < dcoll2_lt, the smallest double whose correctly
+  // rounded root reaches dcoll (fm_create): the same decision without the root.  Terminal step 74 -> 59 us
+  // (profiles/r02_sq_*).  Keeping the cost matrix and the static distances in registers as well made ptxas spill in the
+  // CALLER (80 bytes in the step kernel's hot path: regular steps 27 -> 29 us) and was dropped.
+  double ox[O > 0 ? O : 1], oy[O > 0 ? O : 1];
+#pragma unroll
   for (int k = 0; k < O; ++k) {            // obstacles: 0.8 * U(-ws/2, ws/2)^2, draws 0..O-1 (:271-275)
     float x, y;
     draw_uniform2(p, genv, episode, (uint32_t)k, x, y);
-    PXY(2 * N + k, 0) = __fmul_rn(0.8f, x);
-    PXY(2 * N + k, 1) = __fmul_rn(0.8f, y);
+    x = __fmul_rn(0.8f, x); y = __fmul_rn(0.8f, y);
+    PXY(2 * N + k, 0) = x; PXY(2 * N + k, 1) = y;
+    ox[k] = (double)x; oy[k] = (double)y;
   }
+  auto too_close = [&](double qx, double qy, double cx, double cy) -> bool {   // dist64_sq(q, c) < dcoll2_lt
+    const double dx = __dsub_rn(qx, cx), dy = __dsub_rn(qy, cy);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < p.dcoll2_lt;
+  };
   uint32_t d = (uint32_t)O;
 #pragma unroll 1
-  for (int slot = 0; slot < 2 * N; ++slot) {   // agents (:389-456) then goals (:472-535); entity index == slot
-    const bool goal = slot >= N;
-    const int base = goal ? N : 0;
-    float x, y;
-    while (true) {
-      draw_uniform2(p, genv, episode, d, x, y);
-      ++d;
-      if (goal) { x = __fmul_rn(0.8f, x); y = __fmul_rn(0.8f, y); }
-      bool bad = false;
-#pragma unroll 1
-      // |c - q| < dcoll as |c - q|^2 < dcoll2_lt (the square root is correctly rounded and monotone: same decision, no root)
-      for (int k = 0; k < O; ++k) bad = bad || (dist64_sq(PXY(2 * N + k, 0), PXY(2 * N + k, 1), x, y) < p.dcoll2_lt);
-#pragma unroll 1
-      for (int j = base; j < slot; ++j) bad = bad || (dist64_sq(PXY(j, 0), PXY(j, 1), x, y) < p.dcoll2_lt);
-      if (!bad || d >= (uint32_t)MAX_DRAWS) break;
+  for (int pass = 0; pass < 2; ++pass) {       // agents (:389-456) then goals (:472-535); entity index == pass * N + a
+    double qx[N], qy[N];
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      float x, y;
+      while (true) {
+        draw_uniform2(p, genv, episode, d, x, y);
+        ++d;
+        if (pass) { x = __fmul_rn(0.8f, x); y = __fmul_rn(0.8f, y); }
+        const double cx = (double)x, cy = (double)y;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < O; ++k) bad |= too_close(ox[k], oy[k], cx, cy);
+#pragma unroll
+        for (int j = 0; j < a; ++j) bad |= too_close(qx[j], qy[j], cx, cy);
+        if (!bad || d >= (uint32_t)MAX_DRAWS) break;
+      }
+      qx[a] = (double)x; qy[a] = (double)y;
+      PXY(pass * N + a, 0) = x;
+      PXY(pass * N + a, 1) = y;
     }
-    PXY(slot, 0) = x;
-    PXY(slot, 1) = y;
   }
   double cost[N * N];
   int gm[N];
