@@ -179,10 +179,12 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
 #pragma unroll
   for (int i = 0; i < N; ++i) Sc[(L::RGM + i) * RW] = __int_as_float(gm[i]);
 #pragma unroll 1
-  for (int a = 0; a < M; ++a)
-#pragma unroll 1
-    for (int b = a + 1; b < M; ++b)
-      sd[aw_spair(a, b, M)] = (float)dist64(PXY(N + a, 0), PXY(N + a, 1), PXY(N + b, 0), PXY(N + b, 1));
+  for (int a = 0; a < M; ++a) {
+    const double axx = (double)PXY(N + a, 0), ayy = (double)PXY(N + a, 1);
+#pragma unroll
+    for (int b = 0; b < M; ++b)                  // unrolled: the distances of a row are independent chains
+      if (b > a) sd[aw_spair(a, b, M)] = (float)dist64_d(axx, ayy, PXY(N + b, 0), PXY(N + b, 1));
+  }
 }
 
 // The same reset from the env's entry of the pending block (prefetch_kernel, fm_kernels.cu: placement + assignment of the
