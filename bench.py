@@ -620,7 +620,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         import ctypes as C
         from fair_marl_b200 import _lib
         lib = _lib.load()
-        cap = B * E * (E - 1)
+        cap = B * E * E                                  # what always suffices (include/fairmarl.h): no capacity tests in the emission
         offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
         eidx = torch.empty((2, cap), dtype=torch.int64, device=dev)
         eattr = torch.empty(cap, dtype=torch.float32, device=dev)
@@ -646,7 +646,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         edge_list = {"ms_per_step_with_edge_list": el_ms, "ms_per_step_closed_loop": closed_loop["ms_per_step"],
                      "edges_per_step": n_edges, "edge_bytes_per_step": n_edges * 20,
                      "value": B * N_AGENTS / (el_ms * 1e-3), "unit": "agent-steps/s",
-                     "api": "step_tensor + fm_edge_list (count / scan / emit, one graph per env, int64 edge_index + fp32 attr)"}
+                     "api": "step_tensor + fm_edge_list (form %s: one graph per env, int64 edge_index + fp32 attr)" % os.environ.get("FM_EDGE_FORM", "stream")}
 
     # e2e through the reference-facing API with host buffers
     e2e_steps = max(3, min(args.e2e_steps, K))

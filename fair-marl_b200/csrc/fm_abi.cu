@@ -828,16 +828,26 @@ int fm_edge_list(int device, const float* adj, int32_t num_graphs, int32_t E, do
   cudaStream_t st = (cudaStream_t)stream;
   void* scratch = nullptr;
   cudaError_t e;
-  // The single-pass form (fm_edges.cu) is opt-in (FM_EDGE_FUSED=1): it is bit-identical and reads adj once, but measured no
-  // faster than count / scan / emit at config 3 (448 vs 452 us of kernel time, profiles/r02_j: both are bound by the
-  // compaction's instruction count, and the look-back keeps whole CTAs at a barrier).
-  const char* fused_env = getenv("FM_EDGE_FUSED");        // read per call (tests flip it); ~50 ns beside two to three launches
-  const bool single_pass = fused_env && fused_env[0] == '1';
-  if (single_pass && fm::edge_fused_smem(E) <= 96 * 1024) {
+  // Three bit-identical forms (tests run all of them).  FM_EDGE_FORM = stream (default: count / offsets / persistent emission
+  // with the next graph's loads in flight, fm_edges.cu) | three (count / one-block scan / emit, fm_kernels.cu) | fused (single
+  // pass with a look-back, fm_edges.cu; FM_EDGE_FUSED=1 selects it too).  Measured at config 3: profiles/r02_j_*, r02_es_*.
+  const char* form_env = getenv("FM_EDGE_FORM");          // read per call (tests flip it); ~50 ns beside three launches
+  const char* fused_env = getenv("FM_EDGE_FUSED");
+  int form = 0;                                           // 0 stream, 1 three, 2 fused
+  if (form_env && form_env[0]) form = form_env[0] == 't' ? 1 : (form_env[0] == 'f' ? 2 : 0);
+  else if (fused_env && fused_env[0] == '1') form = 2;
+  if (form == 2 && fm::edge_fused_smem(E) > 96 * 1024) form = 0;
+  if (form == 0 && E > 100) form = 1;                      // the streamed emission divides by E with a 20-bit reciprocal
+  if (form == 2) {
     // adj read once, look-back scan; scratch = one status word per CTA + the tile counter
     FM_CUDA(cudaMallocAsync(&scratch, fm::edge_fused_scratch_bytes(num_graphs), st));
     e = fm::launch_edge_list_fused(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity, scratch,
                                    (long long*)graph_offsets, (long long*)edge_index, edge_attr, (long long*)nnz_out, st);
+  } else if (form == 0) {
+    // scratch: the tile sums followed by the per-graph counts (int32)
+    FM_CUDA(cudaMallocAsync(&scratch, fm::edge_stream_scratch_bytes(num_graphs), st));
+    e = fm::launch_edge_list_stream(adj, num_graphs, E, (float)max_edge_dist, inclusive, repeat, (long long)capacity, scratch,
+                                    (long long*)graph_offsets, (long long*)edge_index, edge_attr, (long long*)nnz_out, st);
   } else {
     // count / scan / emit (fm_kernels.cu); scratch: per-CTA sums / offsets (int64) followed by the per-graph counts (int32)
     const int nb = fm::edge_list_blocks(num_graphs);

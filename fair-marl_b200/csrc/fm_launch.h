@@ -48,6 +48,11 @@ int edge_list_blocks(int num_graphs);             // CTAs of the edge-list kerne
 cudaError_t launch_edge_list(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
                              long long capacity, int* counts, long long* blocksums, long long* graph_offsets,
                              long long* edge_index, float* edge_attr, long long* nnz_out, cudaStream_t st);
+// streamed form (fm_edges.cu, the default): count / offsets / persistent emission
+size_t edge_stream_scratch_bytes(int num_graphs);
+cudaError_t launch_edge_list_stream(const float* adj, int num_graphs, int E, float thr, int inclusive, int repeat,
+                                    long long capacity, void* scratch, long long* graph_offsets, long long* edge_index,
+                                    float* edge_attr, long long* nnz_out, cudaStream_t st);
 // single-pass form (fm_edges.cu)
 size_t edge_fused_smem(int E);
 size_t edge_fused_scratch_bytes(int num_graphs);

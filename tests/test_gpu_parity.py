@@ -406,15 +406,17 @@ def test_next_episode_prefetch_is_bitwise_invisible(N, O, B, lanes, T, mapping, 
         assert torch.equal(x, y), k
 
 
-@pytest.mark.parametrize("single_pass", [False, True])
-def test_edge_list_corner_cases(single_pass, monkeypatch):
-    """Both forms of fm_edge_list (count / scan / emit, and the single-pass look-back kernel of fm_edges.cu, FM_EDGE_FUSED=1;
+@pytest.mark.parametrize("form", ["stream", "three", "fused"])
+def test_edge_list_corner_cases(form, monkeypatch):
+    """All forms of fm_edge_list (FM_EDGE_FORM: the default streamed count / offsets / persistent emission of fm_edges.cu,
+    count / scan / emit, and the single-pass look-back kernel;
     E = 35 x 8 lists needs 78 KB of shared memory, above 96 KB the call falls back).  process_adj on shapes the simulator never produces by itself: no edges at all, every edge, a single graph (2-D
     input), E = 35, more graph copies than lanes (repeat = 40), a graph count that is not a multiple of the 8 graphs
     a CTA handles, and 70 000 graphs (more CTAs than one scan segment)."""
     import torch
     import fair_marl_b200 as fm
-    monkeypatch.setenv("FM_EDGE_FUSED", "1" if single_pass else "0")
+    monkeypatch.delenv("FM_EDGE_FUSED", raising=False)
+    monkeypatch.setenv("FM_EDGE_FORM", form)
     rng = np.random.default_rng(3)
     dev = torch.device("cuda")
 
@@ -441,6 +443,31 @@ def test_edge_list_corner_cases(single_pass, monkeypatch):
     many = (rng.random((70001, 5, 5)) * 2).astype(np.float32)
     check(many, 1.0)
     check(many[:9], 1.0, repeat=3)
+    check(many[:2049], 1.0)                                                          # one graph past a 2 048-graph offsets tile
+    wide = (rng.random((3000, 17, 17)) * 2).astype(np.float32)                     # more graphs than one wave of emission warps take
+    wide[5] = 9.0                                                                  # a graph without edges between graphs with edges
+    check(wide, 1.0)
+    check(wide[:300], 1.0, repeat=7)
+    # graph_offsets of every copy, and a caller-side capacity smaller than the list (the ABI truncates, nnz stays the full count)
+    from fair_marl_b200 import _lib
+    lib = _lib.load()
+    for a_np, repeat in ((wide[:300], 3), (big, 2)):
+        a = torch.as_tensor(a_np, device=dev)
+        G, E = a.shape[0], a.shape[1]
+        ei, ea, off = fm.process_adj(a, 1.0, repeat=repeat, return_offsets=True)
+        per = ((a_np < 1.0) & (a_np > 0)).reshape(G, -1).sum(1)
+        want = np.concatenate([[0], np.cumsum(np.repeat(per, repeat))])
+        assert (off.cpu().numpy() == want).all()
+        n = int(want[-1])
+        cap = n // 2 + 1
+        off2 = torch.empty(G * repeat + 1, dtype=torch.int64, device=dev)
+        ei2 = torch.full((2, cap), -1, dtype=torch.int64, device=dev)
+        ea2 = torch.full((cap,), -1.0, dtype=torch.float32, device=dev)
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.check(lib.fm_edge_list(0, a.data_ptr(), G, E, 1.0, 0, repeat, cap, off2.data_ptr(), ei2.data_ptr(), ea2.data_ptr(),
+                                    nnz.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "fm_edge_list")
+        assert int(nnz.item()) == n and torch.equal(off2, off)
+        assert torch.equal(ei2, ei[:, :cap]) and torch.equal(ea2, ea[:cap, 0])
 
 
 @pytest.mark.parametrize("N,O,B", [(7, 3, 21), (16, 3, 9), (3, 3, 40), (5, 0, 13)])

@@ -2,7 +2,7 @@
 # Round 2, final GPU session: full parity suite, smoke, every bench line in the driver's configuration, ncu launch list +
 # full captures of the headline and formation kernels, steady-state DRAM bytes, compute-sanitizer over the new paths.
 set -u
-OUT=gpurun_out/r02_final; mkdir -p $OUT
+OUT=gpurun_out/${FM_OUT_TAG:-r02_final}; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1; nproc > $OUT/nproc.txt
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
 tail -6 $OUT/pytest_gpu.log | cut -c1-300
