@@ -574,7 +574,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env.algorithmic_bytes_per_step
     kernel_name = {"aw": (f"fm::aw_roll_kernel<{N_AGENTS},{N_OBST},11> (agent-warp, persistent rollout)"
-                          if os.environ.get("FM_ROLL", "0") not in ("", "0") else f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)"),
+                          if os.environ.get("FM_ROLL", "0") not in ("", "0") else (f"fm::aw_kernel<{N_AGENTS},{N_OBST},0,11,{N_WALLS}> (agent-warp, {N_WALLS} wall(s))" if N_WALLS
+                                else f"fm::aw_kernel<{N_AGENTS},{N_OBST},0> (agent-warp)")),
                    "group": f"fm::step_kernel<{4 if N_AGENTS <= 4 else 8 if N_AGENTS <= 8 else 16 if N_AGENTS <= 16 else 32}{', true' if N_WALLS else ''}> (group-per-env)"}[env.mapping]
     # One step = the step kernel's work over the whole batch (agent-warp mapping: (step, tile) items of one persistent
     # launch per chunk of steps; group mapping: concurrent env-range launches on side streams); that kernel is > 99 %

@@ -10,7 +10,7 @@ from typing import Any, Optional
 class SimConfig:
     num_agents: int = 3
     num_obstacles: int = 3
-    num_walls: int = 0          # 0, 1 or 2 wall segments (group-per-env kernels; not with graph_feat_type='global')
+    num_walls: int = 0          # 0, 1 or 2 wall segments (agent-warp kernels at 3 agents / 3 obstacles, else group-per-env; not with graph_feat_type='global')
     world_size: float = 2.0
     max_speed: Optional[float] = 2.0
     collision_rew: float = 5.0

@@ -98,8 +98,9 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_walls must be 0, 1 or 2 (got %d)", cfg->num_walls);
   if (cfg->num_walls > 0 && cfg->graph_feat_global)
     return fail(FM_ERR_UNSUPPORTED, "fm_create: wall entities have no global features (navigation_graph.py:1074-1075)");
-  if (cfg->num_walls > 0 && cfg->mapping == 2)
-    return fail(FM_ERR_UNSUPPORTED, "fm_create: the agent-warp kernels do not take walls");
+  if (cfg->num_walls > 0 && cfg->mapping == 2 && !fm::aw_supported(cfg->num_agents, cfg->num_obstacles, cfg->num_walls))
+    return fail(FM_ERR_UNSUPPORTED, "fm_create: the agent-warp kernels are not compiled for N=%d O=%d with %d wall(s)",
+                cfg->num_agents, cfg->num_obstacles, cfg->num_walls);
   if (cfg->num_obstacles < 0 || cfg->num_obstacles > 64)
     return fail(FM_ERR_INVALID_ARG, "fm_create: num_obstacles must be in 0..64 (got %d)", cfg->num_obstacles);
   if (cfg->episode_length < 1) return fail(FM_ERR_INVALID_ARG, "fm_create: episode_length must be >= 1");
@@ -191,11 +192,11 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
 
   // Kernel mapping (cfg->mapping: 0 auto = agent-warp where compiled for (N, O), else group-per-env;
   // 1 group-per-env; 2 agent-warp).  Both mappings produce identical results.
-  if (cfg->mapping == 2 && !fm::aw_supported(N, O)) {
+  if (cfg->mapping == 2 && !fm::aw_supported(N, O, W)) {
     cudaFree(h->state_block); delete h;
     return fail(FM_ERR_UNSUPPORTED, "fm_create: agent-warp kernels are not compiled for N=%d O=%d", N, O);
   }
-  p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || (W == 0 && fm::aw_supported(N, O))) ? 1 : 0);
+  p.mapping = cfg->mapping == 1 ? 0 : ((cfg->mapping == 2 || fm::aw_supported(N, O, W)) ? 1 : 0);
   p.sd_env_stride = p.mapping == 0 ? SPp : 0;      // group mapping: [env][SPp];  agent-warp mapping: [pair][Bp]
   // pending block of the next-episode prefetch (group mapping with auto-reset; FM_PREFETCH=0 disables it)
   h->lockstep = 1; h->host_step = 0;
@@ -207,7 +208,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     // lane = env (32 envs per warp in lockstep), while prefetch_kernel<4> spends 4 lanes per env on the same serial work and
     // takes the SMs from the memory-bound step kernels it runs beside.
     const int v = ev ? atoi(ev) : 1;
-    h->pf_on = cfg->auto_reset && (p.mapping == 0 ? v != 0 : v == 2);
+    h->pf_on = cfg->auto_reset && (p.mapping == 0 ? v != 0 : (v == 2 && W == 0));   // (the agent-warp wall kernels reset inline)
   }
   if (h->pf_on) {
     const size_t rows = (size_t)(5 * N + 2 * O + 2 * W);
@@ -265,7 +266,7 @@ int fm_create(const FmConfig* cfg, int device, FmHandle** out) {
     // roofline against 93 % for the one-shot kernels on two env-range lanes replayed from a CUDA graph (profiles/r02_*), so
     // the one-shot kernels stay the default path; the rollout kernel is kept, tested, for single-launch use.
     const char* ev = getenv("FM_ROLL");
-    h->roll_on = ev && atoi(ev) != 0;
+    h->roll_on = ev && atoi(ev) != 0 && W == 0;      // (no wall instantiation of the rollout kernel)
     int per_sm = 0, sms = 0;
     e = fm::roll_prepare(p, &per_sm);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

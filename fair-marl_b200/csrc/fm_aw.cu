@@ -19,15 +19,15 @@
 
 namespace fm {
 
-template <int N, int O, int MODE, int NF>
-__global__ void __launch_bounds__(AwLayout<N, O>::THREADS, AwLayout<N, O>::MIN_CTAS)
+template <int N, int O, int MODE, int NF, int W = 0>
+__global__ void __launch_bounds__((AwLayout<N, O, W>::THREADS), (AwLayout<N, O, W>::MIN_CTAS))
 aw_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
   const int env0 = p.env_begin + blockIdx.x * 32;
   AwRoll rs{};
   const FmOutputs out{p.o_obs, p.o_node, p.o_adj, p.o_rew, p.o_done, p.o_info};
   const AwIo io{p.act_idx, p.act_onehot, p.reset_mask, &out};
-  aw_tile<N, O, MODE, NF, false>(p, io, env0, min(32, p.env_end - env0), smem, rs);
+  aw_tile<N, O, MODE, NF, false, W>(p, io, env0, min(32, p.env_end - env0), smem, rs);
 }
 
 // =============================================================================================
@@ -90,7 +90,33 @@ static cudaError_t aw_prepare_no() {
   return e;
 }
 
-bool aw_supported(int N, int O) {
+// Walls (N4): the same tile body with W wall entities behind the obstacles (relative node features only).
+template <int N, int O, int W>
+static cudaError_t aw_launch_w(const DevParams& p, cudaStream_t st, bool is_reset) {
+  using L = AwLayout<N, O, W>;
+  const int blocks = (p.env_end - p.env_begin + 31) / 32;
+  if (blocks <= 0) return cudaSuccess;
+  const size_t smem = (size_t)L::WORDS * sizeof(float);
+  if (is_reset) aw_kernel<N, O, 1, NODE_F, W><<<blocks, L::THREADS, smem, st>>>(p);
+  else aw_kernel<N, O, 0, NODE_F, W><<<blocks, L::THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int N, int O, int W>
+static cudaError_t aw_prepare_w() {
+  const int smem = AwLayout<N, O, W>::WORDS * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(aw_kernel<N, O, 0, NODE_F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aw_kernel<N, O, 1, NODE_F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return e;
+}
+
+bool aw_supported(int N, int O, int W) {
+  if (W > 0) {
+#define X(n, o, w) if (N == n && O == o && W == w) return true;
+    FM_AW_WALL_CASES(X)
+#undef X
+    return false;
+  }
 #define X(n, o) if (N == n && O == o) return true;
   FM_AW_CASES(X)
 #undef X
@@ -100,6 +126,10 @@ bool aw_supported(int N, int O) {
 int aw_stats_rows(int B) { return (B + 31) / 32; }
 
 cudaError_t aw_prepare(const DevParams& p) {
+#define X(n, o, w) if (p.N == n && p.O == o && p.W == w) return aw_prepare_w<n, o, w>();
+  FM_AW_WALL_CASES(X)
+#undef X
+  if (p.W > 0) return cudaErrorInvalidValue;
 #define X(n, o) if (p.N == n && p.O == o) return aw_prepare_no<n, o>();
   FM_AW_CASES(X)
 #undef X
@@ -107,6 +137,10 @@ cudaError_t aw_prepare(const DevParams& p) {
 }
 
 cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset) {
+#define X(n, o, w) if (p.N == n && p.O == o && p.W == w) return aw_launch_w<n, o, w>(p, st, is_reset);
+  FM_AW_WALL_CASES(X)
+#undef X
+  if (p.W > 0) return cudaErrorInvalidValue;
 #define X(n, o) if (p.N == n && p.O == o) return aw_launch_no<n, o>(p, st, is_reset);
   FM_AW_CASES(X)
 #undef X

@@ -27,9 +27,9 @@
 
 namespace fm {
 
-template <int N, int O>
+template <int N, int O, int W = 0>                 // W walls (0..2): entities 2N+O .. E-1, static like landmarks and obstacles
 struct AwLayout {
-  static constexpr int E = 2 * N + O, M = N + O, SP = M * (M - 1) / 2;
+  static constexpr int E = 2 * N + O + W, M = N + O + W, SP = M * (M - 1) / 2;
   static constexpr int WARPS = N + 1, THREADS = 32 * WARPS, ENVS = 32, RW = 32;
   // ---- global state rows ([row][Bp], fm_abi.cu fm_create order)
   static constexpr int PX = 0, PY = PX + N, VX = PY + N, VY = VX + N, PD = VY + N, DTG = PD + N, TREQ = DTG + N,
@@ -40,7 +40,9 @@ struct AwLayout {
   static constexpr int TP = 0,                 // [E][2] positions after the step (after the reset for envs that reset)
                        TV = TP + 2 * E,        // [N][2] velocities
                        TG = TV + 2 * N,        // [N][2] goal (assigned landmark) of agent i
-                       T_ROWS = TG + 2 * N;
+                       TWA = TG + 2 * N,       // [W] wall axis, [W] orientation (0 = 'H'), [1] half-length (W > 0 only)
+                       TWO = TWA + W, TWL = TWO + W,
+                       T_ROWS = TWL + (W > 0 ? 1 : 0);
   static constexpr int OFF_STAGE = T_ROWS * RW;                       // multiple of 32 floats
   static constexpr int OBS_W = N * OBS_F, NODE_W = N * E * NODE_F, ADJ_W = E * E;
   // ---- staging, use 1: adj | obs | reward | done (bytes) | scratch
@@ -114,10 +116,10 @@ __device__ __forceinline__ void cta_copy_out(float* __restrict__ dst, const floa
 // :264-570) + lexifair (:555-561).  Same Philox stream, draw order and acceptance rules as
 // reset_group<G> (fm_device.cuh).  New positions go to the TP table, goal_match / min_time to the
 // RGM / RMINT scratch rows; the distances between static entities are returned in sd[] (float).
-template <int N, int O>
+template <int N, int O, int W = 0>
 __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, uint32_t episode, float* __restrict__ Tc,
                                           float* __restrict__ Sc, float* __restrict__ sd) {
-  using L = AwLayout<N, O>;
+  using L = AwLayout<N, O, W>;
   constexpr int RW = L::RW, M = L::M;
   auto PXY = [&](int e, int c) -> float& { return Tc[(L::TP + 2 * e + c) * RW]; };
   // The obstacles and the entities of the kind being placed are kept in registers as doubles (O <= 3, N <= 4: the loops
@@ -139,7 +141,25 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
     const double dx = __dsub_rn(qx, cx), dy = __dsub_rn(qy, cy);
     return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < p.dcoll2_lt;
   };
-  uint32_t d = (uint32_t)O;
+  // walls (navigation_graph.py:287-324): one draw for the axis offset U(0.2, 0.9) * ws / 2 (wall 0 at +, wall 1 at -), one
+  // draw per wall for the orientation, draws O .. O + W (reset_group<G, true>, fm_device.cuh); the half-length is fixed per env
+  float wax[W > 0 ? W : 1], wlen = 0.f;
+  bool whz[W > 0 ? W : 1];
+  if (W > 0) {
+    float u0, u1;
+    draw_u01(p, genv, episode, (uint32_t)O, u0, u1);
+    const float wp = __fmul_rn(__fadd_rn(0.2f, __fmul_rn(0.7f, u0)), p.half_world);
+    wlen = Tc[L::TWL * RW];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      draw_u01(p, genv, episode, (uint32_t)(O + 1 + k), u0, u1);
+      whz[k] = !(u0 >= 0.5f);
+      wax[k] = k == 0 ? wp : -wp;
+      Tc[(L::TWA + k) * RW] = wax[k]; Tc[(L::TWO + k) * RW] = whz[k] ? 0.0f : 1.0f;
+      PXY(2 * N + O + k, 0) = whz[k] ? 0.0f : wax[k]; PXY(2 * N + O + k, 1) = whz[k] ? wax[k] : 0.0f;   // midpoint
+    }
+  }
+  uint32_t d = (uint32_t)(O + (W > 0 ? 1 + W : 0));
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {       // agents (:389-456) then goals (:472-535); entity index == pass * N + a
     double qx[N], qy[N];
@@ -156,6 +176,8 @@ __device__ __noinline__ void aw_reset_env(const DevParams& p, long long genv, ui
         for (int k = 0; k < O; ++k) bad |= too_close(ox[k], oy[k], cx, cy);
 #pragma unroll
         for (int j = 0; j < a; ++j) bad |= too_close(qx[j], qy[j], cx, cy);
+#pragma unroll
+        for (int k = 0; k < W; ++k) bad |= in_wall_box(x, y, whz[k], wax[k], wlen);   // is_obstacle_collision's wall boxes (:670-683)
         if (!bad || d >= (uint32_t)MAX_DRAWS) break;
       }
       qx[a] = (double)x; qy[a] = (double)y;
@@ -249,6 +271,8 @@ struct AwRoll {
 
 // The (N, O) pairs compiled for this mapping.  Everything else runs the group-per-env kernels.
 #define FM_AW_CASES(X) X(1, 1) X(2, 0) X(3, 0) X(3, 3) X(4, 2)
+// (N, O, W) with walls: the 3-agent / 3-obstacle shape of the BASELINE configs with 1 or 2 walls
+#define FM_AW_WALL_CASES(X) X(3, 3, 1) X(3, 3, 2)
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* q) {
   int v;
@@ -268,10 +292,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // ROLL: called from the persistent rollout kernel: the tile's previous user of the shared memory may still have a bulk
 //       store in flight (waited for at barrier #0), the last bulk store of this call is left in flight, and the tile's
 //       dependency flag is released (see AwRoll).
-template <int N, int O, int MODE, int NF, bool ROLL>
+template <int N, int O, int MODE, int NF, bool ROLL, int W = 0>
 __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, const int env0, const int nenv,
                                         float* __restrict__ smem, AwRoll& rs) {
-  using L = AwLayout<N, O>;
+  using L = AwLayout<N, O, W>;
   constexpr int E = L::E, M = L::M, RW = L::RW, SP = L::SP;
   constexpr int NW = N * E * NF;                   // node_obs words per env (the staging region is sized for NF = 11)
   float* ST = smem + L::OFF_STAGE;
@@ -342,6 +366,15 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
       sxy[2 * (N + k) + 1] = __ldcg(gs + (size_t)(L::OY + k) * Bp);
     }
 #pragma unroll
+    for (int k = 0; k < W; ++k) {                  // wall midpoint: (0, axis) for 'H', (axis, 0) for 'V' (navigation_graph.py:309-324)
+      const float ax = __ldcg(p.wax + (size_t)k * Bp + env);
+      const bool hz = __ldcg(p.wor + (size_t)k * Bp + env) == 0;
+      sxy[2 * (N + O + k)] = hz ? 0.0f : ax;
+      sxy[2 * (N + O + k) + 1] = hz ? ax : 0.0f;
+      Tc[(L::TWA + k) * RW] = ax; Tc[(L::TWO + k) * RW] = hz ? 0.0f : 1.0f;
+    }
+    if (W > 0) Tc[L::TWL * RW] = __ldcg(p.wlen + env);
+#pragma unroll
     for (int q = 0; q < SP; ++q) sd[q] = __ldcg(gs + (size_t)(L::SDIST + q) * Bp);
   };
   auto store_static = [&](const float* sxy) {
@@ -354,9 +387,16 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
   // Reset of this env by its env-warp thread: new placement -> tables, scratch and the state block.
   auto reset_static = [&](float* sd) {
     bool pend = false;
-    if (p.q_tag != nullptr) pend = ld_acquire_gpu(p.q_tag + env) == epis;   // the entry's data is visible once its tag is
-    if (pend) aw_reset_from_pending<N, O>(p, env, Tc, Sc, sd);
-    else aw_reset_env<N, O>(p, genv, (uint32_t)epis, Tc, Sc, sd);
+    if constexpr (W == 0) {                      // (the pending block carries no walls)
+      if (p.q_tag != nullptr) pend = ld_acquire_gpu(p.q_tag + env) == epis;   // the entry's data is visible once its tag is
+      if (pend) aw_reset_from_pending<N, O>(p, env, Tc, Sc, sd);
+    }
+    if (!pend) aw_reset_env<N, O, W>(p, genv, (uint32_t)epis, Tc, Sc, sd);
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      p.wax[(size_t)k * Bp + env] = Tc[(L::TWA + k) * RW];
+      p.wor[(size_t)k * Bp + env] = Tc[(L::TWO + k) * RW] == 0.0f ? 0 : 1;
+    }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       gs[(size_t)(L::LX + j) * Bp] = Tc[(L::TP + 2 * (N + j)) * RW];
@@ -392,6 +432,8 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
     float qx[N + O], qy[N + O];                  // agent warps: partners (agents, own slot unused; obstacles)
     float sxy[2 * M > 0 ? 2 * M : 1], sd0[SP > 0 ? SP : 1];   // env warp: static positions, cached static distances
     float ux = 0.f, uy = 0.f;
+    float wax[W > 0 ? W : 1], wlen = 0.f;          // agent warps: wall axis / orientation / half-length of THIS episode
+    bool whz[W > 0 ? W : 1];
     if (is_agent) {
       const float* gi = gs + (size_t)i * Bp;
       px = __ldcg(gi + (size_t)L::PX * Bp); py = __ldcg(gi + (size_t)L::PY * Bp);
@@ -407,6 +449,9 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
 #pragma unroll
       for (int k = 0; k < O; ++k) { qx[N + k] = __ldcg(gs + (size_t)(L::OX + k) * Bp); qy[N + k] = __ldcg(gs + (size_t)(L::OY + k) * Bp); }
       if (i == 0) { dmean0 = __ldcg(gs + (size_t)L::DMEAN * Bp); dstd0 = __ldcg(gs + (size_t)L::DSTD * Bp); }
+#pragma unroll
+      for (int k = 0; k < W; ++k) { wax[k] = __ldcg(p.wax + (size_t)k * Bp + env); whz[k] = __ldcg(p.wor + (size_t)k * Bp + env) == 0; }
+      if (W > 0) wlen = __ldcg(p.wlen + env);
       if (venv) {                                // environment.py:301-311: u = [a1 - a2, a3 - a4] * sensitivity (5.0)
         if (io.act_idx) {
           const int a = __ldg(io.act_idx + (size_t)env * N + i);
@@ -432,6 +477,12 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
 #pragma unroll
       for (int q = 0; q < N + O; ++q)
         if (q != i) contact_force(p, px, py, qx[q], qy[q], cfx, cfy);
+      // walls: first as circle entities of the pair loop (they close world.entities), then the wall forces proper
+      // (core.py:317-327, :407-462), both from the positions at step entry -- the order of step_kernel<G, true>
+#pragma unroll
+      for (int k = 0; k < W; ++k) contact_force_dmin(p, 0.15f, px, py, whz[k] ? 0.0f : wax[k], whz[k] ? wax[k] : 0.0f, cfx, cfy);
+#pragma unroll
+      for (int k = 0; k < W; ++k) wall_force(px, py, whz[k], wax[k], wlen, cfx, cfy);
       const double Fx = __dadd_rn((double)ux, (double)cfx), Fy = __dadd_rn((double)uy, (double)cfy);   // mass(1.0) * u + contact
       double v64x, v64y, sx, sy;                   // integrate_state (core.py:338-356)
       integrate64(p, vx, vy, Fx, Fy, pd, v64x, v64y, sx, sy, pd64);
@@ -496,7 +547,9 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
       }
       const bool reached = ((reachbits >> (N + gm)) & 1u) != 0;      // dgoal < min_dist_thresh (float64 compare)
       const int ncoll = __popc(collbits & ((1u << N) - 1u));
-      const bool ocoll = (collbits >> (2 * N)) != 0;
+      bool ocoll = W > 0 ? ((collbits >> (2 * N)) & ((1u << O) - 1u)) != 0 : (collbits >> (2 * N)) != 0;   // obstacles only
+#pragma unroll
+      for (int k = 0; k < W; ++k) ocoll = ocoll || in_wall_box(px, py, whz[k], wax[k], wlen);   // :670-683, at the new position
       const bool latched = treq != -1.0f;
       const double treq_new = (!latched && reached) ? (double)nstep * p.dt : (double)treq;   // :588
       float rw = reached ? p.goal_rew : -dgoal_f;  // navigation_graph.py:760-824
@@ -734,7 +787,7 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float epx = Tc[(L::TP + 2 * e) * RW], epy = Tc[(L::TP + 2 * e + 1) * RW];
-        const float ty = (e < N) ? 0.0f : ((e < 2 * N) ? 1.0f : 2.0f);
+        const float ty = (e < N) ? 0.0f : ((e < 2 * N) ? 1.0f : ((e < 2 * N + O) ? 2.0f : 3.0f));
         if (NF == NODE_F_GLOBAL) {                    // [vel, pos, goal, type] in world coordinates, same rows for every ego agent
           float evx = 0.f, evy = 0.f, egx = epx, egy = epy;
           if (e < N) {
@@ -750,7 +803,14 @@ __device__ __forceinline__ void aw_tile(const DevParams& p, const AwIo& io, cons
             rgx = Tc[(L::TG + 2 * e) * RW] - px; rgy = Tc[(L::TG + 2 * e + 1) * RW] - py;
           }
           o[0] = rvx; o[1] = rvy; o[2] = rpx; o[3] = rpy; o[4] = rgx; o[5] = rgy;
-          o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy;
+          if (W > 0 && e >= 2 * N + O) {
+            // wall row (navigation_graph.py:1108-1118): rel_goal = rel_pos, then the two corner offsets
+            // (endpoints[0], axis + width / 2) - p_a and (endpoints[1], axis - width / 2) - p_a
+            const float wa = Tc[(L::TWA + (e - 2 * N - O)) * RW], wl = Tc[L::TWL * RW];
+            o[6] = -wl - px; o[7] = (wa + 0.05f) - py; o[8] = wl - px; o[9] = (wa - 0.05f) - py;
+          } else {
+            o[6] = rpx; o[7] = rpy; o[8] = rpx; o[9] = rpy;
+          }
           o[10] = ty;
         }
         o += NF;

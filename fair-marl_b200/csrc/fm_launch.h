@@ -14,7 +14,7 @@ typedef FmState HostState;   // API-layout device pointers
 int group_size(int n);
 int num_warps(int B, int N);
 // agent-warp mapping (fm_aw.cu): compiled for a fixed list of small (N, O)
-bool aw_supported(int N, int O);
+bool aw_supported(int N, int O, int W = 0);
 int aw_stats_rows(int B);
 cudaError_t aw_prepare(const DevParams& p);
 cudaError_t aw_launch(const DevParams& p, cudaStream_t st, bool is_reset);
