@@ -271,8 +271,9 @@ struct AwRoll {
 
 // The (N, O) pairs compiled for this mapping.  Everything else runs the group-per-env kernels.
 #define FM_AW_CASES(X) X(1, 1) X(2, 0) X(3, 0) X(3, 3) X(4, 2)
-// (N, O, W) with walls: the 3-agent / 3-obstacle shape of the BASELINE configs with 1 or 2 walls
-#define FM_AW_WALL_CASES(X) X(3, 3, 1) X(3, 3, 2)
+// (N, O, W) with walls: the 3-agent / 3-obstacle shape of the BASELINE configs with 1 or 2 walls, and the shape of the
+// reference fixture n4_o2_w1
+#define FM_AW_WALL_CASES(X) X(3, 3, 1) X(3, 3, 2) X(4, 2, 1)
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* q) {
   int v;

@@ -271,7 +271,7 @@ def test_shards_equal_one_batch_bitwise():
 
 @pytest.mark.parametrize("other", ["aw"])
 @pytest.mark.parametrize("N,O,B,W", [(3, 3, 1000, 0), (4, 2, 333, 0), (2, 0, 65, 0), (1, 1, 40, 0), (3, 0, 129, 0),
-                                     (3, 3, 1000, 2), (3, 3, 333, 1)])       # the agent-warp wall instantiations
+                                     (3, 3, 1000, 2), (3, 3, 333, 1), (4, 2, 200, 1)])       # the agent-warp wall instantiations
 def test_mappings_bitwise_equal(N, O, B, W, other):
     """The agent-warp kernels (fm_aw.cu) and the group-per-env kernels (fm_kernels.cu) perform the same
     arithmetic: every output, the state and the statistics agree bit for bit over a rollout with
@@ -532,7 +532,7 @@ def test_walls_reset_and_rollout_match_oracle(N, O, W, B, prefetch, monkeypatch)
     cfg = NavConfig(num_agents=N, num_obstacles=O, num_walls=W, goal_rew=30.0, collision_rew=30.0, episode_length=9)
     env = _env(cfg, B, seed=11, env_offset=5)
     import parity_util
-    want = "aw" if (N, O) == (3, 3) and parity_util.MAPPING == "auto" else "group"
+    want = "aw" if (N, O, W) in ((3, 3, 1), (3, 3, 2), (4, 2, 1)) and parity_util.MAPPING == "auto" else "group"
     assert env.mapping == want and env.num_entities == 2 * N + O + W
     orc = NavGraphOracle(cfg, B, seed=11, env_offset=5)
     out = _np(env.reset_tensor())
