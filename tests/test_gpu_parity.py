@@ -449,6 +449,8 @@ def test_edge_list_corner_cases(form, monkeypatch):
     wide[5] = 9.0                                                                  # a graph without edges between graphs with edges
     check(wide, 1.0)
     check(wide[:300], 1.0, repeat=7)
+    if form == "stream":                                                           # more than 256 offsets tiles: every thread of the
+        check((rng.random((600001, 3, 3)) * 2).astype(np.float32), 1.0)            # look-back sums several tile totals
     # graph_offsets of every copy, and a caller-side capacity smaller than the list (the ABI truncates, nnz stays the full count)
     from fair_marl_b200 import _lib
     lib = _lib.load()
