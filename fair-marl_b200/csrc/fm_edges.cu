@@ -1,9 +1,9 @@
-// Policy-side edge list in ONE pass (TransformerConvNet.process_adj, onpolicy/algorithms/utils/gnn_new.py:381-413):
-// mask (adj < max_edge_dist) & (adj > 0), edges in (b, i, j) order, every graph emitted `repeat` times consecutively.
-//
-// The three-kernel form (fm_kernels.cu: count / scan / emit) reads adj twice and writes each edge with three stores whose
-// warps are mostly empty (7 % of the entries of a distance matrix are edges: 2-3 lanes per ballot, times `repeat` copies).
-// Here a CTA of 8 warps owns 8 consecutive graphs:
+// Policy-side edge list (TransformerConvNet.process_adj, onpolicy/algorithms/utils/gnn_new.py:381-413): mask
+// (adj < max_edge_dist) & (adj > 0), edges in (b, i, j) order, every graph emitted `repeat` times consecutively.
+// Two forms live here (a third, round 1's count / one-block scan / emit, in fm_kernels.cu); all three are bit-identical and
+// under test, FM_EDGE_FORM selects one (fm_abi.cu):
+//   * the STREAMED form, the default (second half of this file): count -> offsets -> persistent emission;
+//   * the SINGLE-PASS form (first half, opt-in), kept because it reads adj once.  A CTA of 8 warps owns 8 consecutive graphs:
 //   1. each warp reads its graph once (8 loads in flight per lane) and compacts the edges -- ballot + popc, (b, i, j) order
 //      -- into a shared-memory list (row, column, distance);
 //   2. the CTA's edge count is published and its exclusive prefix fetched by a decoupled look-back over one 64-bit status
@@ -11,7 +11,8 @@
 //      counter, so a CTA only ever waits for CTAs that are already running;
 //   3. each warp writes its graph's offsets and, per copy, the list with full consecutive lanes: 8-byte / 4-byte stores
 //      to consecutive addresses.
-// adj is read once, nothing is re-read from global memory, and there is no separate count or scan launch.
+//   Measured no faster than three kernels (448 us at config 3): 42 % of its stall samples are the CTA-wide barrier behind
+//   the look-back (profiles/r02_j_edge_fused_kernel_ncu.txt).
 #include <cstdlib>
 
 #include "fm_device.cuh"
