@@ -613,7 +613,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         cl_ms = float(tt.item())
     closed_loop = {"value": B * world * N_AGENTS * cl_steps / (cl_ms * 1e-3), "unit": "agent-steps/s",
                    "ms_per_step": cl_ms / cl_steps, "steps": cl_steps,
-                   "api": "B200GraphVecEnv.step_tensor -> fm_step, one launch per step, device tensors"}
+                   "api": "B200GraphVecEnv.step_tensor -> fm_step, one launch per step (programmatic dependent launch behind the previous step), device tensors"}
 
     # policy-side edge list (a-7, process_adj) emitted after every step: SURVEY 8(d) asks for it at config 3
     edge_list = None

@@ -475,6 +475,10 @@ static int step_common(FmHandle* h, const int32_t* idx, const float* onehot, con
     fm::RollLaunch r{1, 1, h->roll_max_ctas, tiles > h->roll_max_ctas ? h->roll_stagger1_ns : 0, h->roll_ctl, idx, onehot, 0, &o};
     FM_CUDA(fm::roll_launch(p, r, (cudaStream_t)stream));
   } else {
+    // one launch per step (the closed loop): let the next step's kernel be scheduled behind this one's last wave
+    // (programmatic dependent launch; 26.7 -> 25.3 us per step at C2, profiles/r02_pdl_*; FM_STEP_PDL=0: plain stream order)
+    static const int step_pdl = [] { const char* v = getenv("FM_STEP_PDL"); return (v && v[0] == '0') ? 0 : 1; }();
+    p.pdl = step_pdl && p.mapping == 1 && !stream_capturing((cudaStream_t)stream);
     FM_CUDA(fm::launch_step(p, (cudaStream_t)stream, false));
   }
   h->launches += 1;

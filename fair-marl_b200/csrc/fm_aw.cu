@@ -23,6 +23,13 @@ template <int N, int O, int MODE, int NF, int W = 0>
 __global__ void __launch_bounds__((AwLayout<N, O, W>::THREADS), (AwLayout<N, O, W>::MIN_CTAS))
 aw_kernel(const __grid_constant__ DevParams p) {
   extern __shared__ __align__(16) float smem[];
+  // Programmatic dependent launch (fm_step with FM_STEP_PDL, MODE 0): the NEXT step's kernel may be scheduled as soon as every
+  // CTA of this one has started -- its CTAs take the slots the last, partial wave leaves free and wait here until this grid
+  // has completed and its memory is visible.  Without the launch attribute both instructions are no-ops.
+  if (MODE == 0) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   const int env0 = p.env_begin + blockIdx.x * 32;
   AwRoll rs{};
   const FmOutputs out{p.o_obs, p.o_node, p.o_adj, p.o_rew, p.o_done, p.o_info};
@@ -65,6 +72,15 @@ static cudaError_t aw_launch_no(const DevParams& p, cudaStream_t st, bool is_res
   const int blocks = (p.env_end - p.env_begin + 31) / 32;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)L::WORDS * sizeof(float);
+  if (p.pdl && !is_reset && !p.feat_global) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(L::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, aw_kernel<N, O, 0, NODE_F>, p);
+  }
   if (p.feat_global) {
     if (is_reset) aw_kernel<N, O, 1, NODE_F_GLOBAL><<<blocks, L::THREADS, smem, st>>>(p);
     else aw_kernel<N, O, 0, NODE_F_GLOBAL><<<blocks, L::THREADS, smem, st>>>(p);
