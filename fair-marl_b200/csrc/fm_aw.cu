@@ -113,6 +113,15 @@ static cudaError_t aw_launch_w(const DevParams& p, cudaStream_t st, bool is_rese
   const int blocks = (p.env_end - p.env_begin + 31) / 32;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)L::WORDS * sizeof(float);
+  if (p.pdl && !is_reset) {                            // see aw_launch_no
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(L::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, aw_kernel<N, O, 0, NODE_F, W>, p);
+  }
   if (is_reset) aw_kernel<N, O, 1, NODE_F, W><<<blocks, L::THREADS, smem, st>>>(p);
   else aw_kernel<N, O, 0, NODE_F, W><<<blocks, L::THREADS, smem, st>>>(p);
   return cudaGetLastError();
