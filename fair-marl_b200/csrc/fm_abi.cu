@@ -501,7 +501,8 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
   int rc = use_device(h->device);
   if (rc) return rc;
   const size_t stride = (size_t)h->p.B * h->p.N;
-  if (stream_capturing((cudaStream_t)stream)) h->lockstep = 0;      // see step_common
+  const bool capturing = stream_capturing((cudaStream_t)stream);
+  if (capturing) h->lockstep = 0;                                   // see step_common
   if (h->roll_on) {
     // Agent-warp mapping: the whole rollout is (step, tile) items of ONE persistent kernel per chunk of <=
     // FM_ROLL_MAX_STEPS steps (fm_roll.cu).  A tile's next step may start as soon as its state is written back when
@@ -576,6 +577,11 @@ int fm_step_many(FmHandle* h, const int32_t* actions, int32_t num_steps, const F
       cudaStream_t ls = k == 0 ? user : h->lane_stream[k];
       rc = prefetch_before_step(h, p, ls, terminal);
       if (rc) return rc;
+      // The lane's consecutive step kernels as programmatic dependent launches when they are issued eagerly: long run 0.954 ->
+      // 0.975 of the roofline on the same box.  Not under capture (FM_MANY_PDL=2 forces it there: the replayed driver
+      // configuration measured 0.851 / 0.880 with the programmatic edges against 0.855 / 0.890 without, profiles/r02_pdl2_*).
+      static const int many_pdl = [] { const char* v = getenv("FM_MANY_PDL"); return v && v[0] ? atoi(v) : 1; }();
+      p.pdl = p.mapping == 1 && (many_pdl == 2 || (many_pdl == 1 && !capturing));
       FM_CUDA(fm::launch_step(p, ls, false));
       h->launches += 1;
       if (terminal && h->p.auto_reset) { rc = prefetch_after_reset(h, ls, k, p.env_begin, p.env_end); if (rc) return rc; }
