@@ -69,7 +69,7 @@ typedef struct FmConfig {
   int32_t graph_feat_global; /* 0: graph_feat_type 'relative' (node_obs [B,N,E,11], navigation_graph.py:1079-1124);
                                 1: 'global' (node_obs [B,N,E,7] = [vel, pos, goal, type], :1058-1077) */
   int32_t num_walls;       /* W = 0, 1 or 2 axis-aligned wall segments (navigation_graph.py:181-196, :287-324; core.py:36-55,
-                              :407-462); group-per-env kernels only; not with graph_feat_global */
+                              :407-462); agent-warp kernels at N = 3, O = 3 (and 4 / 2 / 1), else group-per-env; not with graph_feat_global */
   int32_t reserved_;
 } FmConfig;
 
